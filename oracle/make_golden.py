@@ -1,0 +1,92 @@
+"""Generate tests/golden/*.npz by RUNNING THE REFERENCE ITSELF (container only).
+
+    python oracle/make_golden.py            # needs /root/reference
+
+Each fixture holds: the input (int16 PCM grid, so float32-exact), the reference's output float
+array exactly as it was handed to soundfile.write (pre-PCM-24 quantisation), the chunk lengths
+of those writes, the state-CSV rows the reference wrote, the kwargs, and the NumPy version.
+The reference has no golden vectors of its own; these are "outputs of the
+reference itself run here".  `guard_skipped` records the one permitted deviation (sr != 48 kHz
+guard lines dropped for standard/xfade).
+"""
+from __future__ import annotations
+
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from oracle import ref_harness as rh                      # noqa: E402
+from tomatis_audio_processor_b200 import synth            # noqa: E402
+
+OUT_DIR = os.path.join(ROOT, "tests", "golden")
+
+
+def _q(x):
+    return synth.pcm16_to_float(synth.quantise_pcm16(x))
+
+
+def cases():
+    """(name, mode, sr, input float32 [N,2] on the int16 grid, kwargs)"""
+    c = []
+    # two limiter chunks (boundary at 239 616), default parameters, loud enough to engage the limiter
+    x = synth.recipe_gated_pink(262144 / 48000, 48000, 11, env_hz=1.0, hi_dbfs=-22.0)
+    c.append(("std_48k_two_chunks", "standard", 48000, _q(x), dict(gate_ui=50)))
+    # linear gate map + output gain + short up-delay
+    x = synth.recipe_gated_pink(1.5, 48000, 12, env_hz=2.0, lo_dbfs=-60.0, hi_dbfs=-30.0)
+    c.append(("std_48k_linear_gain", "standard", 48000, _q(x),
+              dict(gate_ui=58, gate_mode="linear", output_gain_db=-3.0, up_delay_ms=100.0, hysteresis_db=2.0)))
+    # xfade with threshold-straddling ramps (linear map: gate_ui 50 -> T=-50)
+    x = synth.recipe_threshold_ramps(2.0, 48000, 13, t_on=-48.5, t_off=-51.5, period_s=1.0)
+    c.append(("xfade_48k_ramps", "xfade", 48000, _q(x), dict(gate_ui=50, xfade_ms=200.0, up_delay_ms=60.0)))
+    # xfade CLI default: xfade_ms = 0 -> hard switching
+    x = synth.recipe_gated_pink(1.5, 48000, 14, env_hz=2.0, lo_dbfs=-65.0, hi_dbfs=-35.0, bursts=False)
+    c.append(("xfade_48k_hard", "xfade", 48000, _q(x), dict(gate_ui=50, up_delay_ms=50.0)))
+    # adaptive, float32 branch (pre-attenuation active)
+    x = synth.recipe_swept_pink(2.0, 48000, 15, period_s=0.9, peak=0.5)
+    c.append(("adaptive_48k_f32", "adaptive", 48000, _q(x), dict(min_hold_ms=100.0, xfade_ms=200.0)))
+    # adaptive, float64 branch (input peak <= 0.141 -> atten_db is int 0)
+    x = synth.recipe_swept_pink(1.5, 48000, 16, period_s=0.7, peak=0.1)
+    c.append(("adaptive_48k_f64", "adaptive", 48000, _q(x), dict()))
+    # 44.1 kHz standard (guard skipped), ragged length
+    x = synth.recipe_gated_pink(1.5, 44100, 17, env_hz=2.0, hi_dbfs=-28.0)
+    c.append(("std_44k1", "standard", 44100, _q(x), dict(gate_ui=50, up_delay_ms=120.0)))
+    # 96 kHz xfade, total % hop == 0 -> pad_end == 0 (degenerate tail)
+    x = synth.recipe_threshold_ramps(2048 * 40 / 96000, 96000, 18, t_on=-38.5, t_off=-41.5, period_s=0.4)
+    c.append(("xfade_96k_padend0", "xfade", 96000, _q(x)[:2048 * 40], dict(gate_ui=60, xfade_ms=100.0, up_delay_ms=40.0)))
+    # adaptive 44.1 kHz, total % hop == hop-1 (tail reaches the window end)
+    x = synth.recipe_swept_pink(2.0, 44100, 19, period_s=0.8, peak=0.4)
+    c.append(("adaptive_44k1_tail", "adaptive", 44100, _q(x)[:2048 * 30 + 2047], dict(min_hold_ms=90.0, xfade_ms=150.0)))
+    return c
+
+
+def main():
+    assert rh.reference_available(), "run in the build container (needs /root/reference)"
+    os.makedirs(OUT_DIR, exist_ok=True)
+    for name, mode, sr, x, kw in cases():
+        r = rh.run_reference(mode, x, sr, **kw)
+        q = synth.quantise_pcm16(x)
+        assert np.array_equal(synth.pcm16_to_float(q), x)
+        path = os.path.join(OUT_DIR, name + ".npz")
+        np.savez_compressed(
+            path,
+            pcm16=q,
+            out=r["out"],
+            chunk_lengths=np.array(r["chunk_lengths"], dtype=np.int64),
+            meta=np.array(json.dumps(dict(
+                name=name, mode=mode, sr=sr, kwargs=kw, csv=r["csv"], guard_skipped=r["guard_skipped"],
+                out_dtype=str(r["out"].dtype), numpy=np.__version__,
+                reference_files=[rh.MODULES[mode] + ".py"]))),
+        )
+        states = [row[3] for row in r["csv"][1:]]
+        print(f"{name:24s} {mode:9s} sr={sr} N={len(x)} out={r['out'].dtype} chunks={r['chunk_lengths']} "
+              f"frames={len(states)} C2={states.count('C2')}/{len(states)} peak={np.abs(r['out']).max():.4f} "
+              f"{os.path.getsize(path)/1e6:.2f} MB")
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,25 @@
+"""Shared helpers for the parity tests (test infrastructure)."""
+import glob
+import json
+import os
+
+import numpy as np
+
+from tomatis_audio_processor_b200 import synth
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def golden_names():
+    return sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
+
+
+def load_golden(name):
+    z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+    meta = json.loads(str(z["meta"]))
+    x = synth.pcm16_to_float(z["pcm16"])
+    return dict(x=x, out=z["out"], chunk_lengths=[int(v) for v in z["chunk_lengths"]], **meta)
+
+
+def csv_states(rows):
+    return [r[3] for r in rows[1:]]
