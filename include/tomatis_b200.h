@@ -1,0 +1,156 @@
+/* tomatis_b200.h -- C ABI of libtomatis_b200.so (hand-written sm_100a CUDA kernels).
+ *
+ * The reference (xyjk0511/tomatis-audio-processor) has no FFI boundary of its own: its contract is
+ * the Python `process(in_path, out_path, ...)` functions of
+ *     src/process_tomatis.py:160-178, src/process_tomatis_xfade.py:55-71,
+ *     src/process_tomatis_adaptive.py:157-172
+ * whose *inside* (everything between "samples read" and "samples written") this library
+ * replaces.  Each entry point below names the reference code it stands in for.  The host side
+ * (tomatis_audio_processor_b200/*.py) binds these with ctypes; INTEGRATION.md shows the stub a
+ * reference maintainer would add.
+ *
+ * Conventions: plain pointers and sizes only; every function returns 0 (TMT_OK) or a negative
+ * error code and never throws; `stream` is a cudaStream_t passed as void* (NULL = default stream);
+ * "device pointer" arguments are owned by the caller (e.g. torch tensors).  Audio is interleaved
+ * stereo float32, one sample-frame ("sf") = {L, R}.  n_fft = 4096, hop = 2048 (the reference's
+ * defaults, src/process_tomatis.py:174-175) are the supported geometry.
+ */
+#ifndef TOMATIS_B200_H
+#define TOMATIS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TMT_OK 0
+#define TMT_ERR_INVALID (-1)     /* bad argument */
+#define TMT_ERR_CUDA (-2)        /* CUDA runtime error, see tmt_last_error */
+#define TMT_ERR_UNSUPPORTED (-3) /* geometry / parameter outside what the kernels implement */
+#define TMT_ERR_NOMEM (-4)
+
+/* Framing modes (how frames and output blocks are laid over the file). */
+#define TMT_FRAMING_STREAMING 0 /* standard + xfade: first frame at -n_fft/2, tail zero pad `pad_end`,      \
+                                   out/(sum w^2 + 1e-12), per-chunk limiter                                 \
+                                   (src/process_tomatis.py:270-272,310-312,419-426,447-453) */
+#define TMT_FRAMING_WHOLEFILE 1 /* adaptive: frames at k*hop with 0 <= k*hop < total, y/max(sum w^2,1e-8),   \
+                                   one global limiter (src/process_tomatis_adaptive.py:298-345) */
+
+/* Gate automata. */
+#define TMT_GATE_UPDELAY 0 /* hysteresis + up-delay, src/process_tomatis.py:373-385 */
+#define TMT_GATE_MINHOLD 1 /* hysteresis + min-hold, src/process_tomatis_adaptive.py:87-121 */
+
+/* Per-frame / per-track arrays owned by a plan (see tmt_plan_read / tmt_plan_write). */
+#define TMT_ARR_MEANSQ_F32 0   /* float  [frames]  np.mean(mono*mono) of each frame, bit-exact   */
+#define TMT_ARR_MEANSQ_F64 1   /* double [frames]  same in the adaptive float64 branch            */
+#define TMT_ARR_GATE_F64 2     /* double [frames]  caller-supplied gate input (levels in dBFS)    */
+#define TMT_ARR_STATE 3        /* uint8  [frames]  1 = C1, 2 = C2                                 */
+#define TMT_ARR_ROW 4          /* uint16 [frames]  gain-table row (crossfade counter k)           */
+#define TMT_ARR_C2_COUNT 5     /* int32  [tracks]  number of C2 frames                            */
+#define TMT_ARR_CHUNK_PEAK 6   /* float  [chunks]  max |y| of each limiter chunk before limiting  */
+#define TMT_ARR_INPUT_PEAK 7   /* float  [tracks]  max |x|                                        */
+#define TMT_ARR_HOPSUM_F32 8   /* float  [frames + tracks] pairwise sum of each hop block         */
+#define TMT_ARR_HOPSUM_F64 9   /* double [frames + tracks]                                        */
+
+typedef struct tmt_engine tmt_engine; /* per device: window, twiddles, gain rows */
+typedef struct tmt_plan tmt_plan;     /* per batch of tracks (or file shard): geometry + scratch */
+
+/* One track, or one time shard of a long file.  Positions are absolute sample-frame indices in the
+ * file; the in/out device buffers may cover only a window of it (halo sharding). */
+typedef struct tmt_track_desc {
+    const void* pcm_in; /* device, float32 [in_len][2], element 0 is file position in_origin  */
+    void* pcm_out;      /* device, float32 [out_len][2], element 0 is file position out_origin */
+    int64_t total;      /* file length in sample-frames (zero padding / clipping refer to it)  */
+    int64_t in_origin, in_len;
+    int64_t out_origin, out_len;
+    int64_t block_lo, block_hi; /* output hop-blocks [lo,hi) this plan produces; hi < 0 = all  */
+} tmt_track_desc;
+
+int tmt_version(void);
+const char* tmt_error_string(int code);
+/* Last error text of the calling thread (valid until the next failing call on that thread). */
+const char* tmt_last_error(void);
+
+/* ---- engine ------------------------------------------------------------------------------- */
+int tmt_engine_create(tmt_engine** out, int device, int n_fft, int hop);
+int tmt_engine_destroy(tmt_engine* e);
+/* Analysis = synthesis window, `np.hanning(n_fft).astype(float32)` (src/process_tomatis.py:266).
+ * Host pointer. */
+int tmt_engine_set_window(tmt_engine* e, const float* win, int n);
+/* Gain table: n_rows rows of n_fft/2+1 linear gains in natural bin order, as produced by
+ * db_to_lin(build_tilt_gain_db(...)) (src/process_tomatis.py:105-158); row r is used by frames whose
+ * TMT_ARR_ROW value is r (replaces the per-frame `gain = g1 if state == 1 else g2` / dB-domain mix,
+ * src/process_tomatis.py:392, _xfade.py:270-274, _adaptive.py:302-304).  Host pointer. */
+int tmt_engine_set_gain_rows(tmt_engine* e, const float* rows, int n_rows, int n_bins);
+
+/* ---- plan --------------------------------------------------------------------------------- */
+/* unit_blocks: output hop-blocks per CTA work unit of the STFT kernel (0 = default). */
+int tmt_plan_create(tmt_engine* e, tmt_plan** out, int framing, int n_tracks, const tmt_track_desc* tracks,
+                    int unit_blocks);
+int tmt_plan_destroy(tmt_plan* p);
+/* Re-point the audio buffers (same geometry), e.g. to ping-pong staging buffers. */
+int tmt_plan_set_buffers(tmt_plan* p, int track, const void* pcm_in, void* pcm_out);
+
+int tmt_plan_total_frames(const tmt_plan* p);  /* sum of n_frames over tracks                  */
+int tmt_plan_total_chunks(const tmt_plan* p);
+int tmt_plan_total_units(const tmt_plan* p);
+int tmt_plan_track_frames(const tmt_plan* p, int track);      /* n_frames of one track          */
+int tmt_plan_track_frame_base(const tmt_plan* p, int track);  /* its offset in per-frame arrays */
+int tmt_plan_track_chunks(const tmt_plan* p, int track);
+int tmt_plan_track_chunk_base(const tmt_plan* p, int track);
+/* Limiter chunk c of `track`: file sample range [*s0, *s1) (already clipped to [0,total)). */
+int tmt_plan_chunk_range(const tmt_plan* p, int track, int c, int64_t* s0, int64_t* s1);
+
+/* Copy `count` elements starting at `offset` of a plan array to/from `ptr` (host if is_device==0,
+ * else device); synchronises `stream` for host copies. */
+int tmt_plan_read(tmt_plan* p, int which, int64_t offset, int64_t count, void* ptr, int is_device, void* stream);
+int tmt_plan_write(tmt_plan* p, int which, int64_t offset, int64_t count, const void* ptr, int is_device,
+                   void* stream);
+
+/* ---- kernels ------------------------------------------------------------------------------ */
+/* max |x| per track -> TMT_ARR_INPUT_PEAK (src/process_tomatis_adaptive.py:201). */
+int tmt_plan_input_peaks(tmt_plan* p, void* stream);
+
+/* K2a.  Per-frame mean square m = np.mean(mono*mono), mono = sqrt(mean(frame**2, axis=1)), bit-exact
+ * with NumPy's pairwise summation (rms_dbfs + caller, src/process_tomatis.py:43-52,370;
+ * compute_frame_levels, src/process_tomatis_adaptive.py:57-84).  in_scale (host, per track, may be
+ * NULL = 1) is the adaptive pre-attenuation x*atten_lin applied in float32 before squaring
+ * (src/process_tomatis_adaptive.py:215); use_f64 selects the float64 branch of that file.
+ * Result in TMT_ARR_MEANSQ_F32 / _F64. */
+int tmt_plan_levels(tmt_plan* p, int use_f64, const float* in_scale, void* stream);
+
+/* K2b.  Gate automaton + crossfade counter as a block-level scan over frames.
+ * gate_input: TMT_ARR_MEANSQ_F32, TMT_ARR_MEANSQ_F64 or TMT_ARR_GATE_F64.  Frame is "hi" when
+ * value >= on[track], "lo" when value <= off[track] (host arrays of n_tracks doubles; thresholds in the
+ * domain of the gate input).  param = consecutive hi frames needed to switch up (UPDELAY:
+ * ceil(up_delay_samples/hop)+1) or min_hold_frames (MINHOLD).  xfade_frames = 0 -> hard switching.
+ * alpha_init_to_target != 0: the counter starts at the first frame's target (adaptive,
+ * src/process_tomatis_adaptive.py:257) instead of 0 (xfade, _xfade.py:171).
+ * count_only != 0: only TMT_ARR_C2_COUNT is produced (threshold bisection,
+ * src/process_tomatis_adaptive.py:136-152). */
+int tmt_plan_gate(tmt_plan* p, int automaton, int gate_input, const double* on, const double* off, int param,
+                  int xfade_frames, int alpha_init_to_target, int count_only, void* stream);
+
+/* K1+K3+K4 fused: frame gather + Hann window + 4096-pt FFT (stereo packed as L+iR) + gain row +
+ * inverse FFT + synthesis window + overlap-add (each output sample written exactly once, no atomics)
+ * + normalisation + optional output gain, and max|y| per limiter chunk into TMT_ARR_CHUNK_PEAK
+ * (process_available_frames / flush, src/process_tomatis.py:359-426,447-453; _adaptive.py:298-332).
+ * post_gain: linear output gain 10^(output_gain_db/20) (src/process_tomatis.py:349-350), 1 = none. */
+int tmt_plan_stft(tmt_plan* p, float post_gain, void* stream);
+
+/* Peak limiter: every chunk whose peak exceeds `limit` is scaled by limit/peak in place
+ * (write_clamped, src/process_tomatis.py:352-355; global variant _adaptive.py:341-345). */
+int tmt_plan_limiter(tmt_plan* p, float limit, void* stream);
+
+/* Convenience: levels (f32) -> gate -> stft -> limiter on one stream, standard/xfade parameters. */
+int tmt_plan_run_streaming(tmt_plan* p, double m_on, double m_off, int run_frames, int xfade_frames,
+                           float post_gain, float limit, void* stream);
+
+/* Number of kernel launches issued by this plan since creation (bench.py's gpu_launches). */
+int64_t tmt_plan_launch_count(const tmt_plan* p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TOMATIS_B200_H */

@@ -1,0 +1,90 @@
+"""ctypes binding of csrc/libtomatis_b200.so (the C ABI in include/tomatis_b200.h).
+
+There is deliberately no fallback: if the CUDA library is missing or fails to load, importing
+callers get a RuntimeError telling them to build it.  Nothing here imports `oracle/`.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+from .build import LIB_PATH
+
+OK = 0
+FRAMING_STREAMING, FRAMING_WHOLEFILE = 0, 1
+GATE_UPDELAY, GATE_MINHOLD = 0, 1
+(ARR_MEANSQ_F32, ARR_MEANSQ_F64, ARR_GATE_F64, ARR_STATE, ARR_ROW, ARR_C2_COUNT, ARR_CHUNK_PEAK,
+ ARR_INPUT_PEAK, ARR_HOPSUM_F32, ARR_HOPSUM_F64) = range(10)
+
+
+class TrackDesc(C.Structure):
+    """struct tmt_track_desc"""
+    _fields_ = [("pcm_in", C.c_void_p), ("pcm_out", C.c_void_p), ("total", C.c_int64),
+                ("in_origin", C.c_int64), ("in_len", C.c_int64),
+                ("out_origin", C.c_int64), ("out_len", C.c_int64),
+                ("block_lo", C.c_int64), ("block_hi", C.c_int64)]
+
+
+# every symbol include/tomatis_b200.h declares: name -> (restype, argtypes)
+_P = C.c_void_p
+SIGNATURES = {
+    "tmt_version": (C.c_int, []),
+    "tmt_error_string": (C.c_char_p, [C.c_int]),
+    "tmt_last_error": (C.c_char_p, []),
+    "tmt_engine_create": (C.c_int, [C.POINTER(_P), C.c_int, C.c_int, C.c_int]),
+    "tmt_engine_destroy": (C.c_int, [_P]),
+    "tmt_engine_set_window": (C.c_int, [_P, _P, C.c_int]),
+    "tmt_engine_set_gain_rows": (C.c_int, [_P, _P, C.c_int, C.c_int]),
+    "tmt_plan_create": (C.c_int, [_P, C.POINTER(_P), C.c_int, C.c_int, C.POINTER(TrackDesc), C.c_int]),
+    "tmt_plan_destroy": (C.c_int, [_P]),
+    "tmt_plan_set_buffers": (C.c_int, [_P, C.c_int, _P, _P]),
+    "tmt_plan_total_frames": (C.c_int, [_P]),
+    "tmt_plan_total_chunks": (C.c_int, [_P]),
+    "tmt_plan_total_units": (C.c_int, [_P]),
+    "tmt_plan_track_frames": (C.c_int, [_P, C.c_int]),
+    "tmt_plan_track_frame_base": (C.c_int, [_P, C.c_int]),
+    "tmt_plan_track_chunks": (C.c_int, [_P, C.c_int]),
+    "tmt_plan_track_chunk_base": (C.c_int, [_P, C.c_int]),
+    "tmt_plan_chunk_range": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "tmt_plan_read": (C.c_int, [_P, C.c_int, C.c_int64, C.c_int64, _P, C.c_int, _P]),
+    "tmt_plan_write": (C.c_int, [_P, C.c_int, C.c_int64, C.c_int64, _P, C.c_int, _P]),
+    "tmt_plan_input_peaks": (C.c_int, [_P, _P]),
+    "tmt_plan_levels": (C.c_int, [_P, C.c_int, _P, _P]),
+    "tmt_plan_gate": (C.c_int, [_P, C.c_int, C.c_int, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
+    "tmt_plan_stft": (C.c_int, [_P, C.c_float, _P]),
+    "tmt_plan_limiter": (C.c_int, [_P, C.c_float, _P]),
+    "tmt_plan_run_streaming": (C.c_int, [_P, C.c_double, C.c_double, C.c_int, C.c_int, C.c_float, C.c_float, _P]),
+    "tmt_plan_launch_count": (C.c_int64, [_P]),
+}
+
+_lib = None
+
+
+class TomatisError(RuntimeError):
+    pass
+
+
+def load():
+    """Load the library (once).  Raises RuntimeError if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"CUDA library not built: {LIB_PATH} is missing. Run `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(needs nvcc); there is no CPU fallback.")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)       # AttributeError if the .so does not export a declared symbol
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str = ""):
+    if rc != OK:
+        lib = load()
+        msg = lib.tmt_last_error().decode("utf-8", "replace")
+        kind = lib.tmt_error_string(rc).decode()
+        raise TomatisError(f"{what or 'libtomatis_b200'}: {kind} ({rc}): {msg}")

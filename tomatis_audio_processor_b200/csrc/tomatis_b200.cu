@@ -1,0 +1,1031 @@
+// libtomatis_b200.so -- hand-written sm_100a kernels for the Tomatis processing path and the C ABI
+// declared in include/tomatis_b200.h.  See DESIGN.md for the data layout and the roofline of each
+// kernel; reference citations (file:line under /root/reference) are next to each kernel.
+//
+// Kernels
+//   input_peak_kernel   max|x| per track                                  (HBM stream, 8 B/sf read)
+//   levels_kernel<T>    per hop-block pairwise sum of mono^2, bit-exact   (HBM stream, 8 B/sf read)
+//   meansq_kernel<T>    m[k] = (H[k] + H[k+1]) / n_fft
+//   gate_kernel<T,A>    gate automaton + crossfade counter, block-level scan by map composition
+//   stft_kernel         gather + window + FFT + gain + IFFT + window + OLA + normalise + chunk peaks
+//   limiter_kernel      per-chunk in-place rescale
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <cstdio>
+#include <cstdarg>
+#include <cstring>
+#include <cmath>
+#include <vector>
+#include <algorithm>
+#include <new>
+
+#include "../../include/tomatis_b200.h"
+#include "fft4096.cuh"
+#include "host_tables.hpp"
+
+namespace {
+
+using namespace tmt;
+
+constexpr long long kFlushSafe = 48000LL * 5;   // src/process_tomatis.py:420 (a sample count)
+constexpr int kLevelWarps = 8;                   // hop-blocks per CTA of levels_kernel
+constexpr int kMaxGateStates = 255;
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                           \
+    do {                                                                                         \
+        cudaError_t _e = (expr);                                                                 \
+        if (_e != cudaSuccess)                                                                   \
+            return fail(TMT_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e),    \
+                        __FILE__, __LINE__);                                                     \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// device-side descriptors
+struct TrackDev {
+    const float2* in;        // element 0 = file position in_origin
+    float2* out;             // element 0 = file position out_origin
+    long long in_lo, in_hi;  // readable file positions [in_lo, in_hi)  (already clipped to [0,total))
+    long long in_origin;
+    long long out_lo, out_hi;
+    long long out_origin;
+    long long total;
+    long long first_start;   // position of frame 0: -n_fft/2 (streaming) or 0 (whole-file)
+    int n_frames;
+    int frame_base;          // offset of frame 0 in per-frame arrays
+    int hs_base;             // offset of hop-block 0 in the hop-sum array (= frame_base + track index)
+    int hb_lo, hb_hi;        // hop-blocks whose sums this plan computes
+    int f_lo, f_hi;          // frames whose mean square this plan computes
+    int chunk_base, n_chunks;
+};
+struct UnitDev { int track, b0, b1, chunk; };        // STFT work unit: output blocks [b0,b1) of a track
+struct ChunkDev { int track; long long s0, s1; };    // limiter chunk: file positions [s0,s1)
+
+// ------------------------------------------------------------------------------------------------
+// streaming loads/stores: audio is touched once per pass, keep it out of L1
+__device__ __forceinline__ float2 ld_stream(const float2* p) {
+    float2 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0,%1}, [%2];" : "=f"(r.x), "=f"(r.y) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ float4 ld_stream4(const float4* p) {
+    float4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void st_stream(float2* p, float2 v) {
+    asm volatile("st.global.L1::no_allocate.v2.f32 [%0], {%1,%2};" ::"l"(p), "f"(v.x), "f"(v.y) : "memory");
+}
+
+// ------------------------------------------------------------------------------------------------
+// input peak (src/process_tomatis_adaptive.py:201  input_peak = np.max(np.abs(x)))
+__global__ void __launch_bounds__(256) input_peak_kernel(const TrackDev* __restrict__ tracks, float* __restrict__ peaks) {
+    const TrackDev tr = tracks[blockIdx.y];
+    float m = 0.f;
+    const long long n = tr.in_hi - tr.in_lo;
+    const float2* src = tr.in + (tr.in_lo - tr.in_origin);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const float2 x = ld_stream(src + i);
+        m = fmaxf(m, fmaxf(fabsf(x.x), fabsf(x.y)));
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(reinterpret_cast<int*>(peaks + blockIdx.y), __float_as_int(m));
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2a levels.  The reference computes, per frame (src/process_tomatis.py:370, :51):
+//     mono = np.sqrt(np.mean(frame**2, axis=1));  m = np.mean(mono*mono)
+// in float32 (float64 in the adaptive no-attenuation branch) with NumPy's pairwise summation:
+// 128-element leaves, 8 strided accumulators per leaf combined as ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)),
+// leaves combined by a balanced binary tree.  With hop = n_fft/2 = 16 leaves the frame sum is exactly
+// H[k] + H[k+1] with H the pairwise sum of one 2048-sample hop block, so each hop block is reduced once.
+// One warp per hop block: lane = (leaf & 7, accumulator pair); each accumulator is summed sequentially
+// by one lane in NumPy's order; every add/mul/sqrt is an explicit round-to-nearest intrinsic (no FMA
+// contraction), which makes m bit-identical to NumPy's.
+template <typename T> struct Arith;
+template <> struct Arith<float> {
+    static __device__ __forceinline__ float msq(float2 x, float sc) {
+        const float l = __fmul_rn(x.x, sc), r = __fmul_rn(x.y, sc);
+        const float h = __fmul_rn(__fadd_rn(__fmul_rn(l, l), __fmul_rn(r, r)), 0.5f);
+        const float mono = __fsqrt_rn(h);
+        return __fmul_rn(mono, mono);
+    }
+    static __device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); }
+    static __device__ __forceinline__ float div(float a, float b) { return __fdiv_rn(a, b); }
+};
+template <> struct Arith<double> {
+    static __device__ __forceinline__ double msq(float2 x, float sc) {
+        const double l = __dmul_rn((double)x.x, (double)sc), r = __dmul_rn((double)x.y, (double)sc);
+        const double h = __dmul_rn(__dadd_rn(__dmul_rn(l, l), __dmul_rn(r, r)), 0.5);
+        const double mono = __dsqrt_rn(h);
+        return __dmul_rn(mono, mono);
+    }
+    static __device__ __forceinline__ double add(double a, double b) { return __dadd_rn(a, b); }
+    static __device__ __forceinline__ double div(double a, double b) { return __ddiv_rn(a, b); }
+};
+
+template <typename T>
+__global__ void __launch_bounds__(kLevelWarps * 32)
+levels_kernel(const TrackDev* __restrict__ tracks, const float* __restrict__ in_scale, T* __restrict__ hsum) {
+    const TrackDev tr = tracks[blockIdx.y];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int q = tr.hb_lo + blockIdx.x * kLevelWarps + warp;
+    if (q >= tr.hb_hi) return;                       // whole warp exits together
+    const float sc = in_scale ? in_scale[blockIdx.y] : 1.0f;
+    const long long start = tr.first_start + (long long)q * kHop;
+    const int pr = lane & 3, leaf = lane >> 2;
+    const bool inside = (start >= tr.in_lo) && (start + kHop <= tr.in_hi);
+    const bool aligned = (((start - tr.in_origin) & 1LL) == 0) && ((reinterpret_cast<uintptr_t>(tr.in) & 15u) == 0);
+    T tot[2];
+#pragma unroll
+    for (int ps = 0; ps < 2; ++ps) {
+        const long long base = start + (ps * 8 + leaf) * 128 + 2 * pr;
+        float2 x0[16], x1[16];
+        if (inside && aligned) {
+            const float4* src = reinterpret_cast<const float4*>(tr.in + (base - tr.in_origin));
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const float4 v = ld_stream4(src + 4 * i);      // 8 sf = 4 float4 per step
+                x0[i] = make_float2(v.x, v.y);
+                x1[i] = make_float2(v.z, v.w);
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const long long p0 = base + 8 * i, p1 = p0 + 1;
+                x0[i] = (p0 >= tr.in_lo && p0 < tr.in_hi) ? tr.in[p0 - tr.in_origin] : make_float2(0.f, 0.f);
+                x1[i] = (p1 >= tr.in_lo && p1 < tr.in_hi) ? tr.in[p1 - tr.in_origin] : make_float2(0.f, 0.f);
+            }
+        }
+        T a0 = Arith<T>::msq(x0[0], sc), a1 = Arith<T>::msq(x1[0], sc);
+#pragma unroll
+        for (int i = 1; i < 16; ++i) {
+            a0 = Arith<T>::add(a0, Arith<T>::msq(x0[i], sc));
+            a1 = Arith<T>::add(a1, Arith<T>::msq(x1[i], sc));
+        }
+        T s = Arith<T>::add(a0, a1);                                         // r[2p] + r[2p+1]
+        s = Arith<T>::add(s, __shfl_xor_sync(0xffffffffu, s, 1));            // (r0+r1)+(r2+r3) | (r4+r5)+(r6+r7)
+        s = Arith<T>::add(s, __shfl_xor_sync(0xffffffffu, s, 2));            // leaf sum
+        s = Arith<T>::add(s, __shfl_xor_sync(0xffffffffu, s, 4));            // 2 leaves
+        s = Arith<T>::add(s, __shfl_xor_sync(0xffffffffu, s, 8));            // 4 leaves
+        s = Arith<T>::add(s, __shfl_xor_sync(0xffffffffu, s, 16));           // 8 leaves = 1024 samples
+        tot[ps] = s;
+    }
+    if (lane == 0) hsum[tr.hs_base + q] = Arith<T>::add(tot[0], tot[1]);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+meansq_kernel(const TrackDev* __restrict__ tracks, const T* __restrict__ hsum, T* __restrict__ msq) {
+    const TrackDev tr = tracks[blockIdx.y];
+    const int k = tr.f_lo + blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= tr.f_hi) return;
+    const T s = Arith<T>::add(hsum[tr.hs_base + k], hsum[tr.hs_base + k + 1]);   // pairwise split at n/2
+    msq[tr.frame_base + k] = Arith<T>::div(s, (T)kNfft);                          // np.mean: sum / count
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2b gate.  Both automata are finite-state machines driven by two bits per frame
+// (hi: value >= on, lo: value <= off), so a run of frames is a map on the state set and maps compose
+// associatively.  One CTA per track; each thread owns a contiguous segment of frames, builds the
+// segment's map by simulating every start state, the maps are combined by a two-level (warp, CTA) chain,
+// and each thread then replays its segment from its true start state.  The crossfade counter
+// k in [0, X] (alpha = k / X) follows the state by clamped +-1 steps; its segment maps are clamp
+// triples (d, lo, hi) combined the same way.
+//   UPDELAY (src/process_tomatis.py:373-385): states 0..R-1 = C1 after r consecutive hi frames, R = C2.
+//   MINHOLD (src/process_tomatis_adaptive.py:100-119): s = st*(H+1) + c, c = min(frames_since_switch, H).
+template <int AUTO>
+__device__ __forceinline__ int gate_next(int s, bool hi, bool lo, int param) {
+    if (AUTO == TMT_GATE_UPDELAY) {
+        if (s == param) return lo ? 0 : param;
+        return hi ? s + 1 : 0;
+    } else {
+        const int st = (s > param) ? 1 : 0;
+        const int c = s - st * (param + 1);
+        const int c1 = min(c + 1, param);
+        if (c1 >= param) {
+            if (!st && hi) return param + 1;     // -> C2, counter 0
+            if (st && lo) return 0;              // -> C1, counter 0
+        }
+        return st * (param + 1) + c1;
+    }
+}
+template <int AUTO> __device__ __forceinline__ bool gate_is_c2(int s, int param) {
+    return AUTO == TMT_GATE_UPDELAY ? (s == param) : (s > param);
+}
+
+struct Clamp3 { int d, lo, hi; };   // k -> min(max(k + d, lo), hi)
+__device__ __forceinline__ int clamp3_apply(Clamp3 m, int k) { return min(max(k + m.d, m.lo), m.hi); }
+// g after f
+__device__ __forceinline__ Clamp3 clamp3_then(Clamp3 f, Clamp3 g) {
+    Clamp3 r;
+    r.d = f.d + g.d;
+    r.lo = min(max(f.lo + g.d, g.lo), g.hi);
+    r.hi = min(max(f.hi + g.d, g.lo), g.hi);
+    return r;
+}
+
+template <typename T, int AUTO>
+__global__ void gate_kernel(const TrackDev* __restrict__ tracks, const T* __restrict__ vals,
+                            const double* __restrict__ von, const double* __restrict__ voff, int param, int S,
+                            int X, int alpha_init, int count_only, uint8_t* __restrict__ state,
+                            uint16_t* __restrict__ rows, int* __restrict__ c2_count) {
+    extern __shared__ __align__(16) unsigned char gsm[];
+    const int NT = blockDim.x, NW = NT >> 5;
+    const int i = threadIdx.x, w = i >> 5, lane = i & 31;
+    uint8_t* maps = gsm;                     // [S][NT]
+    uint8_t* wmap = maps + S * NT;           // [S][NW]
+    uint8_t* segstart = wmap + S * NW;       // [NT]
+    uint8_t* wstart = segstart + NT;         // [NW]
+    int* ibase = reinterpret_cast<int*>(gsm + ((S * NT + S * NW + NT + NW + 15) & ~15));
+    int* a_d = ibase;                        // [NT] segment clamp maps
+    int* a_lo = a_d + NT;
+    int* a_hi = a_lo + NT;
+    int* aw = a_hi + NT;                     // [3][NW] warp clamp maps
+    int* akstart = aw + 3 * NW;              // [NT]
+    int* awstart = akstart + NT;             // [NW]
+    int* red = awstart + NW;                 // [NW]
+
+    const TrackDev tr = tracks[blockIdx.x];
+    const int F = tr.n_frames;
+    const T* v = vals + tr.frame_base;
+    const T on = (T)von[blockIdx.x], off = (T)voff[blockIdx.x];
+    const int L = (F + NT - 1) / NT;
+    const int f0 = min(F, i * L), f1 = min(F, f0 + L);
+    const int Xe = max(X, 1);
+    const int s_init = (AUTO == TMT_GATE_UPDELAY) ? 0 : param;
+
+    // 1. segment maps
+    for (int s = 0; s < S; ++s) maps[s * NT + i] = (uint8_t)s;
+    for (int f = f0; f < f1; ++f) {
+        const T x = v[f];
+        const bool hi = x >= on, lo = x <= off;
+        for (int s = 0; s < S; ++s) maps[s * NT + i] = (uint8_t)gate_next<AUTO>(maps[s * NT + i], hi, lo, param);
+    }
+    __syncthreads();
+    // 2. two-level chain of the maps
+    for (int s = lane; s < S; s += 32) {
+        int cur = s;
+        for (int j = 0; j < 32; ++j) cur = maps[cur * NT + w * 32 + j];
+        wmap[s * NW + w] = (uint8_t)cur;
+    }
+    __syncthreads();
+    if (i == 0) {
+        int cur = s_init;
+        for (int ww = 0; ww < NW; ++ww) { wstart[ww] = (uint8_t)cur; cur = wmap[cur * NW + ww]; }
+    }
+    __syncthreads();
+    if (lane == 0) {
+        int cur = wstart[w];
+        for (int j = 0; j < 32; ++j) { segstart[w * 32 + j] = (uint8_t)cur; cur = maps[cur * NT + w * 32 + j]; }
+    }
+    __syncthreads();
+    // 3. replay: states, C2 count, crossfade clamp map of the segment
+    int cur = segstart[i];
+    int c2 = 0;
+    Clamp3 am = {0, 0, Xe};
+    for (int f = f0; f < f1; ++f) {
+        const T x = v[f];
+        cur = gate_next<AUTO>(cur, x >= on, x <= off, param);
+        const int t2 = gate_is_c2<AUTO>(cur, param) ? 1 : 0;
+        c2 += t2;
+        if (!count_only) {
+            state[tr.frame_base + f] = (uint8_t)(1 + t2);
+            Clamp3 g;
+            if (alpha_init && f == 0) { g.d = 0; g.lo = g.hi = t2 * Xe; }
+            else { g.d = t2 ? 1 : -1; g.lo = 0; g.hi = Xe; }
+            am = clamp3_then(am, g);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) c2 += __shfl_xor_sync(0xffffffffu, c2, o);
+    if (lane == 0) red[w] = c2;
+    if (!count_only) { a_d[i] = am.d; a_lo[i] = am.lo; a_hi[i] = am.hi; }
+    __syncthreads();
+    if (i == 0) {
+        int tot = 0;
+        for (int ww = 0; ww < NW; ++ww) tot += red[ww];
+        c2_count[blockIdx.x] = tot;
+    }
+    if (count_only) return;
+    // 4. chain the clamp maps
+    if (lane == 0) {
+        Clamp3 m = {0, 0, Xe};
+        for (int j = 0; j < 32; ++j) {
+            const int sidx = w * 32 + j;
+            m = clamp3_then(m, Clamp3{a_d[sidx], a_lo[sidx], a_hi[sidx]});
+        }
+        aw[w] = m.d; aw[NW + w] = m.lo; aw[2 * NW + w] = m.hi;
+    }
+    __syncthreads();
+    if (i == 0) {
+        int k = 0;
+        for (int ww = 0; ww < NW; ++ww) { awstart[ww] = k; k = clamp3_apply(Clamp3{aw[ww], aw[NW + ww], aw[2 * NW + ww]}, k); }
+    }
+    __syncthreads();
+    if (lane == 0) {
+        int k = awstart[w];
+        for (int j = 0; j < 32; ++j) {
+            const int sidx = w * 32 + j;
+            akstart[sidx] = k;
+            k = clamp3_apply(Clamp3{a_d[sidx], a_lo[sidx], a_hi[sidx]}, k);
+        }
+    }
+    __syncthreads();
+    // 5. replay the counter
+    int k = akstart[i];
+    for (int f = f0; f < f1; ++f) {
+        const int t2 = state[tr.frame_base + f] == 2 ? 1 : 0;
+        if (alpha_init && f == 0) k = t2 * Xe;
+        else k = min(max(k + (t2 ? 1 : -1), 0), Xe);
+        rows[tr.frame_base + f] = (uint16_t)k;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1+K3+K4 fused STFT kernel.  See fft4096.cuh for the FFT decomposition.
+// Output block b of a track = positions [first_start + b*hop, +hop) = second half of frame b-1 plus
+// first half of frame b.  A CTA owns a run of blocks [b0,b1) (one limiter chunk or a slice of one),
+// processes frames b0-1 .. b1-1 in order and keeps the running half frame in registers, so every
+// output sample is written exactly once and there is no OLA buffer, no sum-of-w^2 buffer and no atomics
+// on the audio path (reference: out_buf/w_buf accumulation src/process_tomatis.py:400-406, flush :419-426).
+// Thread t holds samples n = 256*j + t of the frame (j = 0..15): global loads/stores are coalesced
+// 256-byte rows, the window and the normalisation live in registers, the carry (j >= 8 -> j-8) stays
+// in the same thread.
+struct StftParams {
+    const TrackDev* tracks;
+    const UnitDev* units;
+    int n_units;
+    const uint16_t* rows;
+    const float* gperm;     // [n_rows][4096] register-order gains, 1/4096 folded in
+    const float* win;       // [4096]
+    const float* rnorm;     // [2048] interior 1/(w2[n+hop]+w2[n] (+eps | clamped))
+    const float2* twA;      // [256]
+    const float2* twB;      // [4096]
+    float* chunk_peaks;
+    int norm_clamp;         // 0: x/(nrm+1e-12)   1: x/max(nrm,1e-8)
+    float post_gain;
+};
+
+constexpr int kStftSmemBytes = (2 * kExchFloat2 + 256 + 4096) * (int)sizeof(float2) + 8 * (int)sizeof(float);
+
+__global__ void __launch_bounds__(kThreads, 2) stft_kernel(const StftParams prm) {
+    extern __shared__ __align__(16) unsigned char smraw[];
+    float2* bufP = reinterpret_cast<float2*>(smraw);
+    float2* bufQ = bufP + kExchFloat2;
+    float2* sA = bufQ + kExchFloat2;
+    float2* sB = sA + 256;
+    float* red = reinterpret_cast<float*>(sB + 4096);
+    const int t = threadIdx.x;
+
+    sA[t] = prm.twA[t];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) sB[j * 256 + t] = prm.twB[j * 256 + t];
+    float w[16], rn[8];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) w[j] = __ldg(prm.win + 256 * j + t);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) rn[j] = __ldg(prm.rnorm + 256 * j + t);
+    __syncthreads();
+
+    for (int u = blockIdx.x; u < prm.n_units; u += gridDim.x) {
+        const UnitDev un = prm.units[u];
+        const TrackDev tr = prm.tracks[un.track];
+        const uint16_t* rows = prm.rows + tr.frame_base;
+        float2 carry[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) carry[j] = make_float2(0.f, 0.f);
+        float peak = 0.f;
+
+        for (int f = un.b0 - 1; f < un.b1; ++f) {
+            float2 v[16];
+            const bool have = (f >= 0) && (f < tr.n_frames);
+            const long long pos0 = tr.first_start + (long long)f * kHop;
+            if (have) {
+                const float2* src = tr.in + (pos0 - tr.in_origin) + t;
+                if (pos0 >= tr.in_lo && pos0 + kNfft <= tr.in_hi) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[j] = ld_stream(src + 256 * j);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const long long p = pos0 + 256 * j + t;
+                        v[j] = (p >= tr.in_lo && p < tr.in_hi) ? ld_stream(src + 256 * j) : make_float2(0.f, 0.f);
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < 16; ++j) { v[j].x *= w[j]; v[j].y *= w[j]; }      // analysis window
+                fwd_a(v, t, sA, bufP);
+                __syncthreads();
+                fwd_b(v, t, sB, bufP, bufQ);
+                __syncthreads();
+                fwd_c(v, t, bufQ);
+                {   // tilt gain x crossfade weight: one real row per frame, register order
+                    const float4* g4 = reinterpret_cast<const float4*>(prm.gperm + (size_t)rows[f] * kNfft + t * 16);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const float4 g = __ldg(g4 + q);
+                        v[4 * q + 0].x *= g.x; v[4 * q + 0].y *= g.x;
+                        v[4 * q + 1].x *= g.y; v[4 * q + 1].y *= g.y;
+                        v[4 * q + 2].x *= g.z; v[4 * q + 2].y *= g.z;
+                        v[4 * q + 3].x *= g.w; v[4 * q + 3].y *= g.w;
+                    }
+                }
+                inv_c(v, t, bufP);
+                __syncthreads();
+                inv_b(v, t, sB, bufP, bufQ);
+                __syncthreads();
+                inv_a(v, t, sA, bufQ);
+#pragma unroll
+                for (int j = 0; j < 16; ++j) { v[j].x *= w[j]; v[j].y *= w[j]; }      // synthesis window
+            } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] = make_float2(0.f, 0.f);
+            }
+
+            if (f >= un.b0) {       // emit output block f
+                const bool interior = (f >= 1) && (f < tr.n_frames);
+                const bool full = (pos0 >= tr.out_lo) && (pos0 + kHop <= tr.out_hi);
+                float2* dst = tr.out + (pos0 - tr.out_origin) + t;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    float2 o = make_float2(carry[j].x + v[j].x, carry[j].y + v[j].y);
+                    if (interior) {
+                        o.x *= rn[j]; o.y *= rn[j];
+                    } else {
+                        const float nrm = ((f >= 1) ? w[j + 8] * w[j + 8] : 0.f) + ((f < tr.n_frames) ? w[j] * w[j] : 0.f);
+                        const float den = prm.norm_clamp ? fmaxf(nrm, 1e-8f) : (nrm + 1e-12f);
+                        o.x = __fdiv_rn(o.x, den); o.y = __fdiv_rn(o.y, den);
+                    }
+                    if (prm.post_gain != 1.0f) { o.x *= prm.post_gain; o.y *= prm.post_gain; }
+                    const long long p = pos0 + 256 * j + t;
+                    if (full || (p >= tr.out_lo && p < tr.out_hi)) {
+                        st_stream(dst + 256 * j, o);
+                        peak = fmaxf(peak, fmaxf(fabsf(o.x), fabsf(o.y)));
+                    }
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) carry[j] = v[j + 8];
+        }
+        // per-chunk peak: one atomic per work unit (values are >= 0, so int ordering == float ordering)
+#pragma unroll
+        for (int o = 16; o; o >>= 1) peak = fmaxf(peak, __shfl_xor_sync(0xffffffffu, peak, o));
+        if ((t & 31) == 0) red[t >> 5] = peak;
+        __syncthreads();
+        if (t == 0) {
+            float m = red[0];
+#pragma unroll
+            for (int q = 1; q < 8; ++q) m = fmaxf(m, red[q]);
+            if (m > 0.f) atomicMax(reinterpret_cast<int*>(prm.chunk_peaks + un.chunk), __float_as_int(m));
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// limiter (src/process_tomatis.py:352-355): if peak > limit: chunk *= limit / peak
+__global__ void __launch_bounds__(256)
+limiter_kernel(const TrackDev* __restrict__ tracks, const ChunkDev* __restrict__ chunks,
+               const float* __restrict__ peaks, float limit) {
+    const float peak = peaks[blockIdx.y];
+    if (!(peak > limit)) return;
+    const float scale = __fdiv_rn(limit, peak);
+    const ChunkDev ch = chunks[blockIdx.y];
+    const TrackDev tr = tracks[ch.track];
+    const long long s0 = max(ch.s0, tr.out_lo), s1 = min(ch.s1, tr.out_hi);
+    float2* dst = tr.out + (s0 - tr.out_origin);
+    const long long n = s1 - s0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        float2 x = dst[i];
+        x.x *= scale; x.y *= scale;
+        dst[i] = x;
+    }
+}
+
+// ================================================================================================
+// host side
+template <typename T> struct DevBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    cudaError_t alloc(size_t count) {
+        release();
+        n = count;
+        if (count == 0) return cudaSuccess;
+        return cudaMalloc(reinterpret_cast<void**>(&p), count * sizeof(T));
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+    ~DevBuf() { release(); }
+};
+
+}  // namespace
+
+struct tmt_engine {
+    int device = 0;
+    int n_sms = 0;
+    DevBuf<float> win;        // [4096]
+    DevBuf<float> rnorm;      // [2][2048]  (eps | clamp)
+    DevBuf<float2> twA, twB;
+    DevBuf<float> gperm;      // [n_rows][4096]
+    int n_rows = 0;
+    bool have_win = false;
+};
+
+struct HostTrack {
+    tmt_track_desc d;
+    int n_frames, frame_base, hs_base, chunk_base, n_chunks;
+    int hb_lo, hb_hi, f_lo, f_hi;
+    long long first_start;
+    std::vector<std::pair<long long, long long>> chunk_ranges;   // clipped sample ranges
+};
+
+struct tmt_plan {
+    tmt_engine* e = nullptr;
+    int framing = 0;
+    int n_tracks = 0, total_frames = 0, total_chunks = 0, n_units = 0;
+    int max_hb = 0, max_frames = 0;
+    long long max_chunk_len = 0, max_in_len = 0;
+    std::vector<HostTrack> ht;
+    std::vector<TrackDev> tracks_h;
+    DevBuf<TrackDev> tracks;
+    DevBuf<UnitDev> units;
+    DevBuf<ChunkDev> chunks;
+    DevBuf<double> hsum;        // float or double view, [total_frames + n_tracks]
+    DevBuf<double> msq;         // float or double view, [total_frames]
+    DevBuf<double> gate_f64;    // [total_frames]
+    DevBuf<uint8_t> state;
+    DevBuf<uint16_t> rows;
+    DevBuf<int> c2;
+    DevBuf<float> chunk_peaks, in_peaks, in_scale;
+    DevBuf<double> von, voff;
+    int64_t launches = 0;
+};
+
+namespace {
+
+int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// frames of one file under each framing (see oracle/tomatis_oracle.py frame_layout_streaming and
+// src/process_tomatis_adaptive.py:298-300)
+int count_frames(int framing, long long total) {
+    if (framing == TMT_FRAMING_STREAMING) {
+        const long long pad = kNfft / 2;
+        long long r = (total - kNfft) % kHop;          // C++ % truncates toward zero: emulate Python's
+        if (r < 0) r += kHop;
+        const long long pad_end = (kHop - r) % kHop;
+        const long long length = pad + total + pad_end;
+        if (length < kNfft) return 0;
+        return (int)((length - kNfft) / kHop + 1);
+    }
+    return (int)(total / kHop);
+}
+
+// limiter chunks in block units [blo, bhi) (block b = positions [first_start + b*hop, +hop))
+void chunk_blocks(int framing, int n_frames, std::vector<std::pair<int, int>>& out) {
+    out.clear();
+    if (n_frames <= 0) return;
+    const int n_blocks = n_frames + 1;
+    if (framing != TMT_FRAMING_STREAMING) { out.push_back({0, n_blocks}); return; }
+    // replay of the flush rule src/process_tomatis.py:419-426: positions relative to out_base = -pad
+    long long out_base = 0, next_start = 0;       // both shifted by +pad
+    int flushed = 0;
+    for (int j = 0; j < n_frames; ++j) {
+        next_start += kHop;
+        const long long safe = (next_start - out_base) - kNfft;
+        if (safe >= kFlushSafe) {
+            const int nb = (int)(safe / kHop);     // safe is a multiple of hop
+            out.push_back({flushed, flushed + nb});
+            flushed += nb;
+            out_base += safe;
+        }
+    }
+    if (flushed < n_blocks) out.push_back({flushed, n_blocks});
+}
+
+int build_tracks_dev(tmt_plan* p) {
+    p->tracks_h.resize(p->n_tracks);
+    for (int i = 0; i < p->n_tracks; ++i) {
+        const HostTrack& h = p->ht[i];
+        TrackDev& t = p->tracks_h[i];
+        t.in = reinterpret_cast<const float2*>(h.d.pcm_in);
+        t.out = reinterpret_cast<float2*>(h.d.pcm_out);
+        t.total = h.d.total;
+        t.in_origin = h.d.in_origin;
+        t.in_lo = std::max<long long>(0, h.d.in_origin);
+        t.in_hi = std::min<long long>(h.d.total, h.d.in_origin + h.d.in_len);
+        t.out_origin = h.d.out_origin;
+        t.out_lo = std::max<long long>(0, h.d.out_origin);
+        t.out_hi = std::min<long long>(h.d.total, h.d.out_origin + h.d.out_len);
+        t.first_start = h.first_start;
+        t.n_frames = h.n_frames;
+        t.frame_base = h.frame_base;
+        t.hs_base = h.hs_base;
+        t.hb_lo = h.hb_lo; t.hb_hi = h.hb_hi; t.f_lo = h.f_lo; t.f_hi = h.f_hi;
+        t.chunk_base = h.chunk_base; t.n_chunks = h.n_chunks;
+    }
+    if (p->n_tracks)
+        CUDA_TRY(cudaMemcpy(p->tracks.p, p->tracks_h.data(), sizeof(TrackDev) * p->n_tracks, cudaMemcpyHostToDevice));
+    return TMT_OK;
+}
+
+template <typename T, int AUTO>
+int launch_gate(tmt_plan* p, const T* vals, int param, int S, int X, int alpha_init, int count_only, cudaStream_t st) {
+    int NT = 1024;
+    auto need = [&](int nt) { return (size_t)((S * nt + S * (nt / 32) + nt + nt / 32 + 15) & ~15) + sizeof(int) * (size_t)(4 * nt + 5 * (nt / 32)); };
+    while (NT > 32 && need(NT) > 96 * 1024) NT >>= 1;
+    const size_t smem = need(NT);
+    if (smem > 200 * 1024) return fail(TMT_ERR_UNSUPPORTED, "gate automaton with %d states needs %zu B of shared memory", S, smem);
+    CUDA_TRY(cudaFuncSetAttribute(gate_kernel<T, AUTO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 48 * 1024)));
+    gate_kernel<T, AUTO><<<p->n_tracks, NT, smem, st>>>(p->tracks.p, vals, p->von.p, p->voff.p, param, S, X, alpha_init,
+                                                         count_only, p->state.p, p->rows.p, p->c2.p);
+    p->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return TMT_OK;
+}
+
+struct ArrInfo { void* ptr; size_t elem; size_t count; };
+int arr_info(tmt_plan* p, int which, ArrInfo* a) {
+    switch (which) {
+        case TMT_ARR_MEANSQ_F32: *a = {p->msq.p, 4, (size_t)p->total_frames}; return TMT_OK;
+        case TMT_ARR_MEANSQ_F64: *a = {p->msq.p, 8, (size_t)p->total_frames}; return TMT_OK;
+        case TMT_ARR_GATE_F64: *a = {p->gate_f64.p, 8, (size_t)p->total_frames}; return TMT_OK;
+        case TMT_ARR_STATE: *a = {p->state.p, 1, (size_t)p->total_frames}; return TMT_OK;
+        case TMT_ARR_ROW: *a = {p->rows.p, 2, (size_t)p->total_frames}; return TMT_OK;
+        case TMT_ARR_C2_COUNT: *a = {p->c2.p, 4, (size_t)p->n_tracks}; return TMT_OK;
+        case TMT_ARR_CHUNK_PEAK: *a = {p->chunk_peaks.p, 4, (size_t)p->total_chunks}; return TMT_OK;
+        case TMT_ARR_INPUT_PEAK: *a = {p->in_peaks.p, 4, (size_t)p->n_tracks}; return TMT_OK;
+        case TMT_ARR_HOPSUM_F32: *a = {p->hsum.p, 4, (size_t)(p->total_frames + p->n_tracks)}; return TMT_OK;
+        case TMT_ARR_HOPSUM_F64: *a = {p->hsum.p, 8, (size_t)(p->total_frames + p->n_tracks)}; return TMT_OK;
+    }
+    return fail(TMT_ERR_INVALID, "unknown plan array %d", which);
+}
+
+}  // namespace
+
+// ================================================================================================
+extern "C" {
+
+int tmt_version(void) { return 100; }
+
+const char* tmt_error_string(int code) {
+    switch (code) {
+        case TMT_OK: return "ok";
+        case TMT_ERR_INVALID: return "invalid argument";
+        case TMT_ERR_CUDA: return "CUDA error";
+        case TMT_ERR_UNSUPPORTED: return "unsupported configuration";
+        case TMT_ERR_NOMEM: return "out of memory";
+    }
+    return "unknown error";
+}
+
+const char* tmt_last_error(void) { return g_err; }
+
+int tmt_engine_create(tmt_engine** out, int device, int n_fft, int hop) {
+    if (!out) return fail(TMT_ERR_INVALID, "out is NULL");
+    *out = nullptr;
+    if (n_fft != kNfft || hop != kHop)
+        return fail(TMT_ERR_UNSUPPORTED, "only n_fft=%d hop=%d is implemented on the GPU path (got %d/%d)", kNfft, kHop, n_fft, hop);
+    CUDA_TRY(cudaSetDevice(device));
+    tmt_engine* e = new (std::nothrow) tmt_engine();
+    if (!e) return fail(TMT_ERR_NOMEM, "host allocation failed");
+    e->device = device;
+    cudaDeviceProp prop;
+    cudaError_t ce = cudaGetDeviceProperties(&prop, device);
+    if (ce != cudaSuccess) { delete e; return fail(TMT_ERR_CUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(ce)); }
+    e->n_sms = prop.multiProcessorCount;
+    auto twA = build_twA();
+    auto twB = build_twB();
+    if (e->twA.alloc(256) != cudaSuccess || e->twB.alloc(4096) != cudaSuccess || e->win.alloc(kNfft) != cudaSuccess ||
+        e->rnorm.alloc(2 * kHop) != cudaSuccess) {
+        delete e;
+        return fail(TMT_ERR_NOMEM, "device allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
+    }
+    cudaMemcpy(e->twA.p, twA.data(), sizeof(float2) * 256, cudaMemcpyHostToDevice);
+    cudaMemcpy(e->twB.p, twB.data(), sizeof(float2) * 4096, cudaMemcpyHostToDevice);
+    ce = cudaFuncSetAttribute(stft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kStftSmemBytes);
+    if (ce != cudaSuccess) { delete e; return fail(TMT_ERR_CUDA, "cudaFuncSetAttribute(stft_kernel): %s", cudaGetErrorString(ce)); }
+    *out = e;
+    return TMT_OK;
+}
+
+int tmt_engine_destroy(tmt_engine* e) {
+    if (!e) return TMT_OK;
+    cudaSetDevice(e->device);
+    delete e;
+    return TMT_OK;
+}
+
+int tmt_engine_set_window(tmt_engine* e, const float* win, int n) {
+    if (!e || !win || n != kNfft) return fail(TMT_ERR_INVALID, "window must have %d taps", kNfft);
+    CUDA_TRY(cudaSetDevice(e->device));
+    // float32 arithmetic exactly as the reference: win2 = (win*win).astype(float32); w_buf = win2[n+hop] + win2[n]
+    std::vector<float> rn(2 * kHop);
+    for (int i = 0; i < kHop; ++i) {
+        const volatile float lo = win[i] * win[i];
+        const volatile float hi = win[i + kHop] * win[i + kHop];
+        const volatile float nrm = hi + lo;
+        const volatile float d0 = nrm + 1e-12f;
+        rn[i] = 1.0f / d0;                                  // src/process_tomatis.py:422
+        rn[kHop + i] = 1.0f / std::max((float)nrm, 1e-8f);  // src/process_tomatis_adaptive.py:330
+    }
+    CUDA_TRY(cudaMemcpy(e->win.p, win, sizeof(float) * kNfft, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(e->rnorm.p, rn.data(), sizeof(float) * 2 * kHop, cudaMemcpyHostToDevice));
+    e->have_win = true;
+    return TMT_OK;
+}
+
+int tmt_engine_set_gain_rows(tmt_engine* e, const float* rows, int n_rows, int n_bins) {
+    if (!e || !rows || n_rows <= 0 || n_bins != kNfft / 2 + 1) return fail(TMT_ERR_INVALID, "gain rows must be [n_rows>0][%d]", kNfft / 2 + 1);
+    if (n_rows > 65535) return fail(TMT_ERR_UNSUPPORTED, "at most 65535 gain rows");
+    CUDA_TRY(cudaSetDevice(e->device));
+    std::vector<float> perm((size_t)n_rows * kNfft);
+    for (int r = 0; r < n_rows; ++r) permute_gain_row(rows + (size_t)r * n_bins, perm.data() + (size_t)r * kNfft);
+    if ((size_t)n_rows * kNfft > e->gperm.n) {
+        if (e->gperm.alloc((size_t)n_rows * kNfft) != cudaSuccess) return fail(TMT_ERR_NOMEM, "gain table allocation failed");
+    }
+    CUDA_TRY(cudaMemcpy(e->gperm.p, perm.data(), sizeof(float) * perm.size(), cudaMemcpyHostToDevice));
+    e->n_rows = n_rows;
+    return TMT_OK;
+}
+
+int tmt_plan_create(tmt_engine* e, tmt_plan** out, int framing, int n_tracks, const tmt_track_desc* tracks, int unit_blocks) {
+    if (!e || !out || n_tracks < 0 || (n_tracks > 0 && !tracks)) return fail(TMT_ERR_INVALID, "bad arguments");
+    if (framing != TMT_FRAMING_STREAMING && framing != TMT_FRAMING_WHOLEFILE) return fail(TMT_ERR_INVALID, "unknown framing %d", framing);
+    if (n_tracks > 65535) return fail(TMT_ERR_UNSUPPORTED, "at most 65535 tracks per plan");
+    *out = nullptr;
+    CUDA_TRY(cudaSetDevice(e->device));
+    tmt_plan* p = new (std::nothrow) tmt_plan();
+    if (!p) return fail(TMT_ERR_NOMEM, "host allocation failed");
+    p->e = e;
+    p->framing = framing;
+    p->n_tracks = n_tracks;
+    if (unit_blocks <= 0) unit_blocks = 59;
+    std::vector<UnitDev> units;
+    std::vector<ChunkDev> chunks;
+    std::vector<std::pair<int, int>> cb;
+    long long frames = 0;
+    for (int i = 0; i < n_tracks; ++i) {
+        HostTrack h;
+        h.d = tracks[i];
+        if (h.d.total < 0 || h.d.in_len < 0 || h.d.out_len < 0) { delete p; return fail(TMT_ERR_INVALID, "track %d: negative length", i); }
+        if (h.d.total > 0 && (!h.d.pcm_in || !h.d.pcm_out)) { delete p; return fail(TMT_ERR_INVALID, "track %d: NULL audio buffer", i); }
+        h.first_start = (framing == TMT_FRAMING_STREAMING) ? -(long long)(kNfft / 2) : 0;
+        h.n_frames = count_frames(framing, h.d.total);
+        h.frame_base = (int)frames;
+        h.hs_base = (int)frames + i;
+        frames += h.n_frames;
+        if (frames > 0x7fff0000LL) { delete p; return fail(TMT_ERR_UNSUPPORTED, "too many frames in one plan"); }
+        const int n_blocks = h.n_frames > 0 ? h.n_frames + 1 : 0;
+        int blo = (int)std::max<long long>(0, h.d.block_lo);
+        int bhi = (h.d.block_hi < 0) ? n_blocks : (int)std::min<long long>(n_blocks, h.d.block_hi);
+        if (bhi < blo) bhi = blo;
+        // hop-block sums / frame mean squares this plan computes: frames touching its blocks
+        h.f_lo = std::max(0, blo - 1);
+        h.f_hi = std::min(h.n_frames, bhi);
+        if (h.d.block_hi < 0 && h.d.block_lo <= 0) { h.f_lo = 0; h.f_hi = h.n_frames; }
+        h.hb_lo = h.f_lo;
+        h.hb_hi = (h.f_hi > h.f_lo) ? h.f_hi + 1 : h.f_lo;
+        chunk_blocks(framing, h.n_frames, cb);
+        h.chunk_base = (int)chunks.size();
+        h.n_chunks = (int)cb.size();
+        for (size_t c = 0; c < cb.size(); ++c) {
+            long long s0 = h.first_start + (long long)cb[c].first * kHop, s1 = h.first_start + (long long)cb[c].second * kHop;
+            s0 = std::max<long long>(0, s0);
+            s1 = std::min<long long>(h.d.total, s1);
+            if (s1 < s0) s1 = s0;
+            h.chunk_ranges.push_back({s0, s1});
+            chunks.push_back(ChunkDev{i, s0, s1});
+            p->max_chunk_len = std::max(p->max_chunk_len, s1 - s0);
+            // work units: slices of this chunk restricted to [blo,bhi), skipping blocks with no file samples
+            int u0 = std::max(cb[c].first, blo), u1 = std::min(cb[c].second, bhi);
+            while (u0 < u1 && h.first_start + (long long)(u0 + 1) * kHop <= 0) ++u0;
+            while (u1 > u0 && h.first_start + (long long)(u1 - 1) * kHop >= h.d.total) --u1;
+            if (u1 <= u0) continue;
+            const int n_sub = ceil_div(u1 - u0, unit_blocks);
+            for (int s = 0; s < n_sub; ++s) {
+                const int a = u0 + (int)((long long)(u1 - u0) * s / n_sub);
+                const int b = u0 + (int)((long long)(u1 - u0) * (s + 1) / n_sub);
+                if (b > a) units.push_back(UnitDev{i, a, b, h.chunk_base + (int)c});
+            }
+        }
+        p->max_hb = std::max(p->max_hb, h.hb_hi - h.hb_lo);
+        p->max_frames = std::max(p->max_frames, h.n_frames);
+        p->max_in_len = std::max<long long>(p->max_in_len, h.d.in_len);
+        p->ht.push_back(std::move(h));
+    }
+    p->total_frames = (int)frames;
+    p->total_chunks = (int)chunks.size();
+    p->n_units = (int)units.size();
+    const size_t nf = (size_t)frames, nt = (size_t)n_tracks;
+    bool ok = p->tracks.alloc(std::max<size_t>(nt, 1)) == cudaSuccess && p->units.alloc(std::max<size_t>(units.size(), 1)) == cudaSuccess &&
+              p->chunks.alloc(std::max<size_t>(chunks.size(), 1)) == cudaSuccess && p->hsum.alloc(nf + nt + 1) == cudaSuccess &&
+              p->msq.alloc(nf + 1) == cudaSuccess && p->gate_f64.alloc(nf + 1) == cudaSuccess && p->state.alloc(nf + 1) == cudaSuccess &&
+              p->rows.alloc(nf + 1) == cudaSuccess && p->c2.alloc(nt + 1) == cudaSuccess &&
+              p->chunk_peaks.alloc(chunks.size() + 1) == cudaSuccess && p->in_peaks.alloc(nt + 1) == cudaSuccess &&
+              p->in_scale.alloc(nt + 1) == cudaSuccess && p->von.alloc(nt + 1) == cudaSuccess && p->voff.alloc(nt + 1) == cudaSuccess;
+    if (!ok) { delete p; return fail(TMT_ERR_NOMEM, "device allocation failed: %s", cudaGetErrorString(cudaGetLastError())); }
+    cudaMemset(p->rows.p, 0, sizeof(uint16_t) * (nf + 1));
+    cudaMemset(p->state.p, 0, nf + 1);
+    cudaMemset(p->hsum.p, 0, sizeof(double) * (nf + nt + 1));
+    cudaMemset(p->msq.p, 0, sizeof(double) * (nf + 1));
+    if (!units.empty()) cudaMemcpy(p->units.p, units.data(), sizeof(UnitDev) * units.size(), cudaMemcpyHostToDevice);
+    if (!chunks.empty()) cudaMemcpy(p->chunks.p, chunks.data(), sizeof(ChunkDev) * chunks.size(), cudaMemcpyHostToDevice);
+    int rc = build_tracks_dev(p);
+    if (rc != TMT_OK) { delete p; return rc; }
+    *out = p;
+    return TMT_OK;
+}
+
+int tmt_plan_destroy(tmt_plan* p) {
+    if (!p) return TMT_OK;
+    cudaSetDevice(p->e->device);
+    delete p;
+    return TMT_OK;
+}
+
+int tmt_plan_set_buffers(tmt_plan* p, int track, const void* pcm_in, void* pcm_out) {
+    if (!p || track < 0 || track >= p->n_tracks) return fail(TMT_ERR_INVALID, "bad track index");
+    p->ht[track].d.pcm_in = pcm_in;
+    p->ht[track].d.pcm_out = pcm_out;
+    p->tracks_h[track].in = reinterpret_cast<const float2*>(pcm_in);
+    p->tracks_h[track].out = reinterpret_cast<float2*>(pcm_out);
+    CUDA_TRY(cudaSetDevice(p->e->device));
+    CUDA_TRY(cudaMemcpy(p->tracks.p + track, &p->tracks_h[track], sizeof(TrackDev), cudaMemcpyHostToDevice));
+    return TMT_OK;
+}
+
+int tmt_plan_total_frames(const tmt_plan* p) { return p ? p->total_frames : -1; }
+int tmt_plan_total_chunks(const tmt_plan* p) { return p ? p->total_chunks : -1; }
+int tmt_plan_total_units(const tmt_plan* p) { return p ? p->n_units : -1; }
+int tmt_plan_track_frames(const tmt_plan* p, int t) { return (p && t >= 0 && t < p->n_tracks) ? p->ht[t].n_frames : -1; }
+int tmt_plan_track_frame_base(const tmt_plan* p, int t) { return (p && t >= 0 && t < p->n_tracks) ? p->ht[t].frame_base : -1; }
+int tmt_plan_track_chunks(const tmt_plan* p, int t) { return (p && t >= 0 && t < p->n_tracks) ? p->ht[t].n_chunks : -1; }
+int tmt_plan_track_chunk_base(const tmt_plan* p, int t) { return (p && t >= 0 && t < p->n_tracks) ? p->ht[t].chunk_base : -1; }
+int tmt_plan_chunk_range(const tmt_plan* p, int t, int c, int64_t* s0, int64_t* s1) {
+    if (!p || t < 0 || t >= p->n_tracks || c < 0 || c >= p->ht[t].n_chunks || !s0 || !s1) return fail(TMT_ERR_INVALID, "bad chunk index");
+    *s0 = p->ht[t].chunk_ranges[c].first;
+    *s1 = p->ht[t].chunk_ranges[c].second;
+    return TMT_OK;
+}
+int64_t tmt_plan_launch_count(const tmt_plan* p) { return p ? p->launches : -1; }
+
+int tmt_plan_read(tmt_plan* p, int which, int64_t offset, int64_t count, void* ptr, int is_device, void* stream) {
+    if (!p || !ptr) return fail(TMT_ERR_INVALID, "bad arguments");
+    ArrInfo a;
+    int rc = arr_info(p, which, &a);
+    if (rc) return rc;
+    if (offset < 0 || count < 0 || (size_t)(offset + count) > a.count) return fail(TMT_ERR_INVALID, "range [%lld,+%lld) outside array %d of %zu", (long long)offset, (long long)count, which, a.count);
+    if (count == 0) return TMT_OK;
+    CUDA_TRY(cudaSetDevice(p->e->device));
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    CUDA_TRY(cudaMemcpyAsync(ptr, static_cast<char*>(a.ptr) + offset * a.elem, count * a.elem,
+                             is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));
+    if (!is_device) CUDA_TRY(cudaStreamSynchronize(st));
+    return TMT_OK;
+}
+
+int tmt_plan_write(tmt_plan* p, int which, int64_t offset, int64_t count, const void* ptr, int is_device, void* stream) {
+    if (!p || !ptr) return fail(TMT_ERR_INVALID, "bad arguments");
+    ArrInfo a;
+    int rc = arr_info(p, which, &a);
+    if (rc) return rc;
+    if (offset < 0 || count < 0 || (size_t)(offset + count) > a.count) return fail(TMT_ERR_INVALID, "range outside array %d", which);
+    if (count == 0) return TMT_OK;
+    CUDA_TRY(cudaSetDevice(p->e->device));
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    CUDA_TRY(cudaMemcpyAsync(static_cast<char*>(a.ptr) + offset * a.elem, ptr, count * a.elem,
+                             is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
+    if (!is_device) CUDA_TRY(cudaStreamSynchronize(st));
+    return TMT_OK;
+}
+
+int tmt_plan_input_peaks(tmt_plan* p, void* stream) {
+    if (!p) return fail(TMT_ERR_INVALID, "plan is NULL");
+    if (p->n_tracks == 0) return TMT_OK;
+    CUDA_TRY(cudaSetDevice(p->e->device));
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    CUDA_TRY(cudaMemsetAsync(p->in_peaks.p, 0, sizeof(float) * p->n_tracks, st));
+    const int gx = (int)std::max<long long>(1, std::min<long long>(8LL * p->e->n_sms, (p->max_in_len + 256 * 8 - 1) / (256 * 8)));
+    input_peak_kernel<<<dim3(gx, p->n_tracks), 256, 0, st>>>(p->tracks.p, p->in_peaks.p);
+    p->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return TMT_OK;
+}
+
+int tmt_plan_levels(tmt_plan* p, int use_f64, const float* in_scale, void* stream) {
+    if (!p) return fail(TMT_ERR_INVALID, "plan is NULL");
+    if (p->n_tracks == 0 || p->max_hb == 0) return TMT_OK;
+    CUDA_TRY(cudaSetDevice(p->e->device));
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const float* sc = nullptr;
+    if (in_scale) {
+        CUDA_TRY(cudaMemcpyAsync(p->in_scale.p, in_scale, sizeof(float) * p->n_tracks, cudaMemcpyHostToDevice, st));
+        sc = p->in_scale.p;
+    }
+    const dim3 g1(ceil_div(p->max_hb, kLevelWarps), p->n_tracks);
+    const dim3 g2(ceil_div(std::max(p->max_frames, 1), 256), p->n_tracks);
+    if (use_f64) {
+        levels_kernel<double><<<g1, kLevelWarps * 32, 0, st>>>(p->tracks.p, sc, p->hsum.p);
+        meansq_kernel<double><<<g2, 256, 0, st>>>(p->tracks.p, p->hsum.p, p->msq.p);
+    } else {
+        levels_kernel<float><<<g1, kLevelWarps * 32, 0, st>>>(p->tracks.p, sc, reinterpret_cast<float*>(p->hsum.p));
+        meansq_kernel<float><<<g2, 256, 0, st>>>(p->tracks.p, reinterpret_cast<const float*>(p->hsum.p), reinterpret_cast<float*>(p->msq.p));
+    }
+    p->launches += 2;
+    CUDA_TRY(cudaGetLastError());
+    return TMT_OK;
+}
+
+int tmt_plan_gate(tmt_plan* p, int automaton, int gate_input, const double* on, const double* off, int param,
+                  int xfade_frames, int alpha_init_to_target, int count_only, void* stream) {
+    if (!p || !on || !off) return fail(TMT_ERR_INVALID, "bad arguments");
+    if (param < 0 || xfade_frames < 0 || xfade_frames > 65534) return fail(TMT_ERR_INVALID, "bad gate parameters");
+    if (p->n_tracks == 0) return TMT_OK;
+    int S;
+    if (automaton == TMT_GATE_UPDELAY) { if (param < 1) return fail(TMT_ERR_INVALID, "run_frames must be >= 1"); S = param + 1; }
+    else if (automaton == TMT_GATE_MINHOLD) S = 2 * (param + 1);
+    else return fail(TMT_ERR_INVALID, "unknown automaton %d", automaton);
+    if (S > kMaxGateStates) return fail(TMT_ERR_UNSUPPORTED, "gate automaton needs %d states (max %d): delay/hold too long for the GPU scan", S, kMaxGateStates);
+    CUDA_TRY(cudaSetDevice(p->e->device));
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    CUDA_TRY(cudaMemcpyAsync(p->von.p, on, sizeof(double) * p->n_tracks, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(p->voff.p, off, sizeof(double) * p->n_tracks, cudaMemcpyHostToDevice, st));
+    const int X = xfade_frames, ai = alpha_init_to_target ? 1 : 0, co = count_only ? 1 : 0;
+    if (gate_input == TMT_ARR_MEANSQ_F32) {
+        const float* v = reinterpret_cast<const float*>(p->msq.p);
+        return automaton == TMT_GATE_UPDELAY ? launch_gate<float, TMT_GATE_UPDELAY>(p, v, param, S, X, ai, co, st)
+                                             : launch_gate<float, TMT_GATE_MINHOLD>(p, v, param, S, X, ai, co, st);
+    }
+    const double* v = (gate_input == TMT_ARR_MEANSQ_F64) ? p->msq.p : (gate_input == TMT_ARR_GATE_F64) ? p->gate_f64.p : nullptr;
+    if (!v) return fail(TMT_ERR_INVALID, "gate_input must be MEANSQ_F32, MEANSQ_F64 or GATE_F64");
+    return automaton == TMT_GATE_UPDELAY ? launch_gate<double, TMT_GATE_UPDELAY>(p, v, param, S, X, ai, co, st)
+                                         : launch_gate<double, TMT_GATE_MINHOLD>(p, v, param, S, X, ai, co, st);
+}
+
+int tmt_plan_stft(tmt_plan* p, float post_gain, void* stream) {
+    if (!p) return fail(TMT_ERR_INVALID, "plan is NULL");
+    tmt_engine* e = p->e;
+    if (!e->have_win || e->n_rows == 0) return fail(TMT_ERR_INVALID, "engine window / gain rows not set");
+    CUDA_TRY(cudaSetDevice(e->device));
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (p->total_chunks) CUDA_TRY(cudaMemsetAsync(p->chunk_peaks.p, 0, sizeof(float) * p->total_chunks, st));
+    if (p->n_units == 0) return TMT_OK;
+    StftParams prm;
+    prm.tracks = p->tracks.p;
+    prm.units = p->units.p;
+    prm.n_units = p->n_units;
+    prm.rows = p->rows.p;
+    prm.gperm = e->gperm.p;
+    prm.win = e->win.p;
+    prm.norm_clamp = (p->framing == TMT_FRAMING_WHOLEFILE) ? 1 : 0;
+    prm.rnorm = e->rnorm.p + (prm.norm_clamp ? kHop : 0);
+    prm.twA = e->twA.p;
+    prm.twB = e->twB.p;
+    prm.chunk_peaks = p->chunk_peaks.p;
+    prm.post_gain = post_gain;
+    const int grid = std::min(p->n_units, 2 * e->n_sms);
+    stft_kernel<<<grid, kThreads, kStftSmemBytes, st>>>(prm);
+    p->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return TMT_OK;
+}
+
+int tmt_plan_limiter(tmt_plan* p, float limit, void* stream) {
+    if (!p) return fail(TMT_ERR_INVALID, "plan is NULL");
+    if (p->total_chunks == 0 || p->max_chunk_len == 0) return TMT_OK;
+    CUDA_TRY(cudaSetDevice(p->e->device));
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const long long per_cta = 256LL * 16;
+    int gx = (int)std::min<long long>((p->max_chunk_len + per_cta - 1) / per_cta, 8LL * p->e->n_sms);
+    gx = std::max(gx, 1);
+    limiter_kernel<<<dim3(gx, p->total_chunks), 256, 0, st>>>(p->tracks.p, p->chunks.p, p->chunk_peaks.p, limit);
+    p->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return TMT_OK;
+}
+
+int tmt_plan_run_streaming(tmt_plan* p, double m_on, double m_off, int run_frames, int xfade_frames, float post_gain,
+                           float limit, void* stream) {
+    if (!p) return fail(TMT_ERR_INVALID, "plan is NULL");
+    int rc = tmt_plan_levels(p, 0, nullptr, stream);
+    if (rc) return rc;
+    std::vector<double> on((size_t)std::max(p->n_tracks, 1), m_on), off((size_t)std::max(p->n_tracks, 1), m_off);
+    rc = tmt_plan_gate(p, TMT_GATE_UPDELAY, TMT_ARR_MEANSQ_F32, on.data(), off.data(), run_frames, xfade_frames, 0, 0, stream);
+    if (rc) return rc;
+    rc = tmt_plan_stft(p, post_gain, stream);
+    if (rc) return rc;
+    return tmt_plan_limiter(p, limit, stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,406 @@
+"""Device pipeline of the Tomatis path: thin Python orchestration over the C ABI.
+
+PyTorch is used for device buffers and streams only; every arithmetic step on audio runs in the
+hand-written kernels of csrc/tomatis_b200.cu.  The three `run_*` functions mirror the inside of the
+reference's `process()` functions (src/process_tomatis.py:160, _xfade.py:55, _adaptive.py:157) on
+in-memory arrays and accept a *batch* of tracks (one plan, one launch sequence for all of them).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+from . import _lib as L
+from . import tables as tb
+
+
+def _torch():
+    import torch
+    if not torch.cuda.is_available():
+        raise RuntimeError("tomatis_audio_processor_b200 needs a CUDA device (no CPU fallback)")
+    return torch
+
+
+def _stream_ptr(torch):
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class Engine:
+    """One per device: window, twiddles and the gain table (tmt_engine)."""
+
+    def __init__(self, device: int = 0, n_fft: int = tb.N_FFT, hop: int = tb.HOP):
+        self.lib = L.load()
+        torch = _torch()
+        self.device = int(device)
+        torch.cuda.set_device(self.device)
+        torch.cuda.current_stream()                      # make sure the primary context exists
+        if n_fft != tb.N_FFT or hop != tb.HOP:
+            raise NotImplementedError(
+                f"GPU path implements n_fft={tb.N_FFT}, hop={tb.HOP} (the reference defaults); got {n_fft}/{hop}")
+        h = C.c_void_p()
+        L.check(self.lib.tmt_engine_create(C.byref(h), self.device, n_fft, hop), "tmt_engine_create")
+        self.h = h
+        self.n_fft, self.hop = n_fft, hop
+        win = np.ascontiguousarray(tb.hann_window(n_fft))
+        L.check(self.lib.tmt_engine_set_window(self.h, win.ctypes.data_as(C.c_void_p), n_fft), "set_window")
+        self._rows_key = None
+
+    def set_gain_rows(self, rows: np.ndarray, key=None):
+        if key is not None and key == self._rows_key:
+            return
+        rows = np.ascontiguousarray(rows, dtype=np.float32)
+        L.check(self.lib.tmt_engine_set_gain_rows(self.h, rows.ctypes.data_as(C.c_void_p), rows.shape[0], rows.shape[1]),
+                "set_gain_rows")
+        self._rows_key = key
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.tmt_engine_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+_ARR_DTYPES = {L.ARR_MEANSQ_F32: np.float32, L.ARR_MEANSQ_F64: np.float64, L.ARR_GATE_F64: np.float64,
+               L.ARR_STATE: np.uint8, L.ARR_ROW: np.uint16, L.ARR_C2_COUNT: np.int32,
+               L.ARR_CHUNK_PEAK: np.float32, L.ARR_INPUT_PEAK: np.float32,
+               L.ARR_HOPSUM_F32: np.float32, L.ARR_HOPSUM_F64: np.float64}
+
+
+class Plan:
+    """Geometry + scratch for one batch of tracks / file shards (tmt_plan)."""
+
+    def __init__(self, engine: Engine, framing: int, descs: Sequence[L.TrackDesc], unit_blocks: int = 0):
+        self.engine, self.lib = engine, engine.lib
+        self.n_tracks = len(descs)
+        arr = (L.TrackDesc * max(1, self.n_tracks))(*descs)
+        h = C.c_void_p()
+        L.check(self.lib.tmt_plan_create(engine.h, C.byref(h), framing, self.n_tracks, arr, unit_blocks), "tmt_plan_create")
+        self.h = h
+        self.framing = framing
+        self.total_frames = self.lib.tmt_plan_total_frames(h)
+        self.total_chunks = self.lib.tmt_plan_total_chunks(h)
+        self.total_units = self.lib.tmt_plan_total_units(h)
+        self.track_frames = [self.lib.tmt_plan_track_frames(h, t) for t in range(self.n_tracks)]
+        self.frame_base = [self.lib.tmt_plan_track_frame_base(h, t) for t in range(self.n_tracks)]
+        self.track_chunks = [self.lib.tmt_plan_track_chunks(h, t) for t in range(self.n_tracks)]
+        self.chunk_base = [self.lib.tmt_plan_track_chunk_base(h, t) for t in range(self.n_tracks)]
+
+    # -- geometry
+    def chunk_ranges(self, track: int):
+        out = []
+        s0, s1 = C.c_int64(), C.c_int64()
+        for c in range(self.track_chunks[track]):
+            L.check(self.lib.tmt_plan_chunk_range(self.h, track, c, C.byref(s0), C.byref(s1)))
+            out.append((s0.value, s1.value))
+        return out
+
+    # -- arrays
+    def _count(self, which):
+        if which in (L.ARR_C2_COUNT, L.ARR_INPUT_PEAK):
+            return self.n_tracks
+        if which == L.ARR_CHUNK_PEAK:
+            return self.total_chunks
+        if which in (L.ARR_HOPSUM_F32, L.ARR_HOPSUM_F64):
+            return self.total_frames + self.n_tracks
+        return self.total_frames
+
+    def read(self, which: int, offset: int = 0, count: Optional[int] = None) -> np.ndarray:
+        torch = _torch()
+        if count is None:
+            count = self._count(which) - offset
+        out = np.empty(count, dtype=_ARR_DTYPES[which])
+        if count:
+            L.check(self.lib.tmt_plan_read(self.h, which, offset, count, out.ctypes.data_as(C.c_void_p), 0,
+                                           _stream_ptr(torch)), "tmt_plan_read")
+        return out
+
+    def write(self, which: int, data: np.ndarray, offset: int = 0):
+        torch = _torch()
+        data = np.ascontiguousarray(data, dtype=_ARR_DTYPES[which])
+        if data.size:
+            L.check(self.lib.tmt_plan_write(self.h, which, offset, data.size, data.ctypes.data_as(C.c_void_p), 0,
+                                            _stream_ptr(torch)), "tmt_plan_write")
+
+    def write_device(self, which: int, dev_ptr: int, count: int, offset: int = 0):
+        torch = _torch()
+        L.check(self.lib.tmt_plan_write(self.h, which, offset, count, C.c_void_p(dev_ptr), 1, _stream_ptr(torch)))
+
+    def read_device(self, which: int, dev_ptr: int, count: int, offset: int = 0):
+        torch = _torch()
+        L.check(self.lib.tmt_plan_read(self.h, which, offset, count, C.c_void_p(dev_ptr), 1, _stream_ptr(torch)))
+
+    # -- kernels
+    def input_peaks(self):
+        L.check(self.lib.tmt_plan_input_peaks(self.h, _stream_ptr(_torch())), "tmt_plan_input_peaks")
+
+    def levels(self, use_f64: bool = False, in_scale: Optional[np.ndarray] = None):
+        ptr = None
+        if in_scale is not None:
+            in_scale = np.ascontiguousarray(in_scale, dtype=np.float32)
+            assert in_scale.size == self.n_tracks
+            ptr = in_scale.ctypes.data_as(C.c_void_p)
+        L.check(self.lib.tmt_plan_levels(self.h, int(use_f64), ptr, _stream_ptr(_torch())), "tmt_plan_levels")
+
+    def gate(self, automaton: int, gate_input: int, on, off, param: int, xfade_frames: int,
+             alpha_init_to_target: bool = False, count_only: bool = False):
+        on = np.ascontiguousarray(np.broadcast_to(np.asarray(on, dtype=np.float64), (max(1, self.n_tracks),)))
+        off = np.ascontiguousarray(np.broadcast_to(np.asarray(off, dtype=np.float64), (max(1, self.n_tracks),)))
+        L.check(self.lib.tmt_plan_gate(self.h, automaton, gate_input, on.ctypes.data_as(C.c_void_p),
+                                       off.ctypes.data_as(C.c_void_p), int(param), int(xfade_frames),
+                                       int(alpha_init_to_target), int(count_only), _stream_ptr(_torch())), "tmt_plan_gate")
+
+    def stft(self, post_gain: float = 1.0):
+        L.check(self.lib.tmt_plan_stft(self.h, float(post_gain), _stream_ptr(_torch())), "tmt_plan_stft")
+
+    def limiter(self, limit: float = tb.PEAK_LIMIT):
+        L.check(self.lib.tmt_plan_limiter(self.h, float(np.float32(limit)), _stream_ptr(_torch())), "tmt_plan_limiter")
+
+    def run_streaming(self, m_on, m_off, run_frames, xfade_frames, post_gain=1.0, limit=tb.PEAK_LIMIT):
+        L.check(self.lib.tmt_plan_run_streaming(self.h, float(m_on), float(m_off), int(run_frames), int(xfade_frames),
+                                                float(post_gain), float(np.float32(limit)), _stream_ptr(_torch())),
+                "tmt_plan_run_streaming")
+
+    def launch_count(self) -> int:
+        return int(self.lib.tmt_plan_launch_count(self.h))
+
+    def set_buffers(self, track: int, in_ptr: int, out_ptr: int):
+        L.check(self.lib.tmt_plan_set_buffers(self.h, track, C.c_void_p(in_ptr), C.c_void_p(out_ptr)))
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.tmt_plan_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def whole_track_desc(x_dev, y_dev, total: Optional[int] = None) -> L.TrackDesc:
+    n = int(x_dev.shape[0]) if total is None else int(total)
+    return L.TrackDesc(x_dev.data_ptr(), y_dev.data_ptr(), n, 0, n, 0, n, 0, -1)
+
+
+_engines = {}
+
+
+def get_engine(device: int = 0) -> Engine:
+    if device not in _engines:
+        _engines[device] = Engine(device)
+    return _engines[device]
+
+
+# ------------------------------------------------------------------------------------------------
+@dataclass
+class StreamingParams:
+    """Scalars of standard / xfade mode after the reference's host-side preamble
+    (src/process_tomatis.py:256-285, _xfade.py:128-155)."""
+    sr: int
+    Ton: float
+    Toff: float
+    run_frames: int
+    xfade_frames: int
+    rows: np.ndarray
+    rows_key: tuple
+    post_gain: float
+    m_on: float = field(default=0.0)
+    m_off: float = field(default=0.0)
+
+
+def streaming_params(mode: str, sr: int, *, gate_ui=50, gate_mode="log_percent", dynamic_range=80.0, gate_scale=1.0,
+                     gate_offset=-100, hysteresis_db=3.0, fc=1000.0, slope=12.0, c1_low=+15.0, c1_high=-15.0,
+                     c2_low=-15.0, c2_high=+15.0, up_delay_ms=250.0, xfade_ms=0.0, n_fft=tb.N_FFT, hop=tb.HOP,
+                     output_gain_db=0.0) -> StreamingParams:
+    if mode == "standard" and gate_mode == "log_percent":
+        T = tb.gate_threshold_log_percent(gate_ui, dynamic_range)
+    else:
+        T = tb.gate_threshold_linear(gate_ui, gate_scale, gate_offset)
+    Ton, Toff = tb.hysteresis_pair(T, hysteresis_db)
+    g1_db, g2_db = tb.tilt_curves_db(sr, n_fft, fc, slope, c1_low, c1_high, c2_low, c2_high)
+    if mode == "xfade":
+        xf = tb.xfade_frame_count(sr, xfade_ms, hop)
+        rows = tb.gain_rows_xfade(g1_db, g2_db, xf) if xf > 0 else tb.gain_rows_standard(g1_db, g2_db)
+    else:
+        xf = 0
+        rows = tb.gain_rows_standard(g1_db, g2_db)
+    key = (mode, sr, fc, slope, c1_low, c1_high, c2_low, c2_high, xf, n_fft)
+    post_gain = 1.0 if output_gain_db == 0.0 else float(np.float32(10.0 ** (output_gain_db / 20.0)))
+    return StreamingParams(sr=sr, Ton=Ton, Toff=Toff, run_frames=tb.updelay_run_frames(sr, up_delay_ms, hop),
+                           xfade_frames=xf, rows=rows, rows_key=key, post_gain=post_gain,
+                           m_on=tb.meansq_threshold_on(Ton), m_off=tb.meansq_threshold_off(Toff))
+
+
+def _to_device(torch, xs, device):
+    out = []
+    for x in xs:
+        if isinstance(x, np.ndarray):
+            x = np.ascontiguousarray(x, dtype=np.float32)
+            if x.ndim != 2 or x.shape[1] != 2:
+                raise ValueError(f"expected interleaved stereo [N,2], got {x.shape}")
+            t = torch.from_numpy(x).to(f"cuda:{device}", non_blocking=False)
+        else:
+            t = x
+            if t.dtype != torch.float32 or t.dim() != 2 or t.shape[1] != 2 or not t.is_contiguous():
+                raise ValueError("device tracks must be contiguous float32 [N,2]")
+        out.append(t)
+    return out
+
+
+def run_streaming(mode: str, xs: Sequence, sr: int, device: int = 0, want_host: bool = True, outs=None,
+                  unit_blocks: int = 0, **params) -> List[dict]:
+    """standard / xfade on a batch of tracks.  Returns one dict per track: out (numpy [N,2] float32 if
+    want_host else the device tensor), chunk_lengths, meansq, levels, states, rows, frame geometry."""
+    torch = _torch()
+    eng = get_engine(device)
+    n_fft, hop = params.get("n_fft", tb.N_FFT), params.get("hop", tb.HOP)
+    if n_fft != eng.n_fft or hop != eng.hop:
+        raise NotImplementedError(f"GPU path implements n_fft={eng.n_fft}, hop={eng.hop}; got {n_fft}/{hop}")
+    sp = streaming_params(mode, sr, **params)
+    eng.set_gain_rows(sp.rows, key=sp.rows_key)
+    xd = _to_device(torch, xs, device)
+    yd = outs if outs is not None else [torch.empty_like(x) for x in xd]
+    plan = Plan(eng, L.FRAMING_STREAMING, [whole_track_desc(x, y) for x, y in zip(xd, yd)], unit_blocks)
+    try:
+        plan.run_streaming(sp.m_on, sp.m_off, sp.run_frames, sp.xfade_frames, sp.post_gain)
+        msq = plan.read(L.ARR_MEANSQ_F32)
+        states = plan.read(L.ARR_STATE)
+        rows = plan.read(L.ARR_ROW)
+        peaks = plan.read(L.ARR_CHUNK_PEAK)
+        res = []
+        for t in range(plan.n_tracks):
+            fb, nf = plan.frame_base[t], plan.track_frames[t]
+            total = int(xd[t].shape[0])
+            ranges = plan.chunk_ranges(t)
+            cb = plan.chunk_base[t]
+            m = msq[fb:fb + nf]
+            starts = -(n_fft // 2) + hop * np.arange(nf, dtype=np.int64)
+            res.append(dict(
+                out=(yd[t].cpu().numpy() if want_host else yd[t]),
+                chunk_lengths=[int(b - a) for (a, b) in ranges if b > a],
+                chunk_ranges=ranges, chunk_peaks=peaks[cb:cb + len(ranges)].copy(),
+                meansq=m.copy(), levels=tb.levels_from_meansq(m), states=states[fb:fb + nf].copy(),
+                rows=rows[fb:fb + nf].copy(), frame_starts=starts, csv_mask=(starts >= 0) & (starts < total),
+                xfade_frames=sp.xfade_frames, sr=sr, Ton=sp.Ton, Toff=sp.Toff, launches=plan.launch_count()))
+        return res
+    finally:
+        plan.close()
+
+
+def _percentile_thresholds(levels, valid):
+    vl = levels[valid]
+    if len(vl) == 0:
+        return None
+    return np.percentile(vl, 5), np.percentile(vl, 95), np.median(vl)
+
+
+def run_adaptive(xs: Sequence, sr: int, device: int = 0, want_host: bool = True, outs=None, unit_blocks: int = 0,
+                 fc=1000.0, slope=12.0, c1_low=15.0, c1_high=-15.0, c2_low=-15.0, c2_high=15.0, target_c2=0.5,
+                 hyst_db=3.0, min_hold_ms=250.0, xfade_ms=500.0, headroom_margin=2.0, n_fft=tb.N_FFT, hop=tb.HOP) -> List[dict]:
+    """adaptive mode on a batch of tracks (src/process_tomatis_adaptive.py:157-373).
+
+    Host: scalars, percentiles and the bisection bookkeeping.  Device: input peaks, levels, every gate
+    simulation of the bisection (count-only scans), the final gate + crossfade counter, STFT, limiter."""
+    torch = _torch()
+    eng = get_engine(device)
+    if n_fft != eng.n_fft or hop != eng.hop:
+        raise NotImplementedError(f"GPU path implements n_fft={eng.n_fft}, hop={eng.hop}; got {n_fft}/{hop}")
+    hold, xf = tb.adaptive_frame_counts(sr, min_hold_ms, xfade_ms, hop)
+    c1_db, c2_db = tb.tilt_curves_db(sr, n_fft, fc, slope, c1_low, c1_high, c2_low, c2_high)
+    eng.set_gain_rows(tb.gain_rows_adaptive(c1_db, c2_db, xf),
+                      key=("adaptive", sr, fc, slope, c1_low, c1_high, c2_low, c2_high, xf, n_fft))
+    xd = _to_device(torch, xs, device)
+    yd = outs if outs is not None else [torch.empty_like(x) for x in xd]
+    results: List[Optional[dict]] = [None] * len(xd)
+
+    # pass 0: input peaks decide pre-attenuation and the float32/float64 branch per track
+    plan0 = Plan(eng, L.FRAMING_WHOLEFILE, [whole_track_desc(x, y) for x, y in zip(xd, yd)], unit_blocks)
+    try:
+        plan0.input_peaks()
+        in_peaks = plan0.read(L.ARR_INPUT_PEAK)
+    finally:
+        plan0.close()
+    branch = [tb.adaptive_attenuation(pk, c1_low, c2_high, headroom_margin) for pk in in_peaks]
+
+    for use_f64 in (False, True):
+        idx = [i for i, b in enumerate(branch) if b[2] == use_f64]
+        if not idx:
+            continue
+        plan = Plan(eng, L.FRAMING_WHOLEFILE, [whole_track_desc(xd[i], yd[i]) for i in idx], unit_blocks)
+        try:
+            scale = np.array([np.float32(branch[i][1]) for i in idx], dtype=np.float32)
+            plan.levels(use_f64=use_f64, in_scale=scale)
+            msq = plan.read(L.ARR_MEANSQ_F64 if use_f64 else L.ARR_MEANSQ_F32)
+            levels_all = tb.levels_from_meansq(msq)
+            plan.write(L.ARR_GATE_F64, levels_all)
+            nt = len(idx)
+            lv = [levels_all[plan.frame_base[t]:plan.frame_base[t] + plan.track_frames[t]] for t in range(nt)]
+            # threshold bisection, all tracks in lock step (src/process_tomatis_adaptive.py:124-154)
+            T_low = np.zeros(nt); T_high = np.zeros(nt); best_T = np.zeros(nt); best_diff = np.ones(nt)
+            active = np.ones(nt, dtype=bool)
+            for t in range(nt):
+                if plan.track_frames[t] == 0:
+                    active[t] = False
+                    continue
+                valid = lv[t] > -70
+                pt = _percentile_thresholds(lv[t], valid)
+                if pt is None:
+                    best_T[t] = np.median(lv[t]); active[t] = False
+                else:
+                    T_low[t], T_high[t], best_T[t] = pt
+            traces = [[] for _ in range(nt)]
+            for _ in range(30):
+                if not active.any():
+                    break
+                T_mid = (T_low + T_high) / 2
+                plan.gate(L.GATE_MINHOLD, L.ARR_GATE_F64, T_mid + hyst_db / 2, T_mid - hyst_db / 2, hold, xf,
+                          alpha_init_to_target=True, count_only=True)
+                c2 = plan.read(L.ARR_C2_COUNT)
+                for t in range(nt):
+                    if not active[t]:
+                        continue
+                    ratio = int(c2[t]) / plan.track_frames[t]
+                    traces[t].append((float(T_mid[t]), ratio))
+                    diff = abs(ratio - target_c2)
+                    if diff < best_diff[t]:
+                        best_diff[t] = diff; best_T[t] = T_mid[t]
+                    if diff < 0.01:
+                        active[t] = False
+                        continue
+                    if ratio < target_c2:
+                        T_high[t] = T_mid[t]
+                    else:
+                        T_low[t] = T_mid[t]
+            plan.gate(L.GATE_MINHOLD, L.ARR_GATE_F64, best_T + hyst_db / 2, best_T - hyst_db / 2, hold, xf,
+                      alpha_init_to_target=True, count_only=False)
+            plan.stft(1.0)
+            plan.limiter()
+            states = plan.read(L.ARR_STATE); rows = plan.read(L.ARR_ROW); peaks = plan.read(L.ARR_CHUNK_PEAK)
+            for t, i in enumerate(idx):
+                fb, nf = plan.frame_base[t], plan.track_frames[t]
+                results[i] = dict(
+                    out=(yd[i].cpu().numpy() if want_host else yd[i]), chunk_lengths=[int(xd[i].shape[0])],
+                    meansq=msq[fb:fb + nf].copy(), levels=lv[t].copy(), states=states[fb:fb + nf].copy(),
+                    rows=rows[fb:fb + nf].copy(), times=[(k + 1) * (hop / sr) for k in range(nf)],
+                    optimal_T=float(best_T[t]), trace=traces[t], atten_db=float(branch[i][0]),
+                    pipeline_dtype="float64" if use_f64 else "float32", min_hold_frames=hold, xfade_frames=xf,
+                    output_peak=float(peaks[plan.chunk_base[t]]) if plan.track_chunks[t] else 0.0, sr=sr,
+                    input_peak=float(in_peaks[i]), launches=plan.launch_count())
+        finally:
+            plan.close()
+    return results
+
+
+def run(mode: str, xs: Sequence, sr: int, **kw) -> List[dict]:
+    if mode == "adaptive":
+        return run_adaptive(xs, sr, **kw)
+    return run_streaming(mode, xs, sr, **kw)
