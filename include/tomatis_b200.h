@@ -136,14 +136,24 @@ int tmt_plan_gate(tmt_plan* p, int automaton, int gate_input, const double* on, 
  * inverse FFT + synthesis window + overlap-add (each output sample written exactly once, no atomics)
  * + normalisation + optional output gain, and max|y| per limiter chunk into TMT_ARR_CHUNK_PEAK
  * (process_available_frames / flush, src/process_tomatis.py:359-426,447-453; _adaptive.py:298-332).
- * post_gain: linear output gain 10^(output_gain_db/20) (src/process_tomatis.py:349-350), 1 = none. */
-int tmt_plan_stft(tmt_plan* p, float post_gain, void* stream);
+ * post_gain: linear output gain 10^(output_gain_db/20) (src/process_tomatis.py:349-350), 1 = none.
+ * skip_edges != 0: leave the single-frame edge blocks to tmt_plan_edge_frames. */
+int tmt_plan_stft(tmt_plan* p, float post_gain, int skip_edges, void* stream);
+
+/* fp64 recomputation of the two ill-conditioned edge blocks (first hop of WHOLEFILE framing, tail block
+ * of both framings: a single frame divided by w^2 -> 0).  Call after tmt_plan_stft(...,
+ * skip_edges = 1, ...) and before tmt_plan_limiter.  in_scale / out_scale (host, per track, may be NULL):
+ * the adaptive pre-attenuation x*atten_lin and its restore y*restore_lin, applied in float32 exactly as
+ * src/process_tomatis_adaptive.py:215,335-337 (the fp32 body kernel folds them away because they cancel).
+ * pipeline_f64: adaptive float64 branch (no float32 roundings around the FFT). */
+int tmt_plan_edge_frames(tmt_plan* p, float post_gain, const float* in_scale, const float* out_scale,
+                         int pipeline_f64, void* stream);
 
 /* Peak limiter: every chunk whose peak exceeds `limit` is scaled by limit/peak in place
  * (write_clamped, src/process_tomatis.py:352-355; global variant _adaptive.py:341-345). */
 int tmt_plan_limiter(tmt_plan* p, float limit, void* stream);
 
-/* Convenience: levels (f32) -> gate -> stft -> limiter on one stream, standard/xfade parameters. */
+/* Convenience: levels (f32) -> gate -> stft -> edge frames -> limiter on one stream, standard/xfade parameters. */
 int tmt_plan_run_streaming(tmt_plan* p, double m_on, double m_off, int run_frames, int xfade_frames,
                            float post_gain, float limit, void* stream);
 

@@ -16,9 +16,9 @@ from helpers import golden_names, load_golden, csv_states
 
 pytestmark = pytest.mark.gpu
 
-PCM_TOL = 1e-5
-EDGE = 64
-EDGE_TOL = 2e-3
+PCM_TOL = 1e-5          # north-star bar: max-abs error of full scale
+EDGE = 256              # ill-conditioned windows (head of adaptive, tail of every mode), SURVEY.md 7.3-C
+EDGE_TOL = 2e-3         # vs the float32-FFT reference inside those windows (its own fp32/fp64 noise: 3e-4)
 
 
 def _engine():
@@ -31,17 +31,21 @@ def _oracle():
     return orc
 
 
-def _split_err(mode, got, ref, total):
+def _split_err(got, ref):
+    """(interior, edge) max-abs error; edge = first and last EDGE samples."""
     d = np.abs(got.astype(np.float64) - ref.astype(np.float64))
-    if total <= 2 * EDGE:
+    if d.ndim == 2:
+        d = d.max(axis=1)
+    if len(d) <= 2 * EDGE:
         return 0.0, float(d.max()) if d.size else 0.0
-    if mode == "adaptive":
-        return float(d[EDGE:].max()), float(d[:EDGE].max())
-    return float(d[:-EDGE].max()), float(d[-EDGE:].max())
+    return float(d[EDGE:-EDGE].max()), float(max(d[:EDGE].max(), d[-EDGE:].max()))
 
 
 @pytest.mark.parametrize("name", golden_names())
 def test_golden_fixture(name):
+    """GPU output against the committed output of the reference itself (float32 pocketfft, NumPy 2.3.5)
+    and against the same source evaluated with a float64 FFT (NumPy-1.x behaviour; the north star's
+    "reference's fp64"), which is the only meaningful yardstick inside the ill-conditioned edge windows."""
     g = load_golden(name)
     eng = _engine()
     res = eng.run(g["mode"], [g["x"]], g["sr"], **g["kwargs"])[0]
@@ -52,10 +56,24 @@ def test_golden_fixture(name):
     else:
         got_states = ["C1" if s == 1 else "C2" for s, m in zip(res["states"], res["csv_mask"]) if m]
     assert got_states == ref_states
-    interior, edge = _split_err(g["mode"], res["out"], g["out"], len(g["x"]))
-    print(f"{name}: interior max-abs {interior:.3e}, edge max-abs {edge:.3e}")
-    assert interior <= PCM_TOL, (name, interior)
-    assert edge <= EDGE_TOL, (name, edge)
+    o64 = _oracle().run(g["mode"], g["x"], g["sr"], fft_dtype="float64", **g["kwargs"])
+    # hard bar: everywhere within 1e-5 of the float64-FFT evaluation of the reference source
+    i64, e64 = _split_err(res["out"], o64["out"])
+    # against the committed reference output (float32 FFT): samples where the reference itself is
+    # well-conditioned (its own float32-vs-float64 difference <= 1e-6) must meet the same bar; the rest
+    # (edge windows, and whole limiter chunks whose peak sits in an edge window) are listed and bounded.
+    self_noise = np.abs(g["out"].astype(np.float64) - o64["out"].astype(np.float64)).max(axis=1)
+    d = np.abs(res["out"].astype(np.float64) - g["out"].astype(np.float64)).max(axis=1)
+    ok = self_noise <= 1e-6
+    well = float(d[ok].max()) if ok.any() else 0.0
+    ill = float(d[~ok].max()) if (~ok).any() else 0.0
+    print(f"{name}: vs fp64-FFT oracle interior {i64:.3e} edge {e64:.3e} | vs reference output: well-conditioned "
+          f"{well:.3e}, ill-conditioned ({int((~ok).sum())} of {len(ok)} samples, reference self-noise "
+          f"{float(self_noise.max()):.1e}) {ill:.3e}")
+    assert max(i64, e64) <= PCM_TOL, (name, i64, e64)
+    assert well <= PCM_TOL, (name, well)
+    assert ill <= EDGE_TOL, (name, ill)
+    assert np.all(d <= PCM_TOL + self_noise), name          # pointwise triangle bound
 
 
 @pytest.mark.parametrize("name", golden_names())
@@ -87,7 +105,7 @@ def test_batch_of_ragged_tracks_matches_single():
         assert np.array_equal(r["meansq"], o["meansq"])
         assert np.array_equal(r["states"], o["states"])
         assert r["chunk_lengths"] == o["chunk_lengths"]
-        interior, edge = _split_err("standard", r["out"], o["out"], len(x))
+        interior, edge = _split_err(r["out"], o["out"])
         assert interior <= PCM_TOL and edge <= EDGE_TOL
 
 
@@ -105,8 +123,11 @@ def test_ragged_short_inputs(mode, n):
     assert np.array_equal(r["states"], o["states"])
     assert np.array_equal(r["meansq"], np.asarray(o["meansq"]))
     assert r["out"].shape == o["out"].shape
+    o64 = _oracle().run(mode, x, 48000, fft_dtype="float64", **kw)
     d = np.abs(r["out"].astype(np.float64) - o["out"].astype(np.float64))
-    # these clips are all edge; bound the error relative to the oracle's own magnitude
+    d64 = np.abs(r["out"].astype(np.float64) - o64["out"].astype(np.float64))
+    # these clips are all edge: bar vs the float64-FFT evaluation, loose bound vs the float32-FFT one
+    assert float(d64.max()) <= PCM_TOL, float(d64.max())
     assert float(d.max()) <= EDGE_TOL * max(1.0, float(np.abs(o["out"]).max()))
 
 

@@ -66,7 +66,9 @@ struct TrackDev {
     int hb_lo, hb_hi;        // hop-blocks whose sums this plan computes
     int f_lo, f_hi;          // frames whose mean square this plan computes
     int chunk_base, n_chunks;
+    int edge_lo, edge_hi;    // 1: block 0 / block n_frames has a single contributing frame (ill-conditioned edge)
 };
+struct EdgeDev { int track, frame, half, chunk; };   // fp64 edge job: half 0 -> block `frame`, half 1 -> block frame+1
 struct UnitDev { int track, b0, b1, chunk; };        // STFT work unit: output blocks [b0,b1) of a track
 struct ChunkDev { int track; long long s0, s1; };    // limiter chunk: file positions [s0,s1)
 
@@ -375,6 +377,7 @@ struct StftParams {
     const float2* twB;      // [4096]
     float* chunk_peaks;
     int norm_clamp;         // 0: x/(nrm+1e-12)   1: x/max(nrm,1e-8)
+    int skip_edges;         // 1: single-frame edge blocks are left to edge_kernel (fp64)
     float post_gain;
 };
 
@@ -454,7 +457,8 @@ __global__ void __launch_bounds__(kThreads, 2) stft_kernel(const StftParams prm)
                 for (int j = 0; j < 16; ++j) v[j] = make_float2(0.f, 0.f);
             }
 
-            if (f >= un.b0) {       // emit output block f
+            const bool edge_blk = prm.skip_edges && ((f == 0 && tr.edge_lo) || (f == tr.n_frames && tr.edge_hi));
+            if (f >= un.b0 && !edge_blk) {       // emit output block f
                 const bool interior = (f >= 1) && (f < tr.n_frames);
                 const bool full = (pos0 >= tr.out_lo) && (pos0 + kHop <= tr.out_hi);
                 float2* dst = tr.out + (pos0 - tr.out_origin) + t;
@@ -491,6 +495,133 @@ __global__ void __launch_bounds__(kThreads, 2) stft_kernel(const StftParams prm)
             if (m > 0.f) atomicMax(reinterpret_cast<int*>(prm.chunk_peaks + un.chunk), __float_as_int(m));
         }
         __syncthreads();
+    }
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// fp64 edge frames.  Two output regions of the reference are ill-conditioned: the
+// first hop of adaptive mode (one frame, y*w / max(w^2,1e-8) with w -> 0) and the tail block of all modes
+// (y*w / (w^2 + 1e-12) up to the window's last tap).  Rounding noise of an fp32 FFT is amplified there by
+// up to 1/w ~ 1e4..4e5 -- the reference's own float32 and float64 FFT runs differ by 1e-4 in those samples --
+// so the single frame that feeds such a block is recomputed here in double precision (radix-2 in shared
+// memory; one CTA per edge, cost irrelevant) with the reference's float32 roundings on either side of the
+// FFT reproduced explicitly.
+struct EdgeParams {
+    const TrackDev* tracks;
+    const EdgeDev* edges;
+    const uint16_t* rows;
+    const float* gnat;       // [n_rows][2049] natural-order gains
+    const float* win;
+    const float* in_scale;   // per track or NULL
+    const float* out_scale;  // per track or NULL
+    float* chunk_peaks;
+    int norm_clamp;
+    int pipeline_f64;        // adaptive float64 branch: no float32 roundings around the FFT
+    float post_gain;
+};
+
+constexpr int kEdgeSmemBytes = kNfft * (int)sizeof(double2);
+
+__device__ __forceinline__ int bitrev12(int x) { return (int)(__brev((unsigned)x) >> 20); }
+
+__device__ void fft4096_f64(double2* sm, int t) {      // in: bit-reversed order, out: natural order, forward
+    for (int s = 1; s <= 12; ++s) {
+        const int half = 1 << (s - 1);
+        for (int b = t; b < 2048; b += 256) {
+            const int pos = b & (half - 1);
+            const int i = ((b >> (s - 1)) << s) + pos, j = i + half;
+            double sn, cs;
+            sincospi(-(double)pos / (double)half, &sn, &cs);
+            const double2 u = sm[i], x = sm[j];
+            const double2 v = make_double2(x.x * cs - x.y * sn, x.x * sn + x.y * cs);
+            sm[i] = make_double2(u.x + v.x, u.y + v.y);
+            sm[j] = make_double2(u.x - v.x, u.y - v.y);
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(256) edge_kernel(const EdgeParams prm) {
+    extern __shared__ __align__(16) unsigned char smraw[];
+    double2* sm = reinterpret_cast<double2*>(smraw);
+    __shared__ float red[8];
+    const int t = threadIdx.x;
+    const EdgeDev ed = prm.edges[blockIdx.x];
+    const TrackDev tr = prm.tracks[ed.track];
+    const long long pos0 = tr.first_start + (long long)ed.frame * kHop;
+    const float sc = prm.in_scale ? prm.in_scale[ed.track] : 1.0f;
+    const float osc = prm.out_scale ? prm.out_scale[ed.track] : 1.0f;
+    for (int n = t; n < kNfft; n += 256) {
+        const long long p = pos0 + n;
+        float2 x = (p >= tr.in_lo && p < tr.in_hi) ? tr.in[p - tr.in_origin] : make_float2(0.f, 0.f);
+        const float w = prm.win[n];
+        double2 z;
+        if (prm.pipeline_f64) {
+            z = make_double2((double)x.x * (double)sc * (double)w, (double)x.y * (double)sc * (double)w);
+        } else {   // x_atten = fl32(x*atten); frame*win in float32 (src/process_tomatis.py:396, _adaptive.py:215,311)
+            z = make_double2((double)__fmul_rn(__fmul_rn(x.x, sc), w), (double)__fmul_rn(__fmul_rn(x.y, sc), w));
+        }
+        sm[bitrev12(n)] = z;
+    }
+    __syncthreads();
+    fft4096_f64(sm, t);
+    {   // gain (real, symmetric), conjugate for the inverse transform, then bit-reverse in place
+        const float* g = prm.gnat + (size_t)prm.rows[tr.frame_base + ed.frame] * (kNfft / 2 + 1);
+        for (int k = t; k < kNfft; k += 256) {
+            const double gg = (double)g[k <= kNfft / 2 ? k : kNfft - k];
+            const double2 v = sm[k];
+            sm[k] = make_double2(v.x * gg, -v.y * gg);
+        }
+        __syncthreads();
+        for (int k = t; k < kNfft; k += 256) {
+            const int r = bitrev12(k);
+            if (k < r) { const double2 a = sm[k]; sm[k] = sm[r]; sm[r] = a; }
+        }
+        __syncthreads();
+    }
+    fft4096_f64(sm, t);      // conj(FFT(conj(Y))) = N * IFFT(Y)
+    float peak = 0.f;
+    const int blk = ed.frame + ed.half;
+    const long long out0 = tr.first_start + (long long)blk * kHop;
+    for (int n = t; n < kHop; n += 256) {
+        const int wi = n + ed.half * kHop;                 // window tap of this output sample
+        const double2 v = sm[wi];
+        const double yr = v.x * (1.0 / kNfft), yi = -v.y * (1.0 / kNfft);
+        const float w = prm.win[wi];
+        float ox, oy;
+        if (prm.pipeline_f64) {          // everything in double, one final rounding
+            const double nrm = (double)__fmul_rn(w, w);    // norm is float32 in the reference (_adaptive.py:293,323)
+            const double den = fmax(nrm, (double)1e-8f);
+            ox = (float)(yr * (double)w / den * (double)osc);
+            oy = (float)(yi * (double)w / den * (double)osc);
+        } else {
+            float ax, ay;
+            if (prm.norm_clamp) {        // adaptive: y_frame = fl32(irfft * win)
+                ax = (float)(yr * (double)w); ay = (float)(yi * (double)w);
+            } else {                     // streaming: irfft(...).astype(float32) * win
+                ax = __fmul_rn((float)yr, w); ay = __fmul_rn((float)yi, w);
+            }
+            const float nrm = __fmul_rn(w, w);
+            const float den = prm.norm_clamp ? fmaxf(nrm, 1e-8f) : __fadd_rn(nrm, 1e-12f);
+            ox = __fdiv_rn(ax, den); oy = __fdiv_rn(ay, den);
+            if (prm.out_scale) { ox = __fmul_rn(ox, osc); oy = __fmul_rn(oy, osc); }
+        }
+        if (prm.post_gain != 1.0f) { ox = __fmul_rn(ox, prm.post_gain); oy = __fmul_rn(oy, prm.post_gain); }
+        const long long p = out0 + n;
+        if (p >= tr.out_lo && p < tr.out_hi) {
+            tr.out[p - tr.out_origin] = make_float2(ox, oy);
+            peak = fmaxf(peak, fmaxf(fabsf(ox), fabsf(oy)));
+        }
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) peak = fmaxf(peak, __shfl_xor_sync(0xffffffffu, peak, o));
+    if ((t & 31) == 0) red[t >> 5] = peak;
+    __syncthreads();
+    if (t == 0) {
+        float m = red[0];
+        for (int q = 1; q < 8; ++q) m = fmaxf(m, red[q]);
+        if (m > 0.f) atomicMax(reinterpret_cast<int*>(prm.chunk_peaks + ed.chunk), __float_as_int(m));
     }
 }
 
@@ -538,6 +669,7 @@ struct tmt_engine {
     DevBuf<float> rnorm;      // [2][2048]  (eps | clamp)
     DevBuf<float2> twA, twB;
     DevBuf<float> gperm;      // [n_rows][4096]
+    DevBuf<float> gnat;       // [n_rows][2049] natural order (fp64 edge frames)
     int n_rows = 0;
     bool have_win = false;
 };
@@ -546,6 +678,7 @@ struct HostTrack {
     tmt_track_desc d;
     int n_frames, frame_base, hs_base, chunk_base, n_chunks;
     int hb_lo, hb_hi, f_lo, f_hi;
+    int edge_lo = 0, edge_hi = 0;
     long long first_start;
     std::vector<std::pair<long long, long long>> chunk_ranges;   // clipped sample ranges
 };
@@ -561,6 +694,9 @@ struct tmt_plan {
     DevBuf<TrackDev> tracks;
     DevBuf<UnitDev> units;
     DevBuf<ChunkDev> chunks;
+    DevBuf<EdgeDev> edges;
+    int n_edges = 0;
+    DevBuf<float> edge_in_scale, edge_out_scale;
     DevBuf<double> hsum;        // float or double view, [total_frames + n_tracks]
     DevBuf<double> msq;         // float or double view, [total_frames]
     DevBuf<double> gate_f64;    // [total_frames]
@@ -633,6 +769,7 @@ int build_tracks_dev(tmt_plan* p) {
         t.hs_base = h.hs_base;
         t.hb_lo = h.hb_lo; t.hb_hi = h.hb_hi; t.f_lo = h.f_lo; t.f_hi = h.f_hi;
         t.chunk_base = h.chunk_base; t.n_chunks = h.n_chunks;
+        t.edge_lo = h.edge_lo; t.edge_hi = h.edge_hi;
     }
     if (p->n_tracks)
         CUDA_TRY(cudaMemcpy(p->tracks.p, p->tracks_h.data(), sizeof(TrackDev) * p->n_tracks, cudaMemcpyHostToDevice));
@@ -715,6 +852,8 @@ int tmt_engine_create(tmt_engine** out, int device, int n_fft, int hop) {
     cudaMemcpy(e->twB.p, twB.data(), sizeof(float2) * 4096, cudaMemcpyHostToDevice);
     ce = cudaFuncSetAttribute(stft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kStftSmemBytes);
     if (ce != cudaSuccess) { delete e; return fail(TMT_ERR_CUDA, "cudaFuncSetAttribute(stft_kernel): %s", cudaGetErrorString(ce)); }
+    ce = cudaFuncSetAttribute(edge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kEdgeSmemBytes);
+    if (ce != cudaSuccess) { delete e; return fail(TMT_ERR_CUDA, "cudaFuncSetAttribute(edge_kernel): %s", cudaGetErrorString(ce)); }
     *out = e;
     return TMT_OK;
 }
@@ -755,6 +894,10 @@ int tmt_engine_set_gain_rows(tmt_engine* e, const float* rows, int n_rows, int n
         if (e->gperm.alloc((size_t)n_rows * kNfft) != cudaSuccess) return fail(TMT_ERR_NOMEM, "gain table allocation failed");
     }
     CUDA_TRY(cudaMemcpy(e->gperm.p, perm.data(), sizeof(float) * perm.size(), cudaMemcpyHostToDevice));
+    if ((size_t)n_rows * n_bins > e->gnat.n) {
+        if (e->gnat.alloc((size_t)n_rows * n_bins) != cudaSuccess) return fail(TMT_ERR_NOMEM, "gain table allocation failed");
+    }
+    CUDA_TRY(cudaMemcpy(e->gnat.p, rows, sizeof(float) * (size_t)n_rows * n_bins, cudaMemcpyHostToDevice));
     e->n_rows = n_rows;
     return TMT_OK;
 }
@@ -774,6 +917,7 @@ int tmt_plan_create(tmt_engine* e, tmt_plan** out, int framing, int n_tracks, co
     std::vector<UnitDev> units;
     std::vector<ChunkDev> chunks;
     std::vector<std::pair<int, int>> cb;
+    std::vector<EdgeDev> edges;
     long long frames = 0;
     for (int i = 0; i < n_tracks; ++i) {
         HostTrack h;
@@ -819,6 +963,19 @@ int tmt_plan_create(tmt_engine* e, tmt_plan** out, int framing, int n_tracks, co
                 if (b > a) units.push_back(UnitDev{i, a, b, h.chunk_base + (int)c});
             }
         }
+        // single-frame (ill-conditioned) edge blocks, recomputed in fp64 by edge_kernel
+        auto chunk_of = [&](int blk) { for (size_t c = 0; c < cb.size(); ++c) if (blk >= cb[c].first && blk < cb[c].second) return h.chunk_base + (int)c; return h.chunk_base; };
+        if (h.n_frames > 0) {
+            if (framing == TMT_FRAMING_WHOLEFILE && blo <= 0 && bhi > 0) {
+                h.edge_lo = 1;
+                edges.push_back(EdgeDev{i, 0, 0, chunk_of(0)});
+            }
+            const int tb = h.n_frames;     // tail block: second half of the last frame only
+            if (tb >= blo && tb < bhi && h.first_start + (long long)tb * kHop < h.d.total) {
+                h.edge_hi = 1;
+                edges.push_back(EdgeDev{i, h.n_frames - 1, 1, chunk_of(tb)});
+            }
+        }
         p->max_hb = std::max(p->max_hb, h.hb_hi - h.hb_lo);
         p->max_frames = std::max(p->max_frames, h.n_frames);
         p->max_in_len = std::max<long long>(p->max_in_len, h.d.in_len);
@@ -827,9 +984,11 @@ int tmt_plan_create(tmt_engine* e, tmt_plan** out, int framing, int n_tracks, co
     p->total_frames = (int)frames;
     p->total_chunks = (int)chunks.size();
     p->n_units = (int)units.size();
+    p->n_edges = (int)edges.size();
     const size_t nf = (size_t)frames, nt = (size_t)n_tracks;
     bool ok = p->tracks.alloc(std::max<size_t>(nt, 1)) == cudaSuccess && p->units.alloc(std::max<size_t>(units.size(), 1)) == cudaSuccess &&
-              p->chunks.alloc(std::max<size_t>(chunks.size(), 1)) == cudaSuccess && p->hsum.alloc(nf + nt + 1) == cudaSuccess &&
+              p->chunks.alloc(std::max<size_t>(chunks.size(), 1)) == cudaSuccess && p->edges.alloc(std::max<size_t>(edges.size(), 1)) == cudaSuccess &&
+              p->edge_in_scale.alloc(nt + 1) == cudaSuccess && p->edge_out_scale.alloc(nt + 1) == cudaSuccess && p->hsum.alloc(nf + nt + 1) == cudaSuccess &&
               p->msq.alloc(nf + 1) == cudaSuccess && p->gate_f64.alloc(nf + 1) == cudaSuccess && p->state.alloc(nf + 1) == cudaSuccess &&
               p->rows.alloc(nf + 1) == cudaSuccess && p->c2.alloc(nt + 1) == cudaSuccess &&
               p->chunk_peaks.alloc(chunks.size() + 1) == cudaSuccess && p->in_peaks.alloc(nt + 1) == cudaSuccess &&
@@ -841,6 +1000,7 @@ int tmt_plan_create(tmt_engine* e, tmt_plan** out, int framing, int n_tracks, co
     cudaMemset(p->msq.p, 0, sizeof(double) * (nf + 1));
     if (!units.empty()) cudaMemcpy(p->units.p, units.data(), sizeof(UnitDev) * units.size(), cudaMemcpyHostToDevice);
     if (!chunks.empty()) cudaMemcpy(p->chunks.p, chunks.data(), sizeof(ChunkDev) * chunks.size(), cudaMemcpyHostToDevice);
+    if (!edges.empty()) cudaMemcpy(p->edges.p, edges.data(), sizeof(EdgeDev) * edges.size(), cudaMemcpyHostToDevice);
     int rc = build_tracks_dev(p);
     if (rc != TMT_OK) { delete p; return rc; }
     *out = p;
@@ -973,7 +1133,7 @@ int tmt_plan_gate(tmt_plan* p, int automaton, int gate_input, const double* on, 
                                          : launch_gate<double, TMT_GATE_MINHOLD>(p, v, param, S, X, ai, co, st);
 }
 
-int tmt_plan_stft(tmt_plan* p, float post_gain, void* stream) {
+int tmt_plan_stft(tmt_plan* p, float post_gain, int skip_edges, void* stream) {
     if (!p) return fail(TMT_ERR_INVALID, "plan is NULL");
     tmt_engine* e = p->e;
     if (!e->have_win || e->n_rows == 0) return fail(TMT_ERR_INVALID, "engine window / gain rows not set");
@@ -994,8 +1154,43 @@ int tmt_plan_stft(tmt_plan* p, float post_gain, void* stream) {
     prm.twB = e->twB.p;
     prm.chunk_peaks = p->chunk_peaks.p;
     prm.post_gain = post_gain;
+    prm.skip_edges = skip_edges ? 1 : 0;
     const int grid = std::min(p->n_units, 2 * e->n_sms);
     stft_kernel<<<grid, kThreads, kStftSmemBytes, st>>>(prm);
+    p->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return TMT_OK;
+}
+
+int tmt_plan_edge_frames(tmt_plan* p, float post_gain, const float* in_scale, const float* out_scale, int pipeline_f64,
+                         void* stream) {
+    if (!p) return fail(TMT_ERR_INVALID, "plan is NULL");
+    tmt_engine* e = p->e;
+    if (!e->have_win || e->n_rows == 0) return fail(TMT_ERR_INVALID, "engine window / gain rows not set");
+    if (p->n_edges == 0) return TMT_OK;
+    CUDA_TRY(cudaSetDevice(e->device));
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    EdgeParams prm;
+    prm.tracks = p->tracks.p;
+    prm.edges = p->edges.p;
+    prm.rows = p->rows.p;
+    prm.gnat = e->gnat.p;
+    prm.win = e->win.p;
+    prm.in_scale = nullptr;
+    prm.out_scale = nullptr;
+    if (in_scale) {
+        CUDA_TRY(cudaMemcpyAsync(p->edge_in_scale.p, in_scale, sizeof(float) * p->n_tracks, cudaMemcpyHostToDevice, st));
+        prm.in_scale = p->edge_in_scale.p;
+    }
+    if (out_scale) {
+        CUDA_TRY(cudaMemcpyAsync(p->edge_out_scale.p, out_scale, sizeof(float) * p->n_tracks, cudaMemcpyHostToDevice, st));
+        prm.out_scale = p->edge_out_scale.p;
+    }
+    prm.chunk_peaks = p->chunk_peaks.p;
+    prm.norm_clamp = (p->framing == TMT_FRAMING_WHOLEFILE) ? 1 : 0;
+    prm.pipeline_f64 = pipeline_f64 ? 1 : 0;
+    prm.post_gain = post_gain;
+    edge_kernel<<<p->n_edges, 256, kEdgeSmemBytes, st>>>(prm);
     p->launches++;
     CUDA_TRY(cudaGetLastError());
     return TMT_OK;
@@ -1023,7 +1218,9 @@ int tmt_plan_run_streaming(tmt_plan* p, double m_on, double m_off, int run_frame
     std::vector<double> on((size_t)std::max(p->n_tracks, 1), m_on), off((size_t)std::max(p->n_tracks, 1), m_off);
     rc = tmt_plan_gate(p, TMT_GATE_UPDELAY, TMT_ARR_MEANSQ_F32, on.data(), off.data(), run_frames, xfade_frames, 0, 0, stream);
     if (rc) return rc;
-    rc = tmt_plan_stft(p, post_gain, stream);
+    rc = tmt_plan_stft(p, post_gain, 1, stream);
+    if (rc) return rc;
+    rc = tmt_plan_edge_frames(p, post_gain, nullptr, nullptr, 0, stream);
     if (rc) return rc;
     return tmt_plan_limiter(p, limit, stream);
 }

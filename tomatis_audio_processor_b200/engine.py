@@ -157,8 +157,19 @@ class Plan:
                                        off.ctypes.data_as(C.c_void_p), int(param), int(xfade_frames),
                                        int(alpha_init_to_target), int(count_only), _stream_ptr(_torch())), "tmt_plan_gate")
 
-    def stft(self, post_gain: float = 1.0):
-        L.check(self.lib.tmt_plan_stft(self.h, float(post_gain), _stream_ptr(_torch())), "tmt_plan_stft")
+    def stft(self, post_gain: float = 1.0, skip_edges: bool = True):
+        L.check(self.lib.tmt_plan_stft(self.h, float(post_gain), int(skip_edges), _stream_ptr(_torch())), "tmt_plan_stft")
+
+    def edge_frames(self, post_gain: float = 1.0, in_scale=None, out_scale=None, pipeline_f64: bool = False):
+        pi = po = None
+        if in_scale is not None:
+            in_scale = np.ascontiguousarray(in_scale, dtype=np.float32)
+            pi = in_scale.ctypes.data_as(C.c_void_p)
+        if out_scale is not None:
+            out_scale = np.ascontiguousarray(out_scale, dtype=np.float32)
+            po = out_scale.ctypes.data_as(C.c_void_p)
+        L.check(self.lib.tmt_plan_edge_frames(self.h, float(post_gain), pi, po, int(pipeline_f64), _stream_ptr(_torch())),
+                "tmt_plan_edge_frames")
 
     def limiter(self, limit: float = tb.PEAK_LIMIT):
         L.check(self.lib.tmt_plan_limiter(self.h, float(np.float32(limit)), _stream_ptr(_torch())), "tmt_plan_limiter")
@@ -382,7 +393,12 @@ def run_adaptive(xs: Sequence, sr: int, device: int = 0, want_host: bool = True,
                         T_low[t] = T_mid[t]
             plan.gate(L.GATE_MINHOLD, L.ARR_GATE_F64, best_T + hyst_db / 2, best_T - hyst_db / 2, hold, xf,
                       alpha_init_to_target=True, count_only=False)
-            plan.stft(1.0)
+            plan.stft(1.0, skip_edges=True)
+            if use_f64:
+                plan.edge_frames(1.0, None, None, pipeline_f64=True)
+            else:      # restore_lin = db_to_lin(atten_db), float32 (src/process_tomatis_adaptive.py:335-337)
+                restore = np.array([np.float32(tb.db_to_lin_keep(branch[i][0])) for i in idx], dtype=np.float32)
+                plan.edge_frames(1.0, scale, restore, pipeline_f64=False)
             plan.limiter()
             states = plan.read(L.ARR_STATE); rows = plan.read(L.ARR_ROW); peaks = plan.read(L.ARR_CHUNK_PEAK)
             for t, i in enumerate(idx):
