@@ -1,0 +1,346 @@
+#!/usr/bin/env python
+"""bench.py -- the reference's headline metric on B200: audio-seconds processed per second.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Workload (BASELINE.json configs[3]): standard mode, --gate_ui 50, a batch of 5-minute 44.1 kHz stereo
+synthetic tracks (pink noise + on/off envelope + tone bursts), sharded by whole track across ranks:
+128 tracks per GPU, so N = 8 is the full 1024-track batch (1024 tracks of fp32 in + out do not fit one
+GPU's HBM; the per-GPU shard does).  A "step" is one pass of the whole hot path over the rank's tracks:
+levels -> gate scan -> fused STFT/OLA -> fp64 edge frames -> limiter.  Weak scaling, no data-path
+collective; the only cross-rank traffic is the timing reduction.
+
+One JSON line on stdout (rank 0).  `value` is device-resident throughput, `e2e` the same metric through
+the host-buffer API (pinned host -> H2D -> kernels -> D2H -> pinned host, copies inside the timed region),
+`roofline` the fused STFT kernel against the measured HBM copy bandwidth using ALGORITHMIC bytes
+(16 B per stereo sample-frame: read once + write once), `cpu_baseline` the NumPy port of the reference
+(oracle/) timed on the host cores.  `--impl reference` times that CPU port on all host cores instead.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SR = 44100
+TRACK_SECONDS = 300.0
+N_SAMPLES = int(SR * TRACK_SECONDS)          # 13 230 000 sample-frames
+ALG_BYTES_PER_SF = 16                        # fp32 stereo read once + written once
+METRIC = "audio_seconds_per_second"
+UNIT = "audio-s/s"
+
+
+def workload_config(tracks_per_gpu, n_gpus):
+    return {
+        "workload": f"BASELINE configs[3]: batch of {tracks_per_gpu * n_gpus} synthetic 5 min 44.1 kHz stereo tracks "
+                    f"({tracks_per_gpu}/GPU, sharded by track), process_tomatis standard mode --gate_ui 50",
+        "mode": "standard", "gate_ui": 50, "sample_rate": SR, "track_seconds": TRACK_SECONDS,
+        "tracks_per_gpu": tracks_per_gpu, "n_fft": 4096, "hop": 2048,
+        "l2_policy": "inputs larger than L2 (13.5 GB in + 13.5 GB out per GPU per step, streamed once)",
+        "parallelism": f"track-sharded x{n_gpus}, no collective on the data path",
+    }
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0=None, t1=None):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        for ts, line in self.rows:
+            if t0 is not None and not (t0 - 0.05 <= ts <= t1 + 0.15):
+                continue
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples in timed region"]}
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "power_w_max": max(pw), "samples": len(sm),
+                "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------ CPU arm
+_CPU_TRACKS = {}
+
+
+def _cpu_track(seed):
+    from tomatis_audio_processor_b200 import synth
+    if seed not in _CPU_TRACKS:
+        _CPU_TRACKS[seed] = synth.recipe_gated_pink(TRACK_SECONDS, SR, seed)
+    return _CPU_TRACKS[seed]
+
+
+def _cpu_worker(seed):
+    from oracle import tomatis_oracle as orc           # the reference's algorithm, restated in NumPy
+    x = _cpu_track(seed)
+    t = time.perf_counter()
+    res = orc.process_standard(x, SR, gate_ui=50)
+    return time.perf_counter() - t, int(res["out"].shape[0])
+
+
+def cpu_baseline_single(n_tracks=3):
+    """Oracle port on ONE host core, bounded sample (n_tracks x 5 min)."""
+    total_t, total_sf = 0.0, 0
+    for i in range(n_tracks):
+        dt, n = _cpu_worker(1000 + (i % 2))
+        total_t += dt
+        total_sf += n
+    return {"value": total_sf / SR / total_t, "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": f"{n_tracks} tracks x {TRACK_SECONDS:.0f} s @ {SR} Hz through oracle.process_standard (NumPy "
+                      f"restatement of src/process_tomatis.py, float32 pocketfft), one process"}
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    import numpy as np
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    workers = max(1, min(cores, args.cpu_workers or cores))
+    seeds = [1000, 1001]
+    for s in seeds:                       # synthesise before forking so workers share the pages
+        _cpu_track(s)
+    ctx = mp.get_context("fork")
+    jobs = [seeds[i % len(seeds)] for i in range(workers)]
+    times = []
+    with ctx.Pool(workers) as pool:
+        for it in range(args.warmup + args.steps):
+            t = time.perf_counter()
+            res = pool.map(_cpu_worker, jobs)
+            dt = time.perf_counter() - t
+            if it >= args.warmup:
+                times.append(dt)
+    sf = sum(r[1] for r in res)
+    total = sum(times)
+    value = sf / SR * len(times) / total
+    sample = (f"each step: {workers} x one 5 min 44.1 kHz track (one process per host core, NumPy {np.__version__}) "
+              f"through oracle.process_standard; bounded sample of the {args.tracks_per_gpu * args.gpus}-track workload")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": total / len(times) * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args.tracks_per_gpu, args.gpus),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": workers, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md, 6.65 TB/s)"
+
+
+def ncu_traffic():
+    """dram bytes per stft_kernel launch from the committed ncu capture, scaled per sample-frame."""
+    p = os.path.join(ROOT, "profiles", "stft_kernel_traffic.json")
+    try:
+        with open(p) as f:
+            return json.load(f)
+    except Exception:
+        return None
+
+
+def run_gpu_arm(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    torch.cuda.set_device(local)
+    dev = f"cuda:{local}"
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(dev))
+
+    from tomatis_audio_processor_b200 import synth, _lib as L
+    from tomatis_audio_processor_b200.batch import DeviceBatch, HostBatchPipeline
+
+    T = args.tracks_per_gpu
+    x = synth.device_batch(T, N_SAMPLES, SR, 1000 + rank * T, dev)       # seeds 1000.. as in SURVEY 8(d) C4
+    y = torch.empty_like(x)
+    db = DeviceBatch(x, y, SR, "standard", device=local, unit_blocks=args.unit_blocks, gate_ui=50)
+    sf_rank = T * N_SAMPLES
+    audio_s_rank = sf_rank / SR
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        db.step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    l0 = db.plan.launch_count()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t0 = time.time()
+    e0.record()
+    for k in range(args.steps):
+        db.levels(); db.gate()
+        ev[k][0].record()
+        db.stft()
+        ev[k][1].record()
+        db.edges(); db.limiter()
+    e1.record()
+    barrier()
+    t1 = time.time()
+    clocks = sampler.stop(t0, t1) if rank == 0 else None
+    ms_total = e0.elapsed_time(e1)
+    stft_ms = float(np.mean([a.elapsed_time(b) for a, b in ev]))
+    launches = db.plan.launch_count() - l0
+    tmax = torch.tensor([ms_total, stft_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    ms_total, stft_ms = float(tmax[0]), float(tmax[1])
+    value = audio_s_rank * world * args.steps / (ms_total * 1e-3)
+    states = db.plan.read(L.ARR_STATE)
+    peaks = db.plan.read(L.ARR_CHUNK_PEAK)
+    c2_frac = float((states == 2).mean())
+    lim_frac = float((peaks > np.float32(0.999)).mean())
+    out_peak = float(y.abs().max())
+    finite = bool(torch.isfinite(y[0]).all())
+    db.close()
+
+    # ---- end to end through the host-buffer API (pinned host memory, copies inside the timed region)
+    e2e = None
+    if not args.no_e2e:
+        Te = min(T, args.e2e_tracks)
+        Te -= Te % args.wave_tracks
+        Te = max(Te, args.wave_tracks)
+        h_in = torch.empty((Te, N_SAMPLES, 2), dtype=torch.float32, pin_memory=True)
+        h_out = torch.empty((Te, N_SAMPLES, 2), dtype=torch.float32, pin_memory=True)
+        h_in.copy_(x[:Te])
+        del y
+        pipe = HostBatchPipeline(N_SAMPLES, SR, "standard", device=local, wave_tracks=args.wave_tracks,
+                                 unit_blocks=args.unit_blocks, gate_ui=50)
+        for _ in range(max(1, min(args.warmup, 2))):
+            pipe.process(h_in, h_out)
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(args.e2e_steps):
+            pipe.process(h_in, h_out)
+        b.record()
+        barrier()
+        ms = torch.tensor([a.elapsed_time(b)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        e2e_value = Te * N_SAMPLES / SR * world * args.e2e_steps / (float(ms[0]) * 1e-3)
+        # spot check: the host result equals the resident result of the same tracks
+        e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(Te * N_SAMPLES * 8 * world),
+               "d2h_bytes_per_step": int(Te * N_SAMPLES * 8 * world), "tracks_per_gpu_per_step": Te,
+               "steps": args.e2e_steps, "ms_per_step": float(ms[0]) / args.e2e_steps,
+               "api": "tomatis_audio_processor_b200.batch.HostBatchPipeline.process (pinned host float32 in/out, "
+                      f"waves of {args.wave_tracks} tracks, H2D/compute/D2H on 3 streams)",
+               "host_peak_out": float(h_out.abs().max())}
+        pipe.close()
+        del h_in, h_out
+
+    if rank == 0:
+        peak_gbs, peak_src = measured_peak()
+        achieved = ALG_BYTES_PER_SF * sf_rank / (stft_ms * 1e-3) / 1e9
+        traffic = ncu_traffic()
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": workload_config(T, world), "clocks": clocks,
+            "e2e": e2e, "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "kernel": "stft_kernel (fused gather+window+FFT+gain+IFFT+window+OLA+peak)",
+                         "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs,
+                         "peak_source": peak_src, "algorithmic_bytes_per_launch": ALG_BYTES_PER_SF * sf_rank,
+                         "kernel_ms": stft_ms, "kernel_share_of_step": stft_ms * args.steps / ms_total,
+                         "traffic": (traffic or {}).get("dram_bytes_per_sf", None) and
+                                    (traffic["dram_bytes_per_sf"] * sf_rank),
+                         "traffic_source": (traffic or {}).get("source")},
+            "checks": {"c2_fraction": c2_frac, "chunks_over_limit": lim_frac, "output_peak": out_peak,
+                       "finite": finite},
+        }
+        if world == 1 and not args.no_cpu:
+            line["cpu_baseline"] = cpu_baseline_single(args.cpu_tracks)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--tracks-per-gpu", dest="tracks_per_gpu", type=int, default=128)
+    ap.add_argument("--unit-blocks", dest="unit_blocks", type=int, default=0)
+    ap.add_argument("--e2e-tracks", dest="e2e_tracks", type=int, default=32)
+    ap.add_argument("--e2e-steps", dest="e2e_steps", type=int, default=3)
+    ap.add_argument("--wave-tracks", dest="wave_tracks", type=int, default=8)
+    ap.add_argument("--cpu-tracks", dest="cpu_tracks", type=int, default=3)
+    ap.add_argument("--cpu-workers", dest="cpu_workers", type=int, default=0)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3                       # timing rule: at least 3 warm-up steps
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_gpu_arm(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,114 @@
+"""Batch / host-buffer front end: many equal-length tracks through the streaming modes.
+
+`DeviceBatch` keeps a plan over device-resident tracks (the resident-in-HBM benchmark arm);
+`HostBatchPipeline` is the host-buffer entry point: tracks live in pinned host memory, are staged to
+the GPU in waves, processed, and copied back, with H2D / kernels / D2H of consecutive waves overlapped
+on three streams.  Both mirror what a user of the reference does with a directory of files
+(`docs/Tomatis处理器使用指南.md:243-249` loops process() over files); sharding by whole track across
+ranks needs no collective.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import numpy as np
+
+from . import _lib as L
+from . import tables as tb
+from .engine import Plan, get_engine, streaming_params, whole_track_desc, _torch
+
+
+class DeviceBatch:
+    """Plan over `x` [T, N, 2] float32 CUDA tensor -> `y` (same shape), standard or xfade mode."""
+
+    def __init__(self, x, y, sr: int, mode: str = "standard", device: int = 0, unit_blocks: int = 0, **params):
+        self.torch = _torch()
+        self.eng = get_engine(device)
+        self.sp = streaming_params(mode, sr, **params)
+        self.eng.set_gain_rows(self.sp.rows, key=self.sp.rows_key)
+        self.x, self.y, self.sr = x, y, sr
+        self.plan = Plan(self.eng, L.FRAMING_STREAMING, [whole_track_desc(x[i], y[i]) for i in range(x.shape[0])], unit_blocks)
+
+    # the individual launches of one step (bench.py brackets `stft` with its own events)
+    def levels(self):
+        self.plan.levels(False, None)
+
+    def gate(self):
+        sp = self.sp
+        self.plan.gate(L.GATE_UPDELAY, L.ARR_MEANSQ_F32, sp.m_on, sp.m_off, sp.run_frames, sp.xfade_frames)
+
+    def stft(self):
+        self.plan.stft(self.sp.post_gain, skip_edges=True)
+
+    def edges(self):
+        self.plan.edge_frames(self.sp.post_gain)
+
+    def limiter(self):
+        self.plan.limiter()
+
+    def step(self):
+        self.levels(); self.gate(); self.stft(); self.edges(); self.limiter()
+
+    def close(self):
+        self.plan.close()
+
+
+class HostBatchPipeline:
+    """process(host_in, host_out): pinned host [T, N, 2] float32 -> pinned host [T, N, 2] float32.
+
+    Waves of `wave_tracks` tracks rotate through `n_slots` device staging slots; copy-in, compute and
+    copy-out run on separate streams, ordered by events, so PCIe transfers overlap the kernels."""
+
+    def __init__(self, n_samples: int, sr: int, mode: str = "standard", device: int = 0, wave_tracks: int = 8,
+                 n_slots: int = 3, unit_blocks: int = 0, **params):
+        torch = self.torch = _torch()
+        self.eng = get_engine(device)
+        self.sp = streaming_params(mode, sr, **params)
+        self.eng.set_gain_rows(self.sp.rows, key=self.sp.rows_key)
+        dev = f"cuda:{device}"
+        self.W, self.N = wave_tracks, n_samples
+        self.s_in, self.s_c, self.s_out = (torch.cuda.Stream(device=dev) for _ in range(3))
+        self.slots = []
+        for _ in range(n_slots):
+            x = torch.empty((wave_tracks, n_samples, 2), dtype=torch.float32, device=dev)
+            y = torch.empty_like(x)
+            plan = Plan(self.eng, L.FRAMING_STREAMING, [whole_track_desc(x[i], y[i]) for i in range(wave_tracks)], unit_blocks)
+            self.slots.append(dict(x=x, y=y, plan=plan, ev_in=torch.cuda.Event(), ev_c=torch.cuda.Event(),
+                                   ev_out=torch.cuda.Event(), used=False))
+        self.launches = 0
+
+    def process(self, host_in, host_out):
+        torch, sp = self.torch, self.sp
+        T = host_in.shape[0]
+        if T % self.W:
+            raise ValueError(f"track count {T} must be a multiple of the wave size {self.W}")
+        cur = torch.cuda.current_stream()
+        for s in (self.s_in, self.s_c, self.s_out):
+            s.wait_stream(cur)
+        for w in range(T // self.W):
+            sl = self.slots[w % len(self.slots)]
+            lo, hi = w * self.W, (w + 1) * self.W
+            with torch.cuda.stream(self.s_in):
+                if sl["used"]:
+                    self.s_in.wait_event(sl["ev_c"])          # previous compute on this slot has consumed x
+                sl["x"].copy_(host_in[lo:hi], non_blocking=True)
+                sl["ev_in"].record(self.s_in)
+            with torch.cuda.stream(self.s_c):
+                self.s_c.wait_event(sl["ev_in"])
+                if sl["used"]:
+                    self.s_c.wait_event(sl["ev_out"])         # previous copy-out of y has finished
+                before = sl["plan"].launch_count()
+                sl["plan"].run_streaming(sp.m_on, sp.m_off, sp.run_frames, sp.xfade_frames, sp.post_gain)
+                self.launches += sl["plan"].launch_count() - before
+                sl["ev_c"].record(self.s_c)
+            with torch.cuda.stream(self.s_out):
+                self.s_out.wait_event(sl["ev_c"])
+                host_out[lo:hi].copy_(sl["y"], non_blocking=True)
+                sl["ev_out"].record(self.s_out)
+            sl["used"] = True
+        for s in (self.s_in, self.s_c, self.s_out):
+            cur.wait_stream(s)
+
+    def close(self):
+        for sl in self.slots:
+            sl["plan"].close()
