@@ -6,8 +6,8 @@
 // and N = 4096 = 16*16*16 is done as three register-resident radix-16 stages with two
 // shared-memory exchanges per direction.  Index split
 //     n = 256*n1 + 16*n2 + n3          k = k1 + 16*k2 + 256*k3
-// forward:  A (threads (n2,n3), DFT over n1, twiddle W256^(n2*k1))  -> smem E1
-//           B (threads (k1,n3), DFT over n2, twiddle W4096^(n3*(k1+16*k2))) -> smem E2
+// forward:  A (threads (n2,n3), DFT over n1, twiddle W4096^((16*n2+n3)*k1))  -> smem E1
+//           B (threads (k1,n3), DFT over n2, twiddle W256^(n3*k2)) -> smem E2
 //           C (threads (k1,k2), DFT over n3)  -> X[k1+16*k2+256*k3] in registers
 // inverse:  exactly the mirror (C' B' A') with conjugate twiddles applied on stage inputs, so
 // the spectrum never leaves registers between forward and inverse and the time-domain result
@@ -28,11 +28,35 @@ constexpr int kThreads = 256;       // one frame per CTA pass, 16 points per thr
 constexpr int kRowPad = 17;         // E2 row stride in float2 (16 + 1): conflict-free both ways
 constexpr int kExchFloat2 = 256 * kRowPad;   // one exchange buffer (34 816 B)
 
+// Complex arithmetic on float2.  On the device every operation is a packed FP32x2 instruction
+// (FADD2 / FMUL2 / FFMA2, new on sm_100): re/im live in one 64-bit register pair, and the swap,
+// per-half sign and scalar broadcast these formulas need are free operand modifiers in SASS
+// (R.F32x2.LO_HI.NP, R.F32), so a complex add is ONE instruction and a complex multiply TWO.
+// The host versions (CPU emulation in tests) are the plain scalar formulas.
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ >= 1000)
+TMT_HD float2 cadd(float2 a, float2 b) { return __fadd2_rn(a, b); }
+TMT_HD float2 csub(float2 a, float2 b) { return __ffma2_rn(b, make_float2(-1.f, -1.f), a); }
+TMT_HD float2 cscale(float2 a, float s) { return __fmul2_rn(a, make_float2(s, s)); }
+// a + (-i)*b = (a.x + b.y, a.y - b.x)
+TMT_HD float2 cadd_mi(float2 a, float2 b) { return __ffma2_rn(make_float2(b.y, b.x), make_float2(1.f, -1.f), a); }
+// a + (+i)*b = (a.x - b.y, a.y + b.x)
+TMT_HD float2 cadd_pi(float2 a, float2 b) { return __ffma2_rn(make_float2(b.y, b.x), make_float2(-1.f, 1.f), a); }
+TMT_HD float2 cmul(float2 a, float2 w) {
+    return __ffma2_rn(make_float2(a.y, a.x), make_float2(-w.y, w.y), __fmul2_rn(a, make_float2(w.x, w.x)));
+}
+// a * conj(w)
+TMT_HD float2 cmulc(float2 a, float2 w) {
+    return __ffma2_rn(make_float2(a.y, a.x), make_float2(w.y, -w.y), __fmul2_rn(a, make_float2(w.x, w.x)));
+}
+#else
 TMT_HD float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
 TMT_HD float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+TMT_HD float2 cscale(float2 a, float s) { return make_float2(a.x * s, a.y * s); }
+TMT_HD float2 cadd_mi(float2 a, float2 b) { return make_float2(a.x + b.y, a.y - b.x); }
+TMT_HD float2 cadd_pi(float2 a, float2 b) { return make_float2(a.x - b.y, a.y + b.x); }
 TMT_HD float2 cmul(float2 a, float2 w) { return make_float2(a.x * w.x - a.y * w.y, a.x * w.y + a.y * w.x); }
-// a * conj(w)
 TMT_HD float2 cmulc(float2 a, float2 w) { return make_float2(a.x * w.x + a.y * w.y, a.y * w.x - a.x * w.y); }
+#endif
 
 // multiply by W16^M (forward, e^{-2*pi*i*M/16}) or its conjugate (INV)
 template <int M, bool INV>
@@ -42,21 +66,14 @@ TMT_HD float2 mul_w16(float2 a) {
     constexpr float kH = 0.70710678118654752440f;    // sqrt(1/2)
     if constexpr (M == 0) {
         return a;
-    } else if constexpr (M == 4) {                   // -i (fwd) / +i (inv)
+    } else if constexpr (M == 4) {                   // -i (fwd) / +i (inv): swap + sign, folded into the consumer
         return INV ? make_float2(-a.y, a.x) : make_float2(a.y, -a.x);
-    } else if constexpr (M == 2) {                   // (1 -/+ i)/sqrt2
-        return INV ? make_float2((a.x - a.y) * kH, (a.x + a.y) * kH)
-                   : make_float2((a.x + a.y) * kH, (a.y - a.x) * kH);
-    } else if constexpr (M == 6) {                   // (-1 -/+ i)/sqrt2
-        return INV ? make_float2((-a.x - a.y) * kH, (a.x - a.y) * kH)
-                   : make_float2((a.y - a.x) * kH, (-a.x - a.y) * kH);
     } else {
-        // general: W16^M = (c, -s) forward, (c, +s) inverse
-        constexpr float c = (M == 1) ? kC1 : (M == 3) ? kS1 : (M == 9) ? -kC1 : 0.f;
-        constexpr float s = (M == 1) ? kS1 : (M == 3) ? kC1 : (M == 9) ? -kS1 : 0.f;
-        static_assert(M == 1 || M == 3 || M == 9, "unsupported W16 power");
-        return INV ? make_float2(a.x * c - a.y * s, a.y * c + a.x * s)
-                   : make_float2(a.x * c + a.y * s, a.y * c - a.x * s);
+        // W16^M = (c, -s) forward, (c, +s) inverse
+        constexpr float c = (M == 1) ? kC1 : (M == 2) ? kH : (M == 3) ? kS1 : (M == 6) ? -kH : (M == 9) ? -kC1 : 0.f;
+        constexpr float s = (M == 1) ? kS1 : (M == 2) ? kH : (M == 3) ? kC1 : (M == 6) ? kH : (M == 9) ? -kS1 : 0.f;
+        static_assert(M == 1 || M == 2 || M == 3 || M == 6 || M == 9, "unsupported W16 power");
+        return INV ? cmul(a, make_float2(c, s)) : cmul(a, make_float2(c, -s));
     }
 }
 
@@ -67,11 +84,11 @@ TMT_HD void radix4(float2& x0, float2& x1, float2& x2, float2& x3) {
     x0 = cadd(t0, t2);
     x2 = csub(t0, t2);
     if (INV) {
-        x1 = make_float2(t1.x - t3.y, t1.y + t3.x);
-        x3 = make_float2(t1.x + t3.y, t1.y - t3.x);
+        x1 = cadd_pi(t1, t3);
+        x3 = cadd_mi(t1, t3);
     } else {
-        x1 = make_float2(t1.x + t3.y, t1.y - t3.x);
-        x3 = make_float2(t1.x - t3.y, t1.y + t3.x);
+        x1 = cadd_mi(t1, t3);
+        x3 = cadd_pi(t1, t3);
     }
 }
 
@@ -117,54 +134,94 @@ TMT_HD int e1_b(int t, int j) { return (t >> 4) * 256 + j * 16 + (t & 15); }
 TMT_HD int e2_b(int t, int j) { return ((t >> 4) * 16 + j) * kRowPad + (t & 15); }
 TMT_HD int e2_c(int t, int j) { return t * kRowPad + j; }
 
-// twiddle tables (built on the host in double precision, see tomatis_b200.cu):
-//   twA[k1*16 + n2]  = W256^(n2*k1)                       (256 entries; warp-broadcast reads)
-//   twB[k2*256 + t]  = W4096^((t&15) * ((t>>4) + 16*k2))  (4096 entries; coalesced reads)
+// Twiddles.  Both twiddle stages have the form v[k] *= b^k with a PER-THREAD base:
+//   stage A (thread t = 16*n2 + n3, output k1):  W256^(n2*k1) * W4096^(n3*k1) = (W4096^t)^k1
+//   stage B (thread (k1,n3),        output k2):  W256^(n3*k2)                 = (W256^n3)^k2
+// ncu showed the shared-memory data pipe (not FP32) to be the limiter of this kernel, and twiddle-table
+// reads were a quarter of its wavefronts, so the powers are recomputed every frame from b and b^4
+// (exact, host-computed in double, 8 registers per thread): 14 extra complex multiplies per stage,
+// chain depth <= 3 roundings, no table traffic at all.
+struct TwBase { float2 b1, b4; };
 
-// ---- forward stages ---------------------------------------------------------------------
-// in : v[j] = windowed z[256*j + t]
-TMT_HD void fwd_a(float2 (&v)[16], int t, const float2* twA, float2* bufP) {
-    dft16<false>(v);
-    const int n2 = t >> 4;
-#pragma unroll
-    for (int j = 1; j < 16; ++j) v[j] = cmul(v[j], twA[j * 16 + n2]);
-#pragma unroll
-    for (int j = 0; j < 16; ++j) bufP[e1_a(t, j)] = v[j];
+template <bool CONJ>
+TMT_HD void tw_pow(float2 (&v)[16], const TwBase w) {
+    const float2 b1 = w.b1, b4 = w.b4;
+    const float2 b2 = cmul(b1, b1), b3 = cmul(b2, b1);
+    const float2 b8 = cmul(b4, b4), b12 = cmul(b8, b4);
+#define TMT_TW(k, p) v[k] = CONJ ? cmulc(v[k], p) : cmul(v[k], p)
+    TMT_TW(1, b1); TMT_TW(2, b2); TMT_TW(3, b3); TMT_TW(4, b4);
+    TMT_TW(5, cmul(b4, b1)); TMT_TW(6, cmul(b4, b2)); TMT_TW(7, cmul(b4, b3)); TMT_TW(8, b8);
+    TMT_TW(9, cmul(b8, b1)); TMT_TW(10, cmul(b8, b2)); TMT_TW(11, cmul(b8, b3)); TMT_TW(12, b12);
+    TMT_TW(13, cmul(b12, b1)); TMT_TW(14, cmul(b12, b2)); TMT_TW(15, cmul(b12, b3));
+#undef TMT_TW
 }
-TMT_HD void fwd_b(float2 (&v)[16], int t, const float2* twB, const float2* bufP, float2* bufQ) {
+
+// ---- exchange pieces -----------------------------------------------------------------------
+TMT_HD void st_e1a(const float2 (&v)[16], int t, float2* buf) {
 #pragma unroll
-    for (int j = 0; j < 16; ++j) v[j] = bufP[e1_b(t, j)];
+    for (int j = 0; j < 16; ++j) buf[e1_a(t, j)] = v[j];
+}
+TMT_HD void ld_e1b(float2 (&v)[16], int t, const float2* buf) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = buf[e1_b(t, j)];
+}
+TMT_HD void st_e2b(const float2 (&v)[16], int t, float2* buf) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) buf[e2_b(t, j)] = v[j];
+}
+TMT_HD void ld_e2c(float2 (&v)[16], int t, const float2* buf) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = buf[e2_c(t, j)];
+}
+TMT_HD void st_e2c(const float2 (&v)[16], int t, float2* buf) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) buf[e2_c(t, j)] = v[j];
+}
+TMT_HD void ld_e2b(float2 (&v)[16], int t, const float2* buf) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = buf[e2_b(t, j)];
+}
+TMT_HD void st_e1b(const float2 (&v)[16], int t, float2* buf) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) buf[e1_b(t, j)] = v[j];
+}
+TMT_HD void ld_e1a(float2 (&v)[16], int t, const float2* buf) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = buf[e1_a(t, j)];
+}
+
+// ---- composite forward stages (in: v[j] = windowed z[256*j + t]) ---------------------------
+TMT_HD void fwd_a(float2 (&v)[16], int t, const TwBase wa, float2* bufP) {
     dft16<false>(v);
-#pragma unroll
-    for (int j = 0; j < 16; ++j) v[j] = cmul(v[j], twB[j * 256 + t]);
-#pragma unroll
-    for (int j = 0; j < 16; ++j) bufQ[e2_b(t, j)] = v[j];
+    tw_pow<false>(v, wa);
+    st_e1a(v, t, bufP);
+}
+TMT_HD void fwd_b(float2 (&v)[16], int t, const TwBase wb, const float2* bufP, float2* bufQ) {
+    ld_e1b(v, t, bufP);
+    dft16<false>(v);
+    tw_pow<false>(v, wb);
+    st_e2b(v, t, bufQ);
 }
 // out: v[j] = Z[(t>>4) + 16*(t&15) + 256*j]
 TMT_HD void fwd_c(float2 (&v)[16], int t, const float2* bufQ) {
-#pragma unroll
-    for (int j = 0; j < 16; ++j) v[j] = bufQ[e2_c(t, j)];
+    ld_e2c(v, t, bufQ);
     dft16<false>(v);
 }
-// ---- inverse stages (unnormalised; the 1/4096 is folded into the gain table) --------------
+// ---- composite inverse stages (unnormalised; the 1/4096 is folded into the gain table) ------
 TMT_HD void inv_c(float2 (&v)[16], int t, float2* bufP) {
     dft16<true>(v);
-#pragma unroll
-    for (int j = 0; j < 16; ++j) bufP[e2_c(t, j)] = v[j];
+    st_e2c(v, t, bufP);
 }
-TMT_HD void inv_b(float2 (&v)[16], int t, const float2* twB, const float2* bufP, float2* bufQ) {
-#pragma unroll
-    for (int j = 0; j < 16; ++j) v[j] = cmulc(bufP[e2_b(t, j)], twB[j * 256 + t]);
+TMT_HD void inv_b(float2 (&v)[16], int t, const TwBase wb, const float2* bufP, float2* bufQ) {
+    ld_e2b(v, t, bufP);
+    tw_pow<true>(v, wb);
     dft16<true>(v);
-#pragma unroll
-    for (int j = 0; j < 16; ++j) bufQ[e1_b(t, j)] = v[j];
+    st_e1b(v, t, bufQ);
 }
 // out: v[j] = 4096 * y[256*j + t]
-TMT_HD void inv_a(float2 (&v)[16], int t, const float2* twA, const float2* bufQ) {
-    const int n2 = t >> 4;
-    v[0] = bufQ[e1_a(t, 0)];
-#pragma unroll
-    for (int j = 1; j < 16; ++j) v[j] = cmulc(bufQ[e1_a(t, j)], twA[j * 16 + n2]);
+TMT_HD void inv_a(float2 (&v)[16], int t, const TwBase wa, const float2* bufQ) {
+    ld_e1a(v, t, bufQ);
+    tw_pow<true>(v, wa);
     dft16<true>(v);
 }
 

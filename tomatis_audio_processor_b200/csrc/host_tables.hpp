@@ -6,29 +6,23 @@
 
 namespace tmt {
 
-// twA[k1*16 + n2] = W256^(n2*k1), W = exp(-2*pi*i/256); double precision, rounded once.
-inline std::vector<float2> build_twA() {
-    std::vector<float2> t(256);
+// Per-thread twiddle bases (see fft4096.cuh tw_pow), double precision rounded once:
+//   base[4*t + 0] = W4096^t      base[4*t + 1] = W4096^(4t)      (stage A, thread t)
+//   base[4*t + 2] = W256^(t&15)  base[4*t + 3] = W256^(4*(t&15)) (stage B, thread t)
+inline std::vector<float2> build_tw_bases() {
+    std::vector<float2> b(4 * 256);
     const double two_pi = 6.283185307179586476925286766559;
-    for (int k1 = 0; k1 < 16; ++k1)
-        for (int n2 = 0; n2 < 16; ++n2) {
-            const double a = -two_pi * double((n2 * k1) % 256) / 256.0;
-            t[k1 * 16 + n2] = make_float2((float)std::cos(a), (float)std::sin(a));
-        }
-    return t;
-}
-
-// twB[k2*256 + t] = W4096^(n3*(k1 + 16*k2)), k1 = t>>4, n3 = t&15.
-inline std::vector<float2> build_twB() {
-    std::vector<float2> t(4096);
-    const double two_pi = 6.283185307179586476925286766559;
-    for (int k2 = 0; k2 < 16; ++k2)
-        for (int th = 0; th < 256; ++th) {
-            const int k1 = th >> 4, n3 = th & 15;
-            const double a = -two_pi * double((n3 * (k1 + 16 * k2)) % 4096) / 4096.0;
-            t[k2 * 256 + th] = make_float2((float)std::cos(a), (float)std::sin(a));
-        }
-    return t;
+    auto w = [&](int num, int den) {
+        const double a = -two_pi * double(num % den) / double(den);
+        return make_float2((float)std::cos(a), (float)std::sin(a));
+    };
+    for (int t = 0; t < 256; ++t) {
+        b[4 * t + 0] = w(t, 4096);
+        b[4 * t + 1] = w(4 * t, 4096);
+        b[4 * t + 2] = w(t & 15, 256);
+        b[4 * t + 3] = w(4 * (t & 15), 256);
+    }
+    return b;
 }
 
 // Natural-order half-spectrum gain row g[0..2048] -> register-order full-spectrum row:

@@ -14,6 +14,7 @@
 #include <cstdio>
 #include <cstdarg>
 #include <cstring>
+#include <cstdlib>
 #include <cmath>
 #include <vector>
 #include <algorithm>
@@ -373,39 +374,53 @@ struct StftParams {
     const float* gperm;     // [n_rows][4096] register-order gains, 1/4096 folded in
     const float* win;       // [4096]
     const float* rnorm;     // [2048] interior 1/(w2[n+hop]+w2[n] (+eps | clamped))
-    const float2* twA;      // [256]
-    const float2* twB;      // [4096]
+    const float2* tw_bases; // [256][4]: per-thread twiddle bases (host_tables.hpp)
     float* chunk_peaks;
     int norm_clamp;         // 0: x/(nrm+1e-12)   1: x/max(nrm,1e-8)
     int skip_edges;         // 1: single-frame edge blocks are left to edge_kernel (fp64)
     float post_gain;
 };
 
-constexpr int kStftSmemBytes = (2 * kExchFloat2 + 256 + 4096) * (int)sizeof(float2) + 8 * (int)sizeof(float);
+// Tuning history (profiles/r01): the kernel is limited by the L1TEX / shared-memory data pipe, not by
+// FP32 issue or DRAM: v0 72 % data-pipe vs 46 % FMA pipe.  Hence (a) all complex math is packed FP32x2
+// (fft4096.cuh), (b) twiddles are recomputed from per-thread bases in registers instead of being read from
+// shared-memory tables (-21 % wavefronts), (c) the window, the normalisation and the overlap-add carry live
+// in registers, (d) only the next frame's new half is prefetched to L2 one frame ahead.
+// Measured and rejected: two frames per CTA with a FlashAttention-3 style token around the shared-memory
+// phases (-40 %), cp.async staging of the next frame into the idle exchange buffer (+26 % wavefronts, no
+// gain), one exchange buffer with three CTAs per SM (-20 %).
+constexpr int kStftSmemBytes = 2 * kExchFloat2 * (int)sizeof(float2) + 8 * (int)sizeof(float);
+
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 __global__ void __launch_bounds__(kThreads, 2) stft_kernel(const StftParams prm) {
     extern __shared__ __align__(16) unsigned char smraw[];
     float2* bufP = reinterpret_cast<float2*>(smraw);
     float2* bufQ = bufP + kExchFloat2;
-    float2* sA = bufQ + kExchFloat2;
-    float2* sB = sA + 256;
-    float* red = reinterpret_cast<float*>(sB + 4096);
+    float* red = reinterpret_cast<float*>(bufQ + kExchFloat2);
     const int t = threadIdx.x;
 
-    sA[t] = prm.twA[t];
-#pragma unroll
-    for (int j = 0; j < 16; ++j) sB[j * 256 + t] = prm.twB[j * 256 + t];
-    float w[16], rn[8];
+    const float4* tb4 = reinterpret_cast<const float4*>(prm.tw_bases) + 2 * t;
+    const float4 ba = __ldg(tb4), bb = __ldg(tb4 + 1);
+    const TwBase wa = {make_float2(ba.x, ba.y), make_float2(ba.z, ba.w)};
+    const TwBase wb = {make_float2(bb.x, bb.y), make_float2(bb.z, bb.w)};
+    float w[16];
 #pragma unroll
     for (int j = 0; j < 16; ++j) w[j] = __ldg(prm.win + 256 * j + t);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) rn[j] = __ldg(prm.rnorm + 256 * j + t);
-    __syncthreads();
 
     for (int u = blockIdx.x; u < prm.n_units; u += gridDim.x) {
         const UnitDev un = prm.units[u];
-        const TrackDev tr = prm.tracks[un.track];
-        const uint16_t* rows = prm.rows + tr.frame_base;
+        // per-unit scalars, all relative to the unit's first frame so they fit 32 bits (register pressure)
+        const TrackDev* trp = prm.tracks + un.track;
+        const int n_frames = trp->n_frames;
+        const long long upos = trp->first_start + (long long)(un.b0 - 1) * kHop;     // position of frame b0-1
+        const float2* in_u = trp->in + (upos - trp->in_origin) + t;                 // thread's sample 0 of frame b0-1
+        float2* out_u = trp->out + (upos - trp->out_origin) + t;
+        const long long span = (long long)(un.b1 - un.b0 + 2) * kHop + kNfft;
+        const int in_lo = (int)max(-span, min(span, trp->in_lo - upos)), in_hi = (int)max(-span, min(span, trp->in_hi - upos));
+        const int out_lo = (int)max(-span, min(span, trp->out_lo - upos)), out_hi = (int)max(-span, min(span, trp->out_hi - upos));
+        const uint16_t* rows = prm.rows + trp->frame_base;
+        const bool edge_lo = prm.skip_edges && trp->edge_lo, edge_hi = prm.skip_edges && trp->edge_hi;
         float2 carry[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) carry[j] = make_float2(0.f, 0.f);
@@ -413,68 +428,82 @@ __global__ void __launch_bounds__(kThreads, 2) stft_kernel(const StftParams prm)
 
         for (int f = un.b0 - 1; f < un.b1; ++f) {
             float2 v[16];
-            const bool have = (f >= 0) && (f < tr.n_frames);
-            const long long pos0 = tr.first_start + (long long)f * kHop;
+            const bool have = (f >= 0) && (f < n_frames);
+            const int rel = (f - (un.b0 - 1)) * kHop;          // frame start relative to the unit
             if (have) {
-                const float2* src = tr.in + (pos0 - tr.in_origin) + t;
-                if (pos0 >= tr.in_lo && pos0 + kNfft <= tr.in_hi) {
+                const float2* src = in_u + rel;
+                if (rel >= in_lo && rel + kNfft + kHop <= in_hi) {
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) v[j] = ld_stream(src + 256 * j);
+                    for (int j = 0; j < 16; ++j) v[j] = __ldg(src + 256 * j);
+                    if ((t & 15) == 0) {           // next frame's new half -> L2 (one 128-B line per 16 lanes)
+#pragma unroll
+                        for (int j = 16; j < 24; ++j) prefetch_l2(src + 256 * j);
+                    }
                 } else {
 #pragma unroll
                     for (int j = 0; j < 16; ++j) {
-                        const long long p = pos0 + 256 * j + t;
-                        v[j] = (p >= tr.in_lo && p < tr.in_hi) ? ld_stream(src + 256 * j) : make_float2(0.f, 0.f);
+                        const int p = rel + 256 * j + t;
+                        v[j] = (p >= in_lo && p < in_hi) ? __ldg(src + 256 * j) : make_float2(0.f, 0.f);
                     }
                 }
+                const int row = rows[f];
 #pragma unroll
-                for (int j = 0; j < 16; ++j) { v[j].x *= w[j]; v[j].y *= w[j]; }      // analysis window
-                fwd_a(v, t, sA, bufP);
+                for (int j = 0; j < 16; ++j) v[j] = cscale(v[j], w[j]);           // analysis window
+                dft16<false>(v);                                                  // A
+                tw_pow<false>(v, wa);
+                st_e1a(v, t, bufP);
                 __syncthreads();
-                fwd_b(v, t, sB, bufP, bufQ);
+                ld_e1b(v, t, bufP);
+                dft16<false>(v);                                                  // B
+                tw_pow<false>(v, wb);
+                st_e2b(v, t, bufQ);
                 __syncthreads();
-                fwd_c(v, t, bufQ);
-                {   // tilt gain x crossfade weight: one real row per frame, register order
-                    const float4* g4 = reinterpret_cast<const float4*>(prm.gperm + (size_t)rows[f] * kNfft + t * 16);
+                ld_e2c(v, t, bufQ);
+                // tilt gain x crossfade weight: one real row per frame, register order; issued before the
+                // butterflies so the L2/L1 latency hides under them
+                const float4* g4 = reinterpret_cast<const float4*>(prm.gperm + (size_t)row * kNfft + t * 16);
+                const float4 g0 = __ldg(g4), g1 = __ldg(g4 + 1), g2 = __ldg(g4 + 2), g3 = __ldg(g4 + 3);
+                dft16<false>(v);                                                  // C
+                v[0] = cscale(v[0], g0.x); v[1] = cscale(v[1], g0.y); v[2] = cscale(v[2], g0.z); v[3] = cscale(v[3], g0.w);
+                v[4] = cscale(v[4], g1.x); v[5] = cscale(v[5], g1.y); v[6] = cscale(v[6], g1.z); v[7] = cscale(v[7], g1.w);
+                v[8] = cscale(v[8], g2.x); v[9] = cscale(v[9], g2.y); v[10] = cscale(v[10], g2.z); v[11] = cscale(v[11], g2.w);
+                v[12] = cscale(v[12], g3.x); v[13] = cscale(v[13], g3.y); v[14] = cscale(v[14], g3.z); v[15] = cscale(v[15], g3.w);
+                dft16<true>(v);                                                   // C'
+                st_e2c(v, t, bufP);
+                __syncthreads();
+                ld_e2b(v, t, bufP);
+                tw_pow<true>(v, wb);
+                dft16<true>(v);                                                   // B'
+                st_e1b(v, t, bufQ);
+                __syncthreads();
+                ld_e1a(v, t, bufQ);
+                tw_pow<true>(v, wa);
+                dft16<true>(v);                                                   // A'
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        const float4 g = __ldg(g4 + q);
-                        v[4 * q + 0].x *= g.x; v[4 * q + 0].y *= g.x;
-                        v[4 * q + 1].x *= g.y; v[4 * q + 1].y *= g.y;
-                        v[4 * q + 2].x *= g.z; v[4 * q + 2].y *= g.z;
-                        v[4 * q + 3].x *= g.w; v[4 * q + 3].y *= g.w;
-                    }
-                }
-                inv_c(v, t, bufP);
-                __syncthreads();
-                inv_b(v, t, sB, bufP, bufQ);
-                __syncthreads();
-                inv_a(v, t, sA, bufQ);
-#pragma unroll
-                for (int j = 0; j < 16; ++j) { v[j].x *= w[j]; v[j].y *= w[j]; }      // synthesis window
+                for (int j = 0; j < 16; ++j) v[j] = cscale(v[j], w[j]);           // synthesis window
             } else {
 #pragma unroll
                 for (int j = 0; j < 16; ++j) v[j] = make_float2(0.f, 0.f);
             }
 
-            const bool edge_blk = prm.skip_edges && ((f == 0 && tr.edge_lo) || (f == tr.n_frames && tr.edge_hi));
+            const bool edge_blk = (f == 0 && edge_lo) || (f == n_frames && edge_hi);
             if (f >= un.b0 && !edge_blk) {       // emit output block f
-                const bool interior = (f >= 1) && (f < tr.n_frames);
-                const bool full = (pos0 >= tr.out_lo) && (pos0 + kHop <= tr.out_hi);
-                float2* dst = tr.out + (pos0 - tr.out_origin) + t;
+                const bool interior = (f >= 1) && (f < n_frames);
+                const bool full = (rel >= out_lo) && (rel + kHop <= out_hi);
+                float2* dst = out_u + rel;
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                    float2 o = make_float2(carry[j].x + v[j].x, carry[j].y + v[j].y);
+                    float2 o = cadd(carry[j], v[j]);
                     if (interior) {
-                        o.x *= rn[j]; o.y *= rn[j];
+                        o = cscale(o, __ldg(prm.rnorm + 256 * j + t));
                     } else {
-                        const float nrm = ((f >= 1) ? w[j + 8] * w[j + 8] : 0.f) + ((f < tr.n_frames) ? w[j] * w[j] : 0.f);
+                        const float nrm = ((f >= 1) ? w[j + 8] * w[j + 8] : 0.f) + ((f < n_frames) ? w[j] * w[j] : 0.f);
                         const float den = prm.norm_clamp ? fmaxf(nrm, 1e-8f) : (nrm + 1e-12f);
                         o.x = __fdiv_rn(o.x, den); o.y = __fdiv_rn(o.y, den);
                     }
-                    if (prm.post_gain != 1.0f) { o.x *= prm.post_gain; o.y *= prm.post_gain; }
-                    const long long p = pos0 + 256 * j + t;
-                    if (full || (p >= tr.out_lo && p < tr.out_hi)) {
+                    if (prm.post_gain != 1.0f) o = cscale(o, prm.post_gain);
+                    const int p = rel + 256 * j + t;
+                    if (full || (p >= out_lo && p < out_hi)) {
                         st_stream(dst + 256 * j, o);
                         peak = fmaxf(peak, fmaxf(fabsf(o.x), fabsf(o.y)));
                     }
@@ -497,7 +526,6 @@ __global__ void __launch_bounds__(kThreads, 2) stft_kernel(const StftParams prm)
         __syncthreads();
     }
 }
-
 
 // ------------------------------------------------------------------------------------------------
 // fp64 edge frames.  Two output regions of the reference are ill-conditioned: the
@@ -667,7 +695,7 @@ struct tmt_engine {
     int n_sms = 0;
     DevBuf<float> win;        // [4096]
     DevBuf<float> rnorm;      // [2][2048]  (eps | clamp)
-    DevBuf<float2> twA, twB;
+    DevBuf<float2> tw_bases;  // [256][4]
     DevBuf<float> gperm;      // [n_rows][4096]
     DevBuf<float> gnat;       // [n_rows][2049] natural order (fp64 edge frames)
     int n_rows = 0;
@@ -841,15 +869,13 @@ int tmt_engine_create(tmt_engine** out, int device, int n_fft, int hop) {
     cudaError_t ce = cudaGetDeviceProperties(&prop, device);
     if (ce != cudaSuccess) { delete e; return fail(TMT_ERR_CUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(ce)); }
     e->n_sms = prop.multiProcessorCount;
-    auto twA = build_twA();
-    auto twB = build_twB();
-    if (e->twA.alloc(256) != cudaSuccess || e->twB.alloc(4096) != cudaSuccess || e->win.alloc(kNfft) != cudaSuccess ||
+    auto twb = build_tw_bases();
+    if (e->tw_bases.alloc(twb.size()) != cudaSuccess || e->win.alloc(kNfft) != cudaSuccess ||
         e->rnorm.alloc(2 * kHop) != cudaSuccess) {
         delete e;
         return fail(TMT_ERR_NOMEM, "device allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
     }
-    cudaMemcpy(e->twA.p, twA.data(), sizeof(float2) * 256, cudaMemcpyHostToDevice);
-    cudaMemcpy(e->twB.p, twB.data(), sizeof(float2) * 4096, cudaMemcpyHostToDevice);
+    cudaMemcpy(e->tw_bases.p, twb.data(), sizeof(float2) * twb.size(), cudaMemcpyHostToDevice);
     ce = cudaFuncSetAttribute(stft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kStftSmemBytes);
     if (ce != cudaSuccess) { delete e; return fail(TMT_ERR_CUDA, "cudaFuncSetAttribute(stft_kernel): %s", cudaGetErrorString(ce)); }
     ce = cudaFuncSetAttribute(edge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kEdgeSmemBytes);
@@ -1150,12 +1176,11 @@ int tmt_plan_stft(tmt_plan* p, float post_gain, int skip_edges, void* stream) {
     prm.win = e->win.p;
     prm.norm_clamp = (p->framing == TMT_FRAMING_WHOLEFILE) ? 1 : 0;
     prm.rnorm = e->rnorm.p + (prm.norm_clamp ? kHop : 0);
-    prm.twA = e->twA.p;
-    prm.twB = e->twB.p;
+    prm.tw_bases = e->tw_bases.p;
     prm.chunk_peaks = p->chunk_peaks.p;
     prm.post_gain = post_gain;
     prm.skip_edges = skip_edges ? 1 : 0;
-    const int grid = std::min(p->n_units, 2 * e->n_sms);
+    const int grid = std::min(p->n_units, 2 * e->n_sms);            // persistent: two CTAs per SM
     stft_kernel<<<grid, kThreads, kStftSmemBytes, st>>>(prm);
     p->launches++;
     CUDA_TRY(cudaGetLastError());
