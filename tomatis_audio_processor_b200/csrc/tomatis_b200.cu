@@ -360,57 +360,153 @@ __global__ void gate_kernel(const TrackDev* __restrict__ tracks, const T* __rest
 // K1+K3+K4 fused STFT kernel.  See fft4096.cuh for the FFT decomposition.
 // Output block b of a track = positions [first_start + b*hop, +hop) = second half of frame b-1 plus
 // first half of frame b.  A CTA owns a run of blocks [b0,b1) (one limiter chunk or a slice of one),
-// processes frames b0-1 .. b1-1 in order and keeps the running half frame in registers, so every
-// output sample is written exactly once and there is no OLA buffer, no sum-of-w^2 buffer and no atomics
-// on the audio path (reference: out_buf/w_buf accumulation src/process_tomatis.py:400-406, flush :419-426).
-// Thread t holds samples n = 256*j + t of the frame (j = 0..15): global loads/stores are coalesced
-// 256-byte rows, the window and the normalisation live in registers, the carry (j >= 8 -> j-8) stays
-// in the same thread.
+// processes frames b0-1 .. b1-1 in order and carries the running half frame from one frame to the next,
+// so every output sample is written exactly once and there is no OLA buffer, no sum-of-w^2 buffer and no
+// atomics on the audio path (reference: out_buf/w_buf accumulation src/process_tomatis.py:400-406,
+// flush :419-426).  Thread t holds samples n = 256*j + t of the frame (j = 0..15): global loads/stores
+// are coalesced 256-byte rows per warp.
+//
+// Register budget.  The three radix-16 stages want ~190 registers when the per-thread constants
+// (analysis window 16, synthesis window x normalisation 16, overlap-add carry 16) also live in registers;
+// at 128 (two CTAs per SM) ptxas spilled 43 of them to local memory, and those spills were 48 % of the
+// L1 data-pipe wavefronts of v1 (profiles/r01).  All three are strictly thread-private, so they are
+// parked in TENSOR MEMORY: each warp owns a 32-lane quarter of the CTA's TMEM allocation and moves 16
+// values per thread with one tcgen05.st / tcgen05.ld (.32x32b.x16).  TMEM is otherwise idle in this
+// kernel (no MMA), its datapath is separate from the L1/shared-memory pipe the exchanges saturate, and
+// nothing stays resident in registers across the butterflies.  kStore == 1 is the shared-memory
+// fall-back of the same structure (A/B comparison; selected with TMT_STFT_STORE=smem).
 struct StftParams {
     const TrackDev* tracks;
     const UnitDev* units;
     int n_units;
     const uint16_t* rows;
     const float* gperm;     // [n_rows][4096] register-order gains, 1/4096 folded in
-    const float* win;       // [4096]
-    const float* rnorm;     // [2048] interior 1/(w2[n+hop]+w2[n] (+eps | clamped))
+    const float* win;       // [4096] analysis window
+    const float* swin;      // [4096] synthesis window x interior normalisation: w[n] / (w2[n%hop] + w2[n%hop + hop] (+eps | clamped))
     const float2* tw_bases; // [256][4]: per-thread twiddle bases (host_tables.hpp)
     float* chunk_peaks;
-    int norm_clamp;         // 0: x/(nrm+1e-12)   1: x/max(nrm,1e-8)
-    int skip_edges;         // 1: single-frame edge blocks are left to edge_kernel (fp64)
     float post_gain;
 };
 
-// Tuning history (profiles/r01): the kernel is limited by the L1TEX / shared-memory data pipe, not by
-// FP32 issue or DRAM: v0 72 % data-pipe vs 46 % FMA pipe.  Hence (a) all complex math is packed FP32x2
-// (fft4096.cuh), (b) twiddles are recomputed from per-thread bases in registers instead of being read from
-// shared-memory tables (-21 % wavefronts), (c) the window, the normalisation and the overlap-add carry live
-// in registers, (d) only the next frame's new half is prefetched to L2 one frame ahead.
-// Measured and rejected: two frames per CTA with a FlashAttention-3 style token around the shared-memory
-// phases (-40 %), cp.async staging of the next frame into the idle exchange buffer (+26 % wavefronts, no
-// gain), one exchange buffer with three CTAs per SM (-20 %).
-constexpr int kStftSmemBytes = 2 * kExchFloat2 * (int)sizeof(float2) + 8 * (int)sizeof(float);
+constexpr int kTmemCols = 128;                       // per CTA: 2 warps per lane quarter x 48 columns, rounded to a power of two
+constexpr int kStftSmemTmem = (4096 + kExchFloat2) * (int)sizeof(float2) + 64;
+constexpr int kStftSmemSmem = kStftSmemTmem + 2 * kNfft * (int)sizeof(float) + kHop * (int)sizeof(float2);
 
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float (&r)[16]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+                 ::"r"(taddr), "f"(r[0]), "f"(r[1]), "f"(r[2]), "f"(r[3]), "f"(r[4]), "f"(r[5]), "f"(r[6]), "f"(r[7]),
+                   "f"(r[8]), "f"(r[9]), "f"(r[10]), "f"(r[11]), "f"(r[12]), "f"(r[13]), "f"(r[14]), "f"(r[15]) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&r)[16]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                 : "=f"(r[0]), "=f"(r[1]), "=f"(r[2]), "=f"(r[3]), "=f"(r[4]), "=f"(r[5]), "=f"(r[6]), "=f"(r[7]),
+                   "=f"(r[8]), "=f"(r[9]), "=f"(r[10]), "=f"(r[11]), "=f"(r[12]), "=f"(r[13]), "=f"(r[14]), "=f"(r[15])
+                 : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// Thread-private parking space: kStore 0 = tensor memory, 1 = shared memory.
+template <int kStore> struct Park;
+template <> struct Park<0> {
+    uint32_t base;       // TMEM address of this warp's 48 columns (lane quarter in bits 31:16)
+    __device__ __forceinline__ void init(unsigned char* smem_tail, int t, const float* win, const float* swin) {
+        uint32_t* slot = reinterpret_cast<uint32_t*>(smem_tail);
+        if ((t >> 5) == 0) {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                         ::"r"((uint32_t)__cvta_generic_to_shared(slot)), "n"(kTmemCols) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int warp = t >> 5;
+        base = *slot + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((warp >> 2) * 48);
+        float r[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) r[j] = __ldg(win + 256 * j + t);
+        tmem_st16(base, r);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) r[j] = __ldg(swin + 256 * j + t);
+        tmem_st16(base + 16, r);
+        tmem_wait_st();
+    }
+    __device__ __forceinline__ void fini(unsigned char* smem_tail, int t) {
+        tmem_wait_st();
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        if ((t >> 5) == 0) {
+            const uint32_t a = *reinterpret_cast<uint32_t*>(smem_tail);
+            asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(a), "n"(kTmemCols) : "memory");
+        }
+    }
+    __device__ __forceinline__ void load_awin(float (&w)[16], int) const { tmem_ld16(base, w); tmem_wait_ld(); }
+    __device__ __forceinline__ void load_tail(float (&s)[16], float2 (&c)[8], int) const {
+        float cr[16];
+        tmem_ld16(base + 16, s);
+        tmem_ld16(base + 32, cr);
+        tmem_wait_ld();
+#pragma unroll
+        for (int j = 0; j < 8; ++j) c[j] = make_float2(cr[2 * j], cr[2 * j + 1]);
+    }
+    __device__ __forceinline__ void store_carry(const float2 (&c)[8], int) const {
+        float cr[16];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { cr[2 * j] = c[j].x; cr[2 * j + 1] = c[j].y; }
+        tmem_st16(base + 32, cr);
+        tmem_wait_st();
+    }
+};
+template <> struct Park<1> {
+    float* aw;        // [4096]
+    float* sw;        // [4096]
+    float2* cy;       // [2048]
+    __device__ __forceinline__ void init(unsigned char* smem_tail, int t, const float* win, const float* swin) {
+        aw = reinterpret_cast<float*>(smem_tail + 64);
+        sw = aw + kNfft;
+        cy = reinterpret_cast<float2*>(sw + kNfft);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) { aw[256 * j + t] = __ldg(win + 256 * j + t); sw[256 * j + t] = __ldg(swin + 256 * j + t); }
+        __syncthreads();
+    }
+    __device__ __forceinline__ void fini(unsigned char*, int) {}
+    __device__ __forceinline__ void load_awin(float (&w)[16], int t) const {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) w[j] = aw[256 * j + t];
+    }
+    __device__ __forceinline__ void load_tail(float (&s)[16], float2 (&c)[8], int t) const {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) s[j] = sw[256 * j + t];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) c[j] = cy[256 * j + t];
+    }
+    __device__ __forceinline__ void store_carry(const float2 (&c)[8], int t) const {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) cy[256 * j + t] = c[j];
+    }
+};
+
+template <int kStore>
 __global__ void __launch_bounds__(kThreads, 2) stft_kernel(const StftParams prm) {
     extern __shared__ __align__(16) unsigned char smraw[];
-    float2* bufP = reinterpret_cast<float2*>(smraw);
-    float2* bufQ = bufP + kExchFloat2;
-    float* red = reinterpret_cast<float*>(bufQ + kExchFloat2);
+    float2* bufP = reinterpret_cast<float2*>(smraw);         // E1 layout only (linear, 32 KB)
+    float2* bufQ = bufP + 4096;                              // E2 layout only (padded rows)
+    unsigned char* tail = reinterpret_cast<unsigned char*>(bufQ + kExchFloat2);
+    float* red = reinterpret_cast<float*>(tail + 16);
     const int t = threadIdx.x;
 
+    Park<kStore> park;
+    park.init(tail, t, prm.win, prm.swin);
     const float4* tb4 = reinterpret_cast<const float4*>(prm.tw_bases) + 2 * t;
     const float4 ba = __ldg(tb4), bb = __ldg(tb4 + 1);
     const TwBase wa = {make_float2(ba.x, ba.y), make_float2(ba.z, ba.w)};
     const TwBase wb = {make_float2(bb.x, bb.y), make_float2(bb.z, bb.w)};
-    float w[16];
-#pragma unroll
-    for (int j = 0; j < 16; ++j) w[j] = __ldg(prm.win + 256 * j + t);
 
     for (int u = blockIdx.x; u < prm.n_units; u += gridDim.x) {
         const UnitDev un = prm.units[u];
-        // per-unit scalars, all relative to the unit's first frame so they fit 32 bits (register pressure)
+        // per-unit scalars, all relative to the unit's first frame so they fit 32 bits
         const TrackDev* trp = prm.tracks + un.track;
         const int n_frames = trp->n_frames;
         const long long upos = trp->first_start + (long long)(un.b0 - 1) * kHop;     // position of frame b0-1
@@ -420,10 +516,13 @@ __global__ void __launch_bounds__(kThreads, 2) stft_kernel(const StftParams prm)
         const int in_lo = (int)max(-span, min(span, trp->in_lo - upos)), in_hi = (int)max(-span, min(span, trp->in_hi - upos));
         const int out_lo = (int)max(-span, min(span, trp->out_lo - upos)), out_hi = (int)max(-span, min(span, trp->out_hi - upos));
         const uint16_t* rows = prm.rows + trp->frame_base;
-        const bool edge_lo = prm.skip_edges && trp->edge_lo, edge_hi = prm.skip_edges && trp->edge_hi;
-        float2 carry[8];
+        const bool edge_lo = trp->edge_lo, edge_hi = trp->edge_hi;
+        {
+            float2 z[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) carry[j] = make_float2(0.f, 0.f);
+            for (int j = 0; j < 8; ++j) z[j] = make_float2(0.f, 0.f);
+            park.store_carry(z, t);
+        }
         float peak = 0.f;
 
         for (int f = un.b0 - 1; f < un.b1; ++f) {
@@ -434,7 +533,7 @@ __global__ void __launch_bounds__(kThreads, 2) stft_kernel(const StftParams prm)
                 const float2* src = in_u + rel;
                 if (rel >= in_lo && rel + kNfft + kHop <= in_hi) {
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) v[j] = __ldg(src + 256 * j);
+                    for (int j = 0; j < 16; ++j) v[j] = ld_stream(src + 256 * j);
                     if ((t & 15) == 0) {           // next frame's new half -> L2 (one 128-B line per 16 lanes)
 #pragma unroll
                         for (int j = 16; j < 24; ++j) prefetch_l2(src + 256 * j);
@@ -447,8 +546,12 @@ __global__ void __launch_bounds__(kThreads, 2) stft_kernel(const StftParams prm)
                     }
                 }
                 const int row = rows[f];
+                {
+                    float w[16];
+                    park.load_awin(w, t);
 #pragma unroll
-                for (int j = 0; j < 16; ++j) v[j] = cscale(v[j], w[j]);           // analysis window
+                    for (int j = 0; j < 16; ++j) v[j] = cscale(v[j], w[j]);       // analysis window
+                }
                 dft16<false>(v);                                                  // A
                 tw_pow<false>(v, wa);
                 st_e1a(v, t, bufP);
@@ -458,49 +561,43 @@ __global__ void __launch_bounds__(kThreads, 2) stft_kernel(const StftParams prm)
                 tw_pow<false>(v, wb);
                 st_e2b(v, t, bufQ);
                 __syncthreads();
-                ld_e2c(v, t, bufQ);
-                // tilt gain x crossfade weight: one real row per frame, register order; issued before the
-                // butterflies so the L2/L1 latency hides under them
+                // tilt gain x crossfade weight: one real row per frame, register order; issued ahead of the
+                // shared-memory reads so the L1/L2 latency hides under them and the butterflies
                 const float4* g4 = reinterpret_cast<const float4*>(prm.gperm + (size_t)row * kNfft + t * 16);
                 const float4 g0 = __ldg(g4), g1 = __ldg(g4 + 1), g2 = __ldg(g4 + 2), g3 = __ldg(g4 + 3);
+                ld_e2c(v, t, bufQ);
                 dft16<false>(v);                                                  // C
                 v[0] = cscale(v[0], g0.x); v[1] = cscale(v[1], g0.y); v[2] = cscale(v[2], g0.z); v[3] = cscale(v[3], g0.w);
                 v[4] = cscale(v[4], g1.x); v[5] = cscale(v[5], g1.y); v[6] = cscale(v[6], g1.z); v[7] = cscale(v[7], g1.w);
                 v[8] = cscale(v[8], g2.x); v[9] = cscale(v[9], g2.y); v[10] = cscale(v[10], g2.z); v[11] = cscale(v[11], g2.w);
                 v[12] = cscale(v[12], g3.x); v[13] = cscale(v[13], g3.y); v[14] = cscale(v[14], g3.z); v[15] = cscale(v[15], g3.w);
                 dft16<true>(v);                                                   // C'
-                st_e2c(v, t, bufP);
+                st_e2c(v, t, bufQ);            // same rows this thread just read: no barrier needed in between
                 __syncthreads();
-                ld_e2b(v, t, bufP);
+                ld_e2b(v, t, bufQ);
                 tw_pow<true>(v, wb);
                 dft16<true>(v);                                                   // B'
-                st_e1b(v, t, bufQ);
+                st_e1b(v, t, bufP);
                 __syncthreads();
-                ld_e1a(v, t, bufQ);
+                ld_e1a(v, t, bufP);            // next frame's st_e1a overwrites exactly the words this thread reads here
                 tw_pow<true>(v, wa);
                 dft16<true>(v);                                                   // A'
-#pragma unroll
-                for (int j = 0; j < 16; ++j) v[j] = cscale(v[j], w[j]);           // synthesis window
             } else {
 #pragma unroll
                 for (int j = 0; j < 16; ++j) v[j] = make_float2(0.f, 0.f);
             }
 
-            const bool edge_blk = (f == 0 && edge_lo) || (f == n_frames && edge_hi);
+            // synthesis window, overlap-add with the carried half, interior normalisation (folded into swin)
+            float s[16];
+            float2 c[8];
+            park.load_tail(s, c, t);
+            const bool edge_blk = (f == 0 && edge_lo) || (f == n_frames && edge_hi);   // single-frame blocks: edge_kernel
             if (f >= un.b0 && !edge_blk) {       // emit output block f
-                const bool interior = (f >= 1) && (f < n_frames);
                 const bool full = (rel >= out_lo) && (rel + kHop <= out_hi);
                 float2* dst = out_u + rel;
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                    float2 o = cadd(carry[j], v[j]);
-                    if (interior) {
-                        o = cscale(o, __ldg(prm.rnorm + 256 * j + t));
-                    } else {
-                        const float nrm = ((f >= 1) ? w[j + 8] * w[j + 8] : 0.f) + ((f < n_frames) ? w[j] * w[j] : 0.f);
-                        const float den = prm.norm_clamp ? fmaxf(nrm, 1e-8f) : (nrm + 1e-12f);
-                        o.x = __fdiv_rn(o.x, den); o.y = __fdiv_rn(o.y, den);
-                    }
+                    float2 o = __ffma2_rn(v[j], make_float2(s[j], s[j]), c[j]);
                     if (prm.post_gain != 1.0f) o = cscale(o, prm.post_gain);
                     const int p = rel + 256 * j + t;
                     if (full || (p >= out_lo && p < out_hi)) {
@@ -510,7 +607,8 @@ __global__ void __launch_bounds__(kThreads, 2) stft_kernel(const StftParams prm)
                 }
             }
 #pragma unroll
-            for (int j = 0; j < 8; ++j) carry[j] = v[j + 8];
+            for (int j = 0; j < 8; ++j) c[j] = cscale(v[j + 8], s[j + 8]);
+            park.store_carry(c, t);
         }
         // per-chunk peak: one atomic per work unit (values are >= 0, so int ordering == float ordering)
 #pragma unroll
@@ -525,6 +623,7 @@ __global__ void __launch_bounds__(kThreads, 2) stft_kernel(const StftParams prm)
         }
         __syncthreads();
     }
+    park.fini(tail, t);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -694,7 +793,8 @@ struct tmt_engine {
     int device = 0;
     int n_sms = 0;
     DevBuf<float> win;        // [4096]
-    DevBuf<float> rnorm;      // [2][2048]  (eps | clamp)
+    DevBuf<float> swin;       // [2][4096]  synthesis window x interior normalisation (eps | clamp)
+    int stft_store = 0;       // 0: thread-private constants + carry in tensor memory, 1: in shared memory
     DevBuf<float2> tw_bases;  // [256][4]
     DevBuf<float> gperm;      // [n_rows][4096]
     DevBuf<float> gnat;       // [n_rows][2049] natural order (fp64 edge frames)
@@ -871,13 +971,15 @@ int tmt_engine_create(tmt_engine** out, int device, int n_fft, int hop) {
     e->n_sms = prop.multiProcessorCount;
     auto twb = build_tw_bases();
     if (e->tw_bases.alloc(twb.size()) != cudaSuccess || e->win.alloc(kNfft) != cudaSuccess ||
-        e->rnorm.alloc(2 * kHop) != cudaSuccess) {
+        e->swin.alloc(2 * kNfft) != cudaSuccess) {
         delete e;
         return fail(TMT_ERR_NOMEM, "device allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
     }
     cudaMemcpy(e->tw_bases.p, twb.data(), sizeof(float2) * twb.size(), cudaMemcpyHostToDevice);
-    ce = cudaFuncSetAttribute(stft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kStftSmemBytes);
+    ce = cudaFuncSetAttribute(stft_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStftSmemTmem);
+    if (ce == cudaSuccess) ce = cudaFuncSetAttribute(stft_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStftSmemSmem);
     if (ce != cudaSuccess) { delete e; return fail(TMT_ERR_CUDA, "cudaFuncSetAttribute(stft_kernel): %s", cudaGetErrorString(ce)); }
+    if (const char* sv = getenv("TMT_STFT_STORE")) e->stft_store = (strcmp(sv, "smem") == 0) ? 1 : 0;
     ce = cudaFuncSetAttribute(edge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kEdgeSmemBytes);
     if (ce != cudaSuccess) { delete e; return fail(TMT_ERR_CUDA, "cudaFuncSetAttribute(edge_kernel): %s", cudaGetErrorString(ce)); }
     *out = e;
@@ -895,17 +997,23 @@ int tmt_engine_set_window(tmt_engine* e, const float* win, int n) {
     if (!e || !win || n != kNfft) return fail(TMT_ERR_INVALID, "window must have %d taps", kNfft);
     CUDA_TRY(cudaSetDevice(e->device));
     // float32 arithmetic exactly as the reference: win2 = (win*win).astype(float32); w_buf = win2[n+hop] + win2[n]
-    std::vector<float> rn(2 * kHop);
+    // interior blocks are covered by two frames: y = (sum of windowed frames) / (w2[n+hop] + w2[n] (+eps | clamped));
+    // the reciprocal is folded into the synthesis window the kernel multiplies with
+    std::vector<float> sw(2 * kNfft);
     for (int i = 0; i < kHop; ++i) {
         const volatile float lo = win[i] * win[i];
         const volatile float hi = win[i + kHop] * win[i + kHop];
         const volatile float nrm = hi + lo;
         const volatile float d0 = nrm + 1e-12f;
-        rn[i] = 1.0f / d0;                                  // src/process_tomatis.py:422
-        rn[kHop + i] = 1.0f / std::max((float)nrm, 1e-8f);  // src/process_tomatis_adaptive.py:330
+        const double r0 = 1.0 / (double)d0;                                  // src/process_tomatis.py:422
+        const double r1 = 1.0 / (double)std::max((float)nrm, 1e-8f);         // src/process_tomatis_adaptive.py:330
+        sw[i] = (float)((double)win[i] * r0);
+        sw[i + kHop] = (float)((double)win[i + kHop] * r0);
+        sw[kNfft + i] = (float)((double)win[i] * r1);
+        sw[kNfft + i + kHop] = (float)((double)win[i + kHop] * r1);
     }
     CUDA_TRY(cudaMemcpy(e->win.p, win, sizeof(float) * kNfft, cudaMemcpyHostToDevice));
-    CUDA_TRY(cudaMemcpy(e->rnorm.p, rn.data(), sizeof(float) * 2 * kHop, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(e->swin.p, sw.data(), sizeof(float) * 2 * kNfft, cudaMemcpyHostToDevice));
     e->have_win = true;
     return TMT_OK;
 }
@@ -1174,16 +1282,18 @@ int tmt_plan_stft(tmt_plan* p, float post_gain, int skip_edges, void* stream) {
     prm.rows = p->rows.p;
     prm.gperm = e->gperm.p;
     prm.win = e->win.p;
-    prm.norm_clamp = (p->framing == TMT_FRAMING_WHOLEFILE) ? 1 : 0;
-    prm.rnorm = e->rnorm.p + (prm.norm_clamp ? kHop : 0);
+    prm.swin = e->swin.p + ((p->framing == TMT_FRAMING_WHOLEFILE) ? kNfft : 0);
     prm.tw_bases = e->tw_bases.p;
     prm.chunk_peaks = p->chunk_peaks.p;
     prm.post_gain = post_gain;
-    prm.skip_edges = skip_edges ? 1 : 0;
     const int grid = std::min(p->n_units, 2 * e->n_sms);            // persistent: two CTAs per SM
-    stft_kernel<<<grid, kThreads, kStftSmemBytes, st>>>(prm);
+    if (e->stft_store == 0) stft_kernel<0><<<grid, kThreads, kStftSmemTmem, st>>>(prm);
+    else stft_kernel<1><<<grid, kThreads, kStftSmemSmem, st>>>(prm);
     p->launches++;
     CUDA_TRY(cudaGetLastError());
+    // the single-frame edge blocks are never produced by stft_kernel; without an explicit
+    // tmt_plan_edge_frames call they are filled in here with default scales
+    if (!skip_edges) return tmt_plan_edge_frames(p, post_gain, nullptr, nullptr, 0, stream);
     return TMT_OK;
 }
 
