@@ -388,7 +388,8 @@ struct StftParams {
     float post_gain;
 };
 
-constexpr int kTmemCols = 128;                       // per CTA: 2 warps per lane quarter x 48 columns, rounded to a power of two
+constexpr int kTmemWarpCols = 80;                    // analysis window 16 | synthesis window 16 | carry 16 | raw input halves 2 x 16
+constexpr int kTmemCols = 256;                       // per CTA: 2 warps per lane quarter x 80 columns, rounded to a power of two (2 CTAs = all 512)
 constexpr int kStftSmemTmem = (4096 + kExchFloat2) * (int)sizeof(float2) + 64;
 constexpr int kStftSmemSmem = kStftSmemTmem + 2 * kNfft * (int)sizeof(float) + kHop * (int)sizeof(float2);
 
@@ -423,7 +424,7 @@ template <> struct Park<0> {
         __syncthreads();
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const int warp = t >> 5;
-        base = *slot + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((warp >> 2) * 48);
+        base = *slot + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((warp >> 2) * kTmemWarpCols);
         float r[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) r[j] = __ldg(win + 256 * j + t);
@@ -456,8 +457,28 @@ template <> struct Park<0> {
 #pragma unroll
         for (int j = 0; j < 8; ++j) { cr[2 * j] = c[j].x; cr[2 * j + 1] = c[j].y; }
         tmem_st16(base + 32, cr);
-        tmem_wait_st();
     }
+    // raw (unwindowed) input half frames, two slots
+    __device__ __forceinline__ void stage_put(int slot, const float2 (&x)[8]) const {
+        float r[16];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { r[2 * j] = x[j].x; r[2 * j + 1] = x[j].y; }
+        tmem_st16(base + 48 + 16 * slot, r);
+    }
+    // v = [half `slot`, half `slot ^ 1`] x analysis window
+    __device__ __forceinline__ void stage_get_windowed(int slot, float2 (&v)[16]) const {
+        float a[16], b[16], w[16];
+        tmem_ld16(base + 48 + 16 * slot, a);
+        tmem_ld16(base + 48 + 16 * (slot ^ 1), b);
+        tmem_ld16(base, w);
+        tmem_wait_ld();
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            v[j] = cscale(make_float2(a[2 * j], a[2 * j + 1]), w[j]);
+            v[j + 8] = cscale(make_float2(b[2 * j], b[2 * j + 1]), w[j + 8]);
+        }
+    }
+    __device__ __forceinline__ void sync_stores() const { tmem_wait_st(); }
 };
 template <> struct Park<1> {
     float* aw;        // [4096]
@@ -486,7 +507,11 @@ template <> struct Park<1> {
 #pragma unroll
         for (int j = 0; j < 8; ++j) cy[256 * j + t] = c[j];
     }
+    __device__ __forceinline__ void sync_stores() const {}
 };
+
+__device__ __forceinline__ void park_put(const Park<0>& p, int slot, const float2 (&x)[8]) { p.stage_put(slot, x); }
+__device__ __forceinline__ void park_put(const Park<1>&, int, const float2 (&)[8]) {}
 
 template <int kStore>
 __global__ void __launch_bounds__(kThreads, 2) stft_kernel(const StftParams prm) {
@@ -524,34 +549,68 @@ __global__ void __launch_bounds__(kThreads, 2) stft_kernel(const StftParams prm)
             park.store_carry(z, t);
         }
         float peak = 0.f;
+        const int last = un.b1 - un.b0;                    // frames of this unit: i = 0 .. last  (f = b0 - 1 + i)
 
-        for (int f = un.b0 - 1; f < un.b1; ++f) {
+        // raw half frame h of the unit = positions [h*hop, (h+1)*hop) relative to the unit, zero outside the file
+        auto load_half = [&](int h, float2 (&x)[8]) {
+            const int p0 = h * kHop;
+            const float2* src = in_u + p0;
+            if (p0 >= in_lo && p0 + kHop <= in_hi) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) x[j] = ld_stream(src + 256 * j);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int p = p0 + 256 * j + t;
+                    x[j] = (p >= in_lo && p < in_hi) ? __ldg(src + 256 * j) : make_float2(0.f, 0.f);
+                }
+            }
+        };
+        if constexpr (kStore == 0) {       // prologue: halves 0 and 1 of the unit -> staging slots 0 and 1
+            float2 x[8];
+            load_half(0, x);
+            park.stage_put(0, x);
+            load_half(1, x);
+            park.stage_put(1, x);
+        }
+
+        for (int i = 0; i <= last; ++i) {
+            const int f = un.b0 - 1 + i;
             float2 v[16];
             const bool have = (f >= 0) && (f < n_frames);
-            const int rel = (f - (un.b0 - 1)) * kHop;          // frame start relative to the unit
+            const int rel = i * kHop;                          // frame start relative to the unit
+            park.sync_stores();
+            // kStore 0: every input sample is read from global memory exactly once, one frame ahead of its
+            // first use, and waits in tensor memory; the loads below belong to frame i+1 and complete under
+            // this frame's butterflies
+            float2 pf[8];
+            const bool do_pf = (kStore == 0) && (i < last);
             if (have) {
-                const float2* src = in_u + rel;
-                if (rel >= in_lo && rel + kNfft + kHop <= in_hi) {
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) v[j] = ld_stream(src + 256 * j);
-                    if ((t & 15) == 0) {           // next frame's new half -> L2 (one 128-B line per 16 lanes)
-#pragma unroll
-                        for (int j = 16; j < 24; ++j) prefetch_l2(src + 256 * j);
-                    }
+                if constexpr (kStore == 0) {
+                    park.stage_get_windowed(i & 1, v);
+                    if (do_pf) load_half(i + 2, pf);
                 } else {
+                    const float2* src = in_u + rel;
+                    if (rel >= in_lo && rel + kNfft + kHop <= in_hi) {
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        const int p = rel + 256 * j + t;
-                        v[j] = (p >= in_lo && p < in_hi) ? __ldg(src + 256 * j) : make_float2(0.f, 0.f);
+                        for (int j = 0; j < 16; ++j) v[j] = ld_stream(src + 256 * j);
+                        if ((t & 15) == 0) {           // next frame's new half -> L2 (one 128-B line per 16 lanes)
+#pragma unroll
+                            for (int j = 16; j < 24; ++j) prefetch_l2(src + 256 * j);
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            const int p = rel + 256 * j + t;
+                            v[j] = (p >= in_lo && p < in_hi) ? __ldg(src + 256 * j) : make_float2(0.f, 0.f);
+                        }
                     }
-                }
-                const int row = rows[f];
-                {
                     float w[16];
                     park.load_awin(w, t);
 #pragma unroll
                     for (int j = 0; j < 16; ++j) v[j] = cscale(v[j], w[j]);       // analysis window
                 }
+                const int row = rows[f];
                 dft16<false>(v);                                                  // A
                 tw_pow<false>(v, wa);
                 st_e1a(v, t, bufP);
@@ -561,6 +620,7 @@ __global__ void __launch_bounds__(kThreads, 2) stft_kernel(const StftParams prm)
                 tw_pow<false>(v, wb);
                 st_e2b(v, t, bufQ);
                 __syncthreads();
+                if (do_pf) park_put(park, i & 1, pf);          // slot of the half this frame no longer needs
                 // tilt gain x crossfade weight: one real row per frame, register order; issued ahead of the
                 // shared-memory reads so the L1/L2 latency hides under them and the butterflies
                 const float4* g4 = reinterpret_cast<const float4*>(prm.gperm + (size_t)row * kNfft + t * 16);
@@ -585,6 +645,7 @@ __global__ void __launch_bounds__(kThreads, 2) stft_kernel(const StftParams prm)
             } else {
 #pragma unroll
                 for (int j = 0; j < 16; ++j) v[j] = make_float2(0.f, 0.f);
+                if (do_pf) { load_half(i + 2, pf); park_put(park, i & 1, pf); }
             }
 
             // synthesis window, overlap-add with the carried half, interior normalisation (folded into swin)
