@@ -1,0 +1,52 @@
+"""torchrun entry (>= 2 GPUs): the sharded long-file path over NCCL against the oracle.  Launched by
+tests/test_gpu_sharded.py::test_nccl_two_gpus_torchrun or by hand:
+    python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 tests/run_sharded_nccl.py"""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from oracle import tomatis_oracle as orc                       # noqa: E402  (checker)
+from tomatis_audio_processor_b200 import sharded, synth        # noqa: E402
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    comm = sharded.Comm(None, f"cuda:{local}")
+    cases = [("standard", 48000, synth.recipe_gated_pink(11.0, 48000, 30, env_hz=0.9, hi_dbfs=-22.0), dict(gate_ui=50)),
+             ("xfade", 48000, synth.recipe_threshold_ramps(4.0, 48000, 3, t_on=-48.5, t_off=-51.5, period_s=1.3), dict(gate_ui=50, xfade_ms=300.0)),
+             ("adaptive", 48000, synth.recipe_swept_pink(4.0, 48000, 4, period_s=1.1, peak=0.5), dict())]
+    for mode, sr, x, kw in cases:
+        total = len(x)
+        framing = sharded.WHOLEFILE if mode == "adaptive" else sharded.STREAMING
+        me = sharded.plan_shards(total, world, framing)[rank]
+        own = torch.from_numpy(x[me.own_lo:me.own_hi].copy()).cuda()
+        if mode == "adaptive":
+            r = sharded.run_adaptive_sharded(own, sr, total, comm, device_index=local, gather_to=0, **kw)
+        else:
+            r = sharded.run_streaming_sharded(mode, own, sr, total, comm, device_index=local, gather_to=0, **kw)
+        o = orc.run(mode, x, sr, **kw)
+        o64 = orc.run(mode, x, sr, fft_dtype="float64", **kw)
+        assert np.array_equal(r["meansq"], np.asarray(o["meansq"])) and np.array_equal(r["states"], o["states"])
+        if rank == 0:
+            y = r["full"].cpu().numpy().astype(np.float64)
+            d = np.abs(y - o["out"]).max(axis=1)
+            d64 = np.abs(y - o64["out"]).max()
+            assert d[256:-256].max() <= 1e-5 and d64 <= 1e-5, (mode, d[256:-256].max(), d64)
+            print(f"{mode}: world {world}, {total} samples, interior err {d[256:-256].max():.2e}, vs fp64-FFT {d64:.2e}, "
+                  f"comm {r['comm_bytes']} B")
+        dist.barrier()
+    if rank == 0:
+        print("SHARDED-NCCL-OK")
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

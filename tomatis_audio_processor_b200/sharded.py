@@ -1,0 +1,333 @@
+"""One long file on several GPUs: time-chunk sharding with one-hop halos.
+
+Rank r owns a contiguous run of output hop-blocks -- aligned to the reference's limiter-chunk boundaries
+(src/process_tomatis.py:419-426) whenever there are at least as many chunks as ranks -- and holds only its
+own samples.  Cross-rank traffic, all over torch.distributed (NCCL on GPUs, gloo in the CPU tests):
+
+  1. halo hand-off: the hop before and the hop after the owned range come from the neighbouring ranks
+     (point-to-point send/recv; a frame overlaps its neighbours by 50 %);
+  2. gate state: every rank reduces its frames' mean squares (bit-exact values, each frame owned by exactly
+     one rank, so an all-reduce(SUM) over zero-filled arrays is an exact gather), then every rank runs the
+     identical gate scan over the whole file -- the "carried gate state" is recomputed instead of passed
+     along, which keeps the ranks independent and deterministic (337 500 frames = 1.35 MB for 2 h @ 96 kHz);
+  3. limiter: all-reduce(MAX) of the per-chunk peaks (adaptive: also of the input peak);
+  4. optional final gather of the output shards to rank 0.
+
+The numeric work is done by a *backend* with the interface of engine.Plan (CudaShardBackend below); the CPU
+tests drive the same code with a NumPy stand-in built from the oracle.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import List, Optional
+
+import numpy as np
+
+from . import tables as tb
+
+STREAMING, WHOLEFILE = 0, 1
+
+
+@dataclass
+class Shard:
+    rank: int
+    world: int
+    total: int            # file length in sample-frames
+    framing: int
+    n_frames: int
+    first_start: int      # position of frame 0
+    block_lo: int         # owned output blocks [block_lo, block_hi)
+    block_hi: int
+    own_lo: int           # owned sample range [own_lo, own_hi) (what the rank holds and produces)
+    own_hi: int
+    in_lo: int            # samples the rank's frames read: [in_lo, in_hi) (own range + halos)
+    in_hi: int
+    frame_lo: int         # frames whose level this rank is the owner of: [frame_lo, frame_hi)
+    frame_hi: int
+
+
+def plan_shards(total: int, world: int, framing: int, n_fft=tb.N_FFT, hop=tb.HOP) -> List[Shard]:
+    """Split the output blocks of one file into `world` contiguous runs."""
+    if framing == STREAMING:
+        n_frames = tb.streaming_frame_count(total, n_fft, hop)
+        first = -(n_fft // 2)
+        chunks = tb.flush_chunk_blocks(n_frames, n_fft, hop)
+    else:
+        n_frames = tb.wholefile_frame_count(total, hop)
+        first = 0
+        chunks = [(0, n_frames + 1)] if n_frames > 0 else []
+    n_blocks = n_frames + 1 if n_frames > 0 else 0
+    if len(chunks) >= world:            # whole limiter chunks per rank: chunk peaks stay rank-local
+        cuts = [chunks[(len(chunks) * r) // world][0] for r in range(world)] + [n_blocks]
+    else:                               # fewer chunks than ranks: split by blocks (peaks are all-reduced anyway)
+        cuts = [(n_blocks * r) // world for r in range(world)] + [n_blocks]
+    shards = []
+    for r in range(world):
+        blo, bhi = cuts[r], cuts[r + 1]
+        pos = lambda b: min(total, max(0, first + b * hop))
+        own_lo = pos(blo) if r > 0 else 0
+        own_hi = pos(bhi) if r < world - 1 else total
+        f_lo, f_hi = max(0, blo - 1), min(n_frames, bhi)
+        if f_hi > f_lo:
+            in_lo, in_hi = max(0, first + f_lo * hop), min(total, first + (f_hi - 1) * hop + n_fft)
+        else:
+            in_lo = in_hi = own_lo
+        in_lo, in_hi = min(in_lo, own_lo), max(in_hi, own_hi)
+        shards.append(Shard(r, world, total, framing, n_frames, first, blo, bhi, own_lo, own_hi, in_lo, in_hi,
+                            min(blo, n_frames), min(bhi, n_frames)))
+    return shards
+
+
+# ------------------------------------------------------------------------------------------------ collectives
+class Comm:
+    """Thin wrapper over a torch.distributed process group (tensors live on `device`)."""
+
+    def __init__(self, group=None, device="cpu"):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist, self.group, self.device = torch, dist, group, torch.device(device)
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+        self.bytes_sent = 0
+
+    def _t(self, a: np.ndarray):
+        return self.torch.from_numpy(np.ascontiguousarray(a)).to(self.device)
+
+    def allreduce(self, a: np.ndarray, op: str) -> np.ndarray:
+        t = self._t(a)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM if op == "sum" else self.dist.ReduceOp.MAX, group=self.group)
+        self.bytes_sent += t.numel() * t.element_size()
+        return t.cpu().numpy()
+
+    def exchange_halos(self, own, shard: Shard, shards: List[Shard]):
+        """own: tensor [own_hi-own_lo, 2] on self.device.  Returns the rank's input window [in_hi-in_lo, 2]:
+        own samples plus the halos fetched from whichever ranks own them (normally the two neighbours)."""
+        torch, dist = self.torch, self.dist
+        win = torch.zeros((shard.in_hi - shard.in_lo, 2), dtype=own.dtype, device=own.device)
+        win[shard.own_lo - shard.in_lo: shard.own_hi - shard.in_lo] = own
+        ops, recvs = [], []
+        for other in shards:
+            if other.rank == shard.rank:
+                continue
+            # what `other` needs from me
+            lo, hi = max(other.in_lo, shard.own_lo), min(other.in_hi, shard.own_hi)
+            if hi > lo:
+                buf = own[lo - shard.own_lo: hi - shard.own_lo].contiguous()
+                ops.append(dist.P2POp(dist.isend, buf, other.rank, group=self.group))
+                self.bytes_sent += buf.numel() * buf.element_size()
+            # what I need from `other`
+            lo, hi = max(shard.in_lo, other.own_lo), min(shard.in_hi, other.own_hi)
+            if hi > lo:
+                buf = torch.empty((hi - lo, 2), dtype=own.dtype, device=own.device)
+                ops.append(dist.P2POp(dist.irecv, buf, other.rank, group=self.group))
+                recvs.append((lo, hi, buf))
+        if ops:
+            for req in dist.batch_isend_irecv(ops):
+                req.wait()
+        for lo, hi, buf in recvs:
+            win[lo - shard.in_lo: hi - shard.in_lo] = buf
+        return win
+
+    def gather_output(self, own_out, shards: List[Shard], dst: int = 0):
+        """Concatenate the ranks' output shards on rank `dst` (None elsewhere)."""
+        torch, dist = self.torch, self.dist
+        if self.rank == dst:
+            total = shards[0].total
+            full = torch.empty((total, 2), dtype=own_out.dtype, device=own_out.device)
+            me = shards[dst]
+            full[me.own_lo:me.own_hi] = own_out
+            ops, bufs = [], []
+            for s in shards:
+                if s.rank != dst and s.own_hi > s.own_lo:
+                    buf = full[s.own_lo:s.own_hi]            # contiguous row slice: receive in place
+                    ops.append(dist.P2POp(dist.irecv, buf, s.rank, group=self.group))
+            for req in (dist.batch_isend_irecv(ops) if ops else []):
+                req.wait()
+            return full
+        if own_out.shape[0] > 0:
+            for req in dist.batch_isend_irecv([dist.P2POp(dist.isend, own_out.contiguous(), dst, group=self.group)]):
+                req.wait()
+            self.bytes_sent += own_out.numel() * own_out.element_size()
+        return None
+
+
+# ------------------------------------------------------------------------------------------------ CUDA backend
+class CudaShardBackend:
+    """engine.Plan over one shard: input window + owned output buffer on this rank's GPU."""
+
+    def __init__(self, shard: Shard, window, device_index: int, gain_rows: np.ndarray, rows_key, unit_blocks: int = 0):
+        import torch
+        from . import _lib as L
+        from .engine import Plan, get_engine
+        self.L, self.shard = L, shard
+        self.eng = get_engine(device_index)
+        self.eng.set_gain_rows(gain_rows, key=rows_key)
+        self.window = window
+        self.out = torch.empty((shard.own_hi - shard.own_lo, 2), dtype=torch.float32, device=window.device)
+        desc = L.TrackDesc(window.data_ptr(), self.out.data_ptr(), shard.total, shard.in_lo, shard.in_hi - shard.in_lo,
+                           shard.own_lo, shard.own_hi - shard.own_lo, shard.block_lo, shard.block_hi)
+        self.plan = Plan(self.eng, L.FRAMING_STREAMING if shard.framing == STREAMING else L.FRAMING_WHOLEFILE, [desc], unit_blocks)
+        assert self.plan.track_frames[0] == shard.n_frames, (self.plan.track_frames, shard.n_frames)
+
+    # -- levels
+    def input_peak(self) -> np.float32:
+        self.plan.input_peaks()
+        return self.plan.read(self.L.ARR_INPUT_PEAK)[0]
+
+    def local_meansq(self, use_f64=False, in_scale=None) -> np.ndarray:
+        self.plan.levels(use_f64=use_f64, in_scale=None if in_scale is None else np.array([in_scale], np.float32))
+        return self.plan.read(self.L.ARR_MEANSQ_F64 if use_f64 else self.L.ARR_MEANSQ_F32)
+
+    def set_meansq(self, m: np.ndarray):
+        self.plan.write(self.L.ARR_MEANSQ_F64 if m.dtype == np.float64 else self.L.ARR_MEANSQ_F32, m)
+
+    def set_gate_input(self, lv: np.ndarray):
+        self.plan.write(self.L.ARR_GATE_F64, lv)
+
+    # -- gate
+    def gate(self, automaton, gate_input, on, off, param, xfade_frames, alpha_init_to_target=False, count_only=False):
+        self.plan.gate(automaton, gate_input, on, off, param, xfade_frames, alpha_init_to_target, count_only)
+
+    def c2_count(self) -> int:
+        return int(self.plan.read(self.L.ARR_C2_COUNT)[0])
+
+    def states_rows(self):
+        return self.plan.read(self.L.ARR_STATE), self.plan.read(self.L.ARR_ROW)
+
+    # -- audio
+    def stft(self, post_gain=1.0):
+        self.plan.stft(post_gain, skip_edges=True)
+
+    def edge_frames(self, post_gain=1.0, in_scale=None, out_scale=None, pipeline_f64=False):
+        self.plan.edge_frames(post_gain, None if in_scale is None else np.array([in_scale], np.float32),
+                              None if out_scale is None else np.array([out_scale], np.float32), pipeline_f64)
+
+    def chunk_peaks(self) -> np.ndarray:
+        return self.plan.read(self.L.ARR_CHUNK_PEAK)
+
+    def set_chunk_peaks(self, p: np.ndarray):
+        self.plan.write(self.L.ARR_CHUNK_PEAK, p)
+
+    def limiter(self):
+        self.plan.limiter()
+
+    def launches(self) -> int:
+        return self.plan.launch_count()
+
+    def close(self):
+        self.plan.close()
+
+
+def _cuda_backend_factory(device_index, unit_blocks=0):
+    def make(shard, window, gain_rows, rows_key):
+        return CudaShardBackend(shard, window, device_index, gain_rows, rows_key, unit_blocks)
+    return make
+
+
+def _owned(shard: Shard, arr: np.ndarray) -> np.ndarray:
+    """Zero everything but the frames this rank owns (so that a SUM all-reduce assembles the array exactly)."""
+    out = np.zeros_like(arr)
+    out[shard.frame_lo:shard.frame_hi] = arr[shard.frame_lo:shard.frame_hi]
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ drivers
+def run_streaming_sharded(mode: str, own, sr: int, total: int, comm: Comm, make_backend=None, device_index: int = 0,
+                          gather_to: Optional[int] = None, unit_blocks: int = 0, **params) -> dict:
+    """standard / xfade on one file of `total` samples spread over comm.world ranks.
+
+    own: this rank's samples (tensor [own_hi-own_lo, 2], float32, on the rank's device) for the shard
+    plan_shards(total, world, STREAMING)[rank].  Returns dict(out = this rank's output shard (same shape as own),
+    full = gathered output on rank gather_to, states/meansq/levels/rows for the whole file, chunk_peaks, shard)."""
+    from . import _lib as L
+    from .engine import streaming_params
+    shards = plan_shards(total, comm.world, STREAMING, params.get("n_fft", tb.N_FFT), params.get("hop", tb.HOP))
+    me = shards[comm.rank]
+    assert own.shape[0] == me.own_hi - me.own_lo, (own.shape, me)
+    sp = streaming_params(mode, sr, **params)
+    window = comm.exchange_halos(own, me, shards)                                  # 1. halo hand-off
+    be = (make_backend or _cuda_backend_factory(device_index, unit_blocks))(me, window, sp.rows, sp.rows_key)
+    try:
+        msq = comm.allreduce(_owned(me, be.local_meansq()), "sum")                 # 2. levels -> every rank
+        be.set_meansq(msq)
+        be.gate(L.GATE_UPDELAY, L.ARR_MEANSQ_F32, sp.m_on, sp.m_off, sp.run_frames, sp.xfade_frames)
+        be.stft(sp.post_gain)
+        be.edge_frames(sp.post_gain)
+        peaks = comm.allreduce(be.chunk_peaks(), "max")                            # 3. limiter chunks that straddle ranks
+        be.set_chunk_peaks(peaks)
+        be.limiter()
+        states, rows = be.states_rows()
+        full = comm.gather_output(be.out, shards, gather_to) if gather_to is not None else None   # 4.
+        n_fft, hop = params.get("n_fft", tb.N_FFT), params.get("hop", tb.HOP)
+        starts = -(n_fft // 2) + hop * np.arange(me.n_frames, dtype=np.int64)
+        return dict(out=be.out, full=full, shard=me, shards=shards, meansq=msq, levels=tb.levels_from_meansq(msq),
+                    states=states, rows=rows, chunk_peaks=peaks, frame_starts=starts,
+                    csv_mask=(starts >= 0) & (starts < total), xfade_frames=sp.xfade_frames, sr=sr,
+                    launches=be.launches(), comm_bytes=comm.bytes_sent)
+    finally:
+        be.close()
+
+
+def run_adaptive_sharded(own, sr: int, total: int, comm: Comm, make_backend=None, device_index: int = 0,
+                         gather_to: Optional[int] = None, unit_blocks: int = 0, fc=1000.0, slope=12.0, c1_low=15.0,
+                         c1_high=-15.0, c2_low=-15.0, c2_high=15.0, target_c2=0.5, hyst_db=3.0, min_hold_ms=250.0,
+                         xfade_ms=500.0, headroom_margin=2.0, n_fft=tb.N_FFT, hop=tb.HOP) -> dict:
+    """adaptive mode on one file spread over comm.world ranks (src/process_tomatis_adaptive.py:157-373)."""
+    from . import _lib as L
+    shards = plan_shards(total, comm.world, WHOLEFILE, n_fft, hop)
+    me = shards[comm.rank]
+    assert own.shape[0] == me.own_hi - me.own_lo, (own.shape, me)
+    hold, xf = tb.adaptive_frame_counts(sr, min_hold_ms, xfade_ms, hop)
+    c1_db, c2_db = tb.tilt_curves_db(sr, n_fft, fc, slope, c1_low, c1_high, c2_low, c2_high)
+    rows_tab = tb.gain_rows_adaptive(c1_db, c2_db, xf)
+    window = comm.exchange_halos(own, me, shards)
+    be = (make_backend or _cuda_backend_factory(device_index, unit_blocks))(
+        me, window, rows_tab, ("adaptive", sr, fc, slope, c1_low, c1_high, c2_low, c2_high, xf, n_fft))
+    try:
+        in_peak = np.float32(comm.allreduce(np.array([be.input_peak()], np.float32), "max")[0])
+        atten_db, atten_lin, use_f64 = tb.adaptive_attenuation(in_peak, c1_low, c2_high, headroom_margin)
+        scale = np.float32(atten_lin)
+        msq = comm.allreduce(_owned(me, be.local_meansq(use_f64, scale)), "sum")
+        levels = tb.levels_from_meansq(msq)
+        be.set_gate_input(levels)
+        # threshold bisection, identical on every rank (src/process_tomatis_adaptive.py:124-154)
+        n = me.n_frames
+        valid = levels > -70
+        trace = []
+        if valid.any():
+            vl = levels[valid]
+            T_low, T_high, best_T, best_diff = np.percentile(vl, 5), np.percentile(vl, 95), np.median(vl), 1.0
+            for _ in range(30):
+                T_mid = (T_low + T_high) / 2
+                be.gate(L.GATE_MINHOLD, L.ARR_GATE_F64, T_mid + hyst_db / 2, T_mid - hyst_db / 2, hold, xf, True, True)
+                ratio = be.c2_count() / n
+                trace.append((float(T_mid), ratio))
+                diff = abs(ratio - target_c2)
+                if diff < best_diff:
+                    best_diff, best_T = diff, T_mid
+                if diff < 0.01:
+                    break
+                if ratio < target_c2:
+                    T_high = T_mid
+                else:
+                    T_low = T_mid
+        else:
+            best_T = np.median(levels)
+        be.gate(L.GATE_MINHOLD, L.ARR_GATE_F64, best_T + hyst_db / 2, best_T - hyst_db / 2, hold, xf, True, False)
+        be.stft(1.0)
+        if use_f64:
+            be.edge_frames(1.0, None, None, True)
+        else:
+            be.edge_frames(1.0, scale, np.float32(tb.db_to_lin_keep(atten_db)), False)
+        peaks = comm.allreduce(be.chunk_peaks(), "max")           # one chunk: the global output peak
+        be.set_chunk_peaks(peaks)
+        be.limiter()
+        states, rows = be.states_rows()
+        full = comm.gather_output(be.out, shards, gather_to) if gather_to is not None else None
+        return dict(out=be.out, full=full, shard=me, shards=shards, meansq=msq, levels=levels, states=states, rows=rows,
+                    optimal_T=float(best_T), trace=trace, atten_db=float(atten_db), input_peak=float(in_peak),
+                    pipeline_dtype="float64" if use_f64 else "float32", output_peak=float(peaks[0]) if len(peaks) else 0.0,
+                    min_hold_frames=hold, xfade_frames=xf, times=[(k + 1) * (hop / sr) for k in range(n)], sr=sr,
+                    launches=be.launches(), comm_bytes=comm.bytes_sent)
+    finally:
+        be.close()

@@ -231,3 +231,41 @@ def alpha_follow_exact(states: np.ndarray, xfade_frames: int, start_at_target: b
                 cur = cur + step * np.sign(diff)
         alpha[i] = cur
     return alpha
+
+
+# ------------------------------------------------------------------ frame / block / chunk geometry
+FLUSH_SAFE = 48000 * 5      # src/process_tomatis.py:420 -- a sample count, whatever the sample rate
+
+
+def streaming_frame_count(total: int, n_fft=N_FFT, hop=HOP) -> int:
+    """Frames of standard/xfade: first frame at -n_fft/2, tail zero-padded by pad_end
+    (src/process_tomatis.py:270-272, 310-312, 447-449)."""
+    pad = n_fft // 2
+    pad_end = (hop - ((total - n_fft) % hop)) % hop
+    length = pad + total + pad_end
+    return 0 if length < n_fft else (length - n_fft) // hop + 1
+
+
+def wholefile_frame_count(total: int, hop=HOP) -> int:
+    """Frames of adaptive: starts k*hop with 0 <= k*hop < total that fit the padded signal
+    (src/process_tomatis_adaptive.py:298-300)."""
+    return total // hop
+
+
+def flush_chunk_blocks(n_frames: int, n_fft=N_FFT, hop=HOP):
+    """Limiter chunks of the streaming modes as output-block ranges [(b0, b1), ...] (block b = positions
+    [-n_fft/2 + b*hop, +hop)): replay of the flush rule src/process_tomatis.py:419-426 + final flush :451-453."""
+    if n_frames <= 0:
+        return []
+    out, flushed, out_base, next_start = [], 0, 0, 0
+    for _ in range(n_frames):
+        next_start += hop
+        safe = (next_start - out_base) - n_fft
+        if safe >= FLUSH_SAFE:
+            nb = safe // hop
+            out.append((flushed, flushed + nb))
+            flushed += nb
+            out_base += safe
+    if flushed < n_frames + 1:
+        out.append((flushed, n_frames + 1))
+    return out
