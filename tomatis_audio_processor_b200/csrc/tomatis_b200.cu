@@ -619,7 +619,9 @@ __global__ void __launch_bounds__(kThreads, 2) stft_kernel(const StftParams prm)
                 dft16<false>(v);                                                  // B
                 tw_pow<false>(v, wb);
                 st_e2b(v, t, bufQ);
-                __syncthreads();
+                // E2 rows k1*16 .. k1*16+15 are written and read only by the 16 threads with t>>4 == k1 (one half
+                // warp), in B, C/C' and B' alike: the E2 exchanges need warp-level ordering only
+                __syncwarp();
                 if (do_pf) park_put(park, i & 1, pf);          // slot of the half this frame no longer needs
                 // tilt gain x crossfade weight: one real row per frame, register order; issued ahead of the
                 // shared-memory reads so the L1/L2 latency hides under them and the butterflies
@@ -633,11 +635,11 @@ __global__ void __launch_bounds__(kThreads, 2) stft_kernel(const StftParams prm)
                 v[12] = cscale(v[12], g3.x); v[13] = cscale(v[13], g3.y); v[14] = cscale(v[14], g3.z); v[15] = cscale(v[15], g3.w);
                 dft16<true>(v);                                                   // C'
                 st_e2c(v, t, bufQ);            // same rows this thread just read: no barrier needed in between
-                __syncthreads();
+                __syncwarp();
                 ld_e2b(v, t, bufQ);
                 tw_pow<true>(v, wb);
                 dft16<true>(v);                                                   // B'
-                st_e1b(v, t, bufP);
+                st_e1b(v, t, bufP);            // the very words this thread read in ld_e1b: no hazard with slower warps still in B
                 __syncthreads();
                 ld_e1a(v, t, bufP);            // next frame's st_e1a overwrites exactly the words this thread reads here
                 tw_pow<true>(v, wa);
