@@ -25,6 +25,18 @@ inline std::vector<float2> build_tw_bases() {
     return b;
 }
 
+// Stage-A twiddles, exact: tw[16*t + k] = W4096^(t*k), k = 0..15 (double precision rounded once).
+inline std::vector<float2> build_tw_stage_a() {
+    std::vector<float2> b(16 * 256);
+    const double two_pi = 6.283185307179586476925286766559;
+    for (int t = 0; t < 256; ++t)
+        for (int k = 0; k < 16; ++k) {
+            const double a = -two_pi * double((t * k) % 4096) / 4096.0;
+            b[16 * t + k] = make_float2((float)std::cos(a), (float)std::sin(a));
+        }
+    return b;
+}
+
 // Natural-order half-spectrum gain row g[0..2048] -> register-order full-spectrum row:
 //   out[t*16 + j] = G[(t>>4) + 16*(t&15) + 256*j] / 4096,  G[k] = g[k] (k<=2048) else g[4096-k].
 inline void permute_gain_row(const float* g_half, float* out) {

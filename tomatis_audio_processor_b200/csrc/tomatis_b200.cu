@@ -384,11 +384,12 @@ struct StftParams {
     const float* win;       // [4096] analysis window
     const float* swin;      // [4096] synthesis window x interior normalisation: w[n] / (w2[n%hop] + w2[n%hop + hop] (+eps | clamped))
     const float2* tw_bases; // [256][4]: per-thread twiddle bases (host_tables.hpp)
+    const float2* tw_a;     // [256][16]: stage-A twiddles (W4096^t)^k, k = 0..15, exact (parked in tensor memory)
     float* chunk_peaks;
     float post_gain;
 };
 
-constexpr int kTmemWarpCols = 80;                    // analysis window 16 | synthesis window 16 | carry 16 | raw input halves 2 x 16
+constexpr int kTmemWarpCols = 112;                   // analysis window 16 | synthesis window 16 | carry 16 | raw input halves 2 x 16 | stage-A twiddles 32
 constexpr int kTmemCols = 256;                       // per CTA: 2 warps per lane quarter x 80 columns, rounded to a power of two (2 CTAs = all 512)
 constexpr int kStftSmemTmem = (4096 + kExchFloat2) * (int)sizeof(float2) + 64;
 constexpr int kStftSmemSmem = kStftSmemTmem + 2 * kNfft * (int)sizeof(float) + kHop * (int)sizeof(float2);
@@ -413,7 +414,7 @@ __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.
 template <int kStore> struct Park;
 template <> struct Park<0> {
     uint32_t base;       // TMEM address of this warp's 48 columns (lane quarter in bits 31:16)
-    __device__ __forceinline__ void init(unsigned char* smem_tail, int t, const float* win, const float* swin) {
+    __device__ __forceinline__ void init(unsigned char* smem_tail, int t, const float* win, const float* swin, const float2* tw_a) {
         uint32_t* slot = reinterpret_cast<uint32_t*>(smem_tail);
         if ((t >> 5) == 0) {
             asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
@@ -432,7 +433,35 @@ template <> struct Park<0> {
 #pragma unroll
         for (int j = 0; j < 16; ++j) r[j] = __ldg(swin + 256 * j + t);
         tmem_st16(base + 16, r);
+        const float4* ta = reinterpret_cast<const float4*>(tw_a + 16 * t);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float4 x = __ldg(ta + 4 * h + q);
+                r[4 * q] = x.x; r[4 * q + 1] = x.y; r[4 * q + 2] = x.z; r[4 * q + 3] = x.w;
+            }
+            tmem_st16(base + 80 + 16 * h, r);
+        }
         tmem_wait_st();
+    }
+    // v[k] *= p^k (CONJ: conj(p^k)), p = W4096^t, powers read from tensor memory
+    template <bool CONJ>
+    __device__ __forceinline__ void twiddle_a(float2 (&v)[16], const TwBase) const {
+        float a[16], b[16];
+        tmem_ld16(base + 80, a);
+        tmem_ld16(base + 96, b);
+        tmem_wait_ld();
+#pragma unroll
+        for (int k = 1; k < 8; ++k) {
+            const float2 p = make_float2(a[2 * k], a[2 * k + 1]);
+            v[k] = CONJ ? cmulc(v[k], p) : cmul(v[k], p);
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const float2 p = make_float2(b[2 * k], b[2 * k + 1]);
+            v[k + 8] = CONJ ? cmulc(v[k + 8], p) : cmul(v[k + 8], p);
+        }
     }
     __device__ __forceinline__ void fini(unsigned char* smem_tail, int t) {
         tmem_wait_st();
@@ -484,7 +513,7 @@ template <> struct Park<1> {
     float* aw;        // [4096]
     float* sw;        // [4096]
     float2* cy;       // [2048]
-    __device__ __forceinline__ void init(unsigned char* smem_tail, int t, const float* win, const float* swin) {
+    __device__ __forceinline__ void init(unsigned char* smem_tail, int t, const float* win, const float* swin, const float2*) {
         aw = reinterpret_cast<float*>(smem_tail + 64);
         sw = aw + kNfft;
         cy = reinterpret_cast<float2*>(sw + kNfft);
@@ -507,6 +536,8 @@ template <> struct Park<1> {
 #pragma unroll
         for (int j = 0; j < 8; ++j) cy[256 * j + t] = c[j];
     }
+    template <bool CONJ>
+    __device__ __forceinline__ void twiddle_a(float2 (&v)[16], const TwBase wa) const { tw_pow<CONJ>(v, wa); }
     __device__ __forceinline__ void sync_stores() const {}
 };
 
@@ -523,7 +554,7 @@ __global__ void __launch_bounds__(kThreads, 2) stft_kernel(const StftParams prm)
     const int t = threadIdx.x;
 
     Park<kStore> park;
-    park.init(tail, t, prm.win, prm.swin);
+    park.init(tail, t, prm.win, prm.swin, prm.tw_a);
     const float4* tb4 = reinterpret_cast<const float4*>(prm.tw_bases) + 2 * t;
     const float4 ba = __ldg(tb4), bb = __ldg(tb4 + 1);
     const TwBase wa = {make_float2(ba.x, ba.y), make_float2(ba.z, ba.w)};
@@ -612,7 +643,7 @@ __global__ void __launch_bounds__(kThreads, 2) stft_kernel(const StftParams prm)
                 }
                 const int row = rows[f];
                 dft16<false>(v);                                                  // A
-                tw_pow<false>(v, wa);
+                park.template twiddle_a<false>(v, wa);
                 st_e1a(v, t, bufP);
                 __syncthreads();
                 ld_e1b(v, t, bufP);
@@ -642,7 +673,7 @@ __global__ void __launch_bounds__(kThreads, 2) stft_kernel(const StftParams prm)
                 st_e1b(v, t, bufP);            // the very words this thread read in ld_e1b: no hazard with slower warps still in B
                 __syncthreads();
                 ld_e1a(v, t, bufP);            // next frame's st_e1a overwrites exactly the words this thread reads here
-                tw_pow<true>(v, wa);
+                park.template twiddle_a<true>(v, wa);
                 dft16<true>(v);                                                   // A'
             } else {
 #pragma unroll
@@ -859,6 +890,7 @@ struct tmt_engine {
     DevBuf<float> swin;       // [2][4096]  synthesis window x interior normalisation (eps | clamp)
     int stft_store = 0;       // 0: thread-private constants + carry in tensor memory, 1: in shared memory
     DevBuf<float2> tw_bases;  // [256][4]
+    DevBuf<float2> tw_a;      // [256][16]
     DevBuf<float> gperm;      // [n_rows][4096]
     DevBuf<float> gnat;       // [n_rows][2049] natural order (fp64 edge frames)
     int n_rows = 0;
@@ -1033,12 +1065,14 @@ int tmt_engine_create(tmt_engine** out, int device, int n_fft, int hop) {
     if (ce != cudaSuccess) { delete e; return fail(TMT_ERR_CUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(ce)); }
     e->n_sms = prop.multiProcessorCount;
     auto twb = build_tw_bases();
-    if (e->tw_bases.alloc(twb.size()) != cudaSuccess || e->win.alloc(kNfft) != cudaSuccess ||
+    auto twa = build_tw_stage_a();
+    if (e->tw_bases.alloc(twb.size()) != cudaSuccess || e->tw_a.alloc(twa.size()) != cudaSuccess || e->win.alloc(kNfft) != cudaSuccess ||
         e->swin.alloc(2 * kNfft) != cudaSuccess) {
         delete e;
         return fail(TMT_ERR_NOMEM, "device allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
     }
     cudaMemcpy(e->tw_bases.p, twb.data(), sizeof(float2) * twb.size(), cudaMemcpyHostToDevice);
+    cudaMemcpy(e->tw_a.p, twa.data(), sizeof(float2) * twa.size(), cudaMemcpyHostToDevice);
     ce = cudaFuncSetAttribute(stft_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStftSmemTmem);
     if (ce == cudaSuccess) ce = cudaFuncSetAttribute(stft_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStftSmemSmem);
     if (ce != cudaSuccess) { delete e; return fail(TMT_ERR_CUDA, "cudaFuncSetAttribute(stft_kernel): %s", cudaGetErrorString(ce)); }
@@ -1347,6 +1381,7 @@ int tmt_plan_stft(tmt_plan* p, float post_gain, int skip_edges, void* stream) {
     prm.win = e->win.p;
     prm.swin = e->swin.p + ((p->framing == TMT_FRAMING_WHOLEFILE) ? kNfft : 0);
     prm.tw_bases = e->tw_bases.p;
+    prm.tw_a = e->tw_a.p;
     prm.chunk_peaks = p->chunk_peaks.p;
     prm.post_gain = post_gain;
     const int grid = std::min(p->n_units, 2 * e->n_sms);            // persistent: two CTAs per SM
