@@ -318,6 +318,173 @@ def run_gpu_arm(args):
         dist.destroy_process_group()
 
 
+# ------------------------------------------------------------------------------------------------ long file (configs[4])
+LF_SR = 96000
+LF_SECONDS = 7200.0
+LF_TOTAL = int(LF_SR * LF_SECONDS)            # 691 200 000 sample-frames = 2048 * 337 500 (pad_end = 0)
+
+
+def longfile_config(n_gpus, total=LF_TOTAL):
+    return {
+        "workload": f"BASELINE configs[4]: single {total / LF_SR / 3600:.2f}-hour 96 kHz stereo synthetic file, process_tomatis standard mode "
+                    f"--gate_ui 50, time-chunk sharded across {n_gpus} GPU(s) on limiter-chunk boundaries with one-hop halos",
+        "mode": "standard", "gate_ui": 50, "sample_rate": LF_SR, "file_seconds": total / LF_SR, "n_fft": 4096, "hop": 2048,
+        "l2_policy": f"inputs larger than L2 ({total * 8 / 1e9:.2f} GB in + out per pass, streamed once)",
+        "parallelism": f"time-chunk sharded x{n_gpus}: NCCL halo hand-off (2 x 16 KB per rank), all-reduce of per-frame mean squares "
+                       f"({total // 2048 * 4 / 1e6:.2f} MB) + redundant gate scan, all-reduce(max) of chunk peaks",
+    }
+
+
+def cpu_baseline_longfile(excerpt_seconds=240.0):
+    """Oracle port on ONE host core (the reference processes one file on one thread), bounded excerpt."""
+    from tomatis_audio_processor_b200 import synth
+    from oracle import tomatis_oracle as orc
+    x = synth.recipe_gated_pink(excerpt_seconds, LF_SR, 5)
+    t = time.perf_counter()
+    orc.process_standard(x, LF_SR, gate_ui=50)
+    dt = time.perf_counter() - t
+    return {"value": excerpt_seconds / dt, "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": f"{excerpt_seconds:.0f} s excerpt @ {LF_SR} Hz through oracle.process_standard, one process (the reference's "
+                      f"streaming loop is single-threaded and sequential in the gate state)"}
+
+
+def run_longfile_reference_arm(args):
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    times = []
+    for it in range(args.warmup + args.steps):
+        cb = cpu_baseline_longfile(args.lf_cpu_seconds)
+        if it >= args.warmup:
+            times.append(args.lf_cpu_seconds / cb["value"])
+    value = args.lf_cpu_seconds * len(times) / sum(times)
+    cb["value"] = value
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": sum(times) / len(times) * 1e3, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": longfile_config(args.gpus, args.lf_total),
+            "cpu_baseline": cb, "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def run_longfile_arm(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = f"cuda:{local}"
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    os.environ.setdefault("MASTER_PORT", "29531")
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device(dev))
+
+    from tomatis_audio_processor_b200 import sharded, synth, _lib as L
+    total = args.lf_total
+    comm = sharded.Comm(None, dev)
+    me = sharded.plan_shards(total, world, sharded.STREAMING)[rank]
+    own = synth.device_long_file_range(me.own_lo, me.own_hi, LF_SR, 5000, dev)
+    sess = sharded.StreamingShardSession("standard", own, LF_SR, total, comm, device_index=local, unit_blocks=args.unit_blocks, gate_ui=50)
+    own = sess.own                      # the session keeps the samples inside its window buffer
+    plan = sess.be.plan
+
+    def barrier():
+        dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        sess.step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    l0 = plan.launch_count()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t0 = time.time()
+    e0.record()
+    for k in range(args.steps):
+        sess.step_timed(ev[k]) if hasattr(sess, "step_timed") else sess.step()
+    e1.record()
+    barrier()
+    t1 = time.time()
+    clocks = sampler.stop(t0, t1) if rank == 0 else None
+    ms_total = e0.elapsed_time(e1)
+    stft_ms = float(np.mean([a.elapsed_time(b) for a, b in ev]))
+    launches = plan.launch_count() - l0
+    marks = []
+    sess.step(marks=marks)
+    torch.cuda.synchronize()
+    breakdown = {b[0]: round(a[1].elapsed_time(b[1]), 4) for a, b in zip(marks, marks[1:])}
+    tmax = torch.tensor([ms_total, stft_ms], device=dev, dtype=torch.float64)
+    dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    ms_total, stft_ms = float(tmax[0]), float(tmax[1])
+    value = total / LF_SR * args.steps / (ms_total * 1e-3)
+    states = plan.read(L.ARR_STATE)
+    peaks = plan.read(L.ARR_CHUNK_PEAK)
+    out_peak = float(sess.out.abs().max()) if sess.out.numel() else 0.0
+    comm_bytes = comm.bytes_sent
+
+    # ---- end to end: the rank's own range from pinned host memory and back, copies inside the timed region
+    e2e = None
+    if not args.no_e2e:
+        n_own = me.own_hi - me.own_lo
+        h_in = torch.empty((n_own, 2), dtype=torch.float32, pin_memory=True)
+        h_out = torch.empty((n_own, 2), dtype=torch.float32, pin_memory=True)
+        h_in.copy_(own)
+
+        def e2e_step():
+            own.copy_(h_in, non_blocking=True)
+            sess.step()
+            h_out.copy_(sess.out, non_blocking=True)
+        e2e_step()
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(args.e2e_steps):
+            e2e_step()
+        b.record()
+        barrier()
+        ms = torch.tensor([a.elapsed_time(b)], device=dev, dtype=torch.float64)
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        e2e = {"value": total / LF_SR * args.e2e_steps / (float(ms[0]) * 1e-3), "unit": UNIT,
+               "h2d_bytes_per_step": int(total * 8), "d2h_bytes_per_step": int(total * 8), "steps": args.e2e_steps,
+               "ms_per_step": float(ms[0]) / args.e2e_steps,
+               "api": "sharded.StreamingShardSession.step with each rank's own range copied from / to pinned host float32 buffers",
+               "host_peak_out": float(h_out.abs().max()) if n_own else 0.0}
+        del h_in, h_out
+
+    if rank == 0:
+        peak_gbs, peak_src = measured_peak()
+        sf_rank = me.own_hi - me.own_lo
+        achieved = ALG_BYTES_PER_SF * sf_rank / (stft_ms * 1e-3) / 1e9
+        traffic = ncu_traffic()
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": longfile_config(world, total), "clocks": clocks, "e2e": e2e,
+            "gpu_launches": int(launches), "comm_bytes_per_step_rank0": int(comm_bytes // max(1, args.warmup + args.steps + 1 + (0 if args.no_e2e else args.e2e_steps + 1))),
+            "roofline": {"bound": "hbm", "kernel": "stft_kernel (fused gather+window+FFT+gain+IFFT+window+OLA+peak), rank 0 shard",
+                         "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": ALG_BYTES_PER_SF * sf_rank, "kernel_ms": stft_ms,
+                         "kernel_share_of_step": stft_ms * args.steps / ms_total,
+                         "traffic": (traffic or {}).get("dram_bytes_per_sf", None) and (traffic["dram_bytes_per_sf"] * sf_rank),
+                         "traffic_source": (traffic or {}).get("source")},
+            "phase_ms_rank0": breakdown,
+            "checks": {"c2_fraction": float((states == 2).mean()), "chunks_over_limit": float((peaks > np.float32(0.999)).mean()),
+                       "output_peak": out_peak, "frames": int(states.size)},
+        }
+        if world == 1 and not args.no_cpu:
+            line["cpu_baseline"] = cpu_baseline_longfile(args.lf_cpu_seconds)
+        print(json.dumps(line), flush=True)
+    sess.close()
+    dist.barrier()
+    dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -331,12 +498,18 @@ def main():
     ap.add_argument("--wave-tracks", dest="wave_tracks", type=int, default=8)
     ap.add_argument("--cpu-tracks", dest="cpu_tracks", type=int, default=3)
     ap.add_argument("--cpu-workers", dest="cpu_workers", type=int, default=0)
+    ap.add_argument("--workload", choices=["batch", "longfile"], default="batch",
+                    help="batch = BASELINE configs[3] (default, weak scaling); longfile = configs[4] (one 2 h file, strong scaling)")
+    ap.add_argument("--lf-total", dest="lf_total", type=int, default=LF_TOTAL, help="long-file length in sample-frames")
+    ap.add_argument("--lf-cpu-seconds", dest="lf_cpu_seconds", type=float, default=240.0)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3                       # timing rule: at least 3 warm-up steps
-    if args.impl == "reference":
+    if args.workload == "longfile":
+        (run_longfile_reference_arm if args.impl == "reference" else run_longfile_arm)(args)
+    elif args.impl == "reference":
         run_reference_arm(args)
     else:
         run_gpu_arm(args)

@@ -155,3 +155,33 @@ def test_linearity_and_silence_properties_full_length():
     a = eng.run("standard", [x * 0.01], 44100, want_host=False, **kw)[0]["out"]
     b = eng.run("standard", [x * 0.02], 44100, want_host=False, **kw)[0]["out"]
     assert float((b - 2 * a).abs().max()) <= 2e-6
+
+
+@pytest.mark.parametrize("nseg", [2, 7, 64])
+def test_multi_segment_gate_scan(nseg):
+    """Long tracks spread the gate scan over many CTAs (three passes); forced here on short inputs through
+    TMT_GATE_NSEG (read at engine creation, so a private engine is used)."""
+    import os
+    from tomatis_audio_processor_b200 import engine as eng, synth
+    orc = _oracle()
+    cases = [("standard", synth.recipe_gated_pink(4.0, 48000, 51, env_hz=1.7), dict(gate_ui=50, up_delay_ms=90.0)),
+             ("xfade", synth.recipe_threshold_ramps(4.0, 48000, 52, t_on=-48.5, t_off=-51.5, period_s=0.9), dict(gate_ui=50, xfade_ms=250.0, up_delay_ms=60.0)),
+             ("adaptive", synth.recipe_swept_pink(4.0, 48000, 53, period_s=0.8, peak=0.5), dict(min_hold_ms=100.0, xfade_ms=200.0))]
+    saved = eng._engines.pop(0, None)
+    os.environ["TMT_GATE_NSEG"] = str(nseg)
+    try:
+        for mode, x, kw in cases:
+            r = eng.run(mode, [x, x[: len(x) // 3]], 48000, **kw)          # two tracks of different length in one plan
+            for xi, ri in zip([x, x[: len(x) // 3]], r):
+                o = orc.run(mode, xi, 48000, **kw)
+                assert np.array_equal(ri["states"], o["states"]), (mode, nseg)
+                assert np.allclose(ri["rows"] / max(ri["xfade_frames"], 1), o["alphas"], atol=1e-9), (mode, nseg)
+                if mode == "adaptive":
+                    assert ri["optimal_T"] == o["optimal_T"] and ri["trace"] == o["trace"]      # count-only passes
+    finally:
+        del os.environ["TMT_GATE_NSEG"]
+        e = eng._engines.pop(0, None)
+        if e is not None:
+            e.close()
+        if saved is not None:
+            eng._engines[0] = saved

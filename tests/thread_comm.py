@@ -29,12 +29,21 @@ class ThreadComm:
         return vals
 
     def allreduce(self, a, op):
-        vals = self._all(np.array(a, copy=True))
-        self.bytes_sent += a.nbytes
-        out = vals[0].copy()
+        if isinstance(a, np.ndarray):
+            vals = self._all(np.array(a, copy=True))
+            self.bytes_sent += a.nbytes
+            out = vals[0].copy()
+            for v in vals[1:]:
+                out = out + v if op == "sum" else np.maximum(out, v)
+            return out.astype(a.dtype)
+        import torch
+        torch.cuda.synchronize()
+        vals = self._all(a.clone())
+        self.bytes_sent += a.numel() * a.element_size()
+        out = vals[0].clone()
         for v in vals[1:]:
-            out = out + v if op == "sum" else np.maximum(out, v)
-        return out.astype(a.dtype)
+            out = out + v if op == "sum" else torch.maximum(out, v)
+        return out
 
     def exchange_halos(self, own, shard, shards):
         import torch

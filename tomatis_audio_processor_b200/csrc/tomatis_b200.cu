@@ -31,6 +31,7 @@ using namespace tmt;
 constexpr long long kFlushSafe = 48000LL * 5;   // src/process_tomatis.py:420 (a sample count)
 constexpr int kLevelWarps = 8;                   // hop-blocks per CTA of levels_kernel
 constexpr int kMaxGateStates = 255;
+constexpr int kGateSegCap = 1024;                // gate-scan segments per plan (multi-segment scan of long tracks)
 
 thread_local char g_err[512] = "";
 
@@ -239,11 +240,25 @@ __device__ __forceinline__ Clamp3 clamp3_then(Clamp3 f, Clamp3 g) {
     return r;
 }
 
-template <typename T, int AUTO>
+constexpr int GATE_FUSED = 0, GATE_MAP = 1, GATE_STATES = 2, GATE_ROWS = 3;
+
+// Multi-segment scan for long tracks: the frames of a track are cut into `nseg` segments, one CTA each.
+//   GATE_MAP     segment transition map (S entries)                 -> segmap   [track][seg][S]
+//   GATE_STATES  start state = chain of the earlier segments' maps; replay -> state[], C2 count,
+//                segment clamp map of the crossfade counter          -> segclamp [track][seg][3]
+//   GATE_ROWS    start counter = chain of the earlier clamp maps; replay -> rows[]
+// GATE_FUSED (nseg == 1) does everything in one launch.
+struct GateSeg {
+    int nseg;
+    uint8_t* segmap;
+    int* segclamp;
+};
+
+template <typename T, int AUTO, int PASS>
 __global__ void gate_kernel(const TrackDev* __restrict__ tracks, const T* __restrict__ vals,
                             const double* __restrict__ von, const double* __restrict__ voff, int param, int S,
                             int X, int alpha_init, int count_only, uint8_t* __restrict__ state,
-                            uint16_t* __restrict__ rows, int* __restrict__ c2_count) {
+                            uint16_t* __restrict__ rows, int* __restrict__ c2_count, GateSeg seg) {
     extern __shared__ __align__(16) unsigned char gsm[];
     const int NT = blockDim.x, NW = NT >> 5;
     const int i = threadIdx.x, w = i >> 5, lane = i & 31;
@@ -259,67 +274,102 @@ __global__ void gate_kernel(const TrackDev* __restrict__ tracks, const T* __rest
     int* akstart = aw + 3 * NW;              // [NT]
     int* awstart = akstart + NT;             // [NW]
     int* red = awstart + NW;                 // [NW]
+    int* cta_init = red + NW;                // [2] start state / start counter of this CTA
+    unsigned char* prior = reinterpret_cast<unsigned char*>(cta_init + 2);   // earlier segments' maps (multi-segment passes)
 
-    const TrackDev tr = tracks[blockIdx.x];
+    const int track = blockIdx.y, c = blockIdx.x, nseg = seg.nseg;
+    const TrackDev tr = tracks[track];
     const int F = tr.n_frames;
     const T* v = vals + tr.frame_base;
-    const T on = (T)von[blockIdx.x], off = (T)voff[blockIdx.x];
-    const int L = (F + NT - 1) / NT;
-    const int f0 = min(F, i * L), f1 = min(F, f0 + L);
+    const T on = (T)von[track], off = (T)voff[track];
+    const int Lc = (F + nseg - 1) / nseg;                       // frames per segment
+    const int cbeg = min(F, c * Lc), cend = min(F, cbeg + Lc);
+    const int L = (Lc + NT - 1) / NT;
+    const int f0 = min(cend, cbeg + i * L), f1 = min(cend, f0 + L);
     const int Xe = max(X, 1);
     const int s_init = (AUTO == TMT_GATE_UPDELAY) ? 0 : param;
 
-    // 1. segment maps
-    for (int s = 0; s < S; ++s) maps[s * NT + i] = (uint8_t)s;
-    for (int f = f0; f < f1; ++f) {
-        const T x = v[f];
-        const bool hi = x >= on, lo = x <= off;
-        for (int s = 0; s < S; ++s) maps[s * NT + i] = (uint8_t)gate_next<AUTO>(maps[s * NT + i], hi, lo, param);
+    if (PASS != GATE_ROWS) {
+        // 1. per-thread maps
+        for (int s = 0; s < S; ++s) maps[s * NT + i] = (uint8_t)s;
+        for (int f = f0; f < f1; ++f) {
+            const T x = v[f];
+            const bool hi = x >= on, lo = x <= off;
+            for (int s = 0; s < S; ++s) maps[s * NT + i] = (uint8_t)gate_next<AUTO>(maps[s * NT + i], hi, lo, param);
+        }
+        if (PASS == GATE_STATES) {               // earlier segments' maps -> shared memory
+            const uint8_t* src = seg.segmap + (size_t)track * nseg * S;
+            for (int q = i; q < c * S; q += NT) prior[q] = src[q];
+        }
+        __syncthreads();
+        // 2. warp maps
+        for (int s = lane; s < S; s += 32) {
+            int cur = s;
+            for (int j = 0; j < 32; ++j) cur = maps[cur * NT + w * 32 + j];
+            wmap[s * NW + w] = (uint8_t)cur;
+        }
+        __syncthreads();
+        if (PASS == GATE_MAP) {                  // segment map: chain of the warp maps for every start state
+            for (int s = i; s < S; s += NT) {
+                int cur = s;
+                for (int ww = 0; ww < NW; ++ww) cur = wmap[cur * NW + ww];
+                seg.segmap[((size_t)track * nseg + c) * S + s] = (uint8_t)cur;
+            }
+            return;
+        }
+        if (i == 0) {
+            int cur = s_init;
+            if (PASS == GATE_STATES)
+                for (int q = 0; q < c; ++q) cur = prior[q * S + cur];
+            for (int ww = 0; ww < NW; ++ww) { wstart[ww] = (uint8_t)cur; cur = wmap[cur * NW + ww]; }
+        }
+        __syncthreads();
+        if (lane == 0) {
+            int cur = wstart[w];
+            for (int j = 0; j < 32; ++j) { segstart[w * 32 + j] = (uint8_t)cur; cur = maps[cur * NT + w * 32 + j]; }
+        }
+        __syncthreads();
     }
-    __syncthreads();
-    // 2. two-level chain of the maps
-    for (int s = lane; s < S; s += 32) {
-        int cur = s;
-        for (int j = 0; j < 32; ++j) cur = maps[cur * NT + w * 32 + j];
-        wmap[s * NW + w] = (uint8_t)cur;
-    }
-    __syncthreads();
-    if (i == 0) {
-        int cur = s_init;
-        for (int ww = 0; ww < NW; ++ww) { wstart[ww] = (uint8_t)cur; cur = wmap[cur * NW + ww]; }
-    }
-    __syncthreads();
-    if (lane == 0) {
-        int cur = wstart[w];
-        for (int j = 0; j < 32; ++j) { segstart[w * 32 + j] = (uint8_t)cur; cur = maps[cur * NT + w * 32 + j]; }
-    }
-    __syncthreads();
-    // 3. replay: states, C2 count, crossfade clamp map of the segment
-    int cur = segstart[i];
+    // 3. replay: states, C2 count, crossfade clamp map of the thread's frames
     int c2 = 0;
     Clamp3 am = {0, 0, Xe};
-    for (int f = f0; f < f1; ++f) {
-        const T x = v[f];
-        cur = gate_next<AUTO>(cur, x >= on, x <= off, param);
-        const int t2 = gate_is_c2<AUTO>(cur, param) ? 1 : 0;
-        c2 += t2;
-        if (!count_only) {
-            state[tr.frame_base + f] = (uint8_t)(1 + t2);
+    if (PASS != GATE_ROWS) {
+        int cur = segstart[i];
+        for (int f = f0; f < f1; ++f) {
+            const T x = v[f];
+            cur = gate_next<AUTO>(cur, x >= on, x <= off, param);
+            const int t2 = gate_is_c2<AUTO>(cur, param) ? 1 : 0;
+            c2 += t2;
+            if (!count_only) {
+                state[tr.frame_base + f] = (uint8_t)(1 + t2);
+                Clamp3 g;
+                if (alpha_init && f == 0) { g.d = 0; g.lo = g.hi = t2 * Xe; }
+                else { g.d = t2 ? 1 : -1; g.lo = 0; g.hi = Xe; }
+                am = clamp3_then(am, g);
+            }
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) c2 += __shfl_xor_sync(0xffffffffu, c2, o);
+        if (lane == 0) red[w] = c2;
+    } else {
+        for (int f = f0; f < f1; ++f) {
+            const int t2 = state[tr.frame_base + f] == 2 ? 1 : 0;
             Clamp3 g;
             if (alpha_init && f == 0) { g.d = 0; g.lo = g.hi = t2 * Xe; }
             else { g.d = t2 ? 1 : -1; g.lo = 0; g.hi = Xe; }
             am = clamp3_then(am, g);
         }
+        const int* src = seg.segclamp + (size_t)track * nseg * 3;
+        int* pr = reinterpret_cast<int*>(prior);
+        for (int q = i; q < c * 3; q += NT) pr[q] = src[q];
     }
-#pragma unroll
-    for (int o = 16; o; o >>= 1) c2 += __shfl_xor_sync(0xffffffffu, c2, o);
-    if (lane == 0) red[w] = c2;
     if (!count_only) { a_d[i] = am.d; a_lo[i] = am.lo; a_hi[i] = am.hi; }
     __syncthreads();
-    if (i == 0) {
+    if (PASS != GATE_ROWS && i == 0) {
         int tot = 0;
         for (int ww = 0; ww < NW; ++ww) tot += red[ww];
-        c2_count[blockIdx.x] = tot;
+        if (PASS == GATE_FUSED) c2_count[track] = tot;
+        else if (tot) atomicAdd(c2_count + track, tot);
     }
     if (count_only) return;
     // 4. chain the clamp maps
@@ -332,8 +382,21 @@ __global__ void gate_kernel(const TrackDev* __restrict__ tracks, const T* __rest
         aw[w] = m.d; aw[NW + w] = m.lo; aw[2 * NW + w] = m.hi;
     }
     __syncthreads();
+    if (PASS == GATE_STATES) {                   // segment clamp map; rows come from the GATE_ROWS pass
+        if (i == 0) {
+            Clamp3 m = {0, 0, Xe};
+            for (int ww = 0; ww < NW; ++ww) m = clamp3_then(m, Clamp3{aw[ww], aw[NW + ww], aw[2 * NW + ww]});
+            int* dst = seg.segclamp + ((size_t)track * nseg + c) * 3;
+            dst[0] = m.d; dst[1] = m.lo; dst[2] = m.hi;
+        }
+        return;
+    }
     if (i == 0) {
         int k = 0;
+        if (PASS == GATE_ROWS) {
+            const int* pr = reinterpret_cast<const int*>(prior);
+            for (int q = 0; q < c; ++q) k = clamp3_apply(Clamp3{pr[3 * q], pr[3 * q + 1], pr[3 * q + 2]}, k);
+        }
         for (int ww = 0; ww < NW; ++ww) { awstart[ww] = k; k = clamp3_apply(Clamp3{aw[ww], aw[NW + ww], aw[2 * NW + ww]}, k); }
     }
     __syncthreads();
@@ -889,6 +952,7 @@ struct tmt_engine {
     DevBuf<float> win;        // [4096]
     DevBuf<float> swin;       // [2][4096]  synthesis window x interior normalisation (eps | clamp)
     int stft_store = 0;       // 0: thread-private constants + carry in tensor memory, 1: in shared memory
+    int gate_nseg = 0;        // > 0: force this many gate-scan segments per track (TMT_GATE_NSEG, tests)
     DevBuf<float2> tw_bases;  // [256][4]
     DevBuf<float2> tw_a;      // [256][16]
     DevBuf<float> gperm;      // [n_rows][4096]
@@ -926,6 +990,9 @@ struct tmt_plan {
     DevBuf<uint8_t> state;
     DevBuf<uint16_t> rows;
     DevBuf<int> c2;
+    DevBuf<uint8_t> segmap;     // gate scan scratch: [tracks][segments][states]
+    DevBuf<int> segclamp;       // [tracks][segments][3]
+    int seg_cap = 0;            // segments available in the scratch (all tracks together)
     DevBuf<float> chunk_peaks, in_peaks, in_scale;
     DevBuf<double> von, voff;
     int64_t launches = 0;
@@ -1001,16 +1068,41 @@ int build_tracks_dev(tmt_plan* p) {
 
 template <typename T, int AUTO>
 int launch_gate(tmt_plan* p, const T* vals, int param, int S, int X, int alpha_init, int count_only, cudaStream_t st) {
-    int NT = 1024;
-    auto need = [&](int nt) { return (size_t)((S * nt + S * (nt / 32) + nt + nt / 32 + 15) & ~15) + sizeof(int) * (size_t)(4 * nt + 5 * (nt / 32)); };
+    // long tracks: cut into segments of >= 8 frames per thread so the scan spreads over the whole GPU
+    int nseg = 1;
+    if (p->max_frames > 16384) nseg = std::min(2 * p->e->n_sms, std::max(1, p->max_frames / 2048));
+    if (p->e->gate_nseg > 0) nseg = p->e->gate_nseg;
+    nseg = std::max(1, std::min(nseg, p->seg_cap / std::max(p->n_tracks, 1)));
+    int NT = (nseg > 1) ? 256 : 1024;
+    auto need = [&](int nt) {
+        return (size_t)((S * nt + S * (nt / 32) + nt + nt / 32 + 15) & ~15) + sizeof(int) * (size_t)(4 * nt + 5 * (nt / 32) + 2) +
+               (size_t)nseg * std::max(S, 12);
+    };
     while (NT > 32 && need(NT) > 96 * 1024) NT >>= 1;
     const size_t smem = need(NT);
     if (smem > 200 * 1024) return fail(TMT_ERR_UNSUPPORTED, "gate automaton with %d states needs %zu B of shared memory", S, smem);
-    CUDA_TRY(cudaFuncSetAttribute(gate_kernel<T, AUTO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 48 * 1024)));
-    gate_kernel<T, AUTO><<<p->n_tracks, NT, smem, st>>>(p->tracks.p, vals, p->von.p, p->voff.p, param, S, X, alpha_init,
-                                                         count_only, p->state.p, p->rows.p, p->c2.p);
-    p->launches++;
-    CUDA_TRY(cudaGetLastError());
+    GateSeg seg{nseg, p->segmap.p, p->segclamp.p};
+    const dim3 grid(nseg, p->n_tracks);
+    const int attr = (int)std::max<size_t>(smem, 48 * 1024);
+#define TMT_GATE_LAUNCH(PASS)                                                                                          \
+    do {                                                                                                               \
+        CUDA_TRY(cudaFuncSetAttribute(gate_kernel<T, AUTO, PASS>, cudaFuncAttributeMaxDynamicSharedMemorySize, attr)); \
+        gate_kernel<T, AUTO, PASS><<<grid, NT, smem, st>>>(p->tracks.p, vals, p->von.p, p->voff.p, param, S, X, alpha_init, \
+                                                           count_only, p->state.p, p->rows.p, p->c2.p, seg);          \
+        p->launches++;                                                                                                 \
+        CUDA_TRY(cudaGetLastError());                                                                                  \
+    } while (0)
+    if (nseg == 1) {
+        TMT_GATE_LAUNCH(GATE_FUSED);
+    } else {
+        if ((size_t)nseg * S > p->segmap.n / std::max(p->n_tracks, 1))
+            return fail(TMT_ERR_UNSUPPORTED, "gate scan scratch too small for %d segments x %d states", nseg, S);
+        CUDA_TRY(cudaMemsetAsync(p->c2.p, 0, sizeof(int) * p->n_tracks, st));
+        TMT_GATE_LAUNCH(GATE_MAP);
+        TMT_GATE_LAUNCH(GATE_STATES);
+        if (!count_only) TMT_GATE_LAUNCH(GATE_ROWS);
+    }
+#undef TMT_GATE_LAUNCH
     return TMT_OK;
 }
 
@@ -1077,6 +1169,7 @@ int tmt_engine_create(tmt_engine** out, int device, int n_fft, int hop) {
     if (ce == cudaSuccess) ce = cudaFuncSetAttribute(stft_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStftSmemSmem);
     if (ce != cudaSuccess) { delete e; return fail(TMT_ERR_CUDA, "cudaFuncSetAttribute(stft_kernel): %s", cudaGetErrorString(ce)); }
     if (const char* sv = getenv("TMT_STFT_STORE")) e->stft_store = (strcmp(sv, "smem") == 0) ? 1 : 0;
+    if (const char* sv = getenv("TMT_GATE_NSEG")) e->gate_nseg = atoi(sv);
     ce = cudaFuncSetAttribute(edge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kEdgeSmemBytes);
     if (ce != cudaSuccess) { delete e; return fail(TMT_ERR_CUDA, "cudaFuncSetAttribute(edge_kernel): %s", cudaGetErrorString(ce)); }
     *out = e;
@@ -1213,6 +1306,7 @@ int tmt_plan_create(tmt_engine* e, tmt_plan** out, int framing, int n_tracks, co
         p->ht.push_back(std::move(h));
     }
     p->total_frames = (int)frames;
+    p->seg_cap = kGateSegCap;
     p->total_chunks = (int)chunks.size();
     p->n_units = (int)units.size();
     p->n_edges = (int)edges.size();
@@ -1222,6 +1316,7 @@ int tmt_plan_create(tmt_engine* e, tmt_plan** out, int framing, int n_tracks, co
               p->edge_in_scale.alloc(nt + 1) == cudaSuccess && p->edge_out_scale.alloc(nt + 1) == cudaSuccess && p->hsum.alloc(nf + nt + 1) == cudaSuccess &&
               p->msq.alloc(nf + 1) == cudaSuccess && p->gate_f64.alloc(nf + 1) == cudaSuccess && p->state.alloc(nf + 1) == cudaSuccess &&
               p->rows.alloc(nf + 1) == cudaSuccess && p->c2.alloc(nt + 1) == cudaSuccess &&
+              p->segmap.alloc((size_t)kGateSegCap * 256) == cudaSuccess && p->segclamp.alloc((size_t)kGateSegCap * 3) == cudaSuccess &&
               p->chunk_peaks.alloc(chunks.size() + 1) == cudaSuccess && p->in_peaks.alloc(nt + 1) == cudaSuccess &&
               p->in_scale.alloc(nt + 1) == cudaSuccess && p->von.alloc(nt + 1) == cudaSuccess && p->voff.alloc(nt + 1) == cudaSuccess;
     if (!ok) { delete p; return fail(TMT_ERR_NOMEM, "device allocation failed: %s", cudaGetErrorString(cudaGetLastError())); }

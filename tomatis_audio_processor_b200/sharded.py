@@ -93,18 +93,25 @@ class Comm:
     def _t(self, a: np.ndarray):
         return self.torch.from_numpy(np.ascontiguousarray(a)).to(self.device)
 
-    def allreduce(self, a: np.ndarray, op: str) -> np.ndarray:
-        t = self._t(a)
+    def allreduce(self, a, op: str):
+        """In-place all-reduce of a tensor already on the communicator's device (no host round trip), or of a NumPy
+        array (copied to the device and back)."""
+        is_np = isinstance(a, np.ndarray)
+        t = self._t(a) if is_np else a
         self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM if op == "sum" else self.dist.ReduceOp.MAX, group=self.group)
         self.bytes_sent += t.numel() * t.element_size()
-        return t.cpu().numpy()
+        return t.cpu().numpy() if is_np else t
 
-    def exchange_halos(self, own, shard: Shard, shards: List[Shard]):
+    def exchange_halos(self, own, shard: Shard, shards: List[Shard], window=None):
         """own: tensor [own_hi-own_lo, 2] on self.device.  Returns the rank's input window [in_hi-in_lo, 2]:
-        own samples plus the halos fetched from whichever ranks own them (normally the two neighbours)."""
+        own samples plus the halos fetched from whichever ranks own them (normally the two neighbours).
+        window: existing window buffer of which `own` is already the middle slice (only the halos are moved)."""
         torch, dist = self.torch, self.dist
-        win = torch.zeros((shard.in_hi - shard.in_lo, 2), dtype=own.dtype, device=own.device)
-        win[shard.own_lo - shard.in_lo: shard.own_hi - shard.in_lo] = own
+        if window is None:
+            win = torch.zeros((shard.in_hi - shard.in_lo, 2), dtype=own.dtype, device=own.device)
+            win[shard.own_lo - shard.in_lo: shard.own_hi - shard.in_lo] = own
+        else:
+            win = window
         ops, recvs = [], []
         for other in shards:
             if other.rank == shard.rank:
@@ -174,12 +181,20 @@ class CudaShardBackend:
         self.plan.input_peaks()
         return self.plan.read(self.L.ARR_INPUT_PEAK)[0]
 
-    def local_meansq(self, use_f64=False, in_scale=None) -> np.ndarray:
+    def local_meansq(self, use_f64=False, in_scale=None):
+        """Mean squares of the frames touching this shard, as a device tensor [n_frames] (zeros elsewhere)."""
+        import torch
         self.plan.levels(use_f64=use_f64, in_scale=None if in_scale is None else np.array([in_scale], np.float32))
-        return self.plan.read(self.L.ARR_MEANSQ_F64 if use_f64 else self.L.ARR_MEANSQ_F32)
+        t = torch.empty(self.shard.n_frames, dtype=torch.float64 if use_f64 else torch.float32, device=self.window.device)
+        if t.numel():
+            self.plan.read_device(self.L.ARR_MEANSQ_F64 if use_f64 else self.L.ARR_MEANSQ_F32, t.data_ptr(), t.numel())
+        return t
 
-    def set_meansq(self, m: np.ndarray):
-        self.plan.write(self.L.ARR_MEANSQ_F64 if m.dtype == np.float64 else self.L.ARR_MEANSQ_F32, m)
+    def set_meansq(self, m):
+        import torch
+        if m.numel():
+            self.plan.write_device(self.L.ARR_MEANSQ_F64 if m.dtype == torch.float64 else self.L.ARR_MEANSQ_F32,
+                                   m.data_ptr(), m.numel())
 
     def set_gate_input(self, lv: np.ndarray):
         self.plan.write(self.L.ARR_GATE_F64, lv)
@@ -202,11 +217,16 @@ class CudaShardBackend:
         self.plan.edge_frames(post_gain, None if in_scale is None else np.array([in_scale], np.float32),
                               None if out_scale is None else np.array([out_scale], np.float32), pipeline_f64)
 
-    def chunk_peaks(self) -> np.ndarray:
-        return self.plan.read(self.L.ARR_CHUNK_PEAK)
+    def chunk_peaks(self):
+        import torch
+        t = torch.empty(self.plan.total_chunks, dtype=torch.float32, device=self.window.device)
+        if t.numel():
+            self.plan.read_device(self.L.ARR_CHUNK_PEAK, t.data_ptr(), t.numel())
+        return t
 
-    def set_chunk_peaks(self, p: np.ndarray):
-        self.plan.write(self.L.ARR_CHUNK_PEAK, p)
+    def set_chunk_peaks(self, p):
+        if p.numel():
+            self.plan.write_device(self.L.ARR_CHUNK_PEAK, p.data_ptr(), p.numel())
 
     def limiter(self):
         self.plan.limiter()
@@ -224,11 +244,16 @@ def _cuda_backend_factory(device_index, unit_blocks=0):
     return make
 
 
-def _owned(shard: Shard, arr: np.ndarray) -> np.ndarray:
-    """Zero everything but the frames this rank owns (so that a SUM all-reduce assembles the array exactly)."""
-    out = np.zeros_like(arr)
+def _owned(shard: Shard, arr):
+    """Zero everything but the frames this rank owns (so that a SUM all-reduce assembles the array exactly).
+    Works on NumPy arrays and torch tensors alike."""
+    out = np.zeros_like(arr) if isinstance(arr, np.ndarray) else arr.new_zeros(arr.shape)
     out[shard.frame_lo:shard.frame_hi] = arr[shard.frame_lo:shard.frame_hi]
     return out
+
+
+def _host(a) -> np.ndarray:
+    return a if isinstance(a, np.ndarray) else a.cpu().numpy()
 
 
 # ------------------------------------------------------------------------------------------------ drivers
@@ -248,7 +273,7 @@ def run_streaming_sharded(mode: str, own, sr: int, total: int, comm: Comm, make_
     window = comm.exchange_halos(own, me, shards)                                  # 1. halo hand-off
     be = (make_backend or _cuda_backend_factory(device_index, unit_blocks))(me, window, sp.rows, sp.rows_key)
     try:
-        msq = comm.allreduce(_owned(me, be.local_meansq()), "sum")                 # 2. levels -> every rank
+        msq = comm.allreduce(_owned(me, be.local_meansq()), "sum")                 # 2. levels -> every rank (on the device)
         be.set_meansq(msq)
         be.gate(L.GATE_UPDELAY, L.ARR_MEANSQ_F32, sp.m_on, sp.m_off, sp.run_frames, sp.xfade_frames)
         be.stft(sp.post_gain)
@@ -258,6 +283,7 @@ def run_streaming_sharded(mode: str, own, sr: int, total: int, comm: Comm, make_
         be.limiter()
         states, rows = be.states_rows()
         full = comm.gather_output(be.out, shards, gather_to) if gather_to is not None else None   # 4.
+        msq, peaks = _host(msq), _host(peaks)
         n_fft, hop = params.get("n_fft", tb.N_FFT), params.get("hop", tb.HOP)
         starts = -(n_fft // 2) + hop * np.arange(me.n_frames, dtype=np.int64)
         return dict(out=be.out, full=full, shard=me, shards=shards, meansq=msq, levels=tb.levels_from_meansq(msq),
@@ -287,7 +313,7 @@ def run_adaptive_sharded(own, sr: int, total: int, comm: Comm, make_backend=None
         in_peak = np.float32(comm.allreduce(np.array([be.input_peak()], np.float32), "max")[0])
         atten_db, atten_lin, use_f64 = tb.adaptive_attenuation(in_peak, c1_low, c2_high, headroom_margin)
         scale = np.float32(atten_lin)
-        msq = comm.allreduce(_owned(me, be.local_meansq(use_f64, scale)), "sum")
+        msq = _host(comm.allreduce(_owned(me, be.local_meansq(use_f64, scale)), "sum"))
         levels = tb.levels_from_meansq(msq)
         be.set_gate_input(levels)
         # threshold bisection, identical on every rank (src/process_tomatis_adaptive.py:124-154)
@@ -324,6 +350,7 @@ def run_adaptive_sharded(own, sr: int, total: int, comm: Comm, make_backend=None
         be.limiter()
         states, rows = be.states_rows()
         full = comm.gather_output(be.out, shards, gather_to) if gather_to is not None else None
+        peaks = _host(peaks)
         return dict(out=be.out, full=full, shard=me, shards=shards, meansq=msq, levels=levels, states=states, rows=rows,
                     optimal_T=float(best_T), trace=trace, atten_db=float(atten_db), input_peak=float(in_peak),
                     pipeline_dtype="float64" if use_f64 else "float32", output_peak=float(peaks[0]) if len(peaks) else 0.0,
@@ -331,3 +358,66 @@ def run_adaptive_sharded(own, sr: int, total: int, comm: Comm, make_backend=None
                     launches=be.launches(), comm_bytes=comm.bytes_sent)
     finally:
         be.close()
+
+
+class StreamingShardSession:
+    """Persistent per-rank state for repeated passes over one sharded file (what bench.py times): the plan, the input
+    window and the output shard are created once; `step()` is one pass of the whole path -- halo hand-off, levels,
+    level all-reduce, gate scan, STFT/OLA, edge frames, peak all-reduce, limiter -- with no host synchronisation."""
+
+    def __init__(self, mode: str, own, sr: int, total: int, comm: Comm, device_index: int = 0, unit_blocks: int = 0, **params):
+        from . import _lib as L
+        from .engine import streaming_params
+        self.L, self.comm, self.own = L, comm, own
+        self.shards = plan_shards(total, comm.world, STREAMING, params.get("n_fft", tb.N_FFT), params.get("hop", tb.HOP))
+        self.me = self.shards[comm.rank]
+        assert own.shape[0] == self.me.own_hi - self.me.own_lo
+        self.sp = streaming_params(mode, sr, **params)
+        window = comm.exchange_halos(own, self.me, self.shards)
+        self.be = CudaShardBackend(self.me, window, device_index, self.sp.rows, self.sp.rows_key, unit_blocks)
+        # from here on the rank's samples live inside the window buffer: refresh them through this view
+        self.own = window[self.me.own_lo - self.me.in_lo: self.me.own_hi - self.me.in_lo]
+
+    def step(self, stft_events=None, marks=None):
+        """marks: optional list that receives (label, torch.cuda.Event) after each phase (bench breakdown)."""
+        comm, be, me, sp, L = self.comm, self.be, self.me, self.sp, self.L
+
+        def mark(label):
+            if marks is not None:
+                import torch
+                e = torch.cuda.Event(enable_timing=True)
+                e.record()
+                marks.append((label, e))
+        mark("start")
+        comm.exchange_halos(self.own, me, self.shards, window=be.window)   # 1. halo hand-off (fresh data every pass)
+        mark("halo")
+        local = be.local_meansq()
+        mark("levels")
+        msq = comm.allreduce(_owned(me, local), "sum")                 # 2.
+        be.set_meansq(msq)
+        mark("allreduce_levels")
+        be.gate(L.GATE_UPDELAY, L.ARR_MEANSQ_F32, sp.m_on, sp.m_off, sp.run_frames, sp.xfade_frames)
+        mark("gate")
+        if stft_events:
+            stft_events[0].record()
+        be.stft(sp.post_gain)
+        if stft_events:
+            stft_events[1].record()
+        mark("stft")
+        be.edge_frames(sp.post_gain)
+        mark("edge")
+        peaks = comm.allreduce(be.chunk_peaks(), "max")                # 3.
+        be.set_chunk_peaks(peaks)
+        mark("allreduce_peaks")
+        be.limiter()
+        mark("limiter")
+
+    def step_timed(self, events):
+        self.step(events)
+
+    @property
+    def out(self):
+        return self.be.out
+
+    def close(self):
+        self.be.close()

@@ -153,3 +153,20 @@ def device_batch(n_tracks: int, n_samples: int, sr: int, seed0: int, device, out
         out[i].copy_(x.t().clamp_(-1.0, 1.0))
         del w, y, x
     return out
+
+
+def device_long_file_range(lo: int, hi: int, sr: int, seed0: int, device, segment_seconds: float = 300.0):
+    """bench.py only: samples [lo, hi) of one long synthetic file made of consecutive 5-minute segments of the
+    C1/C4 recipe (segment k uses seed seed0 + k, so every rank synthesises exactly its own range of the same file)."""
+    import torch
+
+    seg = int(round(segment_seconds * sr))
+    out = torch.empty((hi - lo, 2), dtype=torch.float32, device=device)
+    k = lo // seg
+    while k * seg < hi:
+        a, b = max(lo, k * seg), min(hi, (k + 1) * seg)
+        x = device_batch(1, seg, sr, seed0 + k, device)[0]
+        out[a - lo:b - lo] = x[a - k * seg:b - k * seg]
+        del x
+        k += 1
+    return out
