@@ -7,7 +7,7 @@ Workload (BASELINE.json configs[3]): standard mode, --gate_ui 50, a batch of 5-m
 synthetic tracks (pink noise + on/off envelope + tone bursts), sharded by whole track across ranks:
 128 tracks per GPU, so N = 8 is the full 1024-track batch (1024 tracks of fp32 in + out do not fit one
 GPU's HBM; the per-GPU shard does).  A "step" is one pass of the whole hot path over the rank's tracks:
-levels -> gate scan -> fused STFT/OLA -> fp64 edge frames -> limiter.  Weak scaling, no data-path
+levels -> gate scan -> fp64 edge frames -> fused STFT/OLA with in-kernel per-chunk limiter.  Weak scaling, no data-path
 collective; the only cross-rank traffic is the timing reduction.
 
 One JSON line on stdout (rank 0).  `value` is device-resident throughput, `e2e` the same metric through
@@ -231,11 +231,10 @@ def run_gpu_arm(args):
     t0 = time.time()
     e0.record()
     for k in range(args.steps):
-        db.levels(); db.gate()
+        db.levels(); db.gate(); db.edges()
         ev[k][0].record()
-        db.stft()
+        db.stft()                      # fused STFT/OLA + per-chunk limiter
         ev[k][1].record()
-        db.edges(); db.limiter()
     e1.record()
     barrier()
     t1 = time.time()
@@ -300,7 +299,7 @@ def run_gpu_arm(args):
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "config": workload_config(T, world), "clocks": clocks,
             "e2e": e2e, "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "kernel": "stft_kernel (fused gather+window+FFT+gain+IFFT+window+OLA+peak)",
+            "roofline": {"bound": "hbm", "kernel": "stft_kernel (fused gather+window+FFT+gain+IFFT+window+OLA+peak+chunk limiter)",
                          "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs,
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": ALG_BYTES_PER_SF * sf_rank,
                          "kernel_ms": stft_ms, "kernel_share_of_step": stft_ms * args.steps / ms_total,

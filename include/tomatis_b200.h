@@ -140,6 +140,16 @@ int tmt_plan_gate(tmt_plan* p, int automaton, int gate_input, const double* on, 
  * skip_edges != 0: leave the single-frame edge blocks to tmt_plan_edge_frames. */
 int tmt_plan_stft(tmt_plan* p, float post_gain, int skip_edges, void* stream);
 
+/* Fused K4 + limiter.  Same as tmt_plan_stft(..., skip_edges = 1, ...) followed by tmt_plan_limiter, in one kernel: the
+ * CTA that completes the last work unit of a limiter chunk rescales that chunk while the rest of the GPU keeps computing
+ * (write_clamped after each flush, src/process_tomatis.py:419-426,331-357).  Order of one pass:
+ * tmt_plan_clear_peaks -> tmt_plan_edge_frames -> tmt_plan_stft_limited (the edge blocks and their peaks must already be in
+ * place when a chunk is finished).  Chunks this plan produces only partly (time shards) and whole-file chunks (adaptive) are
+ * left to a trailing limiter_kernel launch, so call it only when their peaks are final on this rank. */
+int tmt_plan_stft_limited(tmt_plan* p, float post_gain, float limit, void* stream);
+/* Zero TMT_ARR_CHUNK_PEAK and the fused limiter's counters (tmt_plan_stft does this itself). */
+int tmt_plan_clear_peaks(tmt_plan* p, void* stream);
+
 /* fp64 recomputation of the two ill-conditioned edge blocks (first hop of WHOLEFILE framing, tail block
  * of both framings: a single frame divided by w^2 -> 0).  Call after tmt_plan_stft(...,
  * skip_edges = 1, ...) and before tmt_plan_limiter.  in_scale / out_scale (host, per track, may be NULL):
@@ -153,7 +163,7 @@ int tmt_plan_edge_frames(tmt_plan* p, float post_gain, const float* in_scale, co
  * (write_clamped, src/process_tomatis.py:352-355; global variant _adaptive.py:341-345). */
 int tmt_plan_limiter(tmt_plan* p, float limit, void* stream);
 
-/* Convenience: levels (f32) -> gate -> stft -> edge frames -> limiter on one stream, standard/xfade parameters. */
+/* Convenience: levels (f32) -> gate -> edge frames -> stft with fused limiter on one stream, standard/xfade parameters. */
 int tmt_plan_run_streaming(tmt_plan* p, double m_on, double m_off, int run_frames, int xfade_frames,
                            float post_gain, float limit, void* stream);
 

@@ -52,6 +52,8 @@ SIGNATURES = {
     "tmt_plan_levels": (C.c_int, [_P, C.c_int, _P, _P]),
     "tmt_plan_gate": (C.c_int, [_P, C.c_int, C.c_int, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "tmt_plan_stft": (C.c_int, [_P, C.c_float, C.c_int, _P]),
+    "tmt_plan_stft_limited": (C.c_int, [_P, C.c_float, C.c_float, _P]),
+    "tmt_plan_clear_peaks": (C.c_int, [_P, _P]),
     "tmt_plan_edge_frames": (C.c_int, [_P, C.c_float, _P, _P, C.c_int, _P]),
     "tmt_plan_limiter": (C.c_int, [_P, C.c_float, _P]),
     "tmt_plan_run_streaming": (C.c_int, [_P, C.c_double, C.c_double, C.c_int, C.c_int, C.c_float, C.c_float, _P]),

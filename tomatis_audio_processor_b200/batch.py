@@ -37,17 +37,16 @@ class DeviceBatch:
         sp = self.sp
         self.plan.gate(L.GATE_UPDELAY, L.ARR_MEANSQ_F32, sp.m_on, sp.m_off, sp.run_frames, sp.xfade_frames)
 
-    def stft(self):
-        self.plan.stft(self.sp.post_gain, skip_edges=True)
-
     def edges(self):
+        self.plan.clear_peaks()
         self.plan.edge_frames(self.sp.post_gain)
 
-    def limiter(self):
-        self.plan.limiter()
+    def stft(self):
+        """Fused STFT/OLA + per-chunk limiter (edge blocks must already be in place: call edges() first)."""
+        self.plan.stft_limited(self.sp.post_gain)
 
     def step(self):
-        self.levels(); self.gate(); self.stft(); self.edges(); self.limiter()
+        self.levels(); self.gate(); self.edges(); self.stft()
 
     def close(self):
         self.plan.close()

@@ -72,7 +72,8 @@ struct TrackDev {
 };
 struct EdgeDev { int track, frame, half, chunk; };   // fp64 edge job: half 0 -> block `frame`, half 1 -> block frame+1
 struct UnitDev { int track, b0, b1, chunk; };        // STFT work unit: output blocks [b0,b1) of a track
-struct ChunkDev { int track; long long s0, s1; };    // limiter chunk: file positions [s0,s1)
+struct ChunkDev { int track; long long s0, s1; int n_units; int fusable; };   // limiter chunk: file positions [s0,s1); fusable: the plan
+                                                                            // produces the whole chunk, so the STFT kernel may limit it itself
 
 // ------------------------------------------------------------------------------------------------
 // streaming loads/stores: audio is touched once per pass, keep it out of L1
@@ -450,6 +451,10 @@ struct StftParams {
     const float2* tw_a;     // [256][16]: stage-A twiddles (W4096^t)^k, k = 0..15, exact (parked in tensor memory)
     float* chunk_peaks;
     float post_gain;
+    const ChunkDev* chunks; // fused limiter (limit > 0): the CTA that finishes a chunk's last work unit rescales the chunk
+    int* chunk_done;
+    int* unit_counter;      // dynamic work distribution (zeroed before every launch)
+    float limit;
 };
 
 constexpr int kTmemWarpCols = 112;                   // analysis window 16 | synthesis window 16 | carry 16 | raw input halves 2 x 16 | stage-A twiddles 32
@@ -623,7 +628,14 @@ __global__ void __launch_bounds__(kThreads, 2) stft_kernel(const StftParams prm)
     const TwBase wa = {make_float2(ba.x, ba.y), make_float2(ba.z, ba.w)};
     const TwBase wb = {make_float2(bb.x, bb.y), make_float2(bb.z, bb.w)};
 
-    for (int u = blockIdx.x; u < prm.n_units; u += gridDim.x) {
+    // Work units are claimed from a global counter: unit lengths are deliberately uneven (see tmt_plan_create), so the
+    // CTAs drift out of lock step and the chunk rescales of the fused limiter do not hit HBM all at once.
+    int* next_unit = reinterpret_cast<int*>(tail + 56);
+    for (;;) {
+        if (t == 0) *next_unit = atomicAdd(prm.unit_counter, 1);
+        __syncthreads();
+        const int u = *next_unit;
+        if (u >= prm.n_units) break;
         const UnitDev un = prm.units[u];
         // per-unit scalars, all relative to the unit's first frame so they fit 32 bits
         const TrackDev* trp = prm.tracks + un.track;
@@ -778,6 +790,56 @@ __global__ void __launch_bounds__(kThreads, 2) stft_kernel(const StftParams prm)
             for (int q = 1; q < 8; ++q) m = fmaxf(m, red[q]);
             if (m > 0.f) atomicMax(reinterpret_cast<int*>(prm.chunk_peaks + un.chunk), __float_as_int(m));
         }
+        if (prm.limit > 0.f) {
+            // Fused limiter (src/process_tomatis.py:352-355).  Every unit publishes its samples and its peak, then bumps
+            // the chunk's counter; whoever bumps it last owns the finished chunk and rescales it if its peak exceeds the
+            // limit.  Nobody waits for anybody, and the pass runs under the butterflies of the other resident CTAs
+            // (the kernel is FP32-bound, HBM is 3/4 idle).
+            const ChunkDev ch = prm.chunks[un.chunk];
+            if (ch.fusable) {
+                __threadfence();
+                __syncthreads();
+                if (t == 0) {
+                    const int prev = atomicAdd(prm.chunk_done + un.chunk, 1);
+                    red[8] = (prev == ch.n_units - 1) ? 1.f : 0.f;
+                }
+                __syncthreads();
+                if (red[8] != 0.f) {
+                    __threadfence();
+                    const float pk = __int_as_float(atomicMax(reinterpret_cast<int*>(prm.chunk_peaks + un.chunk), 0));
+                    if (pk > prm.limit) {
+                        const float sc = __fdiv_rn(prm.limit, pk);
+                        const long long s0 = max(ch.s0, trp->out_lo), s1 = min(ch.s1, trp->out_hi);
+                        float2* base = trp->out + (s0 - trp->out_origin);
+                        const long long n = s1 - s0;
+                        long long q = t;
+                        if ((reinterpret_cast<uintptr_t>(base) & 15u) == 0) {
+                            // a single CTA is latency-bound: keep 64 KB in flight (16 x 16 B per thread)
+                            float4* b4 = reinterpret_cast<float4*>(base);
+                            const long long n4 = n >> 1;
+                            long long r = t;
+                            for (; r + 15 * kThreads < n4; r += 16 * kThreads) {
+                                float4 x[16];
+#pragma unroll
+                                for (int j = 0; j < 16; ++j)
+                                    asm volatile("ld.global.cg.v4.f32 {%0,%1,%2,%3}, [%4];"
+                                                 : "=f"(x[j].x), "=f"(x[j].y), "=f"(x[j].z), "=f"(x[j].w) : "l"(b4 + r + j * kThreads));
+#pragma unroll
+                                for (int j = 0; j < 16; ++j)
+                                    asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(b4 + r + j * kThreads),
+                                                 "f"(x[j].x * sc), "f"(x[j].y * sc), "f"(x[j].z * sc), "f"(x[j].w * sc) : "memory");
+                            }
+                            q = 2 * (r - t) + t;          // samples [0, 2*(r-t)) are done; continue with the scalar tail
+                        }
+                        for (; q < n; q += kThreads) {
+                            float2 x;
+                            asm volatile("ld.global.cg.v2.f32 {%0,%1}, [%2];" : "=f"(x.x), "=f"(x.y) : "l"(base + q));
+                            st_stream(base + q, make_float2(x.x * sc, x.y * sc));
+                        }
+                    }
+                }
+            }
+        }
         __syncthreads();
     }
     park.fini(tail, t);
@@ -913,11 +975,12 @@ __global__ void __launch_bounds__(256) edge_kernel(const EdgeParams prm) {
 // limiter (src/process_tomatis.py:352-355): if peak > limit: chunk *= limit / peak
 __global__ void __launch_bounds__(256)
 limiter_kernel(const TrackDev* __restrict__ tracks, const ChunkDev* __restrict__ chunks,
-               const float* __restrict__ peaks, float limit) {
+               const float* __restrict__ peaks, float limit, int skip_fusable) {
     const float peak = peaks[blockIdx.y];
     if (!(peak > limit)) return;
     const float scale = __fdiv_rn(limit, peak);
     const ChunkDev ch = chunks[blockIdx.y];
+    if (skip_fusable && ch.fusable) return;            // already limited inside stft_kernel
     const TrackDev tr = tracks[ch.track];
     const long long s0 = max(ch.s0, tr.out_lo), s1 = min(ch.s1, tr.out_hi);
     float2* dst = tr.out + (s0 - tr.out_origin);
@@ -981,6 +1044,9 @@ struct tmt_plan {
     DevBuf<TrackDev> tracks;
     DevBuf<UnitDev> units;
     DevBuf<ChunkDev> chunks;
+    DevBuf<int> chunk_done;     // fused limiter: finished work units per chunk
+    DevBuf<int> unit_counter;   // stft_kernel work queue head
+    int n_unfusable = 0;        // chunks the fused limiter must leave to limiter_kernel
     DevBuf<EdgeDev> edges;
     int n_edges = 0;
     DevBuf<float> edge_in_scale, edge_out_scale;
@@ -1273,7 +1339,7 @@ int tmt_plan_create(tmt_engine* e, tmt_plan** out, int framing, int n_tracks, co
             s1 = std::min<long long>(h.d.total, s1);
             if (s1 < s0) s1 = s0;
             h.chunk_ranges.push_back({s0, s1});
-            chunks.push_back(ChunkDev{i, s0, s1});
+            chunks.push_back(ChunkDev{i, s0, s1, 0, 0});
             p->max_chunk_len = std::max(p->max_chunk_len, s1 - s0);
             // work units: slices of this chunk restricted to [blo,bhi), skipping blocks with no file samples
             int u0 = std::max(cb[c].first, blo), u1 = std::min(cb[c].second, bhi);
@@ -1281,11 +1347,21 @@ int tmt_plan_create(tmt_engine* e, tmt_plan** out, int framing, int n_tracks, co
             while (u1 > u0 && h.first_start + (long long)(u1 - 1) * kHop >= h.d.total) --u1;
             if (u1 <= u0) continue;
             const int n_sub = ceil_div(u1 - u0, unit_blocks);
-            for (int s = 0; s < n_sub; ++s) {
-                const int a = u0 + (int)((long long)(u1 - u0) * s / n_sub);
-                const int b = u0 + (int)((long long)(u1 - u0) * (s + 1) / n_sub);
-                if (b > a) units.push_back(UnitDev{i, a, b, h.chunk_base + (int)c});
+            // interior cut points are jittered by up to +-30 % of a unit (deterministic hash of the chunk index): same
+            // number of units and of redundant warm-up frames, but uneven lengths, so the persistent CTAs de-synchronise
+            std::vector<int> cut(n_sub + 1);
+            for (int s = 0; s <= n_sub; ++s) cut[s] = u0 + (int)((long long)(u1 - u0) * s / n_sub);
+            for (int s = 1; s < n_sub; ++s) {
+                const uint32_t hsh = (uint32_t)(chunks.size() * 2654435761u + (uint32_t)s * 40503u) * 2246822519u;
+                const int span = std::min(cut[s] - cut[s - 1], cut[s + 1] - cut[s]);
+                cut[s] += (int)(((int)((hsh >> 12) & 1023) - 512) * (long long)(span * 3 / 10) / 512);
+                cut[s] = std::max(cut[s - 1] + 1, std::min(cut[s], u1 - (n_sub - s)));
             }
+            for (int s = 0; s < n_sub; ++s)
+                if (cut[s + 1] > cut[s]) { units.push_back(UnitDev{i, cut[s], cut[s + 1], h.chunk_base + (int)c}); chunks.back().n_units++; }
+            // the in-kernel limiter needs the whole chunk (every block that holds file samples) in this plan, and
+            // per-chunk limiting at all (streaming framing); a whole-file chunk is far too large for one CTA
+            chunks.back().fusable = (framing == TMT_FRAMING_STREAMING && s1 > s0 && cb[c].first >= blo && cb[c].second <= bhi) ? 1 : 0;
         }
         // single-frame (ill-conditioned) edge blocks, recomputed in fp64 by edge_kernel
         auto chunk_of = [&](int blk) { for (size_t c = 0; c < cb.size(); ++c) if (blk >= cb[c].first && blk < cb[c].second) return h.chunk_base + (int)c; return h.chunk_base; };
@@ -1308,11 +1384,12 @@ int tmt_plan_create(tmt_engine* e, tmt_plan** out, int framing, int n_tracks, co
     p->total_frames = (int)frames;
     p->seg_cap = kGateSegCap;
     p->total_chunks = (int)chunks.size();
+    for (const ChunkDev& c : chunks) p->n_unfusable += (c.fusable || c.s1 <= c.s0) ? 0 : 1;
     p->n_units = (int)units.size();
     p->n_edges = (int)edges.size();
     const size_t nf = (size_t)frames, nt = (size_t)n_tracks;
     bool ok = p->tracks.alloc(std::max<size_t>(nt, 1)) == cudaSuccess && p->units.alloc(std::max<size_t>(units.size(), 1)) == cudaSuccess &&
-              p->chunks.alloc(std::max<size_t>(chunks.size(), 1)) == cudaSuccess && p->edges.alloc(std::max<size_t>(edges.size(), 1)) == cudaSuccess &&
+              p->chunks.alloc(std::max<size_t>(chunks.size(), 1)) == cudaSuccess && p->chunk_done.alloc(chunks.size() + 1) == cudaSuccess && p->unit_counter.alloc(1) == cudaSuccess && p->edges.alloc(std::max<size_t>(edges.size(), 1)) == cudaSuccess &&
               p->edge_in_scale.alloc(nt + 1) == cudaSuccess && p->edge_out_scale.alloc(nt + 1) == cudaSuccess && p->hsum.alloc(nf + nt + 1) == cudaSuccess &&
               p->msq.alloc(nf + 1) == cudaSuccess && p->gate_f64.alloc(nf + 1) == cudaSuccess && p->state.alloc(nf + 1) == cudaSuccess &&
               p->rows.alloc(nf + 1) == cudaSuccess && p->c2.alloc(nt + 1) == cudaSuccess &&
@@ -1459,14 +1536,8 @@ int tmt_plan_gate(tmt_plan* p, int automaton, int gate_input, const double* on, 
                                          : launch_gate<double, TMT_GATE_MINHOLD>(p, v, param, S, X, ai, co, st);
 }
 
-int tmt_plan_stft(tmt_plan* p, float post_gain, int skip_edges, void* stream) {
-    if (!p) return fail(TMT_ERR_INVALID, "plan is NULL");
+static int launch_stft(tmt_plan* p, float post_gain, float limit, cudaStream_t st) {
     tmt_engine* e = p->e;
-    if (!e->have_win || e->n_rows == 0) return fail(TMT_ERR_INVALID, "engine window / gain rows not set");
-    CUDA_TRY(cudaSetDevice(e->device));
-    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    if (p->total_chunks) CUDA_TRY(cudaMemsetAsync(p->chunk_peaks.p, 0, sizeof(float) * p->total_chunks, st));
-    if (p->n_units == 0) return TMT_OK;
     StftParams prm;
     prm.tracks = p->tracks.p;
     prm.units = p->units.p;
@@ -1479,14 +1550,62 @@ int tmt_plan_stft(tmt_plan* p, float post_gain, int skip_edges, void* stream) {
     prm.tw_a = e->tw_a.p;
     prm.chunk_peaks = p->chunk_peaks.p;
     prm.post_gain = post_gain;
+    prm.chunks = p->chunks.p;
+    prm.chunk_done = p->chunk_done.p;
+    prm.unit_counter = p->unit_counter.p;
+    prm.limit = limit;
+    CUDA_TRY(cudaMemsetAsync(p->unit_counter.p, 0, sizeof(int), st));
     const int grid = std::min(p->n_units, 2 * e->n_sms);            // persistent: two CTAs per SM
     if (e->stft_store == 0) stft_kernel<0><<<grid, kThreads, kStftSmemTmem, st>>>(prm);
     else stft_kernel<1><<<grid, kThreads, kStftSmemSmem, st>>>(prm);
     p->launches++;
     CUDA_TRY(cudaGetLastError());
+    return TMT_OK;
+}
+
+int tmt_plan_clear_peaks(tmt_plan* p, void* stream) {
+    if (!p) return fail(TMT_ERR_INVALID, "plan is NULL");
+    CUDA_TRY(cudaSetDevice(p->e->device));
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (p->total_chunks) {
+        CUDA_TRY(cudaMemsetAsync(p->chunk_peaks.p, 0, sizeof(float) * p->total_chunks, st));
+        CUDA_TRY(cudaMemsetAsync(p->chunk_done.p, 0, sizeof(int) * p->total_chunks, st));
+    }
+    return TMT_OK;
+}
+
+int tmt_plan_stft(tmt_plan* p, float post_gain, int skip_edges, void* stream) {
+    if (!p) return fail(TMT_ERR_INVALID, "plan is NULL");
+    tmt_engine* e = p->e;
+    if (!e->have_win || e->n_rows == 0) return fail(TMT_ERR_INVALID, "engine window / gain rows not set");
+    int rc = tmt_plan_clear_peaks(p, stream);
+    if (rc) return rc;
+    if (p->n_units == 0) return TMT_OK;
+    rc = launch_stft(p, post_gain, 0.f, reinterpret_cast<cudaStream_t>(stream));
+    if (rc) return rc;
     // the single-frame edge blocks are never produced by stft_kernel; without an explicit
     // tmt_plan_edge_frames call they are filled in here with default scales
     if (!skip_edges) return tmt_plan_edge_frames(p, post_gain, nullptr, nullptr, 0, stream);
+    return TMT_OK;
+}
+
+int tmt_plan_stft_limited(tmt_plan* p, float post_gain, float limit, void* stream) {
+    if (!p) return fail(TMT_ERR_INVALID, "plan is NULL");
+    tmt_engine* e = p->e;
+    if (!e->have_win || e->n_rows == 0) return fail(TMT_ERR_INVALID, "engine window / gain rows not set");
+    if (!(limit > 0.f)) return fail(TMT_ERR_INVALID, "limit must be positive");
+    CUDA_TRY(cudaSetDevice(e->device));
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (p->n_units) {
+        int rc = launch_stft(p, post_gain, limit, st);
+        if (rc) return rc;
+    }
+    if (p->n_unfusable == 0 || p->max_chunk_len == 0) return TMT_OK;
+    const long long per_cta = 256LL * 16;
+    int gx = (int)std::min<long long>((p->max_chunk_len + per_cta - 1) / per_cta, 8LL * e->n_sms);
+    limiter_kernel<<<dim3(std::max(gx, 1), p->total_chunks), 256, 0, st>>>(p->tracks.p, p->chunks.p, p->chunk_peaks.p, limit, 1);
+    p->launches++;
+    CUDA_TRY(cudaGetLastError());
     return TMT_OK;
 }
 
@@ -1532,7 +1651,7 @@ int tmt_plan_limiter(tmt_plan* p, float limit, void* stream) {
     const long long per_cta = 256LL * 16;
     int gx = (int)std::min<long long>((p->max_chunk_len + per_cta - 1) / per_cta, 8LL * p->e->n_sms);
     gx = std::max(gx, 1);
-    limiter_kernel<<<dim3(gx, p->total_chunks), 256, 0, st>>>(p->tracks.p, p->chunks.p, p->chunk_peaks.p, limit);
+    limiter_kernel<<<dim3(gx, p->total_chunks), 256, 0, st>>>(p->tracks.p, p->chunks.p, p->chunk_peaks.p, limit, 0);
     p->launches++;
     CUDA_TRY(cudaGetLastError());
     return TMT_OK;
@@ -1546,11 +1665,11 @@ int tmt_plan_run_streaming(tmt_plan* p, double m_on, double m_off, int run_frame
     std::vector<double> on((size_t)std::max(p->n_tracks, 1), m_on), off((size_t)std::max(p->n_tracks, 1), m_off);
     rc = tmt_plan_gate(p, TMT_GATE_UPDELAY, TMT_ARR_MEANSQ_F32, on.data(), off.data(), run_frames, xfade_frames, 0, 0, stream);
     if (rc) return rc;
-    rc = tmt_plan_stft(p, post_gain, 1, stream);
+    rc = tmt_plan_clear_peaks(p, stream);
     if (rc) return rc;
-    rc = tmt_plan_edge_frames(p, post_gain, nullptr, nullptr, 0, stream);
-    if (rc) return rc;
-    return tmt_plan_limiter(p, limit, stream);
+    rc = tmt_plan_edge_frames(p, post_gain, nullptr, nullptr, 0, stream);      // edge blocks first: their samples and peaks
+    if (rc) return rc;                                                         // must be in place when a chunk is finished
+    return tmt_plan_stft_limited(p, post_gain, limit, stream);
 }
 
 }  // extern "C"

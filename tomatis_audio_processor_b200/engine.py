@@ -160,6 +160,14 @@ class Plan:
     def stft(self, post_gain: float = 1.0, skip_edges: bool = True):
         L.check(self.lib.tmt_plan_stft(self.h, float(post_gain), int(skip_edges), _stream_ptr(_torch())), "tmt_plan_stft")
 
+    def clear_peaks(self):
+        L.check(self.lib.tmt_plan_clear_peaks(self.h, _stream_ptr(_torch())), "tmt_plan_clear_peaks")
+
+    def stft_limited(self, post_gain: float = 1.0, limit: float = tb.PEAK_LIMIT):
+        """Fused STFT/OLA + per-chunk limiter; call clear_peaks() and edge_frames() first."""
+        L.check(self.lib.tmt_plan_stft_limited(self.h, float(post_gain), float(np.float32(limit)), _stream_ptr(_torch())),
+                "tmt_plan_stft_limited")
+
     def edge_frames(self, post_gain: float = 1.0, in_scale=None, out_scale=None, pipeline_f64: bool = False):
         pi = po = None
         if in_scale is not None:

@@ -50,6 +50,9 @@ def main():
         ("gate", lambda: plan.gate(L.GATE_UPDELAY, L.ARR_MEANSQ_F32, sp.m_on, sp.m_off, sp.run_frames, 0), 0),
         ("stft", lambda: plan.stft(1.0), 16),
         ("limiter", lambda: plan.limiter(), 16),
+        ("stft+lim", lambda: (plan.clear_peaks(), plan.edge_frames(1.0), plan.stft_limited(1.0)), 16),
+        ("stft+lim none", lambda: (plan.clear_peaks(), plan.edge_frames(1.0), plan.stft_limited(1.0, 1e9)), 16),
+        ("stft+lim all", lambda: (plan.clear_peaks(), plan.edge_frames(1.0), plan.stft_limited(1.0, 1e-9)), 16),
         ("step", lambda: plan.run_streaming(sp.m_on, sp.m_off, sp.run_frames, 0), 16),
     ]:
         ms, ts = ev_time(fn)
