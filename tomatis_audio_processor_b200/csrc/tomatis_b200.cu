@@ -482,7 +482,7 @@ __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.
 template <int kStore> struct Park;
 template <> struct Park<0> {
     uint32_t base;       // TMEM address of this warp's 48 columns (lane quarter in bits 31:16)
-    __device__ __forceinline__ void init(unsigned char* smem_tail, int t, const float* win, const float* swin, const float2* tw_a) {
+    __device__ __forceinline__ void init(unsigned char* smem_tail, int t, const float* win, const float* swin, const float2* tw_a, float post_gain) {
         uint32_t* slot = reinterpret_cast<uint32_t*>(smem_tail);
         if ((t >> 5) == 0) {
             asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
@@ -499,7 +499,7 @@ template <> struct Park<0> {
         for (int j = 0; j < 16; ++j) r[j] = __ldg(win + 256 * j + t);
         tmem_st16(base, r);
 #pragma unroll
-        for (int j = 0; j < 16; ++j) r[j] = __ldg(swin + 256 * j + t);
+        for (int j = 0; j < 16; ++j) r[j] = __ldg(swin + 256 * j + t) * post_gain;   // output gain folded into the synthesis window
         tmem_st16(base + 16, r);
         const float4* ta = reinterpret_cast<const float4*>(tw_a + 16 * t);
 #pragma unroll
@@ -530,6 +530,22 @@ template <> struct Park<0> {
             const float2 p = make_float2(b[2 * k], b[2 * k + 1]);
             v[k + 8] = CONJ ? cmulc(v[k + 8], p) : cmul(v[k + 8], p);
         }
+    }
+    // inverse stage-A twiddles plus the operands of the frame's tail (synthesis window, carry) in one batch of tensor-memory
+    // loads: a single wait, and the tail's loads complete under the last butterflies
+    __device__ __forceinline__ void twiddle_a_inv_fetch_tail(float2 (&v)[16], const TwBase, float (&s)[16], float2 (&c)[8], int) const {
+        float a[16], b[16], cr[16];
+        tmem_ld16(base + 80, a);
+        tmem_ld16(base + 96, b);
+        tmem_ld16(base + 16, s);
+        tmem_ld16(base + 32, cr);
+        tmem_wait_ld();
+#pragma unroll
+        for (int k = 1; k < 8; ++k) v[k] = cmulc(v[k], make_float2(a[2 * k], a[2 * k + 1]));
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k + 8] = cmulc(v[k + 8], make_float2(b[2 * k], b[2 * k + 1]));
+#pragma unroll
+        for (int j = 0; j < 8; ++j) c[j] = make_float2(cr[2 * j], cr[2 * j + 1]);
     }
     __device__ __forceinline__ void fini(unsigned char* smem_tail, int t) {
         tmem_wait_st();
@@ -581,12 +597,12 @@ template <> struct Park<1> {
     float* aw;        // [4096]
     float* sw;        // [4096]
     float2* cy;       // [2048]
-    __device__ __forceinline__ void init(unsigned char* smem_tail, int t, const float* win, const float* swin, const float2*) {
+    __device__ __forceinline__ void init(unsigned char* smem_tail, int t, const float* win, const float* swin, const float2*, float post_gain) {
         aw = reinterpret_cast<float*>(smem_tail + 64);
         sw = aw + kNfft;
         cy = reinterpret_cast<float2*>(sw + kNfft);
 #pragma unroll
-        for (int j = 0; j < 16; ++j) { aw[256 * j + t] = __ldg(win + 256 * j + t); sw[256 * j + t] = __ldg(swin + 256 * j + t); }
+        for (int j = 0; j < 16; ++j) { aw[256 * j + t] = __ldg(win + 256 * j + t); sw[256 * j + t] = __ldg(swin + 256 * j + t) * post_gain; }
         __syncthreads();
     }
     __device__ __forceinline__ void fini(unsigned char*, int) {}
@@ -606,6 +622,10 @@ template <> struct Park<1> {
     }
     template <bool CONJ>
     __device__ __forceinline__ void twiddle_a(float2 (&v)[16], const TwBase wa) const { tw_pow<CONJ>(v, wa); }
+    __device__ __forceinline__ void twiddle_a_inv_fetch_tail(float2 (&v)[16], const TwBase wa, float (&s)[16], float2 (&c)[8], int t) const {
+        tw_pow<true>(v, wa);
+        load_tail(s, c, t);
+    }
     __device__ __forceinline__ void sync_stores() const {}
 };
 
@@ -622,7 +642,7 @@ __global__ void __launch_bounds__(kThreads, 2) stft_kernel(const StftParams prm)
     const int t = threadIdx.x;
 
     Park<kStore> park;
-    park.init(tail, t, prm.win, prm.swin, prm.tw_a);
+    park.init(tail, t, prm.win, prm.swin, prm.tw_a, prm.post_gain);
     const float4* tb4 = reinterpret_cast<const float4*>(prm.tw_bases) + 2 * t;
     const float4 ba = __ldg(tb4), bb = __ldg(tb4 + 1);
     const TwBase wa = {make_float2(ba.x, ba.y), make_float2(ba.z, ba.w)};
@@ -690,6 +710,8 @@ __global__ void __launch_bounds__(kThreads, 2) stft_kernel(const StftParams prm)
             // first use, and waits in tensor memory; the loads below belong to frame i+1 and complete under
             // this frame's butterflies
             float2 pf[8];
+            float s[16];                                           // synthesis window x normalisation (x output gain)
+            float2 c[8];                                           // carried half frame
             const bool do_pf = (kStore == 0) && (i < last);
             if (have) {
                 if constexpr (kStore == 0) {
@@ -748,30 +770,35 @@ __global__ void __launch_bounds__(kThreads, 2) stft_kernel(const StftParams prm)
                 st_e1b(v, t, bufP);            // the very words this thread read in ld_e1b: no hazard with slower warps still in B
                 __syncthreads();
                 ld_e1a(v, t, bufP);            // next frame's st_e1a overwrites exactly the words this thread reads here
-                park.template twiddle_a<true>(v, wa);
+                park.twiddle_a_inv_fetch_tail(v, wa, s, c, t);
                 dft16<true>(v);                                                   // A'
             } else {
 #pragma unroll
                 for (int j = 0; j < 16; ++j) v[j] = make_float2(0.f, 0.f);
                 if (do_pf) { load_half(i + 2, pf); park_put(park, i & 1, pf); }
+                park.load_tail(s, c, t);
             }
 
             // synthesis window, overlap-add with the carried half, interior normalisation (folded into swin)
-            float s[16];
-            float2 c[8];
-            park.load_tail(s, c, t);
             const bool edge_blk = (f == 0 && edge_lo) || (f == n_frames && edge_hi);   // single-frame blocks: edge_kernel
             if (f >= un.b0 && !edge_blk) {       // emit output block f
-                const bool full = (rel >= out_lo) && (rel + kHop <= out_hi);
                 float2* dst = out_u + rel;
+                if ((rel >= out_lo) && (rel + kHop <= out_hi)) {          // whole block inside the output window
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    float2 o = __ffma2_rn(v[j], make_float2(s[j], s[j]), c[j]);
-                    if (prm.post_gain != 1.0f) o = cscale(o, prm.post_gain);
-                    const int p = rel + 256 * j + t;
-                    if (full || (p >= out_lo && p < out_hi)) {
+                    for (int j = 0; j < 8; ++j) {
+                        const float2 o = __ffma2_rn(v[j], make_float2(s[j], s[j]), c[j]);
                         st_stream(dst + 256 * j, o);
                         peak = fmaxf(peak, fmaxf(fabsf(o.x), fabsf(o.y)));
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float2 o = __ffma2_rn(v[j], make_float2(s[j], s[j]), c[j]);
+                        const int p = rel + 256 * j + t;
+                        if (p >= out_lo && p < out_hi) {
+                            st_stream(dst + 256 * j, o);
+                            peak = fmaxf(peak, fmaxf(fabsf(o.x), fabsf(o.y)));
+                        }
                     }
                 }
             }
