@@ -257,6 +257,7 @@ def run_gpu_arm(args):
 
     # ---- end to end through the host-buffer API (pinned host memory, copies inside the timed region)
     e2e = None
+    e2e_pcm = None
     if not args.no_e2e:
         Te = min(T, args.e2e_tracks)
         Te -= Te % args.wave_tracks
@@ -288,7 +289,34 @@ def run_gpu_arm(args):
                       f"waves of {args.wave_tracks} tracks, H2D/compute/D2H on 3 streams)",
                "host_peak_out": float(h_out.abs().max())}
         pipe.close()
-        del h_in, h_out
+        # same pipeline with integer PCM crossing PCIe (int16 in as decoded from a 16-bit source, PCM_24 out as the
+        # reference's output files store it): informational, the headline e2e above moves float32 like the reference arm
+        if not args.no_e2e_pcm:
+            s_in = torch.empty((Te, N_SAMPLES, 2), dtype=torch.int16, pin_memory=True)
+            s_in.copy_((h_in * 32767.0).round_().to(torch.int16))
+            del h_in, h_out
+            s_out = torch.empty((Te, N_SAMPLES, 6), dtype=torch.uint8, pin_memory=True)
+            pipe = HostBatchPipeline(N_SAMPLES, SR, "standard", device=local, wave_tracks=args.wave_tracks, unit_blocks=args.unit_blocks,
+                                     in_format="s16", out_format="s24", gate_ui=50)
+            pipe.process(s_in, s_out)
+            barrier()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(args.e2e_steps):
+                pipe.process(s_in, s_out)
+            b.record()
+            barrier()
+            ms = torch.tensor([a.elapsed_time(b)], device=dev, dtype=torch.float64)
+            if world > 1:
+                dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+            e2e_pcm = {"value": Te * N_SAMPLES / SR * world * args.e2e_steps / (float(ms[0]) * 1e-3), "unit": UNIT,
+                       "h2d_bytes_per_step": int(Te * N_SAMPLES * 4 * world), "d2h_bytes_per_step": int(Te * N_SAMPLES * 6 * world),
+                       "ms_per_step": float(ms[0]) / args.e2e_steps,
+                       "api": "HostBatchPipeline(in_format='s16', out_format='s24'): int16 PCM in, packed PCM_24 out, conversions on the device"}
+            pipe.close()
+            del s_in, s_out
+        else:
+            del h_in, h_out
 
     if rank == 0:
         peak_gbs, peak_src = measured_peak()
@@ -298,7 +326,7 @@ def run_gpu_arm(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "config": workload_config(T, world), "clocks": clocks,
-            "e2e": e2e, "gpu_launches": int(launches),
+            "e2e": e2e, "e2e_pcm": e2e_pcm, "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": "stft_kernel (fused gather+window+FFT+gain+IFFT+window+OLA+peak+chunk limiter)",
                          "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs,
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": ALG_BYTES_PER_SF * sf_rank,
@@ -502,6 +530,7 @@ def main():
     ap.add_argument("--lf-total", dest="lf_total", type=int, default=LF_TOTAL, help="long-file length in sample-frames")
     ap.add_argument("--lf-cpu-seconds", dest="lf_cpu_seconds", type=float, default=240.0)
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-e2e-pcm", dest="no_e2e_pcm", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3:

@@ -167,6 +167,16 @@ int tmt_plan_limiter(tmt_plan* p, float limit, void* stream);
 int tmt_plan_run_streaming(tmt_plan* p, double m_on, double m_off, int run_frames, int xfade_frames,
                            float post_gain, float limit, void* stream);
 
+/* ---- PCM edge (device pointers) -------------------------------------------------------------- */
+#define TMT_PCM_S16 0 /* int16 little endian                  -> value / 32768    */
+#define TMT_PCM_S24 1 /* packed 3-byte little endian (PCM_24)  -> value / 8388608  */
+/* Integer PCM -> float32 exactly as soundfile's read(dtype='float32') hands it to the reference
+ * (src/process_tomatis.py:434, _adaptive.py:179).  n_values = samples x channels. */
+int tmt_pcm_to_float(const void* pcm, int format, int64_t n_values, float* out, void* stream);
+/* float32 -> PCM_24 as the reference's output files store it (subtype='PCM_24', src/process_tomatis.py:243,
+ * _adaptive.py:351): rint(x * 0x7FFFFF), clipped to 24 bits. */
+int tmt_float_to_pcm(const float* in, int format, int64_t n_values, void* pcm, void* stream);
+
 /* Number of kernel launches issued by this plan since creation (bench.py's gpu_launches). */
 int64_t tmt_plan_launch_count(const tmt_plan* p);
 

@@ -185,3 +185,60 @@ def test_multi_segment_gate_scan(nseg):
             e.close()
         if saved is not None:
             eng._engines[0] = saved
+
+
+def _pack24(q):
+    """int32 24-bit values -> packed little-endian bytes (what a PCM_24 WAV data chunk holds)."""
+    q = np.asarray(q, np.int32).reshape(-1)
+    out = np.empty((q.size, 3), np.uint8)
+    out[:, 0], out[:, 1], out[:, 2] = q & 0xFF, (q >> 8) & 0xFF, (q >> 16) & 0xFF
+    return out.reshape(-1)
+
+
+@pytest.mark.parametrize("n", [1, 7, 8, 1000, 100003])
+def test_pcm_edge_conversions_bit_exact(n):
+    """On-device PCM edge against the host rules of audio_io (soundfile conventions)."""
+    import torch
+    from tomatis_audio_processor_b200 import audio_io, engine as eng, _lib as L
+    rng = np.random.default_rng(n)
+    s16 = rng.integers(-32768, 32768, size=2 * n, dtype=np.int16)
+    out = torch.empty(2 * n, dtype=torch.float32, device="cuda")
+    eng.pcm_to_float(torch.from_numpy(s16).cuda(), L.PCM_S16, out)
+    assert np.array_equal(out.cpu().numpy(), s16.astype(np.float32) / np.float32(32768.0))
+    q = rng.integers(-8388608, 8388608, size=2 * n, dtype=np.int32)
+    q[:2] = [-8388608, 8388607]
+    eng.pcm_to_float(torch.from_numpy(_pack24(q)).cuda(), L.PCM_S24, out)
+    assert np.array_equal(out.cpu().numpy(), q.astype(np.float32) / np.float32(8388608.0))
+    y = (rng.standard_normal(2 * n) * 0.5).astype(np.float32)
+    y[:2] = [1.5, -1.5]                                                    # clipped
+    packed = torch.empty(6 * n, dtype=torch.uint8, device="cuda")
+    eng.float_to_pcm24(torch.from_numpy(y).cuda(), packed)
+    assert np.array_equal(packed.cpu().numpy(), _pack24(audio_io.quantise_pcm24(y)))
+
+
+def test_host_pipeline_pcm_formats_match_float_path():
+    """HostBatchPipeline with int16 in / PCM_24 out == float path on the same (16-bit) samples, quantised on the host."""
+    import torch
+    from tomatis_audio_processor_b200 import audio_io, synth
+    from tomatis_audio_processor_b200.batch import HostBatchPipeline
+    n, sr, T = 300000, 48000, 4
+    xs = np.stack([synth.pcm16_to_float(synth.quantise_pcm16(synth.recipe_gated_pink(n / sr, sr, 60 + i, env_hz=1.1, hi_dbfs=-22.0)))[:n] for i in range(T)])
+    h_in = torch.from_numpy(xs).pin_memory()
+    h_out = torch.empty_like(h_in).pin_memory()
+    p = HostBatchPipeline(n, sr, "standard", wave_tracks=2, gate_ui=50)
+    p.process(h_in, h_out)
+    torch.cuda.synchronize()
+    p.close()
+    s_in = torch.from_numpy(np.stack([synth.quantise_pcm16(x) for x in xs])).pin_memory()
+    s_out = torch.empty((T, n, 6), dtype=torch.uint8).pin_memory()
+    p = HostBatchPipeline(n, sr, "standard", wave_tracks=2, in_format="s16", out_format="s24", gate_ui=50)
+    assert p.bytes_per_sample_frame() == (4, 6)
+    p.process(s_in, s_out)
+    torch.cuda.synchronize()
+    p.close()
+    for i in range(T):
+        want = _pack24(audio_io.quantise_pcm24(h_out[i].numpy()))
+        assert np.array_equal(s_out[i].numpy().reshape(-1), want), i
+    o = _oracle().run("standard", xs[0], sr, gate_ui=50)
+    d = np.abs(h_out[0].numpy().astype(np.float64) - o["out"]).max(axis=1)
+    assert float(d[:-256].max()) <= PCM_TOL

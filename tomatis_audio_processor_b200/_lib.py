@@ -13,6 +13,7 @@ from .build import LIB_PATH
 OK = 0
 FRAMING_STREAMING, FRAMING_WHOLEFILE = 0, 1
 GATE_UPDELAY, GATE_MINHOLD = 0, 1
+PCM_S16, PCM_S24 = 0, 1
 (ARR_MEANSQ_F32, ARR_MEANSQ_F64, ARR_GATE_F64, ARR_STATE, ARR_ROW, ARR_C2_COUNT, ARR_CHUNK_PEAK,
  ARR_INPUT_PEAK, ARR_HOPSUM_F32, ARR_HOPSUM_F64) = range(10)
 
@@ -58,6 +59,8 @@ SIGNATURES = {
     "tmt_plan_limiter": (C.c_int, [_P, C.c_float, _P]),
     "tmt_plan_run_streaming": (C.c_int, [_P, C.c_double, C.c_double, C.c_int, C.c_int, C.c_float, C.c_float, _P]),
     "tmt_plan_launch_count": (C.c_int64, [_P]),
+    "tmt_pcm_to_float": (C.c_int, [_P, C.c_int, C.c_int64, _P, _P]),
+    "tmt_float_to_pcm": (C.c_int, [_P, C.c_int, C.c_int64, _P, _P]),
 }
 
 _lib = None

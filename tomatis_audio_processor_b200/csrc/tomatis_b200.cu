@@ -1019,6 +1019,72 @@ limiter_kernel(const TrackDev* __restrict__ tracks, const ChunkDev* __restrict__
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// PCM edge: the reference reads integer PCM files as float32 (soundfile: value / 2^(bits-1)) and
+// writes PCM_24 (src/process_tomatis.py:243, _adaptive.py:351).  Doing both conversions on the device lets the host
+// move 2-3 bytes per sample over PCIe instead of 4.
+__global__ void __launch_bounds__(256) s16_to_float_kernel(const int4* __restrict__ in, float4* __restrict__ out, long long n8,
+                                                            const short* __restrict__ in_s, float* __restrict__ out_s, long long n) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += stride) {
+        const int4 v = in[i];
+        const int w[4] = {v.x, v.y, v.z, v.w};
+        float f[8];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            f[2 * k] = (float)(short)(w[k] & 0xffff) * (1.0f / 32768.0f);
+            f[2 * k + 1] = (float)(short)(w[k] >> 16) * (1.0f / 32768.0f);
+        }
+        out[2 * i] = make_float4(f[0], f[1], f[2], f[3]);
+        out[2 * i + 1] = make_float4(f[4], f[5], f[6], f[7]);
+    }
+    for (long long i = 8 * n8 + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        out_s[i] = (float)in_s[i] * (1.0f / 32768.0f);
+}
+
+// packed little-endian 24-bit: 4 samples = 12 bytes = 3 words
+__global__ void __launch_bounds__(256) s24_to_float_kernel(const unsigned* __restrict__ in, float4* __restrict__ out, long long n4,
+                                                            const unsigned char* __restrict__ in_b, float* __restrict__ out_s, long long n) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+        const unsigned a = in[3 * i], b = in[3 * i + 1], c = in[3 * i + 2];
+        const int s0 = (int)(a << 8) >> 8;
+        const int s1 = (int)(((a >> 24) | (b << 8)) << 8) >> 8;
+        const int s2 = (int)(((b >> 16) | (c << 16)) << 8) >> 8;
+        const int s3 = (int)c >> 8;
+        const float k = 1.0f / 8388608.0f;
+        out[i] = make_float4((float)s0 * k, (float)s1 * k, (float)s2 * k, (float)s3 * k);
+    }
+    for (long long i = 4 * n4 + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const int v = (int)((unsigned)in_b[3 * i] | ((unsigned)in_b[3 * i + 1] << 8) | ((unsigned)in_b[3 * i + 2] << 16));
+        out_s[i] = (float)((v << 8) >> 8) * (1.0f / 8388608.0f);
+    }
+}
+
+// float -> PCM_24, libsndfile's rule as restated in audio_io.quantise_pcm24: rint(x * 0x7FFFFF) in double, clipped
+__device__ __forceinline__ int quant24(float x) {
+    const int v = __double2int_rn((double)x * 8388607.0);
+    return max(-8388608, min(8388607, v));
+}
+__global__ void __launch_bounds__(256) float_to_s24_kernel(const float4* __restrict__ in, unsigned* __restrict__ out, long long n4,
+                                                            const float* __restrict__ in_s, unsigned char* __restrict__ out_b, long long n) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+        const float4 x = in[i];
+        const unsigned s0 = (unsigned)quant24(x.x) & 0xffffffu, s1 = (unsigned)quant24(x.y) & 0xffffffu;
+        const unsigned s2 = (unsigned)quant24(x.z) & 0xffffffu, s3 = (unsigned)quant24(x.w) & 0xffffffu;
+        out[3 * i] = s0 | (s1 << 24);
+        out[3 * i + 1] = (s1 >> 8) | (s2 << 16);
+        out[3 * i + 2] = (s2 >> 16) | (s3 << 8);
+    }
+    for (long long i = 4 * n4 + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const unsigned v = (unsigned)quant24(in_s[i]);
+        out_b[3 * i] = (unsigned char)(v & 0xff);
+        out_b[3 * i + 1] = (unsigned char)((v >> 8) & 0xff);
+        out_b[3 * i + 2] = (unsigned char)((v >> 16) & 0xff);
+    }
+}
+
 // ================================================================================================
 // host side
 template <typename T> struct DevBuf {
@@ -1697,6 +1763,40 @@ int tmt_plan_run_streaming(tmt_plan* p, double m_on, double m_off, int run_frame
     rc = tmt_plan_edge_frames(p, post_gain, nullptr, nullptr, 0, stream);      // edge blocks first: their samples and peaks
     if (rc) return rc;                                                         // must be in place when a chunk is finished
     return tmt_plan_stft_limited(p, post_gain, limit, stream);
+}
+
+int tmt_pcm_to_float(const void* pcm, int format, int64_t n_values, float* out, void* stream) {
+    if (n_values < 0 || (n_values > 0 && (!pcm || !out))) return fail(TMT_ERR_INVALID, "bad arguments");
+    if (n_values == 0) return TMT_OK;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const bool aligned = ((reinterpret_cast<uintptr_t>(pcm) | reinterpret_cast<uintptr_t>(out)) & 15u) == 0;
+    const int grid = 148 * 8;
+    if (format == TMT_PCM_S16) {
+        const long long n8 = aligned ? n_values / 8 : 0;
+        s16_to_float_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const int4*>(pcm), reinterpret_cast<float4*>(out), n8,
+                                                  reinterpret_cast<const short*>(pcm), out, n_values);
+    } else if (format == TMT_PCM_S24) {
+        const long long n4 = aligned ? n_values / 4 : 0;
+        s24_to_float_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const unsigned*>(pcm), reinterpret_cast<float4*>(out), n4,
+                                                  reinterpret_cast<const unsigned char*>(pcm), out, n_values);
+    } else {
+        return fail(TMT_ERR_INVALID, "unknown PCM format %d", format);
+    }
+    CUDA_TRY(cudaGetLastError());
+    return TMT_OK;
+}
+
+int tmt_float_to_pcm(const float* in, int format, int64_t n_values, void* pcm, void* stream) {
+    if (n_values < 0 || (n_values > 0 && (!pcm || !in))) return fail(TMT_ERR_INVALID, "bad arguments");
+    if (n_values == 0) return TMT_OK;
+    if (format != TMT_PCM_S24) return fail(TMT_ERR_UNSUPPORTED, "only PCM_24 output is implemented (the reference writes PCM_24)");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const bool aligned = ((reinterpret_cast<uintptr_t>(pcm) | reinterpret_cast<uintptr_t>(in)) & 15u) == 0;
+    const long long n4 = aligned ? n_values / 4 : 0;
+    float_to_s24_kernel<<<148 * 8, 256, 0, st>>>(reinterpret_cast<const float4*>(in), reinterpret_cast<unsigned*>(pcm), n4, in,
+                                                 reinterpret_cast<unsigned char*>(pcm), n_values);
+    CUDA_TRY(cudaGetLastError());
+    return TMT_OK;
 }
 
 }  // extern "C"

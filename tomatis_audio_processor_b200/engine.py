@@ -205,6 +205,21 @@ class Plan:
             pass
 
 
+def pcm_to_float(pcm_dev, fmt: int, out_dev):
+    """Device tensors: integer PCM (int16 values, or uint8 bytes of packed PCM_24) -> float32, on the current stream."""
+    torch = _torch()
+    n = out_dev.numel()
+    L.check(L.load().tmt_pcm_to_float(C.c_void_p(pcm_dev.data_ptr()), int(fmt), n, C.c_void_p(out_dev.data_ptr()),
+                                      _stream_ptr(torch)), "tmt_pcm_to_float")
+
+
+def float_to_pcm24(x_dev, out_bytes_dev):
+    """Device tensors: float32 -> packed PCM_24 bytes (3 per value), on the current stream."""
+    torch = _torch()
+    L.check(L.load().tmt_float_to_pcm(C.c_void_p(x_dev.data_ptr()), L.PCM_S24, x_dev.numel(),
+                                      C.c_void_p(out_bytes_dev.data_ptr()), _stream_ptr(torch)), "tmt_float_to_pcm")
+
+
 def whole_track_desc(x_dev, y_dev, total: Optional[int] = None) -> L.TrackDesc:
     n = int(x_dev.shape[0]) if total is None else int(total)
     return L.TrackDesc(x_dev.data_ptr(), y_dev.data_ptr(), n, 0, n, 0, n, 0, -1)
