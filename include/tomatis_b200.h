@@ -37,6 +37,11 @@ extern "C" {
 #define TMT_FRAMING_WHOLEFILE 1 /* adaptive: frames at k*hop with 0 <= k*hop < total, y/max(sum w^2,1e-8),   \
                                    one global limiter (src/process_tomatis_adaptive.py:298-345) */
 
+#define TMT_FRAMING_EQ_PAD 2    /* static EQ: n_fft/2 zeros on both sides, frames at -n_fft/2 + k*hop while they  \
+                                   fit, EVERY position the frames cover is output (length (n_frames+1)*hop, shifted by n_fft/2),  \
+                                   out/(sum w^2 + 1e-12), one global peak (src/layer2_apply_eq.py:100-215) */
+#define TMT_FRAMING_EQ_NOPAD 3  /* same without padding (--no_pad): frames at k*hop */
+
 /* Gate automata. */
 #define TMT_GATE_UPDELAY 0 /* hysteresis + up-delay, src/process_tomatis.py:373-385 */
 #define TMT_GATE_MINHOLD 1 /* hysteresis + min-hold, src/process_tomatis_adaptive.py:87-121 */
@@ -176,6 +181,10 @@ int tmt_pcm_to_float(const void* pcm, int format, int64_t n_values, float* out, 
 /* float32 -> PCM_24 as the reference's output files store it (subtype='PCM_24', src/process_tomatis.py:243,
  * _adaptive.py:351): rint(x * 0x7FFFFF), clipped to 24 bits. */
 int tmt_float_to_pcm(const float* in, int format, int64_t n_values, void* pcm, void* stream);
+
+/* y = dequantise(quantise_PCM24(y)) * scale in place: the PCM_24 write / read round trip of the static EQ's gain-protect
+ * pass (src/layer2_apply_eq.py:220-234). */
+int tmt_requantise_scale(float* y, int64_t n_values, float scale, void* stream);
 
 /* Number of kernel launches issued by this plan since creation (bench.py's gpu_launches). */
 int64_t tmt_plan_launch_count(const tmt_plan* p);

@@ -64,9 +64,34 @@ def cases():
     return c
 
 
+EQ_CURVE = ([20.0, 100.0, 500.0, 1000.0, 4000.0, 12000.0, 20000.0], [6.0, 4.0, 0.0, -2.0, 3.0, 8.0, 10.0])
+
+
+def eq_cases():
+    """(name, input, kwargs) for the static-EQ processor src/layer2_apply_eq.py."""
+    x = _q(synth.recipe_gated_pink(1.0, 48000, 71, env_hz=2.0, hi_dbfs=-14.0))
+    return [("eq_48k_pad_gainprotect", x, dict()),
+            ("eq_48k_nopad_gain", x[:40000], dict(pad=False, global_gain_db=-3.0, auto_gain_protect=False))]
+
+
+def make_eq():
+    for name, x, kw in eq_cases():
+        r = rh.run_reference_eq(x, 48000, EQ_CURVE[0], EQ_CURVE[1], **kw)
+        path = os.path.join(OUT_DIR, name + ".npz")
+        np.savez_compressed(
+            path, pcm16=synth.quantise_pcm16(x), out=r["out"],
+            out_gp=(r["out_gp"] if r["out_gp"] is not None else np.zeros((0, 2), np.float32)),
+            gain_bins=r["gain_bins"], eq_freqs=r["eq_freqs"], eq_db=r["eq_db"],
+            meta=np.array(json.dumps(dict(name=name, mode="eq", sr=48000, kwargs=kw, has_gp=r["out_gp"] is not None,
+                                          numpy=np.__version__, reference_files=["layer2_apply_eq.py"]))))
+        print(f"{name:24s} eq        N={len(x)} out={r['out'].shape} peak={np.abs(r['out']).max():.4f} "
+              f"gp={'yes' if r['out_gp'] is not None else 'no'} {os.path.getsize(path)/1e6:.2f} MB")
+
+
 def main():
     assert rh.reference_available(), "run in the build container (needs /root/reference)"
     os.makedirs(OUT_DIR, exist_ok=True)
+    make_eq()
     for name, mode, sr, x, kw in cases():
         r = rh.run_reference(mode, x, sr, **kw)
         q = synth.quantise_pcm16(x)

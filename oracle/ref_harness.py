@@ -35,6 +35,7 @@ MODULES = {
     "standard": "process_tomatis",
     "adaptive": "process_tomatis_adaptive",
     "xfade": "process_tomatis_xfade",
+    "eq": "layer2_apply_eq",
 }
 
 
@@ -59,6 +60,9 @@ def make_soundfile_standin(store: _Store) -> types.ModuleType:
         def __init__(self, path, mode="r", samplerate=None, channels=None, format=None, subtype=None):
             self.path, self.mode = path, mode
             if mode == "r":
+                if path not in store.inputs and path in store.outputs:       # a file the reference wrote itself
+                    rec = store.outputs[path]
+                    store.inputs[path] = (_as_written(np.concatenate(rec["chunks"], axis=0), rec["subtype"]), rec["sr"])
                 data, sr = store.inputs[path]
                 self._data = data
                 self.samplerate = sr
@@ -105,6 +109,14 @@ def make_soundfile_standin(store: _Store) -> types.ModuleType:
     mod.write = write
     mod.__version__ = "standin"
     return mod
+
+
+def _as_written(y, subtype):
+    """Samples as a later read(dtype='float32') returns them: libsndfile's PCM_24 rule, see audio_io.quantise_pcm24."""
+    if subtype == "PCM_24":
+        q = np.clip(np.rint(np.asarray(y, dtype=np.float64) * 8388607.0), -8388608, 8388607)
+        return (q / 8388608.0).astype(np.float32)
+    return np.asarray(y, dtype=np.float32)
 
 
 _GUARD_MARKERS = ("if sr != 48000:", "if ch != 2:")
@@ -182,3 +194,33 @@ def run_reference(mode: str, x: np.ndarray, sr: int, want_csv: bool = True, **pa
     out = np.concatenate(chunks, axis=0) if chunks else np.zeros((0, x.shape[1]), np.float32)
     return dict(out=out, chunk_lengths=[len(c) for c in chunks], csv=rows, stdout=buf.getvalue(),
                 guard_skipped=skip_guard, subtype=rec["subtype"], format=rec["format"])
+
+
+def run_reference_eq(x: np.ndarray, sr: int, eq_freqs, eq_db, **params) -> dict:
+    """Run the reference `apply_eq_stft` (src/layer2_apply_eq.py:66) on float32 x [N, 2] with the EQ curve given as
+    (freq_hz, delta_db) points.  Returns dict(out = what it wrote to the output file (float, pre-quantisation),
+    out_gp = what it wrote to the gain-protected "_gp" file or None, stdout)."""
+    assert reference_available(), "reference sources not present"
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    store = _Store()
+    store.inputs["in.flac"] = (x, sr)
+    mod = load_reference_module("eq", store, skip_guard=False)
+    fd, tmp = tempfile.mkstemp(suffix=".csv")
+    os.close(fd)
+    try:
+        with open(tmp, "w", newline="", encoding="utf-8") as f:
+            w = csv.writer(f)
+            w.writerow(["freq_hz", "delta_db"])
+            for a, b in zip(eq_freqs, eq_db):
+                w.writerow([repr(float(a)), repr(float(b))])
+        buf = io.StringIO()
+        with contextlib.redirect_stdout(buf):
+            mod.apply_eq_stft("in.flac", "out.flac", tmp, **params)
+            freqs, dbs = mod.load_eq_csv(tmp)
+            gain = mod.build_gain_per_bin(sr, params.get("n_fft", 4096), freqs, dbs)
+    finally:
+        os.unlink(tmp)
+    out = np.concatenate(store.outputs["out.flac"]["chunks"], axis=0)
+    gp = store.outputs.get("out_gp.flac")
+    return dict(out=out, out_gp=(np.concatenate(gp["chunks"], axis=0) if gp else None), stdout=buf.getvalue(),
+                gain_bins=gain, eq_freqs=freqs, eq_db=dbs)

@@ -11,7 +11,21 @@ GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
 def golden_names():
-    return sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
+    """Fixtures of the Tomatis path (standard / xfade / adaptive)."""
+    return sorted(n for n in (os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
+                  if not n.startswith("eq_"))
+
+
+def eq_golden_names():
+    """Fixtures of the static-EQ processor (src/layer2_apply_eq.py)."""
+    return sorted(n for n in (os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, "eq_*.npz"))))
+
+
+def load_eq_golden(name):
+    z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+    meta = json.loads(str(z["meta"]))
+    return dict(x=synth.pcm16_to_float(z["pcm16"]), out=z["out"], out_gp=(z["out_gp"] if meta["has_gp"] else None),
+                gain_bins=z["gain_bins"], eq_freqs=z["eq_freqs"], eq_db=z["eq_db"], **meta)
 
 
 def load_golden(name):

@@ -11,7 +11,7 @@ import os
 from .build import LIB_PATH
 
 OK = 0
-FRAMING_STREAMING, FRAMING_WHOLEFILE = 0, 1
+FRAMING_STREAMING, FRAMING_WHOLEFILE, FRAMING_EQ_PAD, FRAMING_EQ_NOPAD = 0, 1, 2, 3
 GATE_UPDELAY, GATE_MINHOLD = 0, 1
 PCM_S16, PCM_S24 = 0, 1
 (ARR_MEANSQ_F32, ARR_MEANSQ_F64, ARR_GATE_F64, ARR_STATE, ARR_ROW, ARR_C2_COUNT, ARR_CHUNK_PEAK,
@@ -61,6 +61,7 @@ SIGNATURES = {
     "tmt_plan_launch_count": (C.c_int64, [_P]),
     "tmt_pcm_to_float": (C.c_int, [_P, C.c_int, C.c_int64, _P, _P]),
     "tmt_float_to_pcm": (C.c_int, [_P, C.c_int, C.c_int64, _P, _P]),
+    "tmt_requantise_scale": (C.c_int, [_P, C.c_int64, C.c_float, _P]),
 }
 
 _lib = None

@@ -1085,6 +1085,14 @@ __global__ void __launch_bounds__(256) float_to_s24_kernel(const float4* __restr
     }
 }
 
+// what a PCM_24 file hands back after a write/read round trip, times a gain: the static-EQ gain-protect pass re-reads its
+// own output file (src/layer2_apply_eq.py:220-234)
+__global__ void __launch_bounds__(256) requantise_scale_kernel(float* __restrict__ y, long long n, float scale) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        y[i] = __fmul_rn((float)quant24(y[i]) * (1.0f / 8388608.0f), scale);
+}
+
 // ================================================================================================
 // host side
 template <typename T> struct DevBuf {
@@ -1123,6 +1131,7 @@ struct HostTrack {
     int hb_lo, hb_hi, f_lo, f_hi;
     int edge_lo = 0, edge_hi = 0;
     long long first_start;
+    long long oc_lo = 0, oc_hi = 0;                              // output positions [oc_lo, oc_hi)
     std::vector<std::pair<long long, long long>> chunk_ranges;   // clipped sample ranges
 };
 
@@ -1173,6 +1182,8 @@ int count_frames(int framing, long long total) {
         if (length < kNfft) return 0;
         return (int)((length - kNfft) / kHop + 1);
     }
+    if (framing == TMT_FRAMING_EQ_PAD) return (int)(total / kHop + 1);          // n_fft/2 zeros on both sides, src/layer2_apply_eq.py:112-125,205-208
+    if (framing == TMT_FRAMING_EQ_NOPAD) return total >= kNfft ? (int)((total - kNfft) / kHop + 1) : 0;
     return (int)(total / kHop);
 }
 
@@ -1210,8 +1221,8 @@ int build_tracks_dev(tmt_plan* p) {
         t.in_lo = std::max<long long>(0, h.d.in_origin);
         t.in_hi = std::min<long long>(h.d.total, h.d.in_origin + h.d.in_len);
         t.out_origin = h.d.out_origin;
-        t.out_lo = std::max<long long>(0, h.d.out_origin);
-        t.out_hi = std::min<long long>(h.d.total, h.d.out_origin + h.d.out_len);
+        t.out_lo = std::max<long long>(h.oc_lo, h.d.out_origin);
+        t.out_hi = std::min<long long>(h.oc_hi, h.d.out_origin + h.d.out_len);
         t.first_start = h.first_start;
         t.n_frames = h.n_frames;
         t.frame_base = h.frame_base;
@@ -1387,7 +1398,8 @@ int tmt_engine_set_gain_rows(tmt_engine* e, const float* rows, int n_rows, int n
 
 int tmt_plan_create(tmt_engine* e, tmt_plan** out, int framing, int n_tracks, const tmt_track_desc* tracks, int unit_blocks) {
     if (!e || !out || n_tracks < 0 || (n_tracks > 0 && !tracks)) return fail(TMT_ERR_INVALID, "bad arguments");
-    if (framing != TMT_FRAMING_STREAMING && framing != TMT_FRAMING_WHOLEFILE) return fail(TMT_ERR_INVALID, "unknown framing %d", framing);
+    if (framing < TMT_FRAMING_STREAMING || framing > TMT_FRAMING_EQ_NOPAD) return fail(TMT_ERR_INVALID, "unknown framing %d", framing);
+    const bool eq_framing = (framing == TMT_FRAMING_EQ_PAD || framing == TMT_FRAMING_EQ_NOPAD);
     if (n_tracks > 65535) return fail(TMT_ERR_UNSUPPORTED, "at most 65535 tracks per plan");
     *out = nullptr;
     CUDA_TRY(cudaSetDevice(e->device));
@@ -1407,8 +1419,11 @@ int tmt_plan_create(tmt_engine* e, tmt_plan** out, int framing, int n_tracks, co
         h.d = tracks[i];
         if (h.d.total < 0 || h.d.in_len < 0 || h.d.out_len < 0) { delete p; return fail(TMT_ERR_INVALID, "track %d: negative length", i); }
         if (h.d.total > 0 && (!h.d.pcm_in || !h.d.pcm_out)) { delete p; return fail(TMT_ERR_INVALID, "track %d: NULL audio buffer", i); }
-        h.first_start = (framing == TMT_FRAMING_STREAMING) ? -(long long)(kNfft / 2) : 0;
+        h.first_start = (framing == TMT_FRAMING_STREAMING || framing == TMT_FRAMING_EQ_PAD) ? -(long long)(kNfft / 2) : 0;
         h.n_frames = count_frames(framing, h.d.total);
+        // positions that belong to the output: the file itself, or (static EQ) everything the frames cover
+        h.oc_lo = eq_framing ? h.first_start : 0;
+        h.oc_hi = eq_framing ? h.first_start + (h.n_frames > 0 ? (long long)(h.n_frames + 1) * kHop : 0) : h.d.total;
         h.frame_base = (int)frames;
         h.hs_base = (int)frames + i;
         frames += h.n_frames;
@@ -1428,16 +1443,16 @@ int tmt_plan_create(tmt_engine* e, tmt_plan** out, int framing, int n_tracks, co
         h.n_chunks = (int)cb.size();
         for (size_t c = 0; c < cb.size(); ++c) {
             long long s0 = h.first_start + (long long)cb[c].first * kHop, s1 = h.first_start + (long long)cb[c].second * kHop;
-            s0 = std::max<long long>(0, s0);
-            s1 = std::min<long long>(h.d.total, s1);
+            s0 = std::max<long long>(h.oc_lo, s0);
+            s1 = std::min<long long>(h.oc_hi, s1);
             if (s1 < s0) s1 = s0;
             h.chunk_ranges.push_back({s0, s1});
             chunks.push_back(ChunkDev{i, s0, s1, 0, 0});
             p->max_chunk_len = std::max(p->max_chunk_len, s1 - s0);
             // work units: slices of this chunk restricted to [blo,bhi), skipping blocks with no file samples
             int u0 = std::max(cb[c].first, blo), u1 = std::min(cb[c].second, bhi);
-            while (u0 < u1 && h.first_start + (long long)(u0 + 1) * kHop <= 0) ++u0;
-            while (u1 > u0 && h.first_start + (long long)(u1 - 1) * kHop >= h.d.total) --u1;
+            while (u0 < u1 && h.first_start + (long long)(u0 + 1) * kHop <= h.oc_lo) ++u0;
+            while (u1 > u0 && h.first_start + (long long)(u1 - 1) * kHop >= h.oc_hi) --u1;
             if (u1 <= u0) continue;
             const int n_sub = ceil_div(u1 - u0, unit_blocks);
             // interior cut points are jittered by up to +-30 % of a unit (deterministic hash of the chunk index): same
@@ -1459,12 +1474,12 @@ int tmt_plan_create(tmt_engine* e, tmt_plan** out, int framing, int n_tracks, co
         // single-frame (ill-conditioned) edge blocks, recomputed in fp64 by edge_kernel
         auto chunk_of = [&](int blk) { for (size_t c = 0; c < cb.size(); ++c) if (blk >= cb[c].first && blk < cb[c].second) return h.chunk_base + (int)c; return h.chunk_base; };
         if (h.n_frames > 0) {
-            if (framing == TMT_FRAMING_WHOLEFILE && blo <= 0 && bhi > 0) {
+            if ((framing == TMT_FRAMING_WHOLEFILE || eq_framing) && blo <= 0 && bhi > 0) {
                 h.edge_lo = 1;
                 edges.push_back(EdgeDev{i, 0, 0, chunk_of(0)});
             }
             const int tb = h.n_frames;     // tail block: second half of the last frame only
-            if (tb >= blo && tb < bhi && h.first_start + (long long)tb * kHop < h.d.total) {
+            if (tb >= blo && tb < bhi && h.first_start + (long long)tb * kHop < h.oc_hi) {
                 h.edge_hi = 1;
                 edges.push_back(EdgeDev{i, h.n_frames - 1, 1, chunk_of(tb)});
             }
@@ -1782,6 +1797,14 @@ int tmt_pcm_to_float(const void* pcm, int format, int64_t n_values, float* out, 
     } else {
         return fail(TMT_ERR_INVALID, "unknown PCM format %d", format);
     }
+    CUDA_TRY(cudaGetLastError());
+    return TMT_OK;
+}
+
+int tmt_requantise_scale(float* y, int64_t n_values, float scale, void* stream) {
+    if (n_values < 0 || (n_values > 0 && !y)) return fail(TMT_ERR_INVALID, "bad arguments");
+    if (n_values == 0) return TMT_OK;
+    requantise_scale_kernel<<<148 * 8, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(y, n_values, scale);
     CUDA_TRY(cudaGetLastError());
     return TMT_OK;
 }

@@ -443,3 +443,54 @@ def run(mode: str, xs: Sequence, sr: int, **kw) -> List[dict]:
     if mode == "adaptive":
         return run_adaptive(xs, sr, **kw)
     return run_streaming(mode, xs, sr, **kw)
+
+
+# ------------------------------------------------------------------------------------------------ static EQ (N1)
+def run_eq(xs: Sequence, sr: int, gain_bins: np.ndarray, device: int = 0, pad: bool = True, global_gain_db: float = 0.0,
+           auto_gain_protect: bool = True, peak_target: float = 0.99, want_host: bool = True, unit_blocks: int = 0,
+           n_fft=tb.N_FFT, hop=tb.HOP) -> List[dict]:
+    """Static EQ through the same fused STFT/OLA kernel with a one-row gain table (src/layer2_apply_eq.py:66-237).
+
+    Per track: out = what the reference writes to its output file (every position its frames cover: length
+    (n_frames+1)*hop, shifted by n_fft/2 when pad), peak_seen, scale and out_gp = the gain-protected second file
+    (PCM_24 round trip of `out` times peak_target/peak) when the peak exceeds peak_target."""
+    torch = _torch()
+    eng = get_engine(device)
+    if n_fft != eng.n_fft or hop != eng.hop:
+        raise NotImplementedError(f"GPU path implements n_fft={eng.n_fft}, hop={eng.hop}; got {n_fft}/{hop}")
+    gain_bins = np.ascontiguousarray(gain_bins, dtype=np.float32).reshape(1, -1)
+    eng.set_gain_rows(gain_bins, key=None)
+    g_global = 10.0 ** (global_gain_db / 20.0)                      # db_to_lin, src/layer2_apply_eq.py:8-9,115
+    xd = _to_device(torch, xs, device)
+    framing = L.FRAMING_EQ_PAD if pad else L.FRAMING_EQ_NOPAD
+    first = -(n_fft // 2) if pad else 0
+    descs, yd = [], []
+    for x in xd:
+        n = int(x.shape[0])
+        nf = (n // hop + 1) if pad else ((n - n_fft) // hop + 1 if n >= n_fft else 0)
+        out_len = (nf + 1) * hop if nf > 0 else 0
+        y = torch.empty((out_len, 2), dtype=torch.float32, device=x.device)
+        yd.append(y)
+        descs.append(L.TrackDesc(x.data_ptr(), y.data_ptr(), n, 0, n, first, out_len, 0, -1))
+    plan = Plan(eng, framing, descs, unit_blocks)
+    try:
+        nt = plan.n_tracks
+        plan.stft(float(np.float32(g_global)), skip_edges=True)      # rows are all zero: the single EQ row
+        plan.edge_frames(1.0, in_scale=np.full(nt, np.float32(g_global), np.float32) if global_gain_db != 0.0 else None)
+        peaks = plan.read(L.ARR_CHUNK_PEAK)
+        res = []
+        for t in range(nt):
+            peak_seen = float(peaks[plan.chunk_base[t]]) if plan.track_chunks[t] else 0.0
+            scale, y_gp = None, None
+            if auto_gain_protect and peak_seen > peak_target:
+                scale = peak_target / max(peak_seen, tb.EPS)
+                y_gp = yd[t].clone()
+                L.check(eng.lib.tmt_requantise_scale(C.c_void_p(y_gp.data_ptr()), y_gp.numel(), float(np.float32(scale)),
+                                                     _stream_ptr(torch)), "tmt_requantise_scale")
+            res.append(dict(out=(yd[t].cpu().numpy() if want_host else yd[t]), peak_seen=peak_seen, scale=scale,
+                            out_gp=(None if y_gp is None else (y_gp.cpu().numpy() if want_host else y_gp)),
+                            n_frames=plan.track_frames[t], launches=plan.launch_count()))
+        return res
+    finally:
+        plan.close()
+        eng._rows_key = None
