@@ -121,9 +121,12 @@ int tmt_plan_input_peaks(tmt_plan* p, void* stream);
  * with NumPy's pairwise summation (rms_dbfs + caller, src/process_tomatis.py:43-52,370;
  * compute_frame_levels, src/process_tomatis_adaptive.py:57-84).  in_scale (host, per track, may be
  * NULL = 1) is the adaptive pre-attenuation x*atten_lin applied in float32 before squaring
- * (src/process_tomatis_adaptive.py:215); use_f64 selects the float64 branch of that file.
+ * (src/process_tomatis_adaptive.py:215); flags: TMT_LEVELS_F64 selects the float64 branch of that file,
+ * TMT_LEVELS_MONO the single-channel level formula.
  * Result in TMT_ARR_MEANSQ_F32 / _F64. */
-int tmt_plan_levels(tmt_plan* p, int use_f64, const float* in_scale, void* stream);
+#define TMT_LEVELS_F64 1  /* float64 branch of the adaptive mode */
+#define TMT_LEVELS_MONO 2 /* single-channel file carried in the L lane (R = 0): mono = sqrt(x*x), _adaptive.py:74,180-181 */
+int tmt_plan_levels(tmt_plan* p, int flags, const float* in_scale, void* stream);
 
 /* K2b.  Gate automaton + crossfade counter as a block-level scan over frames.
  * gate_input: TMT_ARR_MEANSQ_F32, TMT_ARR_MEANSQ_F64 or TMT_ARR_GATE_F64.  Frame is "hi" when

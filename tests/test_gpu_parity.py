@@ -242,3 +242,19 @@ def test_host_pipeline_pcm_formats_match_float_path():
     o = _oracle().run("standard", xs[0], sr, gate_ui=50)
     d = np.abs(h_out[0].numpy().astype(np.float64) - o["out"]).max(axis=1)
     assert float(d[:-256].max()) <= PCM_TOL
+
+
+@pytest.mark.parametrize("peak", [0.5, 0.1])
+def test_adaptive_mono_file(peak):
+    """Single-channel input in adaptive mode (both dtype branches): levels use mono = sqrt(x*x), output is [N, 1]."""
+    from tomatis_audio_processor_b200 import synth
+    x = synth.recipe_swept_pink(3.0, 48000, 8, period_s=1.1, peak=peak)[:, :1]
+    o = _oracle().run("adaptive", x, 48000)
+    o64 = _oracle().run("adaptive", x, 48000, fft_dtype="float64")
+    r = _engine().run("adaptive", [x], 48000)[0]
+    assert r["out"].shape == (len(x), 1) and r["pipeline_dtype"] == o["pipeline_dtype"]
+    assert np.array_equal(r["meansq"], np.asarray(o["meansq"])) and np.array_equal(r["states"], o["states"])
+    assert r["optimal_T"] == o["optimal_T"] and r["trace"] == o["trace"]
+    i64, e64 = _split_err(r["out"], o64["out"])
+    interior, _ = _split_err(r["out"], o["out"])
+    assert max(i64, e64) <= PCM_TOL and interior <= PCM_TOL

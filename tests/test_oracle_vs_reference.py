@@ -66,3 +66,10 @@ def test_reference_error_behaviour_pinned():
         rh.run_reference("adaptive", x0, 48000)
     with pytest.raises(ZeroDivisionError):
         rh.run_reference("adaptive", np.zeros((100, 2), np.float32) + 0.1, 48000)
+
+
+def test_adaptive_mono_file():
+    """The adaptive script accepts single-channel files (src/process_tomatis_adaptive.py:180-181)."""
+    x = synth.recipe_swept_pink(3.0, 48000, 8, period_s=1.1, peak=0.5)[:, :1]
+    o = _check("adaptive", x, 48000)
+    assert o["out"].shape == (len(x), 1)

@@ -126,6 +126,12 @@ template <> struct Arith<float> {
         const float mono = __fsqrt_rn(h);
         return __fmul_rn(mono, mono);
     }
+    // single-channel file: mono = sqrt(mean(frame**2, axis=1)) = sqrt(x*x) (src/process_tomatis_adaptive.py:74 with ch == 1)
+    static __device__ __forceinline__ float msq_mono(float2 x, float sc) {
+        const float l = __fmul_rn(x.x, sc);
+        const float mono = __fsqrt_rn(__fmul_rn(l, l));
+        return __fmul_rn(mono, mono);
+    }
     static __device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); }
     static __device__ __forceinline__ float div(float a, float b) { return __fdiv_rn(a, b); }
 };
@@ -136,13 +142,18 @@ template <> struct Arith<double> {
         const double mono = __dsqrt_rn(h);
         return __dmul_rn(mono, mono);
     }
+    static __device__ __forceinline__ double msq_mono(float2 x, float sc) {
+        const double l = __dmul_rn((double)x.x, (double)sc);
+        const double mono = __dsqrt_rn(__dmul_rn(l, l));
+        return __dmul_rn(mono, mono);
+    }
     static __device__ __forceinline__ double add(double a, double b) { return __dadd_rn(a, b); }
     static __device__ __forceinline__ double div(double a, double b) { return __ddiv_rn(a, b); }
 };
 
 template <typename T>
 __global__ void __launch_bounds__(kLevelWarps * 32)
-levels_kernel(const TrackDev* __restrict__ tracks, const float* __restrict__ in_scale, T* __restrict__ hsum) {
+levels_kernel(const TrackDev* __restrict__ tracks, const float* __restrict__ in_scale, T* __restrict__ hsum, int mono) {
     const TrackDev tr = tracks[blockIdx.y];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int q = tr.hb_lo + blockIdx.x * kLevelWarps + warp;
@@ -173,11 +184,21 @@ levels_kernel(const TrackDev* __restrict__ tracks, const float* __restrict__ in_
                 x1[i] = (p1 >= tr.in_lo && p1 < tr.in_hi) ? tr.in[p1 - tr.in_origin] : make_float2(0.f, 0.f);
             }
         }
-        T a0 = Arith<T>::msq(x0[0], sc), a1 = Arith<T>::msq(x1[0], sc);
+        T a0, a1;
+        if (!mono) {
+            a0 = Arith<T>::msq(x0[0], sc); a1 = Arith<T>::msq(x1[0], sc);
 #pragma unroll
-        for (int i = 1; i < 16; ++i) {
-            a0 = Arith<T>::add(a0, Arith<T>::msq(x0[i], sc));
-            a1 = Arith<T>::add(a1, Arith<T>::msq(x1[i], sc));
+            for (int i = 1; i < 16; ++i) {
+                a0 = Arith<T>::add(a0, Arith<T>::msq(x0[i], sc));
+                a1 = Arith<T>::add(a1, Arith<T>::msq(x1[i], sc));
+            }
+        } else {
+            a0 = Arith<T>::msq_mono(x0[0], sc); a1 = Arith<T>::msq_mono(x1[0], sc);
+#pragma unroll
+            for (int i = 1; i < 16; ++i) {
+                a0 = Arith<T>::add(a0, Arith<T>::msq_mono(x0[i], sc));
+                a1 = Arith<T>::add(a1, Arith<T>::msq_mono(x1[i], sc));
+            }
         }
         T s = Arith<T>::add(a0, a1);                                         // r[2p] + r[2p+1]
         s = Arith<T>::add(s, __shfl_xor_sync(0xffffffffu, s, 1));            // (r0+r1)+(r2+r3) | (r4+r5)+(r6+r7)
@@ -1594,7 +1615,8 @@ int tmt_plan_input_peaks(tmt_plan* p, void* stream) {
     return TMT_OK;
 }
 
-int tmt_plan_levels(tmt_plan* p, int use_f64, const float* in_scale, void* stream) {
+int tmt_plan_levels(tmt_plan* p, int flags, const float* in_scale, void* stream) {
+    const int use_f64 = flags & TMT_LEVELS_F64, mono = (flags & TMT_LEVELS_MONO) ? 1 : 0;
     if (!p) return fail(TMT_ERR_INVALID, "plan is NULL");
     if (p->n_tracks == 0 || p->max_hb == 0) return TMT_OK;
     CUDA_TRY(cudaSetDevice(p->e->device));
@@ -1607,10 +1629,10 @@ int tmt_plan_levels(tmt_plan* p, int use_f64, const float* in_scale, void* strea
     const dim3 g1(ceil_div(p->max_hb, kLevelWarps), p->n_tracks);
     const dim3 g2(ceil_div(std::max(p->max_frames, 1), 256), p->n_tracks);
     if (use_f64) {
-        levels_kernel<double><<<g1, kLevelWarps * 32, 0, st>>>(p->tracks.p, sc, p->hsum.p);
+        levels_kernel<double><<<g1, kLevelWarps * 32, 0, st>>>(p->tracks.p, sc, p->hsum.p, mono);
         meansq_kernel<double><<<g2, 256, 0, st>>>(p->tracks.p, p->hsum.p, p->msq.p);
     } else {
-        levels_kernel<float><<<g1, kLevelWarps * 32, 0, st>>>(p->tracks.p, sc, reinterpret_cast<float*>(p->hsum.p));
+        levels_kernel<float><<<g1, kLevelWarps * 32, 0, st>>>(p->tracks.p, sc, reinterpret_cast<float*>(p->hsum.p), mono);
         meansq_kernel<float><<<g2, 256, 0, st>>>(p->tracks.p, reinterpret_cast<const float*>(p->hsum.p), reinterpret_cast<float*>(p->msq.p));
     }
     p->launches += 2;

@@ -141,13 +141,14 @@ class Plan:
     def input_peaks(self):
         L.check(self.lib.tmt_plan_input_peaks(self.h, _stream_ptr(_torch())), "tmt_plan_input_peaks")
 
-    def levels(self, use_f64: bool = False, in_scale: Optional[np.ndarray] = None):
+    def levels(self, use_f64: bool = False, in_scale: Optional[np.ndarray] = None, mono: bool = False):
         ptr = None
         if in_scale is not None:
             in_scale = np.ascontiguousarray(in_scale, dtype=np.float32)
             assert in_scale.size == self.n_tracks
             ptr = in_scale.ctypes.data_as(C.c_void_p)
-        L.check(self.lib.tmt_plan_levels(self.h, int(use_f64), ptr, _stream_ptr(_torch())), "tmt_plan_levels")
+        L.check(self.lib.tmt_plan_levels(self.h, int(bool(use_f64)) | (2 if mono else 0), ptr, _stream_ptr(_torch())),
+                "tmt_plan_levels")
 
     def gate(self, automaton: int, gate_input: int, on, off, param: int, xfade_frames: int,
              alpha_init_to_target: bool = False, count_only: bool = False):
@@ -352,6 +353,13 @@ def run_adaptive(xs: Sequence, sr: int, device: int = 0, want_host: bool = True,
     c1_db, c2_db = tb.tilt_curves_db(sr, n_fft, fc, slope, c1_low, c1_high, c2_low, c2_high)
     eng.set_gain_rows(tb.gain_rows_adaptive(c1_db, c2_db, xf),
                       key=("adaptive", sr, fc, slope, c1_low, c1_high, c2_low, c2_high, xf, n_fft))
+    # single-channel files (accepted by the reference, _adaptive.py:180-181) ride in the L lane with R = 0
+    mono_in = [isinstance(x, np.ndarray) and (x.ndim == 1 or x.shape[1] == 1) for x in xs]
+    if any(mono_in) and not all(mono_in):
+        raise ValueError("mono and stereo tracks cannot share one adaptive batch")
+    mono = bool(mono_in) and all(mono_in)
+    if mono:
+        xs = [np.stack([np.asarray(x, np.float32).reshape(-1), np.zeros(len(x), np.float32)], axis=1) for x in xs]
     xd = _to_device(torch, xs, device)
     yd = outs if outs is not None else [torch.empty_like(x) for x in xd]
     results: List[Optional[dict]] = [None] * len(xd)
@@ -372,7 +380,7 @@ def run_adaptive(xs: Sequence, sr: int, device: int = 0, want_host: bool = True,
         plan = Plan(eng, L.FRAMING_WHOLEFILE, [whole_track_desc(xd[i], yd[i]) for i in idx], unit_blocks)
         try:
             scale = np.array([np.float32(branch[i][1]) for i in idx], dtype=np.float32)
-            plan.levels(use_f64=use_f64, in_scale=scale)
+            plan.levels(use_f64=use_f64, in_scale=scale, mono=mono)
             msq = plan.read(L.ARR_MEANSQ_F64 if use_f64 else L.ARR_MEANSQ_F32)
             levels_all = tb.levels_from_meansq(msq)
             plan.write(L.ARR_GATE_F64, levels_all)
@@ -427,7 +435,8 @@ def run_adaptive(xs: Sequence, sr: int, device: int = 0, want_host: bool = True,
             for t, i in enumerate(idx):
                 fb, nf = plan.frame_base[t], plan.track_frames[t]
                 results[i] = dict(
-                    out=(yd[i].cpu().numpy() if want_host else yd[i]), chunk_lengths=[int(xd[i].shape[0])],
+                    out=((yd[i].cpu().numpy()[:, :1] if mono else yd[i].cpu().numpy()) if want_host else yd[i]),
+                    chunk_lengths=[int(xd[i].shape[0])],
                     meansq=msq[fb:fb + nf].copy(), levels=lv[t].copy(), states=states[fb:fb + nf].copy(),
                     rows=rows[fb:fb + nf].copy(), times=[(k + 1) * (hop / sr) for k in range(nf)],
                     optimal_T=float(best_T[t]), trace=traces[t], atten_db=float(branch[i][0]),

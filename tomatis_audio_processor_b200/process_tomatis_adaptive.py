@@ -7,8 +7,9 @@ reference).  Whole file in HBM; input peak, per-frame levels, every gate simulat
 bisection, the final gate + alpha counter, STFT/OLA, restore gain and the global limiter run on the device
 (engine.run_adaptive); percentiles and the bisection bookkeeping stay on the host.
 
-Difference from the reference: mono / multi-channel input (accepted there, :180-181) raises
-NotImplementedError here -- the kernels pack the stereo pair as one complex signal.
+Mono files are accepted like in the reference (:180-181; they ride in the L lane of the stereo kernels).  Difference
+from the reference: more than two channels raise NotImplementedError -- the kernels pack a channel pair as one
+complex signal.
 """
 from __future__ import annotations
 
@@ -48,8 +49,8 @@ def process(
     ch = x.shape[1]
     total = len(x)
     print(f"  sample rate: {sr} Hz\n  channels: {ch}\n  duration: {total / sr:.2f} s")
-    if ch != 2:
-        raise NotImplementedError(f"the B200 path processes stereo files; got {ch} channel(s)")
+    if ch > 2:
+        raise NotImplementedError(f"the B200 path processes mono and stereo files; got {ch} channels")
     if total == 0:
         raise ValueError("zero-size array to reduction operation maximum which has no identity")   # np.max(np.abs(x)), :201
 
