@@ -86,3 +86,32 @@ def test_nccl_two_gpus_torchrun():
     p = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-3000:]
     assert "SHARDED-NCCL-OK" in p.stdout
+
+
+def test_full_size_two_hour_file_sharded_equals_unsharded():
+    """BASELINE configs[4] at full size (2 h @ 96 kHz = 691 200 000 sample-frames, pad_end = 0): 4 time shards (threads
+    on one GPU) against the unsharded run -- bit-identical output, states and peaks; plus size-independent properties."""
+    import torch
+    from tomatis_audio_processor_b200 import engine, sharded, synth
+    total, sr = 691_200_000, 96000
+    x = synth.device_long_file_range(0, total, sr, 5000, "cuda:0")
+    whole = engine.run("standard", [x], sr, want_host=False, gate_ui=50)[0]
+    y = whole["out"]
+    assert y.shape == x.shape and bool(torch.isfinite(y[::97]).all())
+    assert float(y.abs().max()) <= 0.999 + 1e-6
+    assert len(whole["states"]) == 337_500 and len(whole["chunk_lengths"]) == 2861
+    assert whole["chunk_lengths"][0] == 239_616 and sum(whole["chunk_lengths"]) == total
+    st = whole["states"]
+    assert (st == 1).any() and (st == 2).any()
+    world = 4
+    shards = sharded.plan_shards(total, world, sharded.STREAMING)
+    assert all(s.block_lo % 118 == 0 for s in shards)
+
+    def rank_fn(comm, r):
+        me = shards[r]
+        out = sharded.run_streaming_sharded("standard", x[me.own_lo:me.own_hi], sr, total, comm, gate_ui=50)
+        ok = bool(torch.equal(out["out"], y[me.own_lo:me.own_hi]))
+        return ok, np.array_equal(out["states"], st), out["comm_bytes"]
+    res = _run_threads(world, rank_fn)
+    assert all(r[0] for r in res), [r[0] for r in res]
+    assert all(r[1] for r in res)
