@@ -76,11 +76,12 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
+    path = os.environ.get("TMT_LIB", LIB_PATH)            # dev: A/B a differently built library
+    if not os.path.exists(path):
         raise RuntimeError(
-            f"CUDA library not built: {LIB_PATH} is missing. Run `python -c 'import __graft_entry__ as g; g.build()'` "
+            f"CUDA library not built: {path} is missing. Run `python -c 'import __graft_entry__ as g; g.build()'` "
             "(needs nvcc); there is no CPU fallback.")
-    lib = C.CDLL(LIB_PATH)
+    lib = C.CDLL(path)
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)       # AttributeError if the .so does not export a declared symbol
         fn.restype = res

@@ -554,12 +554,20 @@ template <> struct Park<0> {
     }
     // inverse stage-A twiddles plus the operands of the frame's tail (synthesis window, carry) in one batch of tensor-memory
     // loads: a single wait, and the tail's loads complete under the last butterflies
-    __device__ __forceinline__ void twiddle_a_inv_fetch_tail(float2 (&v)[16], const TwBase, float (&s)[16], float2 (&c)[8], int) const {
-        float a[16], b[16], cr[16];
-        tmem_ld16(base + 80, a);
-        tmem_ld16(base + 96, b);
+    __device__ __forceinline__ void twiddle_a_fwd(float2 (&v)[16], const TwBase, const float (&a)[16], const float (&b)[16]) const {
+#pragma unroll
+        for (int k = 1; k < 8; ++k) v[k] = cmul(v[k], make_float2(a[2 * k], a[2 * k + 1]));
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k + 8] = cmul(v[k + 8], make_float2(b[2 * k], b[2 * k + 1]));
+    }
+    __device__ __forceinline__ void inv_fetch_issue(float (&a)[16], float (&b)[16], float (&s)[16], float (&cr)[16], int) const {
+        tmem_ld16(base + 80, a);           // issued before the CTA barrier that precedes stage A': the loads fly while the
+        tmem_ld16(base + 96, b);           // warp waits for the slower warps
         tmem_ld16(base + 16, s);
         tmem_ld16(base + 32, cr);
+    }
+    __device__ __forceinline__ void inv_fetch_apply(float2 (&v)[16], const TwBase, const float (&a)[16], const float (&b)[16],
+                                                    const float (&cr)[16], float2 (&c)[8]) const {
         tmem_wait_ld();
 #pragma unroll
         for (int k = 1; k < 8; ++k) v[k] = cmulc(v[k], make_float2(a[2 * k], a[2 * k + 1]));
@@ -600,11 +608,13 @@ template <> struct Park<0> {
         tmem_st16(base + 48 + 16 * slot, r);
     }
     // v = [half `slot`, half `slot ^ 1`] x analysis window
-    __device__ __forceinline__ void stage_get_windowed(int slot, float2 (&v)[16]) const {
+    __device__ __forceinline__ void stage_get_windowed(int slot, float2 (&v)[16], float (&ta)[16], float (&tb2)[16]) const {
         float a[16], b[16], w[16];
         tmem_ld16(base + 48 + 16 * slot, a);
         tmem_ld16(base + 48 + 16 * (slot ^ 1), b);
         tmem_ld16(base, w);
+        tmem_ld16(base + 80, ta);          // stage-A twiddles ride along: one wait for the whole frame prologue
+        tmem_ld16(base + 96, tb2);
         tmem_wait_ld();
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -643,9 +653,18 @@ template <> struct Park<1> {
     }
     template <bool CONJ>
     __device__ __forceinline__ void twiddle_a(float2 (&v)[16], const TwBase wa) const { tw_pow<CONJ>(v, wa); }
-    __device__ __forceinline__ void twiddle_a_inv_fetch_tail(float2 (&v)[16], const TwBase wa, float (&s)[16], float2 (&c)[8], int t) const {
+    __device__ __forceinline__ void twiddle_a_fwd(float2 (&v)[16], const TwBase wa, const float (&)[16], const float (&)[16]) const { tw_pow<false>(v, wa); }
+    __device__ __forceinline__ void inv_fetch_issue(float (&)[16], float (&)[16], float (&s)[16], float (&cr)[16], int t) const {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) s[j] = sw[256 * j + t];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { const float2 x = cy[256 * j + t]; cr[2 * j] = x.x; cr[2 * j + 1] = x.y; }
+    }
+    __device__ __forceinline__ void inv_fetch_apply(float2 (&v)[16], const TwBase wa, const float (&)[16], const float (&)[16],
+                                                    const float (&cr)[16], float2 (&c)[8]) const {
         tw_pow<true>(v, wa);
-        load_tail(s, c, t);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) c[j] = make_float2(cr[2 * j], cr[2 * j + 1]);
     }
     __device__ __forceinline__ void sync_stores() const {}
 };
@@ -731,12 +750,13 @@ __global__ void __launch_bounds__(kThreads, 2) stft_kernel(const StftParams prm)
             // first use, and waits in tensor memory; the loads below belong to frame i+1 and complete under
             // this frame's butterflies
             float2 pf[8];
+            float fa[16], fb[16];                                  // forward stage-A twiddles (tensor-memory variant)
             float s[16];                                           // synthesis window x normalisation (x output gain)
             float2 c[8];                                           // carried half frame
             const bool do_pf = (kStore == 0) && (i < last);
             if (have) {
                 if constexpr (kStore == 0) {
-                    park.stage_get_windowed(i & 1, v);
+                    park.stage_get_windowed(i & 1, v, fa, fb);
                     if (do_pf) load_half(i + 2, pf);
                 } else {
                     const float2* src = in_u + rel;
@@ -760,9 +780,13 @@ __global__ void __launch_bounds__(kThreads, 2) stft_kernel(const StftParams prm)
                     for (int j = 0; j < 16; ++j) v[j] = cscale(v[j], w[j]);       // analysis window
                 }
                 const int row = rows[f];
+                // tilt gain x crossfade weight: one real row per frame, register order; issued a whole stage ahead so the
+                // L1/L2 latency is long gone when stage C needs it
+                const float4* g4 = reinterpret_cast<const float4*>(prm.gperm + (size_t)row * kNfft + t * 16);
                 dft16<false>(v);                                                  // A
-                park.template twiddle_a<false>(v, wa);
+                park.twiddle_a_fwd(v, wa, fa, fb);
                 st_e1a(v, t, bufP);
+                const float4 g0 = __ldg(g4), g1 = __ldg(g4 + 1), g2 = __ldg(g4 + 2), g3 = __ldg(g4 + 3);
                 __syncthreads();
                 ld_e1b(v, t, bufP);
                 dft16<false>(v);                                                  // B
@@ -772,10 +796,6 @@ __global__ void __launch_bounds__(kThreads, 2) stft_kernel(const StftParams prm)
                 // warp), in B, C/C' and B' alike: the E2 exchanges need warp-level ordering only
                 __syncwarp();
                 if (do_pf) park_put(park, i & 1, pf);          // slot of the half this frame no longer needs
-                // tilt gain x crossfade weight: one real row per frame, register order; issued ahead of the
-                // shared-memory reads so the L1/L2 latency hides under them and the butterflies
-                const float4* g4 = reinterpret_cast<const float4*>(prm.gperm + (size_t)row * kNfft + t * 16);
-                const float4 g0 = __ldg(g4), g1 = __ldg(g4 + 1), g2 = __ldg(g4 + 2), g3 = __ldg(g4 + 3);
                 ld_e2c(v, t, bufQ);
                 dft16<false>(v);                                                  // C
                 v[0] = cscale(v[0], g0.x); v[1] = cscale(v[1], g0.y); v[2] = cscale(v[2], g0.z); v[3] = cscale(v[3], g0.w);
@@ -789,9 +809,11 @@ __global__ void __launch_bounds__(kThreads, 2) stft_kernel(const StftParams prm)
                 tw_pow<true>(v, wb);
                 dft16<true>(v);                                                   // B'
                 st_e1b(v, t, bufP);            // the very words this thread read in ld_e1b: no hazard with slower warps still in B
+                float ta[16], tb2[16], cr[16];
+                park.inv_fetch_issue(ta, tb2, s, cr, t);
                 __syncthreads();
                 ld_e1a(v, t, bufP);            // next frame's st_e1a overwrites exactly the words this thread reads here
-                park.twiddle_a_inv_fetch_tail(v, wa, s, c, t);
+                park.inv_fetch_apply(v, wa, ta, tb2, cr, c);
                 dft16<true>(v);                                                   // A'
             } else {
 #pragma unroll
