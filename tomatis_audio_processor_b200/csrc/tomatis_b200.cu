@@ -515,6 +515,10 @@ template <> struct Park<0> {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const int warp = t >> 5;
         base = *slot + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((warp >> 2) * kTmemWarpCols);
+        fill_tables(t, win, swin, tw_a, post_gain);
+    }
+    // thread-private constants -> this region's columns: analysis window | synthesis window x normalisation x output gain | stage-A twiddles
+    __device__ __forceinline__ void fill_tables(int t, const float* win, const float* swin, const float2* tw_a, float post_gain) const {
         float r[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) r[j] = __ldg(win + 256 * j + t);
@@ -668,6 +672,72 @@ template <> struct Park<1> {
     }
     __device__ __forceinline__ void sync_stores() const {}
 };
+
+// End of a work unit: publish the unit's peak; with the fused limiter, the CTA that completes a chunk's last unit rescales it.
+// Called by all threads of the CTA (contains CTA barriers).  red: 9 floats of shared memory.
+__device__ __forceinline__ void unit_epilogue(const StftParams& prm, int chunk, const TrackDev* trp, float peak, int t, float* red) {
+    // per-chunk peak: one atomic per work unit (values are >= 0, so int ordering == float ordering)
+#pragma unroll
+    for (int o = 16; o; o >>= 1) peak = fmaxf(peak, __shfl_xor_sync(0xffffffffu, peak, o));
+    if ((t & 31) == 0) red[t >> 5] = peak;
+    __syncthreads();
+    if (t == 0) {
+        float m = red[0];
+#pragma unroll
+        for (int q = 1; q < 8; ++q) m = fmaxf(m, red[q]);
+        if (m > 0.f) atomicMax(reinterpret_cast<int*>(prm.chunk_peaks + chunk), __float_as_int(m));
+    }
+    if (prm.limit > 0.f) {
+        // Fused limiter (src/process_tomatis.py:352-355).  Every unit publishes its samples and its peak, then bumps
+        // the chunk's counter; whoever bumps it last owns the finished chunk and rescales it if its peak exceeds the
+        // limit.  Nobody waits for anybody, and the pass runs under the butterflies of the other resident CTAs
+        // (the kernel is FP32-bound, HBM is 3/4 idle).
+        const ChunkDev ch = prm.chunks[chunk];
+        if (ch.fusable) {
+            __threadfence();
+            __syncthreads();
+            if (t == 0) {
+                const int prev = atomicAdd(prm.chunk_done + chunk, 1);
+                red[8] = (prev == ch.n_units - 1) ? 1.f : 0.f;
+            }
+            __syncthreads();
+            if (red[8] != 0.f) {
+                __threadfence();
+                const float pk = __int_as_float(atomicMax(reinterpret_cast<int*>(prm.chunk_peaks + chunk), 0));
+                if (pk > prm.limit) {
+                    const float sc = __fdiv_rn(prm.limit, pk);
+                    const long long s0 = max(ch.s0, trp->out_lo), s1 = min(ch.s1, trp->out_hi);
+                    float2* base = trp->out + (s0 - trp->out_origin);
+                    const long long n = s1 - s0;
+                    long long q = t;
+                    if ((reinterpret_cast<uintptr_t>(base) & 15u) == 0) {
+                        // a single CTA is latency-bound: keep 64 KB in flight (16 x 16 B per thread)
+                        float4* b4 = reinterpret_cast<float4*>(base);
+                        const long long n4 = n >> 1;
+                        long long r = t;
+                        for (; r + 15 * kThreads < n4; r += 16 * kThreads) {
+                            float4 x[16];
+#pragma unroll
+                            for (int j = 0; j < 16; ++j)
+                                asm volatile("ld.global.cg.v4.f32 {%0,%1,%2,%3}, [%4];"
+                                             : "=f"(x[j].x), "=f"(x[j].y), "=f"(x[j].z), "=f"(x[j].w) : "l"(b4 + r + j * kThreads));
+#pragma unroll
+                            for (int j = 0; j < 16; ++j)
+                                asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(b4 + r + j * kThreads),
+                                             "f"(x[j].x * sc), "f"(x[j].y * sc), "f"(x[j].z * sc), "f"(x[j].w * sc) : "memory");
+                        }
+                        q = 2 * (r - t) + t;          // samples [0, 2*(r-t)) are done; continue with the scalar tail
+                    }
+                    for (; q < n; q += kThreads) {
+                        float2 x;
+                        asm volatile("ld.global.cg.v2.f32 {%0,%1}, [%2];" : "=f"(x.x), "=f"(x.y) : "l"(base + q));
+                        st_stream(base + q, make_float2(x.x * sc, x.y * sc));
+                    }
+                }
+            }
+        }
+    }
+}
 
 __device__ __forceinline__ void park_put(const Park<0>& p, int slot, const float2 (&x)[8]) { p.stage_put(slot, x); }
 __device__ __forceinline__ void park_put(const Park<1>&, int, const float2 (&)[8]) {}
@@ -849,67 +919,7 @@ __global__ void __launch_bounds__(kThreads, 2) stft_kernel(const StftParams prm)
             for (int j = 0; j < 8; ++j) c[j] = cscale(v[j + 8], s[j + 8]);
             park.store_carry(c, t);
         }
-        // per-chunk peak: one atomic per work unit (values are >= 0, so int ordering == float ordering)
-#pragma unroll
-        for (int o = 16; o; o >>= 1) peak = fmaxf(peak, __shfl_xor_sync(0xffffffffu, peak, o));
-        if ((t & 31) == 0) red[t >> 5] = peak;
-        __syncthreads();
-        if (t == 0) {
-            float m = red[0];
-#pragma unroll
-            for (int q = 1; q < 8; ++q) m = fmaxf(m, red[q]);
-            if (m > 0.f) atomicMax(reinterpret_cast<int*>(prm.chunk_peaks + un.chunk), __float_as_int(m));
-        }
-        if (prm.limit > 0.f) {
-            // Fused limiter (src/process_tomatis.py:352-355).  Every unit publishes its samples and its peak, then bumps
-            // the chunk's counter; whoever bumps it last owns the finished chunk and rescales it if its peak exceeds the
-            // limit.  Nobody waits for anybody, and the pass runs under the butterflies of the other resident CTAs
-            // (the kernel is FP32-bound, HBM is 3/4 idle).
-            const ChunkDev ch = prm.chunks[un.chunk];
-            if (ch.fusable) {
-                __threadfence();
-                __syncthreads();
-                if (t == 0) {
-                    const int prev = atomicAdd(prm.chunk_done + un.chunk, 1);
-                    red[8] = (prev == ch.n_units - 1) ? 1.f : 0.f;
-                }
-                __syncthreads();
-                if (red[8] != 0.f) {
-                    __threadfence();
-                    const float pk = __int_as_float(atomicMax(reinterpret_cast<int*>(prm.chunk_peaks + un.chunk), 0));
-                    if (pk > prm.limit) {
-                        const float sc = __fdiv_rn(prm.limit, pk);
-                        const long long s0 = max(ch.s0, trp->out_lo), s1 = min(ch.s1, trp->out_hi);
-                        float2* base = trp->out + (s0 - trp->out_origin);
-                        const long long n = s1 - s0;
-                        long long q = t;
-                        if ((reinterpret_cast<uintptr_t>(base) & 15u) == 0) {
-                            // a single CTA is latency-bound: keep 64 KB in flight (16 x 16 B per thread)
-                            float4* b4 = reinterpret_cast<float4*>(base);
-                            const long long n4 = n >> 1;
-                            long long r = t;
-                            for (; r + 15 * kThreads < n4; r += 16 * kThreads) {
-                                float4 x[16];
-#pragma unroll
-                                for (int j = 0; j < 16; ++j)
-                                    asm volatile("ld.global.cg.v4.f32 {%0,%1,%2,%3}, [%4];"
-                                                 : "=f"(x[j].x), "=f"(x[j].y), "=f"(x[j].z), "=f"(x[j].w) : "l"(b4 + r + j * kThreads));
-#pragma unroll
-                                for (int j = 0; j < 16; ++j)
-                                    asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(b4 + r + j * kThreads),
-                                                 "f"(x[j].x * sc), "f"(x[j].y * sc), "f"(x[j].z * sc), "f"(x[j].w * sc) : "memory");
-                            }
-                            q = 2 * (r - t) + t;          // samples [0, 2*(r-t)) are done; continue with the scalar tail
-                        }
-                        for (; q < n; q += kThreads) {
-                            float2 x;
-                            asm volatile("ld.global.cg.v2.f32 {%0,%1}, [%2];" : "=f"(x.x), "=f"(x.y) : "l"(base + q));
-                            st_stream(base + q, make_float2(x.x * sc, x.y * sc));
-                        }
-                    }
-                }
-            }
-        }
+        unit_epilogue(prm, un.chunk, trp, peak, t, red);
         __syncthreads();
     }
     park.fini(tail, t);
@@ -1383,6 +1393,7 @@ int tmt_engine_create(tmt_engine** out, int device, int n_fft, int hop) {
     if (ce != cudaSuccess) { delete e; return fail(TMT_ERR_CUDA, "cudaFuncSetAttribute(stft_kernel): %s", cudaGetErrorString(ce)); }
     if (const char* sv = getenv("TMT_STFT_STORE")) e->stft_store = (strcmp(sv, "smem") == 0) ? 1 : 0;
     if (const char* sv = getenv("TMT_GATE_NSEG")) e->gate_nseg = atoi(sv);
+
     ce = cudaFuncSetAttribute(edge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kEdgeSmemBytes);
     if (ce != cudaSuccess) { delete e; return fail(TMT_ERR_CUDA, "cudaFuncSetAttribute(edge_kernel): %s", cudaGetErrorString(ce)); }
     *out = e;
