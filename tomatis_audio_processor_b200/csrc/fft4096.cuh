@@ -25,7 +25,8 @@ namespace tmt {
 constexpr int kNfft = 4096;
 constexpr int kHop = 2048;
 constexpr int kThreads = 256;       // one frame per CTA pass, 16 points per thread
-constexpr int kRowPad = 17;         // E2 row stride in float2 (16 + 1): conflict-free both ways
+constexpr int kRowPad = 18;         // E2 row stride in float2 (16 + 2): rows stay 16-byte aligned, so the C side moves two
+                                    // points per 128-bit access (8 instead of 16 instructions); conflict-free both ways
 constexpr int kExchFloat2 = 256 * kRowPad;   // one exchange buffer (34 816 B)
 
 // Complex arithmetic on float2.  On the device every operation is a packed FP32x2 instruction
@@ -128,7 +129,7 @@ TMT_HD void dft16(float2 (&v)[16]) {
 
 // ---- shared-memory exchange layouts (float2 units) -------------------------------------
 // E1 (linear):  idx = k1*256 + n2*16 + n3        A side: j*256 + t       B side: (t>>4)*256 + j*16 + (t&15)
-// E2 (padded):  idx = (k1*16 + k2)*17 + n3       B side: ((t>>4)*16 + j)*17 + (t&15)    C side: t*17 + j
+// E2 (padded):  idx = (k1*16 + k2)*18 + n3       B side: ((t>>4)*16 + j)*18 + (t&15)    C side: t*18 + j
 TMT_HD int e1_a(int t, int j) { return j * 256 + t; }
 TMT_HD int e1_b(int t, int j) { return (t >> 4) * 256 + j * 16 + (t & 15); }
 TMT_HD int e2_b(int t, int j) { return ((t >> 4) * 16 + j) * kRowPad + (t & 15); }
@@ -170,12 +171,18 @@ TMT_HD void st_e2b(const float2 (&v)[16], int t, float2* buf) {
     for (int j = 0; j < 16; ++j) buf[e2_b(t, j)] = v[j];
 }
 TMT_HD void ld_e2c(float2 (&v)[16], int t, const float2* buf) {
+    const float4* row = reinterpret_cast<const float4*>(buf + e2_c(t, 0));
 #pragma unroll
-    for (int j = 0; j < 16; ++j) v[j] = buf[e2_c(t, j)];
+    for (int j = 0; j < 8; ++j) {
+        const float4 x = row[j];
+        v[2 * j] = make_float2(x.x, x.y);
+        v[2 * j + 1] = make_float2(x.z, x.w);
+    }
 }
 TMT_HD void st_e2c(const float2 (&v)[16], int t, float2* buf) {
+    float4* row = reinterpret_cast<float4*>(buf + e2_c(t, 0));
 #pragma unroll
-    for (int j = 0; j < 16; ++j) buf[e2_c(t, j)] = v[j];
+    for (int j = 0; j < 8; ++j) row[j] = make_float4(v[2 * j].x, v[2 * j].y, v[2 * j + 1].x, v[2 * j + 1].y);
 }
 TMT_HD void ld_e2b(float2 (&v)[16], int t, const float2* buf) {
 #pragma unroll
