@@ -1462,7 +1462,19 @@ int tmt_plan_create(tmt_engine* e, tmt_plan** out, int framing, int n_tracks, co
     p->e = e;
     p->framing = framing;
     p->n_tracks = n_tracks;
-    if (unit_blocks <= 0) unit_blocks = 59;
+    if (unit_blocks <= 0) {
+        // default unit length: a unit costs one redundant warm-up frame (1/u of its work), and the dynamic queue leaves about
+        // one unit of idle time per CTA at the end (u * CTAs / blocks of the work); the sum is smallest at
+        // u = sqrt(blocks / CTAs).  59 (half a limiter chunk) is the cap: 128 tracks x 5 min gives 53.
+        long long blocks = 0;
+        for (int i = 0; i < n_tracks; ++i) {
+            const long long nb = count_frames(framing, tracks[i].total) + 1;
+            const long long lo = std::max<long long>(0, tracks[i].block_lo), hi = tracks[i].block_hi < 0 ? nb : std::min<long long>(nb, tracks[i].block_hi);
+            blocks += std::max<long long>(0, hi - lo);
+        }
+        unit_blocks = (int)std::lround(std::sqrt((double)blocks / (2.0 * e->n_sms)));
+        unit_blocks = std::max(8, std::min(59, unit_blocks));
+    }
     std::vector<UnitDev> units;
     std::vector<ChunkDev> chunks;
     std::vector<std::pair<int, int>> cb;
