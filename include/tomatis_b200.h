@@ -97,6 +97,11 @@ int tmt_plan_destroy(tmt_plan* p);
 /* Re-point the audio buffers (same geometry), e.g. to ping-pong staging buffers. */
 int tmt_plan_set_buffers(tmt_plan* p, int track, const void* pcm_in, void* pcm_out);
 
+/* Restrict / widen what tmt_plan_levels computes for one track: hop-block sums for blocks [hb_lo, hb_hi), mean squares for
+ * frames [f_lo, f_hi).  A time shard sums only the hop blocks it owns (no halo needed), all-reduces TMT_ARR_HOPSUM_* and
+ * then derives every frame's mean square locally, while its halo hand-off is still in flight. */
+int tmt_plan_set_level_ranges(tmt_plan* p, int track, int hb_lo, int hb_hi, int f_lo, int f_hi);
+
 int tmt_plan_total_frames(const tmt_plan* p);  /* sum of n_frames over tracks                  */
 int tmt_plan_total_chunks(const tmt_plan* p);
 int tmt_plan_total_units(const tmt_plan* p);
@@ -125,6 +130,8 @@ int tmt_plan_input_peaks(tmt_plan* p, void* stream);
  * TMT_LEVELS_MONO the single-channel level formula.
  * Result in TMT_ARR_MEANSQ_F32 / _F64. */
 #define TMT_LEVELS_F64 1  /* float64 branch of the adaptive mode */
+#define TMT_LEVELS_HOPSUM_ONLY 8  /* only the hop-block sums (TMT_ARR_HOPSUM_*), no frame mean squares */
+#define TMT_LEVELS_MEANSQ_ONLY 16 /* only m[k] = (H[k] + H[k+1]) / n_fft from the hop-block sums already in the plan */
 #define TMT_LEVELS_MONO 2 /* single-channel file carried in the L lane (R = 0): mono = sqrt(x*x), _adaptive.py:74,180-181 */
 int tmt_plan_levels(tmt_plan* p, int flags, const float* in_scale, void* stream);
 

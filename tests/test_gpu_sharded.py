@@ -77,6 +77,39 @@ def test_sharded_equals_unsharded(world, mode, sr, seconds, kw):
     assert np.array_equal(res[0]["full"], whole["out"])
 
 
+@pytest.mark.parametrize("world", [2, 3])
+def test_shard_session_repeated_steps(world):
+    """The persistent per-rank session bench.py times: halo hand-off overlapped with the hop sums of the owned blocks,
+    all-reduce of the hop sums instead of the mean squares.  Two passes with different data, each equal to the unsharded run."""
+    import torch
+    from tomatis_audio_processor_b200 import engine, sharded, synth
+    sr = 48000
+    xa = synth.recipe_gated_pink(11.0, sr, 33, env_hz=0.9, hi_dbfs=-22.0)
+    xb = synth.recipe_gated_pink(11.0, sr, 34, env_hz=1.3, hi_dbfs=-24.0)
+    total = len(xa)
+    wa = engine.run("standard", [xa], sr, gate_ui=50)[0]
+    wb = engine.run("standard", [xb], sr, gate_ui=50)[0]
+    shards = sharded.plan_shards(total, world, sharded.STREAMING)
+
+    def rank_fn(comm, r):
+        me = shards[r]
+        sess = sharded.StreamingShardSession("standard", torch.from_numpy(xa[me.own_lo:me.own_hi].copy()).cuda(), sr, total, comm, gate_ui=50)
+        try:
+            sess.step()
+            ya = sess.out.cpu().numpy().copy()
+            sess.own.copy_(torch.from_numpy(xb[me.own_lo:me.own_hi].copy()).cuda())
+            sess.step()
+            yb = sess.out.cpu().numpy().copy()
+        finally:
+            sess.close()
+        return ya, yb
+    res = _run_threads(world, rank_fn)
+    for r, (ya, yb) in enumerate(res):
+        me = shards[r]
+        assert np.array_equal(ya, wa["out"][me.own_lo:me.own_hi]), r
+        assert np.array_equal(yb, wb["out"][me.own_lo:me.own_hi]), r
+
+
 def test_nccl_two_gpus_torchrun():
     import torch
     if torch.cuda.device_count() < 2:

@@ -59,6 +59,26 @@ class ThreadComm:
         self.w.barrier.wait()
         return win
 
+    def exchange_halos_begin(self, own, shard, shards):
+        import torch
+        torch.cuda.synchronize()
+        owns = self._all(own)
+        recvs = []
+        for other in shards:
+            if other.rank == shard.rank:
+                continue
+            lo, hi = max(shard.in_lo, other.own_lo), min(shard.in_hi, other.own_hi)
+            if hi > lo:
+                recvs.append((lo, hi, owns[other.rank][lo - other.own_lo:hi - other.own_lo].clone()))
+                self.bytes_sent += (hi - lo) * 8
+        torch.cuda.synchronize()
+        self.w.barrier.wait()
+        return [], recvs
+
+    def exchange_halos_end(self, pending, shard, window):
+        for lo, hi, buf in pending[1]:
+            window[lo - shard.in_lo:hi - shard.in_lo] = buf
+
     def gather_output(self, own_out, shards, dst=0):
         import torch
         outs = self._all(own_out)

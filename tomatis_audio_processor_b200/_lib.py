@@ -39,6 +39,7 @@ SIGNATURES = {
     "tmt_plan_create": (C.c_int, [_P, C.POINTER(_P), C.c_int, C.c_int, C.POINTER(TrackDesc), C.c_int]),
     "tmt_plan_destroy": (C.c_int, [_P]),
     "tmt_plan_set_buffers": (C.c_int, [_P, C.c_int, _P, _P]),
+    "tmt_plan_set_level_ranges": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
     "tmt_plan_total_frames": (C.c_int, [_P]),
     "tmt_plan_total_chunks": (C.c_int, [_P]),
     "tmt_plan_total_units": (C.c_int, [_P]),

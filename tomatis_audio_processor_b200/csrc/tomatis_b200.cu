@@ -1602,6 +1602,22 @@ int tmt_plan_set_buffers(tmt_plan* p, int track, const void* pcm_in, void* pcm_o
     return TMT_OK;
 }
 
+int tmt_plan_set_level_ranges(tmt_plan* p, int track, int hb_lo, int hb_hi, int f_lo, int f_hi) {
+    if (!p || track < 0 || track >= p->n_tracks) return fail(TMT_ERR_INVALID, "bad track index");
+    HostTrack& h = p->ht[track];
+    const int nb = h.n_frames > 0 ? h.n_frames + 1 : 0;
+    if (hb_lo < 0 || hb_hi > nb || hb_hi < hb_lo || f_lo < 0 || f_hi > h.n_frames || f_hi < f_lo)
+        return fail(TMT_ERR_INVALID, "level ranges outside the track (%d hop blocks, %d frames)", nb, h.n_frames);
+    h.hb_lo = hb_lo; h.hb_hi = hb_hi; h.f_lo = f_lo; h.f_hi = f_hi;
+    TrackDev& t = p->tracks_h[track];
+    t.hb_lo = hb_lo; t.hb_hi = hb_hi; t.f_lo = f_lo; t.f_hi = f_hi;
+    p->max_hb = 0;
+    for (const HostTrack& x : p->ht) p->max_hb = std::max(p->max_hb, x.hb_hi - x.hb_lo);
+    CUDA_TRY(cudaSetDevice(p->e->device));
+    CUDA_TRY(cudaMemcpy(p->tracks.p + track, &t, sizeof(TrackDev), cudaMemcpyHostToDevice));
+    return TMT_OK;
+}
+
 int tmt_plan_total_frames(const tmt_plan* p) { return p ? p->total_frames : -1; }
 int tmt_plan_total_chunks(const tmt_plan* p) { return p ? p->total_chunks : -1; }
 int tmt_plan_total_units(const tmt_plan* p) { return p ? p->n_units : -1; }
@@ -1663,7 +1679,7 @@ int tmt_plan_input_peaks(tmt_plan* p, void* stream) {
 int tmt_plan_levels(tmt_plan* p, int flags, const float* in_scale, void* stream) {
     const int use_f64 = flags & TMT_LEVELS_F64, mono = (flags & TMT_LEVELS_MONO) ? 1 : 0;
     if (!p) return fail(TMT_ERR_INVALID, "plan is NULL");
-    if (p->n_tracks == 0 || p->max_hb == 0) return TMT_OK;
+    if (p->n_tracks == 0 || (p->max_hb == 0 && !(flags & TMT_LEVELS_MEANSQ_ONLY))) return TMT_OK;
     CUDA_TRY(cudaSetDevice(p->e->device));
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     const float* sc = nullptr;
@@ -1671,16 +1687,17 @@ int tmt_plan_levels(tmt_plan* p, int flags, const float* in_scale, void* stream)
         CUDA_TRY(cudaMemcpyAsync(p->in_scale.p, in_scale, sizeof(float) * p->n_tracks, cudaMemcpyHostToDevice, st));
         sc = p->in_scale.p;
     }
-    const dim3 g1(ceil_div(p->max_hb, kLevelWarps), p->n_tracks);
+    const bool do_sums = !(flags & TMT_LEVELS_MEANSQ_ONLY), do_msq = !(flags & TMT_LEVELS_HOPSUM_ONLY);
+    const dim3 g1(ceil_div(std::max(p->max_hb, 1), kLevelWarps), p->n_tracks);
     const dim3 g2(ceil_div(std::max(p->max_frames, 1), 256), p->n_tracks);
     if (use_f64) {
-        levels_kernel<double><<<g1, kLevelWarps * 32, 0, st>>>(p->tracks.p, sc, p->hsum.p, mono);
-        meansq_kernel<double><<<g2, 256, 0, st>>>(p->tracks.p, p->hsum.p, p->msq.p);
+        if (do_sums) levels_kernel<double><<<g1, kLevelWarps * 32, 0, st>>>(p->tracks.p, sc, p->hsum.p, mono);
+        if (do_msq) meansq_kernel<double><<<g2, 256, 0, st>>>(p->tracks.p, p->hsum.p, p->msq.p);
     } else {
-        levels_kernel<float><<<g1, kLevelWarps * 32, 0, st>>>(p->tracks.p, sc, reinterpret_cast<float*>(p->hsum.p), mono);
-        meansq_kernel<float><<<g2, 256, 0, st>>>(p->tracks.p, reinterpret_cast<const float*>(p->hsum.p), reinterpret_cast<float*>(p->msq.p));
+        if (do_sums) levels_kernel<float><<<g1, kLevelWarps * 32, 0, st>>>(p->tracks.p, sc, reinterpret_cast<float*>(p->hsum.p), mono);
+        if (do_msq) meansq_kernel<float><<<g2, 256, 0, st>>>(p->tracks.p, reinterpret_cast<const float*>(p->hsum.p), reinterpret_cast<float*>(p->msq.p));
     }
-    p->launches += 2;
+    p->launches += (do_sums ? 1 : 0) + (do_msq ? 1 : 0);
     CUDA_TRY(cudaGetLastError());
     return TMT_OK;
 }

@@ -141,13 +141,18 @@ class Plan:
     def input_peaks(self):
         L.check(self.lib.tmt_plan_input_peaks(self.h, _stream_ptr(_torch())), "tmt_plan_input_peaks")
 
-    def levels(self, use_f64: bool = False, in_scale: Optional[np.ndarray] = None, mono: bool = False):
+    def set_level_ranges(self, track: int, hb_lo: int, hb_hi: int, f_lo: int, f_hi: int):
+        L.check(self.lib.tmt_plan_set_level_ranges(self.h, track, hb_lo, hb_hi, f_lo, f_hi), "tmt_plan_set_level_ranges")
+
+    def levels(self, use_f64: bool = False, in_scale: Optional[np.ndarray] = None, mono: bool = False, part: str = "all"):
+        """part: "all" | "hopsums" (hop-block sums only) | "meansq" (mean squares from the sums already in the plan)"""
         ptr = None
         if in_scale is not None:
             in_scale = np.ascontiguousarray(in_scale, dtype=np.float32)
             assert in_scale.size == self.n_tracks
             ptr = in_scale.ctypes.data_as(C.c_void_p)
-        L.check(self.lib.tmt_plan_levels(self.h, int(bool(use_f64)) | (2 if mono else 0), ptr, _stream_ptr(_torch())),
+        flags = int(bool(use_f64)) | (2 if mono else 0) | {"all": 0, "hopsums": 8, "meansq": 16}[part]
+        L.check(self.lib.tmt_plan_levels(self.h, flags, ptr, _stream_ptr(_torch())),
                 "tmt_plan_levels")
 
     def gate(self, automaton: int, gate_input: int, on, off, param: int, xfade_frames: int,

@@ -135,6 +135,33 @@ class Comm:
             win[lo - shard.in_lo: hi - shard.in_lo] = buf
         return win
 
+    def exchange_halos_begin(self, own, shard: Shard, shards: List[Shard]):
+        """Start the halo hand-off without waiting (the sends read `own`, the receives land in fresh buffers); finish it
+        with exchange_halos_end.  Lets the rank sum its own hop blocks and reduce the levels while the halos travel."""
+        torch, dist = self.torch, self.dist
+        ops, recvs = [], []
+        for other in shards:
+            if other.rank == shard.rank:
+                continue
+            lo, hi = max(other.in_lo, shard.own_lo), min(other.in_hi, shard.own_hi)
+            if hi > lo:
+                buf = own[lo - shard.own_lo: hi - shard.own_lo].contiguous()
+                ops.append(dist.P2POp(dist.isend, buf, other.rank, group=self.group))
+                self.bytes_sent += buf.numel() * buf.element_size()
+            lo, hi = max(shard.in_lo, other.own_lo), min(shard.in_hi, other.own_hi)
+            if hi > lo:
+                buf = torch.empty((hi - lo, 2), dtype=own.dtype, device=own.device)
+                ops.append(dist.P2POp(dist.irecv, buf, other.rank, group=self.group))
+                recvs.append((lo, hi, buf))
+        return (dist.batch_isend_irecv(ops) if ops else []), recvs
+
+    def exchange_halos_end(self, pending, shard: Shard, window):
+        reqs, recvs = pending
+        for req in reqs:
+            req.wait()
+        for lo, hi, buf in recvs:
+            window[lo - shard.in_lo: hi - shard.in_lo] = buf
+
     def gather_output(self, own_out, shards: List[Shard], dst: int = 0):
         """Concatenate the ranks' output shards on rank `dst` (None elsewhere)."""
         torch, dist = self.torch, self.dist
@@ -189,6 +216,27 @@ class CudaShardBackend:
         if t.numel():
             self.plan.read_device(self.L.ARR_MEANSQ_F64 if use_f64 else self.L.ARR_MEANSQ_F32, t.data_ptr(), t.numel())
         return t
+
+    def own_hop_sums(self):
+        """Pairwise sums of the hop blocks this rank owns (needs no halo), device tensor [n_frames + 1], zeros elsewhere."""
+        import torch
+        s = self.shard
+        nb = s.n_frames + 1 if s.n_frames > 0 else 0
+        if not getattr(self, "_ranges_set", False):
+            self.plan.set_level_ranges(0, min(s.block_lo, nb), min(s.block_hi, nb), 0, s.n_frames)
+            self._ranges_set = True
+        self.plan.levels(part="hopsums")
+        t = torch.zeros(nb, dtype=torch.float32, device=self.window.device)
+        lo, hi = min(s.block_lo, nb), min(s.block_hi, nb)
+        if hi > lo:
+            self.plan.read_device(self.L.ARR_HOPSUM_F32, t[lo:].data_ptr(), hi - lo, offset=lo)
+        return t
+
+    def set_hop_sums(self, h):
+        """All hop-block sums of the file -> frame mean squares of every frame."""
+        if h.numel():
+            self.plan.write_device(self.L.ARR_HOPSUM_F32, h.data_ptr(), h.numel())
+        self.plan.levels(part="meansq")
 
     def set_meansq(self, m):
         import torch
@@ -389,15 +437,16 @@ class StreamingShardSession:
                 e.record()
                 marks.append((label, e))
         mark("start")
-        comm.exchange_halos(self.own, me, self.shards, window=be.window)   # 1. halo hand-off (fresh data every pass)
-        mark("halo")
-        local = be.local_meansq()
+        pending = comm.exchange_halos_begin(self.own, me, self.shards)    # 1. halo hand-off starts (fresh data every pass) ...
+        mark("halo_issue")
+        hsum = be.own_hop_sums()                                        # ... while the rank sums the hop blocks it owns
         mark("levels")
-        msq = comm.allreduce(_owned(me, local), "sum")                 # 2.
-        be.set_meansq(msq)
+        be.set_hop_sums(comm.allreduce(hsum, "sum"))                     # 2. every hop block has one owner: exact gather
         mark("allreduce_levels")
         be.gate(L.GATE_UPDELAY, L.ARR_MEANSQ_F32, sp.m_on, sp.m_off, sp.run_frames, sp.xfade_frames)
         mark("gate")
+        comm.exchange_halos_end(pending, me, be.window)                  # the STFT is the first consumer of the halos
+        mark("halo_wait")
         if stft_events:
             stft_events[0].record()
         be.stft(sp.post_gain)
