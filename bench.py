@@ -522,7 +522,7 @@ def main():
     ap.add_argument("--unit-blocks", dest="unit_blocks", type=int, default=0)
     ap.add_argument("--e2e-tracks", dest="e2e_tracks", type=int, default=32)
     ap.add_argument("--e2e-steps", dest="e2e_steps", type=int, default=3)
-    ap.add_argument("--wave-tracks", dest="wave_tracks", type=int, default=8)
+    ap.add_argument("--wave-tracks", dest="wave_tracks", type=int, default=2)
     ap.add_argument("--cpu-tracks", dest="cpu_tracks", type=int, default=3)
     ap.add_argument("--cpu-workers", dest="cpu_workers", type=int, default=0)
     ap.add_argument("--workload", choices=["batch", "longfile"], default="batch",

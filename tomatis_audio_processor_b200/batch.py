@@ -56,7 +56,9 @@ class HostBatchPipeline:
     """process(host_in, host_out): pinned host tracks -> pinned host tracks.
 
     Waves of `wave_tracks` tracks rotate through `n_slots` device staging slots; copy-in, compute and
-    copy-out run on separate streams, ordered by events, so PCIe transfers overlap the kernels.
+    copy-out run on separate streams, ordered by events, so PCIe transfers overlap the kernels.  Small waves keep the
+    pipeline's fill and drain short: 2 x 5-minute tracks per wave measured 14 % faster end to end than 8 (PCIe gives
+    46-48 GB/s each way on this box when both directions run; the pipeline reaches ~45).
 
     in_format / out_format select what crosses PCIe:
       "f32"  float32 [T, N, 2]                       8 B per sample-frame each way (what the reference holds in memory)
@@ -65,7 +67,7 @@ class HostBatchPipeline:
                                                      the reference's output files are PCM_24 (src/process_tomatis.py:243)
     """
 
-    def __init__(self, n_samples: int, sr: int, mode: str = "standard", device: int = 0, wave_tracks: int = 8,
+    def __init__(self, n_samples: int, sr: int, mode: str = "standard", device: int = 0, wave_tracks: int = 2,
                  n_slots: int = 3, unit_blocks: int = 0, in_format: str = "f32", out_format: str = "f32", **params):
         torch = self.torch = _torch()
         from .engine import pcm_to_float, float_to_pcm24
