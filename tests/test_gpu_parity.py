@@ -279,3 +279,35 @@ def test_full_size_adaptive_ten_minutes_properties():
     assert runs[1:-1].min() >= r["min_hold_frames"]                       # interior runs respect the 6-frame minimum hold
     rows = r["rows"]
     assert rows.max() == r["xfade_frames"] and rows.min() == 0 and np.abs(np.diff(rows.astype(int))).max() <= 1
+
+
+def test_many_short_tracks_one_plan_and_no_leak():
+    """1024 short tracks in one plan (the batch shape of BASELINE configs[3], shortened), spot-checked against the oracle;
+    then repeated plan creation / destruction must not leak device memory."""
+    import torch
+    from tomatis_audio_processor_b200 import synth
+    eng, orc = _engine(), _oracle()
+    sr, T = 44100, 1024
+    base = [synth.recipe_gated_pink(0.9 + 0.1 * k, sr, 200 + k, env_hz=2.0 + k, hi_dbfs=-24.0) for k in range(4)]
+    xs = [base[i % 4][: len(base[i % 4]) - 37 * (i % 11)] for i in range(T)]
+    rs = eng.run("standard", xs, sr, gate_ui=50, up_delay_ms=60.0, want_host=False)
+    assert len(rs) == T
+    for i in (0, 1, 2, 3, 517, 1023):
+        o = orc.run("standard", xs[i], sr, gate_ui=50, up_delay_ms=60.0)
+        o64 = orc.run("standard", xs[i], sr, gate_ui=50, up_delay_ms=60.0, fft_dtype="float64")
+        assert np.array_equal(rs[i]["states"], o["states"]) and np.array_equal(rs[i]["meansq"], o["meansq"])
+        y = rs[i]["out"].cpu().numpy()
+        assert float(np.abs(y.astype(np.float64) - o64["out"]).max()) <= PCM_TOL
+    del rs
+    torch.cuda.synchronize()
+    x = base[0]
+    eng.run("xfade", [x], sr, gate_ui=55, xfade_ms=100.0)
+    torch.cuda.empty_cache()
+    free0 = torch.cuda.mem_get_info()[0]
+    for _ in range(100):
+        eng.run("xfade", [x], sr, gate_ui=55, xfade_ms=100.0)
+        eng.run("adaptive", [x], sr)
+    torch.cuda.synchronize()
+    torch.cuda.empty_cache()
+    free1 = torch.cuda.mem_get_info()[0]
+    assert free0 - free1 < 64 * 1024 * 1024, (free0, free1)

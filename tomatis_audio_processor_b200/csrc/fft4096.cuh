@@ -27,7 +27,7 @@ constexpr int kHop = 2048;
 constexpr int kThreads = 256;       // one frame per CTA pass, 16 points per thread
 constexpr int kRowPad = 18;         // E2 row stride in float2 (16 + 2): rows stay 16-byte aligned, so the C side moves two
                                     // points per 128-bit access (8 instead of 16 instructions); conflict-free both ways
-constexpr int kExchFloat2 = 256 * kRowPad;   // one exchange buffer (34 816 B)
+constexpr int kExchFloat2 = 256 * kRowPad;   // the E2 exchange buffer (36 864 B)
 
 // Complex arithmetic on float2.  On the device every operation is a packed FP32x2 instruction
 // (FADD2 / FMUL2 / FFMA2, new on sm_100): re/im live in one 64-bit register pair, and the swap,

@@ -6,9 +6,11 @@
 //   input_peak_kernel   max|x| per track                                  (HBM stream, 8 B/sf read)
 //   levels_kernel<T>    per hop-block pairwise sum of mono^2, bit-exact   (HBM stream, 8 B/sf read)
 //   meansq_kernel<T>    m[k] = (H[k] + H[k+1]) / n_fft
-//   gate_kernel<T,A>    gate automaton + crossfade counter, block-level scan by map composition
-//   stft_kernel         gather + window + FFT + gain + IFFT + window + OLA + normalise + chunk peaks
-//   limiter_kernel      per-chunk in-place rescale
+//   gate_kernel<T,A,P>  gate automaton + crossfade counter, scan by map composition (one launch; three passes for long tracks)
+//   stft_kernel         gather + window + FFT + gain + IFFT + window + OLA + normalise + chunk peaks + fused chunk limiter
+//   edge_kernel         fp64 recomputation of the single-frame (ill-conditioned) edge blocks
+//   limiter_kernel      per-chunk in-place rescale (whole-file chunks, chunks a shard owns only partly)
+//   s16/s24_to_float, float_to_s24, requantise_scale     PCM edge
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <cstdio>
