@@ -49,6 +49,15 @@ TMT_HD float2 cmul(float2 a, float2 w) {
 TMT_HD float2 cmulc(float2 a, float2 w) {
     return __ffma2_rn(make_float2(a.y, a.x), make_float2(w.y, -w.y), __fmul2_rn(a, make_float2(w.x, w.x)));
 }
+// acc + a * w  /  acc + a * conj(w): two FFMA2, no separate add
+TMT_HD float2 cfma(float2 acc, float2 a, float2 w) {
+    return __ffma2_rn(make_float2(a.y, a.x), make_float2(-w.y, w.y), __ffma2_rn(a, make_float2(w.x, w.x), acc));
+}
+TMT_HD float2 cfmac(float2 acc, float2 a, float2 w) {
+    return __ffma2_rn(make_float2(a.y, a.x), make_float2(w.y, -w.y), __ffma2_rn(a, make_float2(w.x, w.x), acc));
+}
+// 2*p - t  (the other output of a twiddled radix-2 butterfly: p - w*b = 2p - (p + w*b))
+TMT_HD float2 twice_minus(float2 p, float2 t) { return __ffma2_rn(p, make_float2(2.f, 2.f), make_float2(-t.x, -t.y)); }
 #else
 TMT_HD float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
 TMT_HD float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
@@ -57,6 +66,9 @@ TMT_HD float2 cadd_mi(float2 a, float2 b) { return make_float2(a.x + b.y, a.y - 
 TMT_HD float2 cadd_pi(float2 a, float2 b) { return make_float2(a.x - b.y, a.y + b.x); }
 TMT_HD float2 cmul(float2 a, float2 w) { return make_float2(a.x * w.x - a.y * w.y, a.x * w.y + a.y * w.x); }
 TMT_HD float2 cmulc(float2 a, float2 w) { return make_float2(a.x * w.x + a.y * w.y, a.y * w.x - a.x * w.y); }
+TMT_HD float2 cfma(float2 acc, float2 a, float2 w) { return make_float2(acc.x + a.x * w.x - a.y * w.y, acc.y + a.x * w.y + a.y * w.x); }
+TMT_HD float2 cfmac(float2 acc, float2 a, float2 w) { return make_float2(acc.x + a.x * w.x + a.y * w.y, acc.y + a.y * w.x - a.x * w.y); }
+TMT_HD float2 twice_minus(float2 p, float2 t) { return make_float2(2.f * p.x - t.x, 2.f * p.y - t.y); }
 #endif
 
 // multiply by W16^M (forward, e^{-2*pi*i*M/16}) or its conjugate (INV)
@@ -93,31 +105,55 @@ TMT_HD void radix4(float2& x0, float2& x1, float2& x2, float2& x3) {
     }
 }
 
-// 16-point DFT, natural order in and out, fully in registers:
-//   n = 4a + b, k = c + 4d:  V[c+4d] = sum_b W4^(bd) * W16^(bc) * sum_a W4^(ac) v[4a+b]
+// 4-point DFT of (x0, w1*x1, w2*x2, w3*x3) (CONJ: conj(w)), twiddles fused into the first butterfly level:
+// p + w*b costs two FFMA2 and p - w*b = 2p - (p + w*b) one more, instead of multiply (2) + add + subtract.
+// TW0: x0 is also multiplied by w0.  12 packed instructions (14 with TW0) instead of 14 (16).
+template <bool INV, bool CONJ, bool TW0>
+TMT_HD void radix4_tw(float2& x0, float2& x1, float2& x2, float2& x3, float2 w0, float2 w1, float2 w2, float2 w3) {
+    const float2 p0 = TW0 ? (CONJ ? cmulc(x0, w0) : cmul(x0, w0)) : x0;
+    const float2 t0 = CONJ ? cfmac(p0, x2, w2) : cfma(p0, x2, w2);
+    const float2 t1 = twice_minus(p0, t0);
+    const float2 p1 = CONJ ? cmulc(x1, w1) : cmul(x1, w1);
+    const float2 t2 = CONJ ? cfmac(p1, x3, w3) : cfma(p1, x3, w3);
+    const float2 t3 = twice_minus(p1, t2);
+    x0 = cadd(t0, t2);
+    x2 = csub(t0, t2);
+    if (INV) {
+        x1 = cadd_pi(t1, t3);
+        x3 = cadd_mi(t1, t3);
+    } else {
+        x1 = cadd_mi(t1, t3);
+        x3 = cadd_pi(t1, t3);
+    }
+}
+
+// W16^M as a value (forward e^{-2*pi*i*M/16}; the inverse transform uses its conjugate)
+template <int M>
+TMT_HD float2 w16() {
+    constexpr float kC1 = 0.92387953251128673848f, kS1 = 0.38268343236508978178f, kH = 0.70710678118654752440f;
+    static_assert(M == 1 || M == 2 || M == 3 || M == 6 || M == 9, "unsupported W16 power");
+    return (M == 1) ? make_float2(kC1, -kS1) : (M == 2) ? make_float2(kH, -kH) : (M == 3) ? make_float2(kS1, -kC1)
+         : (M == 6) ? make_float2(-kH, -kH) : make_float2(-kC1, kS1);
+}
+
+// second radix-4 layer of the 16-point DFT: over b for each c, twiddles W16^(b*c) fused in, then the 4x4 transpose of the
+// register names (free after unrolling); V[c + 4d] ends up in v[c + 4d]
 template <bool INV>
-TMT_HD void dft16(float2 (&v)[16]) {
-    // step 1: radix-4 over a for each b; u_b[c] is left in v[4c + b]
-    radix4<INV>(v[0], v[4], v[8], v[12]);
-    radix4<INV>(v[1], v[5], v[9], v[13]);
-    radix4<INV>(v[2], v[6], v[10], v[14]);
-    radix4<INV>(v[3], v[7], v[11], v[15]);
-    // step 2: twiddle u_b[c] *= W16^(b*c)   (v index 4c + b)
-    v[5] = mul_w16<1, INV>(v[5]);
-    v[6] = mul_w16<2, INV>(v[6]);
-    v[7] = mul_w16<3, INV>(v[7]);
-    v[9] = mul_w16<2, INV>(v[9]);
-    v[10] = mul_w16<4, INV>(v[10]);
-    v[11] = mul_w16<6, INV>(v[11]);
-    v[13] = mul_w16<3, INV>(v[13]);
-    v[14] = mul_w16<6, INV>(v[14]);
-    v[15] = mul_w16<9, INV>(v[15]);
-    // step 3: radix-4 over b for each c; V[c + 4d] is left in v[4c + d]
-    radix4<INV>(v[0], v[1], v[2], v[3]);
-    radix4<INV>(v[4], v[5], v[6], v[7]);
-    radix4<INV>(v[8], v[9], v[10], v[11]);
-    radix4<INV>(v[12], v[13], v[14], v[15]);
-    // step 4: 4x4 transpose of the register names (free after unrolling)
+TMT_HD void dft16_layer2(float2 (&v)[16]) {
+    radix4<INV>(v[0], v[1], v[2], v[3]);                                                           // c = 0: no twiddles
+    radix4_tw<INV, INV, false>(v[4], v[5], v[6], v[7], make_float2(1.f, 0.f), w16<1>(), w16<2>(), w16<3>());       // c = 1
+    {                                                                                              // c = 2: W^0, W^2, W^4 = -+i, W^6
+        const float2 t0 = INV ? cadd_pi(v[8], v[10]) : cadd_mi(v[8], v[10]);
+        const float2 t1 = INV ? cadd_mi(v[8], v[10]) : cadd_pi(v[8], v[10]);
+        const float2 p1 = INV ? cmulc(v[9], w16<2>()) : cmul(v[9], w16<2>());
+        const float2 t2 = INV ? cfmac(p1, v[11], w16<6>()) : cfma(p1, v[11], w16<6>());
+        const float2 t3 = twice_minus(p1, t2);
+        v[8] = cadd(t0, t2);
+        v[10] = csub(t0, t2);
+        v[9] = INV ? cadd_pi(t1, t3) : cadd_mi(t1, t3);
+        v[11] = INV ? cadd_mi(t1, t3) : cadd_pi(t1, t3);
+    }
+    radix4_tw<INV, INV, false>(v[12], v[13], v[14], v[15], make_float2(1.f, 0.f), w16<3>(), w16<6>(), w16<9>());   // c = 3
     float2 t;
     t = v[1]; v[1] = v[4]; v[4] = t;
     t = v[2]; v[2] = v[8]; v[8] = t;
@@ -125,6 +161,28 @@ TMT_HD void dft16(float2 (&v)[16]) {
     t = v[6]; v[6] = v[9]; v[9] = t;
     t = v[7]; v[7] = v[13]; v[13] = t;
     t = v[11]; v[11] = v[14]; v[14] = t;
+}
+
+// 16-point DFT, natural order in and out, fully in registers:
+//   n = 4a + b, k = c + 4d:  V[c+4d] = sum_b W4^(bd) * W16^(bc) * sum_a W4^(ac) v[4a+b]
+template <bool INV>
+TMT_HD void dft16(float2 (&v)[16]) {
+    // first layer: radix-4 over a for each b; u_b[c] is left in v[4c + b]
+    radix4<INV>(v[0], v[4], v[8], v[12]);
+    radix4<INV>(v[1], v[5], v[9], v[13]);
+    radix4<INV>(v[2], v[6], v[10], v[14]);
+    radix4<INV>(v[3], v[7], v[11], v[15]);
+    dft16_layer2<INV>(v);
+}
+
+// Inverse 16-point DFT of (v[k] * conj(p[k])), k = 0..15, p[0] = 1: the inter-stage twiddles of the inverse transform are
+// fused into the first radix-4 layer (8 packed instructions fewer than multiply-then-transform).
+TMT_HD void dft16_inv_tw(float2 (&v)[16], const float2 (&p)[16]) {
+    radix4_tw<true, true, false>(v[0], v[4], v[8], v[12], p[0], p[4], p[8], p[12]);
+    radix4_tw<true, true, true>(v[1], v[5], v[9], v[13], p[1], p[5], p[9], p[13]);
+    radix4_tw<true, true, true>(v[2], v[6], v[10], v[14], p[2], p[6], p[10], p[14]);
+    radix4_tw<true, true, true>(v[3], v[7], v[11], v[15], p[3], p[7], p[11], p[15]);
+    dft16_layer2<true>(v);
 }
 
 // ---- shared-memory exchange layouts (float2 units) -------------------------------------
@@ -155,6 +213,17 @@ TMT_HD void tw_pow(float2 (&v)[16], const TwBase w) {
     TMT_TW(9, cmul(b8, b1)); TMT_TW(10, cmul(b8, b2)); TMT_TW(11, cmul(b8, b3)); TMT_TW(12, b12);
     TMT_TW(13, cmul(b12, b1)); TMT_TW(14, cmul(b12, b2)); TMT_TW(15, cmul(b12, b3));
 #undef TMT_TW
+}
+
+// p[k] = b^k, k = 0..15, from the per-thread bases (same products as tw_pow)
+TMT_HD void tw_table(float2 (&p)[16], const TwBase w) {
+    const float2 b1 = w.b1, b4 = w.b4;
+    const float2 b2 = cmul(b1, b1), b3 = cmul(b2, b1);
+    const float2 b8 = cmul(b4, b4), b12 = cmul(b8, b4);
+    p[0] = make_float2(1.f, 0.f); p[1] = b1; p[2] = b2; p[3] = b3;
+    p[4] = b4; p[5] = cmul(b4, b1); p[6] = cmul(b4, b2); p[7] = cmul(b4, b3);
+    p[8] = b8; p[9] = cmul(b8, b1); p[10] = cmul(b8, b2); p[11] = cmul(b8, b3);
+    p[12] = b12; p[13] = cmul(b12, b1); p[14] = cmul(b12, b2); p[15] = cmul(b12, b3);
 }
 
 // ---- exchange pieces -----------------------------------------------------------------------
@@ -221,15 +290,17 @@ TMT_HD void inv_c(float2 (&v)[16], int t, float2* bufP) {
 }
 TMT_HD void inv_b(float2 (&v)[16], int t, const TwBase wb, const float2* bufP, float2* bufQ) {
     ld_e2b(v, t, bufP);
-    tw_pow<true>(v, wb);
-    dft16<true>(v);
+    float2 p[16];
+    tw_table(p, wb);
+    dft16_inv_tw(v, p);
     st_e1b(v, t, bufQ);
 }
 // out: v[j] = 4096 * y[256*j + t]
 TMT_HD void inv_a(float2 (&v)[16], int t, const TwBase wa, const float2* bufQ) {
     ld_e1a(v, t, bufQ);
-    tw_pow<true>(v, wa);
-    dft16<true>(v);
+    float2 p[16];
+    tw_table(p, wa);
+    dft16_inv_tw(v, p);
 }
 
 // bin held in register j of thread t after fwd_c (and expected by inv_c)

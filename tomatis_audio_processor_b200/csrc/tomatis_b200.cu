@@ -575,10 +575,10 @@ template <> struct Park<0> {
     __device__ __forceinline__ void inv_fetch_apply(float2 (&v)[16], const TwBase, const float (&a)[16], const float (&b)[16],
                                                     const float (&cr)[16], float2 (&c)[8]) const {
         tmem_wait_ld();
+        float2 p[16];
 #pragma unroll
-        for (int k = 1; k < 8; ++k) v[k] = cmulc(v[k], make_float2(a[2 * k], a[2 * k + 1]));
-#pragma unroll
-        for (int k = 0; k < 8; ++k) v[k + 8] = cmulc(v[k + 8], make_float2(b[2 * k], b[2 * k + 1]));
+        for (int k = 0; k < 8; ++k) { p[k] = make_float2(a[2 * k], a[2 * k + 1]); p[k + 8] = make_float2(b[2 * k], b[2 * k + 1]); }
+        dft16_inv_tw(v, p);                                                       // stage A' with its twiddles fused in
 #pragma unroll
         for (int j = 0; j < 8; ++j) c[j] = make_float2(cr[2 * j], cr[2 * j + 1]);
     }
@@ -668,7 +668,9 @@ template <> struct Park<1> {
     }
     __device__ __forceinline__ void inv_fetch_apply(float2 (&v)[16], const TwBase wa, const float (&)[16], const float (&)[16],
                                                     const float (&cr)[16], float2 (&c)[8]) const {
-        tw_pow<true>(v, wa);
+        float2 p[16];
+        tw_table(p, wa);
+        dft16_inv_tw(v, p);
 #pragma unroll
         for (int j = 0; j < 8; ++j) c[j] = make_float2(cr[2 * j], cr[2 * j + 1]);
     }
@@ -878,15 +880,17 @@ __global__ void __launch_bounds__(kThreads, 2) stft_kernel(const StftParams prm)
                 st_e2c(v, t, bufQ);            // same rows this thread just read: no barrier needed in between
                 __syncwarp();
                 ld_e2b(v, t, bufQ);
-                tw_pow<true>(v, wb);
-                dft16<true>(v);                                                   // B'
+                {
+                    float2 pw[16];
+                    tw_table(pw, wb);
+                    dft16_inv_tw(v, pw);                                          // B' (twiddles fused into the first butterflies)
+                }
                 st_e1b(v, t, bufP);            // the very words this thread read in ld_e1b: no hazard with slower warps still in B
                 float ta[16], tb2[16], cr[16];
                 park.inv_fetch_issue(ta, tb2, s, cr, t);
                 __syncthreads();
                 ld_e1a(v, t, bufP);            // next frame's st_e1a overwrites exactly the words this thread reads here
-                park.inv_fetch_apply(v, wa, ta, tb2, cr, c);
-                dft16<true>(v);                                                   // A'
+                park.inv_fetch_apply(v, wa, ta, tb2, cr, c);                    // A' (twiddles fused into the first butterflies)
             } else {
 #pragma unroll
                 for (int j = 0; j < 16; ++j) v[j] = make_float2(0.f, 0.f);
