@@ -73,3 +73,20 @@ def test_adaptive_mono_file():
     x = synth.recipe_swept_pink(3.0, 48000, 8, period_s=1.1, peak=0.5)[:, :1]
     o = _check("adaptive", x, 48000)
     assert o["out"].shape == (len(x), 1)
+
+
+@pytest.mark.parametrize("kw", [dict(), dict(pad=False, global_gain_db=-3.0), dict(auto_gain_protect=False, global_gain_db=2.0)])
+def test_static_eq_restatement(kw):
+    """oracle/layer2_oracle.py against src/layer2_apply_eq.py executed in place, including the gain-protected second file
+    the reference makes by re-reading its own PCM_24 output."""
+    from oracle import layer2_oracle as l2
+    x = synth.recipe_gated_pink(2.0, 48000, 71, env_hz=1.0, hi_dbfs=-14.0)
+    fr, db = [20.0, 100.0, 500.0, 1000.0, 4000.0, 12000.0, 20000.0], [6.0, 4.0, 0.0, -2.0, 3.0, 8.0, 10.0]
+    r = rh.run_reference_eq(x, 48000, fr, db, **kw)
+    g = l2.build_gain_per_bin(48000, 4096, r["eq_freqs"], r["eq_db"])
+    assert np.array_equal(g, r["gain_bins"])
+    o = l2.apply_eq(x, 48000, g, **kw)
+    assert np.array_equal(o["out"], r["out"])
+    assert (o["out_gp"] is None) == (r["out_gp"] is None)
+    if r["out_gp"] is not None:
+        assert np.array_equal(o["out_gp"], r["out_gp"])
