@@ -21,6 +21,7 @@
 #include <vector>
 #include <algorithm>
 #include <new>
+#include <mutex>
 
 #include "../../include/tomatis_b200.h"
 #include "fft4096.cuh"
@@ -1157,14 +1158,29 @@ __global__ void __launch_bounds__(256) requantise_scale_kernel(float* __restrict
 template <typename T> struct DevBuf {
     T* p = nullptr;
     size_t n = 0;
+    bool owned = true;
     cudaError_t alloc(size_t count) {
         release();
         n = count;
         if (count == 0) return cudaSuccess;
         return cudaMalloc(reinterpret_cast<void**>(&p), count * sizeof(T));
     }
-    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+    void view(void* base, size_t count) { release(); p = reinterpret_cast<T*>(base); n = count; owned = false; }   // slice of an arena
+    void release() { if (p && owned) cudaFree(p); p = nullptr; n = 0; owned = true; }
     ~DevBuf() { release(); }
+};
+
+// One device allocation per plan, carved into its arrays (256-byte aligned).  cudaMalloc / cudaFree are the expensive part of
+// a plan's life (two dozen of each cost tens of milliseconds and cudaFree synchronises the device), so the engine also keeps
+// the arena of the last destroyed plan and hands it to the next one that fits.
+struct Arena {
+    unsigned char* base = nullptr;
+    size_t size = 0, used = 0;
+    void* take(size_t bytes) {
+        const size_t off = (used + 255) & ~size_t(255);
+        used = off + bytes;
+        return base ? base + off : nullptr;
+    }
 };
 
 }  // namespace
@@ -1174,6 +1190,9 @@ struct tmt_engine {
     int n_sms = 0;
     DevBuf<float> win;        // [4096]
     DevBuf<float> swin;       // [2][4096]  synthesis window x interior normalisation (eps | clamp)
+    std::mutex arena_mu;                    // plans of one engine may be created / destroyed from several host threads
+    unsigned char* spare_arena = nullptr;   // arena of the last destroyed plan, reused by the next plan that fits
+    size_t spare_arena_size = 0;
     int stft_store = 0;       // 0: thread-private constants + carry in tensor memory, 1: in shared memory
     int gate_nseg = 0;        // > 0: force this many gate-scan segments per track (TMT_GATE_NSEG, tests)
     DevBuf<float2> tw_bases;  // [256][4]
@@ -1195,6 +1214,7 @@ struct HostTrack {
 };
 
 struct tmt_plan {
+    ~tmt_plan() { if (arena.base) cudaFree(arena.base); }      // only on error paths; tmt_plan_destroy recycles the arena first
     tmt_engine* e = nullptr;
     int framing = 0;
     int n_tracks = 0, total_frames = 0, total_chunks = 0, n_units = 0;
@@ -1202,6 +1222,7 @@ struct tmt_plan {
     long long max_chunk_len = 0, max_in_len = 0;
     std::vector<HostTrack> ht;
     std::vector<TrackDev> tracks_h;
+    Arena arena;
     DevBuf<TrackDev> tracks;
     DevBuf<UnitDev> units;
     DevBuf<ChunkDev> chunks;
@@ -1409,6 +1430,7 @@ int tmt_engine_create(tmt_engine** out, int device, int n_fft, int hop) {
 int tmt_engine_destroy(tmt_engine* e) {
     if (!e) return TMT_OK;
     cudaSetDevice(e->device);
+    if (e->spare_arena) cudaFree(e->spare_arena);
     delete e;
     return TMT_OK;
 }
@@ -1568,15 +1590,51 @@ int tmt_plan_create(tmt_engine* e, tmt_plan** out, int framing, int n_tracks, co
     p->n_units = (int)units.size();
     p->n_edges = (int)edges.size();
     const size_t nf = (size_t)frames, nt = (size_t)n_tracks;
-    bool ok = p->tracks.alloc(std::max<size_t>(nt, 1)) == cudaSuccess && p->units.alloc(std::max<size_t>(units.size(), 1)) == cudaSuccess &&
-              p->chunks.alloc(std::max<size_t>(chunks.size(), 1)) == cudaSuccess && p->chunk_done.alloc(chunks.size() + 1) == cudaSuccess && p->unit_counter.alloc(1) == cudaSuccess && p->edges.alloc(std::max<size_t>(edges.size(), 1)) == cudaSuccess &&
-              p->edge_in_scale.alloc(nt + 1) == cudaSuccess && p->edge_out_scale.alloc(nt + 1) == cudaSuccess && p->hsum.alloc(nf + nt + 1) == cudaSuccess &&
-              p->msq.alloc(nf + 1) == cudaSuccess && p->gate_f64.alloc(nf + 1) == cudaSuccess && p->state.alloc(nf + 1) == cudaSuccess &&
-              p->rows.alloc(nf + 1) == cudaSuccess && p->c2.alloc(nt + 1) == cudaSuccess &&
-              p->segmap.alloc((size_t)kGateSegCap * 256) == cudaSuccess && p->segclamp.alloc((size_t)kGateSegCap * 3) == cudaSuccess &&
-              p->chunk_peaks.alloc(chunks.size() + 1) == cudaSuccess && p->in_peaks.alloc(nt + 1) == cudaSuccess &&
-              p->in_scale.alloc(nt + 1) == cudaSuccess && p->von.alloc(nt + 1) == cudaSuccess && p->voff.alloc(nt + 1) == cudaSuccess;
-    if (!ok) { delete p; return fail(TMT_ERR_NOMEM, "device allocation failed: %s", cudaGetErrorString(cudaGetLastError())); }
+    // one arena for every per-plan device array: first pass sizes it, second pass hands out the slices
+    for (int pass = 0; pass < 2; ++pass) {
+        Arena& a = p->arena;
+        a.used = 0;
+#define TMT_SLICE(buf, count) (buf).view(a.take(sizeof(*(buf).p) * (count)), (count))
+        TMT_SLICE(p->tracks, std::max<size_t>(nt, 1));
+        TMT_SLICE(p->units, std::max<size_t>(units.size(), 1));
+        TMT_SLICE(p->chunks, std::max<size_t>(chunks.size(), 1));
+        TMT_SLICE(p->chunk_done, chunks.size() + 1);
+        TMT_SLICE(p->unit_counter, 1);
+        TMT_SLICE(p->edges, std::max<size_t>(edges.size(), 1));
+        TMT_SLICE(p->edge_in_scale, nt + 1);
+        TMT_SLICE(p->edge_out_scale, nt + 1);
+        TMT_SLICE(p->hsum, nf + nt + 1);
+        TMT_SLICE(p->msq, nf + 1);
+        TMT_SLICE(p->gate_f64, nf + 1);
+        TMT_SLICE(p->state, nf + 1);
+        TMT_SLICE(p->rows, nf + 1);
+        TMT_SLICE(p->c2, nt + 1);
+        TMT_SLICE(p->segmap, (size_t)kGateSegCap * 256);
+        TMT_SLICE(p->segclamp, (size_t)kGateSegCap * 3);
+        TMT_SLICE(p->chunk_peaks, chunks.size() + 1);
+        TMT_SLICE(p->in_peaks, nt + 1);
+        TMT_SLICE(p->in_scale, nt + 1);
+        TMT_SLICE(p->von, nt + 1);
+        TMT_SLICE(p->voff, nt + 1);
+#undef TMT_SLICE
+        if (pass == 0) {
+            const size_t need = a.used + 256;
+            {
+                std::lock_guard<std::mutex> lock(e->arena_mu);
+                if (e->spare_arena && e->spare_arena_size >= need) {
+                    a.base = e->spare_arena; a.size = e->spare_arena_size;
+                    e->spare_arena = nullptr; e->spare_arena_size = 0;
+                }
+            }
+            if (a.base) {
+            } else if (cudaMalloc(reinterpret_cast<void**>(&a.base), need) == cudaSuccess) {
+                a.size = need;
+            } else {
+                delete p;
+                return fail(TMT_ERR_NOMEM, "device allocation of %zu bytes failed: %s", need, cudaGetErrorString(cudaGetLastError()));
+            }
+        }
+    }
     cudaMemset(p->rows.p, 0, sizeof(uint16_t) * (nf + 1));
     cudaMemset(p->state.p, 0, nf + 1);
     cudaMemset(p->hsum.p, 0, sizeof(double) * (nf + nt + 1));
@@ -1592,7 +1650,23 @@ int tmt_plan_create(tmt_engine* e, tmt_plan** out, int framing, int n_tracks, co
 
 int tmt_plan_destroy(tmt_plan* p) {
     if (!p) return TMT_OK;
-    cudaSetDevice(p->e->device);
+    tmt_engine* e = p->e;
+    cudaSetDevice(e->device);
+    if (p->arena.base) {
+        // work queued on the plan's arrays may still be running: the next owner only touches the arena through stream-ordered
+        // calls on the same device after a device-wide synchronisation here (cudaFree would have implied the same)
+        cudaDeviceSynchronize();
+        unsigned char* to_free = p->arena.base;
+        {
+            std::lock_guard<std::mutex> lock(e->arena_mu);
+            if (p->arena.size > e->spare_arena_size && p->arena.size <= (size_t(1) << 30)) {
+                to_free = e->spare_arena;
+                e->spare_arena = p->arena.base; e->spare_arena_size = p->arena.size;
+            }
+        }
+        if (to_free) cudaFree(to_free);
+        p->arena.base = nullptr;
+    }
     delete p;
     return TMT_OK;
 }

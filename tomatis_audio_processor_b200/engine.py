@@ -340,7 +340,8 @@ def _percentile_thresholds(levels, valid):
     vl = levels[valid]
     if len(vl) == 0:
         return None
-    return np.percentile(vl, 5), np.percentile(vl, 95), np.median(vl)
+    p5, p95 = np.percentile(vl, [5, 95])          # same linear interpolation as two separate calls
+    return p5, p95, np.median(vl)
 
 
 def run_adaptive(xs: Sequence, sr: int, device: int = 0, want_host: bool = True, outs=None, unit_blocks: int = 0,
@@ -374,15 +375,19 @@ def run_adaptive(xs: Sequence, sr: int, device: int = 0, want_host: bool = True,
     try:
         plan0.input_peaks()
         in_peaks = plan0.read(L.ARR_INPUT_PEAK)
-    finally:
+    except Exception:
         plan0.close()
+        raise
     branch = [tb.adaptive_attenuation(pk, c1_low, c2_high, headroom_margin) for pk in in_peaks]
+    single_branch = len({b[2] for b in branch}) <= 1          # the usual case: the first plan serves the whole call
+    if not single_branch:
+        plan0.close()
 
     for use_f64 in (False, True):
         idx = [i for i, b in enumerate(branch) if b[2] == use_f64]
         if not idx:
             continue
-        plan = Plan(eng, L.FRAMING_WHOLEFILE, [whole_track_desc(xd[i], yd[i]) for i in idx], unit_blocks)
+        plan = plan0 if single_branch else Plan(eng, L.FRAMING_WHOLEFILE, [whole_track_desc(xd[i], yd[i]) for i in idx], unit_blocks)
         try:
             scale = np.array([np.float32(branch[i][1]) for i in idx], dtype=np.float32)
             plan.levels(use_f64=use_f64, in_scale=scale, mono=mono)
@@ -443,7 +448,7 @@ def run_adaptive(xs: Sequence, sr: int, device: int = 0, want_host: bool = True,
                     out=((yd[i].cpu().numpy()[:, :1] if mono else yd[i].cpu().numpy()) if want_host else yd[i]),
                     chunk_lengths=[int(xd[i].shape[0])],
                     meansq=msq[fb:fb + nf].copy(), levels=lv[t].copy(), states=states[fb:fb + nf].copy(),
-                    rows=rows[fb:fb + nf].copy(), times=[(k + 1) * (hop / sr) for k in range(nf)],
+                    rows=rows[fb:fb + nf].copy(), times=(np.arange(1, nf + 1) * (hop / sr)),
                     optimal_T=float(best_T[t]), trace=traces[t], atten_db=float(branch[i][0]),
                     pipeline_dtype="float64" if use_f64 else "float32", min_hold_frames=hold, xfade_frames=xf,
                     output_peak=float(peaks[plan.chunk_base[t]]) if plan.track_chunks[t] else 0.0, sr=sr,

@@ -402,7 +402,7 @@ def run_adaptive_sharded(own, sr: int, total: int, comm: Comm, make_backend=None
         return dict(out=be.out, full=full, shard=me, shards=shards, meansq=msq, levels=levels, states=states, rows=rows,
                     optimal_T=float(best_T), trace=trace, atten_db=float(atten_db), input_peak=float(in_peak),
                     pipeline_dtype="float64" if use_f64 else "float32", output_peak=float(peaks[0]) if len(peaks) else 0.0,
-                    min_hold_frames=hold, xfade_frames=xf, times=[(k + 1) * (hop / sr) for k in range(n)], sr=sr,
+                    min_hold_frames=hold, xfade_frames=xf, times=(np.arange(1, n + 1) * (hop / sr)), sr=sr,
                     launches=be.launches(), comm_bytes=comm.bytes_sent)
     finally:
         be.close()
