@@ -71,25 +71,6 @@ TMT_HD float2 cfmac(float2 acc, float2 a, float2 w) { return make_float2(acc.x +
 TMT_HD float2 twice_minus(float2 p, float2 t) { return make_float2(2.f * p.x - t.x, 2.f * p.y - t.y); }
 #endif
 
-// multiply by W16^M (forward, e^{-2*pi*i*M/16}) or its conjugate (INV)
-template <int M, bool INV>
-TMT_HD float2 mul_w16(float2 a) {
-    constexpr float kC1 = 0.92387953251128673848f;   // cos(pi/8)
-    constexpr float kS1 = 0.38268343236508978178f;   // sin(pi/8)
-    constexpr float kH = 0.70710678118654752440f;    // sqrt(1/2)
-    if constexpr (M == 0) {
-        return a;
-    } else if constexpr (M == 4) {                   // -i (fwd) / +i (inv): swap + sign, folded into the consumer
-        return INV ? make_float2(-a.y, a.x) : make_float2(a.y, -a.x);
-    } else {
-        // W16^M = (c, -s) forward, (c, +s) inverse
-        constexpr float c = (M == 1) ? kC1 : (M == 2) ? kH : (M == 3) ? kS1 : (M == 6) ? -kH : (M == 9) ? -kC1 : 0.f;
-        constexpr float s = (M == 1) ? kS1 : (M == 2) ? kH : (M == 3) ? kC1 : (M == 6) ? kH : (M == 9) ? -kS1 : 0.f;
-        static_assert(M == 1 || M == 2 || M == 3 || M == 6 || M == 9, "unsupported W16 power");
-        return INV ? cmul(a, make_float2(c, s)) : cmul(a, make_float2(c, -s));
-    }
-}
-
 // 4-point DFT in place: (x0..x3) -> (X0..X3), forward W4 = -i, inverse W4 = +i
 template <bool INV>
 TMT_HD void radix4(float2& x0, float2& x1, float2& x2, float2& x3) {
