@@ -65,7 +65,8 @@ typedef struct tmt_plan tmt_plan;     /* per batch of tracks (or file shard): ge
  * file; the in/out device buffers may cover only a window of it (halo sharding). */
 typedef struct tmt_track_desc {
     const void* pcm_in; /* device, float32 [in_len][2], element 0 is file position in_origin  */
-    void* pcm_out;      /* device, float32 [out_len][2], element 0 is file position out_origin */
+    void* pcm_out;      /* device, float32 [out_len][2], element 0 is file position out_origin; must not
+                           overlap pcm_in (work units read their neighbours' input while those write output) */
     int64_t total;      /* file length in sample-frames (zero padding / clipping refer to it)  */
     int64_t in_origin, in_len;
     int64_t out_origin, out_len;
