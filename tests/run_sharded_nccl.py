@@ -43,6 +43,22 @@ def main():
             print(f"{mode}: world {world}, {total} samples, interior err {d[256:-256].max():.2e}, vs fp64-FFT {d64:.2e}, "
                   f"comm {r['comm_bytes']} B")
         dist.barrier()
+    # the persistent session bench.py times: all-gather halo hand-off + hop-sum all-reduce, two passes
+    x = cases[0][2]
+    total = len(x)
+    me = sharded.plan_shards(total, world, sharded.STREAMING)[rank]
+    o = orc.run("standard", x, 48000, gate_ui=50)
+    sess = sharded.StreamingShardSession("standard", torch.from_numpy(x[me.own_lo:me.own_hi].copy()).cuda(), 48000, total, comm,
+                                         device_index=local, gate_ui=50)
+    for _ in range(2):
+        sess.step()
+    y = sess.out.cpu().numpy().astype(np.float64)
+    d = np.abs(y - o["out"][me.own_lo:me.own_hi]).max(axis=1)
+    if rank == world - 1:
+        d = d[:-256]
+    assert d.max() <= 1e-5, (rank, d.max())
+    sess.close()
+    dist.barrier()
     if rank == 0:
         print("SHARDED-NCCL-OK")
     dist.destroy_process_group()

@@ -73,10 +73,10 @@ class ThreadComm:
                 self.bytes_sent += (hi - lo) * 8
         torch.cuda.synchronize()
         self.w.barrier.wait()
-        return [], recvs
+        return "p2p", [], recvs
 
     def exchange_halos_end(self, pending, shard, window):
-        for lo, hi, buf in pending[1]:
+        for lo, hi, buf in pending[2]:
             window[lo - shard.in_lo:hi - shard.in_lo] = buf
 
     def gather_output(self, own_out, shards, dst=0):

@@ -136,9 +136,23 @@ class Comm:
         return win
 
     def exchange_halos_begin(self, own, shard: Shard, shards: List[Shard]):
-        """Start the halo hand-off without waiting (the sends read `own`, the receives land in fresh buffers); finish it
-        with exchange_halos_end.  Lets the rank sum its own hop blocks and reduce the levels while the halos travel."""
+        """Start the halo hand-off without waiting; finish it with exchange_halos_end.  Lets the rank sum its own hop blocks
+        and reduce the levels while the halos travel.
+
+        Usual case (every halo is at most one hop and comes from the adjacent rank): ONE all-gather of each rank's first
+        and last hop (32 KB per rank) instead of a group of point-to-point transfers -- the group's host-side launch cost
+        (~0.25 ms) was a fifth of the 8-GPU step.  Anything else falls back to point-to-point."""
         torch, dist = self.torch, self.dist
+        hop = tb.HOP
+        simple = all(s.own_hi - s.own_lo >= hop and s.own_lo - s.in_lo <= hop and s.in_hi - s.own_hi <= hop for s in shards)
+        if simple:
+            edge = torch.empty((2, hop, 2), dtype=own.dtype, device=own.device)
+            edge[0] = own[:hop]
+            edge[1] = own[-hop:]
+            allg = torch.empty((len(shards), 2, hop, 2), dtype=own.dtype, device=own.device)
+            work = dist.all_gather_into_tensor(allg, edge, group=self.group, async_op=True)
+            self.bytes_sent += edge.numel() * edge.element_size()
+            return ("allgather", work, allg)
         ops, recvs = [], []
         for other in shards:
             if other.rank == shard.rank:
@@ -153,13 +167,21 @@ class Comm:
                 buf = torch.empty((hi - lo, 2), dtype=own.dtype, device=own.device)
                 ops.append(dist.P2POp(dist.irecv, buf, other.rank, group=self.group))
                 recvs.append((lo, hi, buf))
-        return (dist.batch_isend_irecv(ops) if ops else []), recvs
+        return ("p2p", (dist.batch_isend_irecv(ops) if ops else []), recvs)
 
     def exchange_halos_end(self, pending, shard: Shard, window):
-        reqs, recvs = pending
-        for req in reqs:
+        kind, work, data = pending
+        if kind == "allgather":
+            work.wait()
+            left, right = shard.own_lo - shard.in_lo, shard.in_hi - shard.own_hi
+            if left > 0:                                     # tail of the previous rank's last hop
+                window[:left] = data[shard.rank - 1, 1, tb.HOP - left:]
+            if right > 0:                                    # head of the next rank's first hop
+                window[window.shape[0] - right:] = data[shard.rank + 1, 0, :right]
+            return
+        for req in work:
             req.wait()
-        for lo, hi, buf in recvs:
+        for lo, hi, buf in data:
             window[lo - shard.in_lo: hi - shard.in_lo] = buf
 
     def gather_output(self, own_out, shards: List[Shard], dst: int = 0):
