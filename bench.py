@@ -434,7 +434,7 @@ def run_longfile_arm(args):
     t0 = time.time()
     e0.record()
     for k in range(args.steps):
-        sess.step_timed(ev[k]) if hasattr(sess, "step_timed") else sess.step()
+        sess.step(ev[k])
     e1.record()
     barrier()
     t1 = time.time()

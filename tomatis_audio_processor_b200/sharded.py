@@ -15,6 +15,11 @@ own samples.  Cross-rank traffic, all over torch.distributed (NCCL on GPUs, gloo
 
 The numeric work is done by a *backend* with the interface of engine.Plan (CudaShardBackend below); the CPU
 tests drive the same code with a NumPy stand-in built from the oracle.
+
+`run_streaming_sharded` / `run_adaptive_sharded` are the one-shot drivers (they also return the per-frame data of the
+whole file on every rank).  `StreamingShardSession` keeps plan, window and output on the device for repeated passes and
+trims the hand-offs: halos as one all-gather of each rank's first and last hop, issued first and awaited only before the
+STFT; levels as an all-reduce of hop-block sums, which need no halo at all.
 """
 from __future__ import annotations
 
@@ -482,9 +487,6 @@ class StreamingShardSession:
         mark("allreduce_peaks")
         be.limiter()
         mark("limiter")
-
-    def step_timed(self, events):
-        self.step(events)
 
     @property
     def out(self):
