@@ -254,9 +254,32 @@ def wholefile_frame_count(total: int, hop=HOP) -> int:
 
 def flush_chunk_blocks(n_frames: int, n_fft=N_FFT, hop=HOP):
     """Limiter chunks of the streaming modes as output-block ranges [(b0, b1), ...] (block b = positions
-    [-n_fft/2 + b*hop, +hop)): replay of the flush rule src/process_tomatis.py:419-426 + final flush :451-453."""
+    [-n_fft/2 + b*hop, +hop)): the flush rule src/process_tomatis.py:419-426 + final flush :451-453.
+
+    The rule flushes `safe = (next_start - out_base) - n_fft` samples whenever safe >= 240 000 after a frame.  With
+    n_fft a multiple of hop that is periodic: the first flush happens after ceil((240000 + n_fft) / hop) frames, every
+    later one ceil(240000 / hop) frames after the previous (120 and 118 frames at the defaults: chunks of 118 blocks)."""
     if n_frames <= 0:
         return []
+    if n_fft % hop:
+        return _flush_chunk_blocks_replay(n_frames, n_fft, hop)
+    first = -(-(FLUSH_SAFE + n_fft) // hop)               # frames before the first flush
+    nb1 = first - n_fft // hop                            # blocks it writes
+    per = -(-FLUSH_SAFE // hop)                           # frames (= blocks) between later flushes
+    out, flushed = [], 0
+    if n_frames >= first:
+        out.append((0, nb1))
+        flushed = nb1
+        k = (n_frames - first) // per
+        out.extend((nb1 + i * per, nb1 + (i + 1) * per) for i in range(k))
+        flushed += k * per
+    if flushed < n_frames + 1:
+        out.append((flushed, n_frames + 1))
+    return out
+
+
+def _flush_chunk_blocks_replay(n_frames: int, n_fft=N_FFT, hop=HOP):
+    """Frame-by-frame replay of the same rule (any n_fft / hop); also the cross-check of the closed form in the tests."""
     out, flushed, out_base, next_start = [], 0, 0, 0
     for _ in range(n_frames):
         next_start += hop
