@@ -66,7 +66,8 @@ typedef struct tmt_plan tmt_plan;     /* per batch of tracks (or file shard): ge
 typedef struct tmt_track_desc {
     const void* pcm_in; /* device, float32 [in_len][2], element 0 is file position in_origin  */
     void* pcm_out;      /* device, float32 [out_len][2], element 0 is file position out_origin; must not
-                           overlap pcm_in (work units read their neighbours' input while those write output) */
+                           overlap pcm_in (work units read their neighbours' input while those write output);
+                           may be NULL with out_len = 0 for a plan that only runs levels / gate (analysis) */
     int64_t total;      /* file length in sample-frames (zero padding / clipping refer to it)  */
     int64_t in_origin, in_len;
     int64_t out_origin, out_len;
@@ -134,6 +135,8 @@ int tmt_plan_input_peaks(tmt_plan* p, void* stream);
 #define TMT_LEVELS_HOPSUM_ONLY 8  /* only the hop-block sums (TMT_ARR_HOPSUM_*), no frame mean squares */
 #define TMT_LEVELS_MEANSQ_ONLY 16 /* only m[k] = (H[k] + H[k+1]) / n_fft from the hop-block sums already in the plan */
 #define TMT_LEVELS_MONO 2 /* single-channel file carried in the L lane (R = 0): mono = sqrt(x*x), _adaptive.py:74,180-181 */
+#define TMT_LEVELS_LEFT 32  /* level of the left channel alone, np.mean(x*x) (src/analyze_stereo_state.py:16-19,112) */
+#define TMT_LEVELS_RIGHT 64 /* level of the right channel alone (src/analyze_stereo_state.py:113) */
 int tmt_plan_levels(tmt_plan* p, int flags, const float* in_scale, void* stream);
 
 /* K2b.  Gate automaton + crossfade counter as a block-level scan over frames.

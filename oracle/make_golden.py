@@ -88,9 +88,39 @@ def make_eq():
               f"gp={'yes' if r['out_gp'] is not None else 'no'} {os.path.getsize(path)/1e6:.2f} MB")
 
 
+def chan_cases():
+    """(name, sr, input, kwargs) for the per-channel state analyser src/analyze_stereo_state.py.
+    The right channel is a delayed, quieter copy so that the two channels get different thresholds and states."""
+    def two(x, shift, gain):
+        y = x.copy()
+        y[:, 1] = np.roll(x[:, 1], shift) * gain
+        return _q(y)
+    return [("chan_48k_default", 48000, two(synth.recipe_swept_pink(3.0, 48000, 31, period_s=0.9, peak=0.5), 5000, 0.6), dict()),
+            ("chan_44k1_target30", 44100, two(synth.recipe_gated_pink(2.5, 44100, 32, env_hz=1.5, hi_dbfs=-28.0), 7000, 0.5),
+             dict(target_c2=0.3, hyst_db=2.0, min_hold_ms=100.0)),
+            ("chan_96k_ragged", 96000, two(synth.recipe_swept_pink(2.0, 96000, 33, period_s=0.5, peak=0.1), 9000, 0.7)[:2048 * 60 + 777],
+             dict(min_hold_ms=60.0))]
+
+
+def make_chan():
+    for name, sr, x, kw in chan_cases():
+        r = rh.run_reference_stereo_state(x, sr, **kw)
+        assert r["rc"] == 0
+        path = os.path.join(OUT_DIR, name + ".npz")
+        np.savez_compressed(path, pcm16=synth.quantise_pcm16(x), meta=np.array(json.dumps(dict(
+            name=name, mode="stereo_state", sr=sr, kwargs=kw, csv=r["rows"], stdout=r["stdout"], numpy=np.__version__,
+            reference_files=["analyze_stereo_state.py"]))))
+        st = [row[4] + row[6] for row in r["rows"][1:]]
+        print(f"{name:24s} channels  sr={sr} N={len(x)} frames={len(st)} L-C2={sum(s[:2] == 'C2' for s in st)} "
+              f"R-C2={sum(s[2:] == 'C2' for s in st)} {os.path.getsize(path)/1e6:.2f} MB")
+
+
 def main():
     assert rh.reference_available(), "run in the build container (needs /root/reference)"
     os.makedirs(OUT_DIR, exist_ok=True)
+    if "--only-chan" in sys.argv:
+        return make_chan()
+    make_chan()
     make_eq()
     for name, mode, sr, x, kw in cases():
         r = rh.run_reference(mode, x, sr, **kw)

@@ -36,6 +36,7 @@ MODULES = {
     "adaptive": "process_tomatis_adaptive",
     "xfade": "process_tomatis_xfade",
     "eq": "layer2_apply_eq",
+    "stereo_state": "analyze_stereo_state",
 }
 
 
@@ -224,3 +225,24 @@ def run_reference_eq(x: np.ndarray, sr: int, eq_freqs, eq_db, **params) -> dict:
     gp = store.outputs.get("out_gp.flac")
     return dict(out=out, out_gp=(np.concatenate(gp["chunks"], axis=0) if gp else None), stdout=buf.getvalue(),
                 gain_bins=gain, eq_freqs=freqs, eq_db=dbs)
+
+
+def run_reference_stereo_state(x: np.ndarray, sr: int, **params) -> dict:
+    """Run the reference `analyze()` (src/analyze_stereo_state.py:79) on float32 x [N, 2].  Returns dict(rc, rows = the
+    CSV it wrote (lists of str), stdout)."""
+    assert reference_available(), "reference sources not present"
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    store = _Store()
+    store.inputs["in.flac"] = (x, sr)
+    mod = load_reference_module("stereo_state", store, skip_guard=False)
+    fd, tmp = tempfile.mkstemp(suffix=".csv")
+    os.close(fd)
+    try:
+        buf = io.StringIO()
+        with contextlib.redirect_stdout(buf):
+            rc = mod.analyze("in.flac", tmp, **params)
+        with open(tmp, "r", encoding="utf-8", newline="") as f:
+            rows = list(csv.reader(f))
+    finally:
+        os.unlink(tmp)
+    return dict(rc=rc, rows=rows, stdout=buf.getvalue())

@@ -13,7 +13,7 @@ GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 def golden_names():
     """Fixtures of the Tomatis path (standard / xfade / adaptive)."""
     return sorted(n for n in (os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
-                  if not n.startswith("eq_"))
+                  if not n.startswith(("eq_", "chan_")))
 
 
 def eq_golden_names():
@@ -26,6 +26,17 @@ def load_eq_golden(name):
     meta = json.loads(str(z["meta"]))
     return dict(x=synth.pcm16_to_float(z["pcm16"]), out=z["out"], out_gp=(z["out_gp"] if meta["has_gp"] else None),
                 gain_bins=z["gain_bins"], eq_freqs=z["eq_freqs"], eq_db=z["eq_db"], **meta)
+
+
+def chan_golden_names():
+    """Fixtures of the per-channel state analyser (src/analyze_stereo_state.py)."""
+    return sorted(n for n in (os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, "chan_*.npz"))))
+
+
+def load_chan_golden(name):
+    z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+    meta = json.loads(str(z["meta"]))
+    return dict(x=synth.pcm16_to_float(z["pcm16"]), **meta)
 
 
 def load_golden(name):

@@ -50,3 +50,11 @@ def test_adaptive_attenuation_dtype_branch():
     assert (not f64) and isinstance(a_db, np.floating) and a_db > 0
     x = np.float32(0.5)
     assert a_db == max(0, 20 * np.log10(x + 1e-12) + 15.0 + 2.0)
+
+
+def test_flush_schedule_closed_form_equals_the_frame_by_frame_replay():
+    for n in list(range(0, 700)) + [1292, 6460, 14063, 337500, 337501]:
+        assert tb.flush_chunk_blocks(n) == tb._flush_chunk_blocks_replay(n), n
+    for nf, hp in ((2048, 1024), (8192, 4096), (4096, 1024), (4096, 4096)):
+        for n in (0, 1, 100, 500, 1000, 5000):
+            assert tb.flush_chunk_blocks(n, nf, hp) == tb._flush_chunk_blocks_replay(n, nf, hp), (nf, hp, n)

@@ -14,6 +14,7 @@ OK = 0
 FRAMING_STREAMING, FRAMING_WHOLEFILE, FRAMING_EQ_PAD, FRAMING_EQ_NOPAD = 0, 1, 2, 3
 GATE_UPDELAY, GATE_MINHOLD = 0, 1
 PCM_S16, PCM_S24 = 0, 1
+LEVELS_F64, LEVELS_MONO, LEVELS_HOPSUM_ONLY, LEVELS_MEANSQ_ONLY, LEVELS_LEFT, LEVELS_RIGHT = 1, 2, 8, 16, 32, 64
 (ARR_MEANSQ_F32, ARR_MEANSQ_F64, ARR_GATE_F64, ARR_STATE, ARR_ROW, ARR_C2_COUNT, ARR_CHUNK_PEAK,
  ARR_INPUT_PEAK, ARR_HOPSUM_F32, ARR_HOPSUM_F64) = range(10)
 

@@ -135,6 +135,11 @@ template <> struct Arith<float> {
         const float mono = __fsqrt_rn(__fmul_rn(l, l));
         return __fmul_rn(mono, mono);
     }
+    // one channel on its own: np.mean(x_mono * x_mono) (src/analyze_stereo_state.py:16-19,112-113)
+    static __device__ __forceinline__ float sq(float x, float sc) {
+        const float v = __fmul_rn(x, sc);
+        return __fmul_rn(v, v);
+    }
     static __device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); }
     static __device__ __forceinline__ float div(float a, float b) { return __fdiv_rn(a, b); }
 };
@@ -149,6 +154,10 @@ template <> struct Arith<double> {
         const double l = __dmul_rn((double)x.x, (double)sc);
         const double mono = __dsqrt_rn(__dmul_rn(l, l));
         return __dmul_rn(mono, mono);
+    }
+    static __device__ __forceinline__ double sq(float x, float sc) {
+        const double v = __dmul_rn((double)x, (double)sc);
+        return __dmul_rn(v, v);
     }
     static __device__ __forceinline__ double add(double a, double b) { return __dadd_rn(a, b); }
     static __device__ __forceinline__ double div(double a, double b) { return __ddiv_rn(a, b); }
@@ -195,12 +204,20 @@ levels_kernel(const TrackDev* __restrict__ tracks, const float* __restrict__ in_
                 a0 = Arith<T>::add(a0, Arith<T>::msq(x0[i], sc));
                 a1 = Arith<T>::add(a1, Arith<T>::msq(x1[i], sc));
             }
-        } else {
+        } else if (mono == 1) {
             a0 = Arith<T>::msq_mono(x0[0], sc); a1 = Arith<T>::msq_mono(x1[0], sc);
 #pragma unroll
             for (int i = 1; i < 16; ++i) {
                 a0 = Arith<T>::add(a0, Arith<T>::msq_mono(x0[i], sc));
                 a1 = Arith<T>::add(a1, Arith<T>::msq_mono(x1[i], sc));
+            }
+        } else {                                     // 2: left channel alone, 3: right channel alone
+            const bool right = (mono == 3);
+            a0 = Arith<T>::sq(right ? x0[0].y : x0[0].x, sc); a1 = Arith<T>::sq(right ? x1[0].y : x1[0].x, sc);
+#pragma unroll
+            for (int i = 1; i < 16; ++i) {
+                a0 = Arith<T>::add(a0, Arith<T>::sq(right ? x0[i].y : x0[i].x, sc));
+                a1 = Arith<T>::add(a1, Arith<T>::sq(right ? x1[i].y : x1[i].x, sc));
             }
         }
         T s = Arith<T>::add(a0, a1);                                         // r[2p] + r[2p+1]
@@ -1512,7 +1529,7 @@ int tmt_plan_create(tmt_engine* e, tmt_plan** out, int framing, int n_tracks, co
         HostTrack h;
         h.d = tracks[i];
         if (h.d.total < 0 || h.d.in_len < 0 || h.d.out_len < 0) { delete p; return fail(TMT_ERR_INVALID, "track %d: negative length", i); }
-        if (h.d.total > 0 && (!h.d.pcm_in || !h.d.pcm_out)) { delete p; return fail(TMT_ERR_INVALID, "track %d: NULL audio buffer", i); }
+        if (h.d.total > 0 && (!h.d.pcm_in || (!h.d.pcm_out && h.d.out_len > 0))) { delete p; return fail(TMT_ERR_INVALID, "track %d: NULL audio buffer", i); }
         h.first_start = (framing == TMT_FRAMING_STREAMING || framing == TMT_FRAMING_EQ_PAD) ? -(long long)(kNfft / 2) : 0;
         h.n_frames = count_frames(framing, h.d.total);
         // positions that belong to the output: the file itself, or (static EQ) everything the frames cover
@@ -1757,8 +1774,11 @@ int tmt_plan_input_peaks(tmt_plan* p, void* stream) {
 }
 
 int tmt_plan_levels(tmt_plan* p, int flags, const float* in_scale, void* stream) {
-    const int use_f64 = flags & TMT_LEVELS_F64, mono = (flags & TMT_LEVELS_MONO) ? 1 : 0;
+    const int use_f64 = flags & TMT_LEVELS_F64;
+    const int mono = (flags & TMT_LEVELS_MONO) ? 1 : (flags & TMT_LEVELS_LEFT) ? 2 : (flags & TMT_LEVELS_RIGHT) ? 3 : 0;
     if (!p) return fail(TMT_ERR_INVALID, "plan is NULL");
+    if (((flags & TMT_LEVELS_MONO) != 0) + ((flags & TMT_LEVELS_LEFT) != 0) + ((flags & TMT_LEVELS_RIGHT) != 0) > 1)
+        return fail(TMT_ERR_INVALID, "TMT_LEVELS_MONO, _LEFT and _RIGHT exclude each other");
     if (p->n_tracks == 0 || (p->max_hb == 0 && !(flags & TMT_LEVELS_MEANSQ_ONLY))) return TMT_OK;
     CUDA_TRY(cudaSetDevice(p->e->device));
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);

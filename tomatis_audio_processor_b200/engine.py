@@ -144,14 +144,18 @@ class Plan:
     def set_level_ranges(self, track: int, hb_lo: int, hb_hi: int, f_lo: int, f_hi: int):
         L.check(self.lib.tmt_plan_set_level_ranges(self.h, track, hb_lo, hb_hi, f_lo, f_hi), "tmt_plan_set_level_ranges")
 
-    def levels(self, use_f64: bool = False, in_scale: Optional[np.ndarray] = None, mono: bool = False, part: str = "all"):
-        """part: "all" | "hopsums" (hop-block sums only) | "meansq" (mean squares from the sums already in the plan)"""
+    def levels(self, use_f64: bool = False, in_scale: Optional[np.ndarray] = None, mono: bool = False, part: str = "all",
+               channel: Optional[str] = None):
+        """part: "all" | "hopsums" (hop-block sums only) | "meansq" (mean squares from the sums already in the plan);
+        channel: None (the mode's stereo / mono formula) | "left" | "right" (np.mean(x*x) of that channel alone)"""
         ptr = None
         if in_scale is not None:
             in_scale = np.ascontiguousarray(in_scale, dtype=np.float32)
             assert in_scale.size == self.n_tracks
             ptr = in_scale.ctypes.data_as(C.c_void_p)
-        flags = int(bool(use_f64)) | (2 if mono else 0) | {"all": 0, "hopsums": 8, "meansq": 16}[part]
+        flags = (int(bool(use_f64)) | (L.LEVELS_MONO if mono else 0)
+                 | {"all": 0, "hopsums": L.LEVELS_HOPSUM_ONLY, "meansq": L.LEVELS_MEANSQ_ONLY}[part]
+                 | {None: 0, "left": L.LEVELS_LEFT, "right": L.LEVELS_RIGHT}[channel])
         L.check(self.lib.tmt_plan_levels(self.h, flags, ptr, _stream_ptr(_torch())),
                 "tmt_plan_levels")
 
@@ -456,6 +460,70 @@ def run_adaptive(xs: Sequence, sr: int, device: int = 0, want_host: bool = True,
         finally:
             plan.close()
     return results
+
+
+# ------------------------------------------------------------------------------ per-channel state analysis (N3)
+def run_channel_states(xs: Sequence, sr: int, device: int = 0, target_c2=0.5, hyst_db=3.0, min_hold_ms=250.0,
+                       n_fft=tb.N_FFT, hop=tb.HOP) -> List[dict]:
+    """Left and right channel analysed on their own: level per frame, threshold search, min-hold gate
+    (src/analyze_stereo_state.py:79-128).  Device: both level passes and every gate simulation of the two searches, all
+    tracks in lock step; host: percentiles and the search bookkeeping.  No audio is written (analysis-only plan)."""
+    torch = _torch()
+    eng = get_engine(device)
+    if n_fft != eng.n_fft or hop != eng.hop:
+        raise NotImplementedError(f"GPU path implements n_fft={eng.n_fft}, hop={eng.hop}; got {n_fft}/{hop}")
+    frame_ms = hop / sr * 1000                                        # :89-90
+    hold = int(np.ceil(min_hold_ms / frame_ms))
+    xd = _to_device(torch, xs, device)
+    descs = [L.TrackDesc(x.data_ptr(), None, int(x.shape[0]), 0, int(x.shape[0]), 0, 0, 0, -1) for x in xd]
+    plan = Plan(eng, L.FRAMING_WHOLEFILE, descs)
+    try:
+        nt = plan.n_tracks
+        res = [dict(min_hold_frames=hold, sr=sr, times=np.arange(plan.track_frames[t]) * hop / sr)
+               for t in range(nt)]                                   # frame i covers [i*hop, i*hop + n_fft): orig_start / sr (:114)
+        for name in ("left", "right"):
+            plan.levels(channel=name)
+            levels_all = tb.levels_from_meansq(plan.read(L.ARR_MEANSQ_F32))      # float32 chain of rms_dbfs (:16-19)
+            plan.write(L.ARR_GATE_F64, levels_all)
+            lv = [levels_all[plan.frame_base[t]:plan.frame_base[t] + plan.track_frames[t]] for t in range(nt)]
+            # find_optimal_threshold (:52-76): returns the midpoint that hits the target, else the last one tried
+            T_low = np.zeros(nt); T_high = np.zeros(nt); T = np.zeros(nt)
+            active = np.ones(nt, dtype=bool)
+            for t in range(nt):
+                pt = _percentile_thresholds(lv[t], lv[t] > -70)
+                if pt is None:
+                    with np.errstate(invalid="ignore"):
+                        T[t] = np.median(lv[t]) if len(lv[t]) else np.nan
+                    active[t] = False
+                else:
+                    T_low[t], T_high[t], T[t] = pt
+            for _ in range(30):
+                if not active.any():
+                    break
+                T_mid = np.where(active, (T_low + T_high) / 2, T)
+                T_mid = np.nan_to_num(T_mid)                          # frameless tracks carry NaN (np.median of nothing)
+                plan.gate(L.GATE_MINHOLD, L.ARR_GATE_F64, T_mid + hyst_db / 2, T_mid - hyst_db / 2, hold, 0, count_only=True)
+                c2 = plan.read(L.ARR_C2_COUNT)
+                for t in np.nonzero(active)[0]:
+                    ratio = int(c2[t]) / plan.track_frames[t]
+                    T[t] = T_mid[t]
+                    if abs(ratio - target_c2) < 0.01:
+                        active[t] = False
+                    elif ratio < target_c2:
+                        T_high[t] = T_mid[t]
+                    else:
+                        T_low[t] = T_mid[t]
+            Tg = np.nan_to_num(T)
+            plan.gate(L.GATE_MINHOLD, L.ARR_GATE_F64, Tg + hyst_db / 2, Tg - hyst_db / 2, hold, 0, count_only=False)
+            states = plan.read(L.ARR_STATE)
+            for t in range(nt):
+                fb, nf = plan.frame_base[t], plan.track_frames[t]
+                st = states[fb:fb + nf].copy()
+                res[t].update({name + "_levels": lv[t].copy(), name + "_T": float(T[t]), name + "_states": st,
+                               name + "_c2": (int((st == 2).sum()) / nf if nf else float("nan"))})
+        return res
+    finally:
+        plan.close()
 
 
 def run(mode: str, xs: Sequence, sr: int, **kw) -> List[dict]:

@@ -280,6 +280,8 @@ def flush_chunk_blocks(n_frames: int, n_fft=N_FFT, hop=HOP):
 
 def _flush_chunk_blocks_replay(n_frames: int, n_fft=N_FFT, hop=HOP):
     """Frame-by-frame replay of the same rule (any n_fft / hop); also the cross-check of the closed form in the tests."""
+    if n_frames <= 0:
+        return []
     out, flushed, out_base, next_start = [], 0, 0, 0
     for _ in range(n_frames):
         next_start += hop
