@@ -200,6 +200,17 @@ int tmt_float_to_pcm(const float* in, int format, int64_t n_values, void* pcm, v
  * pass (src/layer2_apply_eq.py:220-234). */
 int tmt_requantise_scale(float* y, int64_t n_values, float scale, void* stream);
 
+/* ---- validators ------------------------------------------------------------ */
+/* Conditional spectrum of an input / output file pair: for every listed frame f (positions [f*hop, f*hop + n_fft), which
+ * must lie inside the file) ratio_f[k] = mean_c |rfft(y_c * hann)[k]| / max(mean_c |rfft(x_c * hann)[k]|, 1e-10),
+ * then median over the frames per bin -> median_out (host, n_fft/2 + 1 floats); the caller takes 20*log10(. + 1e-12).
+ * Replaces the frame loops of compute_conditional_spectrum (src/validate_layer1.py:338-374) and, with
+ * anchor_bin_lo <= anchor_bin_hi (each frame's ratio divided by its mean over those bins when that mean is > 0), of
+ * compute_conditional_spectrum_v2 (src/verify_tomatis_15db_v2.py:307-354); pass anchor_bin_hi < anchor_bin_lo for none.
+ * x, y: device, float32 [total][2]; frames: host.  Synchronises the stream before returning. */
+int tmt_cond_spectrum(tmt_engine* e, const void* x, const void* y, int64_t total, const int32_t* frames, int n_frames,
+                      int anchor_bin_lo, int anchor_bin_hi, float* median_out, void* stream);
+
 /* Number of kernel launches issued by this plan since creation (bench.py's gpu_launches). */
 int64_t tmt_plan_launch_count(const tmt_plan* p);
 

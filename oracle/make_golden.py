@@ -115,12 +115,44 @@ def make_chan():
               f"R-C2={sum(s[2:] == 'C2' for s in st)} {os.path.getsize(path)/1e6:.2f} MB")
 
 
+def val_cases():
+    """(name, sr, x, y, kwargs) for the validator kernels.  y is the oracle's standard-mode output of x
+    on the int16 grid: to the validators it is just a second input file."""
+    from oracle import tomatis_oracle as orc
+    out = []
+    for name, sr, seed, secs, kw in (("val_48k_default", 48000, 51, 5.0, dict(threshold_dbfs=-40.0, hyst_db=3.0, up_delay_ms=250.0)),
+                                     ("val_44k1_anchor", 44100, 52, 4.0, dict(threshold_dbfs=-40.0, hyst_db=2.0, up_delay_ms=100.0,
+                                                                             level_percentile=20, anchor_band=(800, 1250)))):
+        x = _q(synth.recipe_gated_pink(secs, sr, seed, env_hz=0.6, hi_dbfs=-24.0))
+        y = _q(orc.run("standard", x, sr, gate_ui=50, hysteresis_db=kw["hyst_db"], up_delay_ms=kw["up_delay_ms"])["out"])
+        out.append((name, sr, x, y, kw))
+    return out
+
+
+def make_val():
+    for name, sr, x, y, kw in val_cases():
+        r = rh.run_reference_validators(x, y, sr, **kw)
+        path = os.path.join(OUT_DIR, name + ".npz")
+        np.savez_compressed(
+            path, pcm16_x=synth.quantise_pcm16(x), pcm16_y=synth.quantise_pcm16(y), levels=r["levels"],
+            states=np.array([1 if s == "C1" else 2 for s in r["states"]], dtype=np.uint8),
+            c1_db=r["c1_db"], c2_db=r["c2_db"], v2_c1_db=r["v2_c1_db"], v2_c2_db=r["v2_c2_db"],
+            meta=np.array(json.dumps(dict(name=name, mode="validators", sr=sr, kwargs=kw, n_c1=r["n_c1"], n_c2=r["n_c2"],
+                                          v2_n_c1=r["v2_n_c1"], v2_n_c2=r["v2_n_c2"], numpy=np.__version__,
+                                          reference_files=["validate_layer1.py", "verify_tomatis_15db_v2.py"]))))
+        print(f"{name:24s} validate  sr={sr} N={len(x)} frames={len(r['states'])} stable C1/C2 used {r['n_c1']}/{r['n_c2']} "
+              f"(v2 {r['v2_n_c1']}/{r['v2_n_c2']}) {os.path.getsize(path)/1e6:.2f} MB")
+
+
 def main():
     assert rh.reference_available(), "run in the build container (needs /root/reference)"
     os.makedirs(OUT_DIR, exist_ok=True)
     if "--only-chan" in sys.argv:
         return make_chan()
+    if "--only-val" in sys.argv:
+        return make_val()
     make_chan()
+    make_val()
     make_eq()
     for name, mode, sr, x, kw in cases():
         r = rh.run_reference(mode, x, sr, **kw)

@@ -37,6 +37,8 @@ MODULES = {
     "xfade": "process_tomatis_xfade",
     "eq": "layer2_apply_eq",
     "stereo_state": "analyze_stereo_state",
+    "validate": "validate_layer1",
+    "verify_v2": "verify_tomatis_15db_v2",
 }
 
 
@@ -246,3 +248,25 @@ def run_reference_stereo_state(x: np.ndarray, sr: int, **params) -> dict:
     finally:
         os.unlink(tmp)
     return dict(rc=rc, rows=rows, stdout=buf.getvalue())
+
+
+def run_reference_validators(x: np.ndarray, y: np.ndarray, sr: int, threshold_dbfs: float, hyst_db: float, up_delay_ms: float,
+                             n_fft: int = 4096, hop: int = 2048, level_threshold: float = -60, level_percentile: float = 10,
+                             anchor_band=(900, 1100)) -> dict:
+    """Run the reference's validator kernels on an input / output pair: simulate_gate + compute_conditional_spectrum
+    (src/validate_layer1.py:110-163,261-389) and compute_conditional_spectrum_v2 (src/verify_tomatis_15db_v2.py:270-369),
+    the latter on the states and levels of the former."""
+    assert reference_available(), "reference sources not present"
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    y = np.ascontiguousarray(y, dtype=np.float32)
+    store = _Store()
+    v1 = load_reference_module("validate", store)
+    v2 = load_reference_module("verify_v2", store)
+    buf = io.StringIO()
+    with contextlib.redirect_stdout(buf):
+        states, levels = v1.simulate_gate(x, sr, n_fft, hop, threshold_dbfs, hyst_db, up_delay_ms)
+        freqs, c1_db, c2_db, n1, n2 = v1.compute_conditional_spectrum(x, y, sr, states, n_fft, hop, level_threshold)
+        f2, a1_db, a2_db, m1, m2 = v2.compute_conditional_spectrum_v2(x, y, sr, states, np.array(levels), n_fft, hop,
+                                                                     level_percentile, anchor_band)
+    return dict(states=states, levels=np.array(levels), freqs=freqs, c1_db=np.asarray(c1_db), c2_db=np.asarray(c2_db),
+                n_c1=n1, n_c2=n2, v2_c1_db=np.asarray(a1_db), v2_c2_db=np.asarray(a2_db), v2_n_c1=m1, v2_n_c2=m2)

@@ -13,7 +13,7 @@ GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 def golden_names():
     """Fixtures of the Tomatis path (standard / xfade / adaptive)."""
     return sorted(n for n in (os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
-                  if not n.startswith(("eq_", "chan_")))
+                  if not n.startswith(("eq_", "chan_", "val_")))
 
 
 def eq_golden_names():
@@ -37,6 +37,19 @@ def load_chan_golden(name):
     z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
     meta = json.loads(str(z["meta"]))
     return dict(x=synth.pcm16_to_float(z["pcm16"]), **meta)
+
+
+def val_golden_names():
+    """Fixtures of the validator kernels (src/validate_layer1.py, src/verify_tomatis_15db_v2.py)."""
+    return sorted(n for n in (os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, "val_*.npz"))))
+
+
+def load_val_golden(name):
+    z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+    meta = json.loads(str(z["meta"]))
+    return dict(x=synth.pcm16_to_float(z["pcm16_x"]), y=synth.pcm16_to_float(z["pcm16_y"]), levels=z["levels"],
+                states=["C1" if s == 1 else "C2" for s in z["states"]], c1_db=z["c1_db"], c2_db=z["c2_db"],
+                v2_c1_db=z["v2_c1_db"], v2_c2_db=z["v2_c2_db"], **meta)
 
 
 def load_golden(name):

@@ -90,3 +90,40 @@ def test_static_eq_restatement(kw):
     assert (o["out_gp"] is None) == (r["out_gp"] is None)
     if r["out_gp"] is not None:
         assert np.array_equal(o["out_gp"], r["out_gp"])
+
+
+@pytest.mark.parametrize("sr,n,kw", [(48000, 150000, dict()), (44100, 100000, dict(target_c2=0.35, hyst_db=2.0, min_hold_ms=120.0)),
+                                      (96000, 2048 * 50 + 1, dict(min_hold_ms=50.0)), (48000, 30000, dict())])
+def test_stereo_state_restatement(sr, n, kw):
+    """oracle/analysis_oracle.py against src/analyze_stereo_state.py executed in place: the CSV it writes, verbatim."""
+    from oracle import analysis_oracle as ao
+    x = synth.recipe_swept_pink(n / sr + 0.01, sr, 81, period_s=0.7, peak=0.4)[:n]
+    x[:, 1] = np.roll(x[:, 1], 4321) * 0.55
+    if n == 30000:
+        x[:] = 0.0                                                      # silence: no valid level, median fallback
+    x = synth.pcm16_to_float(synth.quantise_pcm16(x))
+    r = rh.run_reference_stereo_state(x, sr, **kw)
+    o = ao.analyze(x, sr, **kw)
+    assert r["rc"] == 0 and r["rows"] == o["rows"]
+    assert f"T={o['left_T']:.2f} dBFS, C2={o['left_c2'] * 100:.1f}%" in r["stdout"]
+
+
+@pytest.mark.parametrize("sr,kw", [(48000, dict(threshold_dbfs=-40.0, hyst_db=3.0, up_delay_ms=250.0)),
+                                   (96000, dict(threshold_dbfs=-38.0, hyst_db=4.0, up_delay_ms=0.0, level_threshold=-45,
+                                                level_percentile=30, anchor_band=(500, 2000)))])
+def test_validators_restatement(sr, kw):
+    """oracle/validate_oracle.py against simulate_gate / compute_conditional_spectrum (src/validate_layer1.py) and
+    compute_conditional_spectrum_v2 (src/verify_tomatis_15db_v2.py) executed in place: bit-identical."""
+    from oracle import validate_oracle as vo
+    x = synth.pcm16_to_float(synth.quantise_pcm16(synth.recipe_gated_pink(4.0, sr, 82, env_hz=0.7, hi_dbfs=-25.0)))
+    y = orc.run("standard", x, sr, gate_ui=50)["out"].astype(np.float32)
+    r = rh.run_reference_validators(x, y, sr, **kw)
+    gate = {k: kw[k] for k in ("threshold_dbfs", "hyst_db", "up_delay_ms")}
+    st, lv = vo.simulate_gate(x, sr, 4096, 2048, **gate)
+    assert st == r["states"] and np.array_equal(np.array(lv), r["levels"])
+    _, c1, c2, n1, n2, _ = vo.compute_conditional_spectrum(x, y, sr, st, 4096, 2048, kw.get("level_threshold", -60))
+    assert (n1, n2) == (r["n_c1"], r["n_c2"]) and np.array_equal(c1, r["c1_db"]) and np.array_equal(c2, r["c2_db"])
+    _, a1, a2, m1, m2, _ = vo.compute_conditional_spectrum_v2(x, y, sr, st, np.array(lv), 4096, 2048,
+                                                             kw.get("level_percentile", 10), kw.get("anchor_band", (900, 1100)))
+    assert (m1, m2) == (r["v2_n_c1"], r["v2_n_c2"]) and np.array_equal(a1, r["v2_c1_db"]) and np.array_equal(a2, r["v2_c2_db"])
+    assert vo.find_stable_frames(st) == rh.load_reference_module("validate", rh._Store()).find_stable_frames(st)

@@ -2,8 +2,10 @@
 // Runs the very same __host__ __device__ stage functions as the GPU kernel, thread by thread,
 // so index maps / twiddles / layouts can be verified in the GPU-less build container.
 #include <vector>
+#include <cmath>
 #include <cstring>
 #include "fft4096.cuh"
+#include "spectrum.cuh"
 #include "host_tables.hpp"
 
 using namespace tmt;
@@ -66,6 +68,42 @@ int tmt_emul_filter(const float* z_in, const float* g_half, float* z_out) {
             z_out[2 * (256 * j + t)] = v[j].x;
             z_out[2 * (256 * j + t) + 1] = v[j].y;
         }
+    }
+    return 0;
+}
+
+// One CTA of spectrum_ratio_kernel: x_frame / y_frame = 4096 interleaved stereo sample-frames, ratio_out[2049].  The
+// device code's fp64 FFT (fft4096_f64, exercised on the GPU by the edge-frame parity tests) is replaced by a plain
+// radix-2 transform in double; everything around it is the shared __host__ __device__ code of spectrum.cuh.
+int tmt_emul_spectrum_ratio(const float* x_frame, const float* y_frame, const float* win, int a0, int a1, float* ratio_out) {
+    std::vector<float> mag(2 * kBins);
+    std::vector<cplx64> Z(kNfft);
+    for (int side = 0; side < 2; ++side) {
+        const float2* src = reinterpret_cast<const float2*>(side == 0 ? x_frame : y_frame);
+        for (int n = 0; n < kNfft; ++n) {
+            int r = 0;
+            for (int b = 0; b < 12; ++b) r |= ((n >> b) & 1) << (11 - b);
+            Z[r] = spec_window_sample(src[n], win[n]);
+        }
+        for (int len = 2; len <= kNfft; len <<= 1) {
+            const int half = len >> 1;
+            for (int i0 = 0; i0 < kNfft; i0 += len)
+                for (int p = 0; p < half; ++p) {
+                    const double ang = -3.14159265358979323846 * (double)p / (double)half;
+                    const double cs = std::cos(ang), sn = std::sin(ang);
+                    const cplx64 u = Z[i0 + p], w = Z[i0 + p + half];
+                    const cplx64 v = {w.x * cs - w.y * sn, w.x * sn + w.y * cs};
+                    Z[i0 + p] = cplx64{u.x + v.x, u.y + v.y};
+                    Z[i0 + p + half] = cplx64{u.x - v.x, u.y - v.y};
+                }
+        }
+        for (int t = 0; t < 256; ++t)
+            for (int i = 0; i < spec_bins_of_thread(t); ++i) mag[side * kBins + spec_bin(t, i)] = spec_mean_mag(Z.data(), spec_bin(t, i));
+    }
+    for (int k = 0; k < kBins; ++k) ratio_out[k] = spec_ratio(mag[kBins + k], mag[k]);
+    if (a1 >= a0) {
+        const float g = spec_anchor_gain(ratio_out, a0, a1);
+        if (g > 0.f) for (int k = 0; k < kBins; ++k) ratio_out[k] = ratio_out[k] / g;
     }
     return 0;
 }

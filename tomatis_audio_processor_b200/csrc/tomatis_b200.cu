@@ -25,6 +25,7 @@
 
 #include "../../include/tomatis_b200.h"
 #include "fft4096.cuh"
+#include "spectrum.cuh"
 #include "host_tables.hpp"
 
 namespace {
@@ -1170,6 +1171,94 @@ __global__ void __launch_bounds__(256) requantise_scale_kernel(float* __restrict
         y[i] = __fmul_rn((float)quant24(y[i]) * (1.0f / 8388608.0f), scale);
 }
 
+// ------------------------------------------------------------------------------------------------
+// N3 validator: conditional spectrum (src/validate_layer1.py:261-389, src/verify_tomatis_15db_v2.py:270-369).
+// One CTA per selected frame: Hann-windowed 4096-point transform of L + iR for the input and the output file with the fp64
+// FFT of edge_kernel (see spectrum.cuh for why not the float32 stages of stft_kernel -- this is a report, not the hot
+// path), channel spectra separated by symmetry, ratio[k] = mean_c|Y_c[k]| / max(mean_c|X_c[k]|, 1e-10), optionally divided
+// by its mean over the anchor band.  Ratios are stored bin-major ([2049][ld]): the per-bin median reads a contiguous column.
+constexpr int kSpecSmemBytes = kEdgeSmemBytes;
+
+__global__ void __launch_bounds__(256)
+spectrum_ratio_kernel(const float2* __restrict__ x, const float2* __restrict__ y, const int* __restrict__ frames, long long ld,
+                      const float* __restrict__ win, int a0, int a1, float* __restrict__ ratio) {
+    extern __shared__ __align__(16) unsigned char spec_smem[];
+    double2* sm = reinterpret_cast<double2*>(spec_smem);
+    const int t = threadIdx.x, s = blockIdx.x;
+    const long long start = (long long)frames[s] * kHop;
+    const int nb = spec_bins_of_thread(t);
+    float mag[2][9];
+#pragma unroll
+    for (int side = 0; side < 2; ++side) {
+        const float2* src = (side == 0 ? x : y) + start;
+        for (int n = t; n < kNfft; n += 256) {
+            const cplx64 z = spec_window_sample(src[n], win[n]);
+            sm[bitrev12(n)] = make_double2(z.x, z.y);
+        }
+        __syncthreads();
+        fft4096_f64(sm, t);                                 // ends with a barrier
+#pragma unroll
+        for (int i = 0; i < 9; ++i) mag[side][i] = (i < nb) ? spec_mean_mag(reinterpret_cast<const cplx64*>(sm), spec_bin(t, i)) : 0.f;
+        __syncthreads();                                    // the next side overwrites the buffer
+    }
+    float r[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) r[i] = spec_ratio(mag[1][i], mag[0][i]);
+    if (a1 >= a0) {
+        float* R = reinterpret_cast<float*>(spec_smem);
+#pragma unroll
+        for (int i = 0; i < 9; ++i) if (i < nb) R[spec_bin(t, i)] = r[i];
+        __syncthreads();
+        const float g = spec_anchor_gain(R, a0, a1);
+        if (g > 0.f) {
+#pragma unroll
+            for (int i = 0; i < 9; ++i) r[i] = r[i] / g;
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 9; ++i) if (i < nb) ratio[(long long)spec_bin(t, i) * ld + s] = r[i];
+}
+
+// np.median(ratios, axis=0): one CTA per bin, radix select (4 x 8 bits, most significant first) on the bit patterns of the
+// non-negative floats of one column; even counts average the two middle elements in float32 like np.mean.
+__global__ void __launch_bounds__(256)
+column_median_kernel(const float* __restrict__ ratio, int n, long long ld, float* __restrict__ med) {
+    __shared__ unsigned hist[256];
+    __shared__ unsigned s_prefix, s_rank;
+    const unsigned* col = reinterpret_cast<const unsigned*>(ratio + (long long)blockIdx.x * ld);
+    float vals[2] = {0.f, 0.f};
+    for (int which = 0; which < 2; ++which) {
+        unsigned rank = which == 0 ? (unsigned)(n - 1) / 2u : (unsigned)n / 2u;
+        unsigned prefix = 0, mask = 0;
+        for (int shift = 24; shift >= 0; shift -= 8) {
+            hist[threadIdx.x] = 0;
+            __syncthreads();
+            for (int i = threadIdx.x; i < n; i += 256) {
+                const unsigned b = col[i];
+                if ((b & mask) == prefix) atomicAdd(&hist[(b >> shift) & 255u], 1u);
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                unsigned cum = 0;
+                int d = 0;
+                for (; d < 255; ++d) {
+                    if (cum + hist[d] > rank) break;
+                    cum += hist[d];
+                }
+                s_prefix = prefix | ((unsigned)d << shift);
+                s_rank = rank - cum;
+            }
+            __syncthreads();
+            prefix = s_prefix;
+            rank = s_rank;
+            mask |= 0xffu << shift;
+            __syncthreads();
+        }
+        vals[which] = __uint_as_float(prefix);
+    }
+    if (threadIdx.x == 0) med[blockIdx.x] = (n & 1) ? vals[0] : __fmul_rn(__fadd_rn(vals[0], vals[1]), 0.5f);
+}
+
 // ================================================================================================
 // host side
 template <typename T> struct DevBuf {
@@ -2003,6 +2092,36 @@ int tmt_float_to_pcm(const float* in, int format, int64_t n_values, void* pcm, v
     float_to_s24_kernel<<<148 * 8, 256, 0, st>>>(reinterpret_cast<const float4*>(in), reinterpret_cast<unsigned*>(pcm), n4, in,
                                                  reinterpret_cast<unsigned char*>(pcm), n_values);
     CUDA_TRY(cudaGetLastError());
+    return TMT_OK;
+}
+
+int tmt_cond_spectrum(tmt_engine* e, const void* x, const void* y, int64_t total, const int32_t* frames, int n_frames,
+                      int anchor_bin_lo, int anchor_bin_hi, float* median_out, void* stream) {
+    if (!e || !frames || !median_out || n_frames < 0 || total < 0) return fail(TMT_ERR_INVALID, "bad arguments");
+    if (!e->have_win) return fail(TMT_ERR_INVALID, "engine window not set");
+    if (n_frames == 0) return TMT_OK;
+    if (!x || !y) return fail(TMT_ERR_INVALID, "NULL audio buffer");
+    if (anchor_bin_hi >= anchor_bin_lo && (anchor_bin_lo < 0 || anchor_bin_hi >= kBins)) return fail(TMT_ERR_INVALID, "anchor band outside [0, %d]", kBins - 1);
+    for (int i = 0; i < n_frames; ++i)
+        if (frames[i] < 0 || (long long)frames[i] * kHop + kNfft > total)
+            return fail(TMT_ERR_INVALID, "frame %d (index %d) does not lie inside the file", i, frames[i]);
+    CUDA_TRY(cudaSetDevice(e->device));
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    CUDA_TRY(cudaFuncSetAttribute(spectrum_ratio_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSpecSmemBytes));
+    DevBuf<int> d_frames;
+    DevBuf<float> d_ratio, d_med;
+    CUDA_TRY(d_frames.alloc((size_t)n_frames));
+    CUDA_TRY(d_ratio.alloc((size_t)kBins * (size_t)n_frames));
+    CUDA_TRY(d_med.alloc(kBins));
+    CUDA_TRY(cudaMemcpyAsync(d_frames.p, frames, sizeof(int) * (size_t)n_frames, cudaMemcpyHostToDevice, st));
+    spectrum_ratio_kernel<<<n_frames, 256, kSpecSmemBytes, st>>>(reinterpret_cast<const float2*>(x), reinterpret_cast<const float2*>(y),
+                                                                 d_frames.p, (long long)n_frames, e->win.p,
+                                                                 anchor_bin_lo, anchor_bin_hi, d_ratio.p);
+    CUDA_TRY(cudaGetLastError());
+    column_median_kernel<<<kBins, 256, 0, st>>>(d_ratio.p, n_frames, (long long)n_frames, d_med.p);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(median_out, d_med.p, sizeof(float) * kBins, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
     return TMT_OK;
 }
 

@@ -526,6 +526,46 @@ def run_channel_states(xs: Sequence, sr: int, device: int = 0, target_c2=0.5, hy
         plan.close()
 
 
+# ------------------------------------------------------------------------------------------- validators (N3)
+def frame_levels_wholefile(x, device: int = 0, mono: bool = False):
+    """float32 mean squares + levels of the frames [i*hop, i*hop + n_fft), i < len(x) // hop (zero padded past the end):
+    the frames validate_layer1.simulate_gate keeps (src/validate_layer1.py:132-141).  Returns (meansq f32, levels f64,
+    plan) -- the analysis-only plan stays open for gate runs; the caller closes it."""
+    torch = _torch()
+    eng = get_engine(device)
+    xd = _to_device(torch, [x], device)[0]
+    n = int(xd.shape[0])
+    plan = Plan(eng, L.FRAMING_WHOLEFILE, [L.TrackDesc(xd.data_ptr(), None, n, 0, n, 0, 0, 0, -1)])
+    try:
+        plan.levels(mono=mono)
+        msq = plan.read(L.ARR_MEANSQ_F32)
+    except Exception:
+        plan.close()
+        raise
+    plan._keep = xd                                            # the plan reads this buffer
+    return msq, tb.levels_from_meansq(msq), plan
+
+
+def to_device(arrays, device: int = 0):
+    """float32 [N, 2] host arrays -> device tensors (device tensors pass through)."""
+    return _to_device(_torch(), arrays, device)
+
+
+def cond_spectrum_median(x, y, frames, anchor_bins=None, device: int = 0) -> np.ndarray:
+    """Per-bin median over `frames` of |Y| / |X| (tmt_cond_spectrum); x, y float32 [N, 2] (host or device)."""
+    torch = _torch()
+    eng = get_engine(device)
+    xd, yd = _to_device(torch, [x, y], device)
+    frames = np.ascontiguousarray(frames, dtype=np.int32)
+    total = int(min(xd.shape[0], yd.shape[0]))
+    a0, a1 = (0, -1) if anchor_bins is None else (int(anchor_bins[0]), int(anchor_bins[1]))
+    out = np.zeros(eng.n_fft // 2 + 1, dtype=np.float32)
+    L.check(eng.lib.tmt_cond_spectrum(eng.h, C.c_void_p(xd.data_ptr()), C.c_void_p(yd.data_ptr()), total,
+                                      frames.ctypes.data_as(C.c_void_p), int(frames.size), a0, a1,
+                                      out.ctypes.data_as(C.c_void_p), _stream_ptr(torch)), "tmt_cond_spectrum")
+    return out
+
+
 def run(mode: str, xs: Sequence, sr: int, **kw) -> List[dict]:
     if mode == "adaptive":
         return run_adaptive(xs, sr, **kw)
