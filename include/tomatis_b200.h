@@ -137,6 +137,7 @@ int tmt_plan_input_peaks(tmt_plan* p, void* stream);
 #define TMT_LEVELS_MONO 2 /* single-channel file carried in the L lane (R = 0): mono = sqrt(x*x), _adaptive.py:74,180-181 */
 #define TMT_LEVELS_LEFT 32  /* level of the left channel alone, np.mean(x*x) (src/analyze_stereo_state.py:16-19,112) */
 #define TMT_LEVELS_RIGHT 64 /* level of the right channel alone (src/analyze_stereo_state.py:113) */
+#define TMT_LEVELS_POWER_EPS 128 /* mono = sqrt(0.5*(l*l + r*r) + 1e-12): calibration front end (src/calibrate_to_baseline_v2.py:8-15) */
 int tmt_plan_levels(tmt_plan* p, int flags, const float* in_scale, void* stream);
 
 /* K2b.  Gate automaton + crossfade counter as a block-level scan over frames.
@@ -210,6 +211,30 @@ int tmt_requantise_scale(float* y, int64_t n_values, float scale, void* stream);
  * x, y: device, float32 [total][2]; frames: host.  Synchronises the stream before returning. */
 int tmt_cond_spectrum(tmt_engine* e, const void* x, const void* y, int64_t total, const int32_t* frames, int n_frames,
                       int anchor_bin_lo, int anchor_bin_hi, float* median_out, void* stream);
+
+/* ---- calibration front end (src/calibrate_to_baseline_v2.py) ---------------- */
+/* Envelope for the delay estimate: power_mono(x) (:8-11) resampled like scipy.signal.resample_poly(env, up, down) applies
+ * its FIR (upfirdn with zero extension, :60,73), then the mean removed (:61,74).  x: device float32 [n_in][2];
+ * h: host, the zero-padded float32 filter resample_poly builds (firwin with a Kaiser(5) window, times up), len_h taps;
+ * out[j] = upfirdn(h, env, up, down)[j + n_pre_remove], j < n_out (device).  Synchronises the stream. */
+int tmt_calib_envelope_decimate(tmt_engine* e, const void* x, int64_t n_in, const float* h, int len_h, int up, int down,
+                                int64_t n_pre_remove, int64_t n_out, float* out, void* stream);
+/* corr[k] = sum_j a[k + j] * b[j], k = 0 .. na - nb: fftconvolve(a, b[::-1], mode="valid") (:77-78), computed directly with
+ * float32 products and double accumulation.  All pointers device. */
+int tmt_calib_xcorr_valid(tmt_engine* e, const float* a, int64_t na, const float* b, int64_t nb, float* corr, void* stream);
+/* stft_band_tilt's two band energies (:17-30) for the frames [i*hop, i*hop + n_fft), i < n_frames, of x (device):
+ * sum of |rfft(power_mono(frame) * hann)|^2 over bins [lo0, lo1) and [hi0, hi1) -> e_lo / e_hi (host, float32).  The caller
+ * finishes 10*log10((e_hi + 1e-12) / (e_lo + 1e-12) + 1e-12).  Frame levels of the same frames: tmt_plan_levels with
+ * TMT_LEVELS_POWER_EPS on a TMT_FRAMING_EQ_NOPAD plan.  Synchronises the stream. */
+int tmt_calib_band_energies(tmt_engine* e, const void* x, int64_t total, int n_frames, int lo0, int lo1, int hi0, int hi1,
+                            float* e_lo, float* e_hi, void* stream);
+/* The grid search's inner loop (:253-262): simulate_state (:88-112) over n frames at positions start[] for n_combos
+ * parameter sets at once (one thread each): thresholds on/off as float32 (NumPy compares a float32 level with a Python
+ * float in float32), up-delay in samples; mismatches against want[] (1 = C1, 2 = C2) and number of state switches per set;
+ * states (optional, [n_combos][n]) receives every frame's state.  All pointers host.  Synchronises the stream. */
+int tmt_calib_gate_grid(tmt_engine* e, const float* level, const int64_t* start, const uint8_t* want, int n, const float* on,
+                        const float* off, const int64_t* delay, int n_combos, int32_t* mismatches, int32_t* switches,
+                        uint8_t* states, void* stream);
 
 /* Number of kernel launches issued by this plan since creation (bench.py's gpu_launches). */
 int64_t tmt_plan_launch_count(const tmt_plan* p);

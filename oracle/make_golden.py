@@ -144,15 +144,61 @@ def make_val():
               f"(v2 {r['v2_n_c1']}/{r['v2_n_c2']}) {os.path.getsize(path)/1e6:.2f} MB")
 
 
+def cal_cases():
+    """(name, sr, orig, base, true delay, command-line words) for the calibration front end
+    src/calibrate_to_baseline_v2.py.  The baseline stands in for the hardware recording: the oracle's
+    standard-mode output of a delayed stretch of the original, attenuated, with a little noise, on the int16 grid."""
+    from oracle import tomatis_oracle as orc
+    out = []
+    for name, sr, seed, secs_o, secs_b, d, proc, words in (
+            ("cal_48k_default", 48000, 91, 11.0, 8.0, 33210, dict(gate_ui=50, up_delay_ms=100.0, hysteresis_db=2.0),
+             ["--hyst_list", 0, 2, 4, "--delay_list_ms", 0, 100, 200]),
+            ("cal_44k1_bands", 44100, 92, 9.0, 6.5, 21007, dict(gate_ui=52, up_delay_ms=50.0, hysteresis_db=4.0),
+             ["--hyst_list", 2, 4, 6, "--delay_list_ms", 50, 150, "--tilt_lo", 150, 800, "--tilt_hi", 2500, 9000,
+              "--tilt_medfilt", 3, "--music_dbfs", -60, "--gain_step_db", 1.0, "--T_step_db", 0.5])):
+        x = _q(synth.recipe_level_steps(secs_o, sr, seed, min_s=0.25, max_s=0.9))
+        seg = x[d:d + int(secs_b * sr)]
+        y = orc.run("standard", seg, sr, **proc)["out"].astype(np.float32)
+        rng = np.random.default_rng(seed + 1000)
+        base = _q(0.8 * y + 1e-4 * rng.standard_normal(y.shape).astype(np.float32))
+        out.append((name, sr, x, base, d, words))
+    return out
+
+
+def make_cal():
+    for name, sr, x, base, d, words in cal_cases():
+        r = rh.run_reference_calibration(x, base, sr, words)
+        lo = tuple(words[words.index("--tilt_lo") + 1:words.index("--tilt_lo") + 3]) if "--tilt_lo" in words else (200, 1000)
+        hi = tuple(words[words.index("--tilt_hi") + 1:words.index("--tilt_hi") + 3]) if "--tilt_hi" in words else (2000, 8000)
+        parts = rh.run_reference_calibration_parts(x, base, sr, r["json"]["delay_samples_orig_minus_base"], lo=lo, hi=hi)
+        path = os.path.join(OUT_DIR, name + ".npz")
+        np.savez_compressed(
+            path, pcm16_orig=synth.quantise_pcm16(x), pcm16_base=synth.quantise_pcm16(base), mo_ds=parts["mo_ds"],
+            mb_ds=parts["mb_ds"], corr=parts["corr"].astype(np.float32), orig_level=parts["orig_level"],
+            base_level=parts["base_level"], tilts=parts["tilts"],
+            meta=np.array(json.dumps(dict(name=name, mode="calibrate", sr=sr, words=words, true_delay=d, k=parts["k"],
+                                          json={k: v for k, v in r["json"].items() if k not in ("orig", "base")},
+                                          stdout=r["stdout"], tilt_lo=lo, tilt_hi=hi, numpy=np.__version__,
+                                          scipy=__import__("scipy").__version__,
+                                          reference_files=["calibrate_to_baseline_v2.py"]))))
+        j = r["json"]
+        print(f"{name:24s} calibrate sr={sr} N={len(x)}/{len(base)} delay={j['delay_samples_orig_minus_base']} (true {d}) "
+              f"T_raw={j['T_raw_dbfs']:.2f} hyst={j['hyst_db']} up={j['up_delay_ms']} mismatch={j['mismatch']:.4f} "
+              f"{os.path.getsize(path)/1e6:.2f} MB")
+
+
 def main():
     assert rh.reference_available(), "run in the build container (needs /root/reference)"
     os.makedirs(OUT_DIR, exist_ok=True)
+    if "--only-cal" in sys.argv:
+        return make_cal()
     if "--only-chan" in sys.argv:
         return make_chan()
     if "--only-val" in sys.argv:
         return make_val()
     make_chan()
     make_val()
+    make_cal()
     make_eq()
     for name, mode, sr, x, kw in cases():
         r = rh.run_reference(mode, x, sr, **kw)

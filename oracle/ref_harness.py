@@ -39,6 +39,7 @@ MODULES = {
     "stereo_state": "analyze_stereo_state",
     "validate": "validate_layer1",
     "verify_v2": "verify_tomatis_15db_v2",
+    "calibrate": "calibrate_to_baseline_v2",
 }
 
 
@@ -82,6 +83,10 @@ def make_soundfile_standin(store: _Store) -> types.ModuleType:
             out = np.array(self._data[self._pos:self._pos + n], dtype=dtype, copy=True)
             self._pos += n
             return out
+
+        def seek(self, frames):
+            self._pos = max(0, min(int(frames), self.frames))
+            return self._pos
 
         def write(self, data):
             store.outputs[self.path]["chunks"].append(np.array(data, copy=True))
@@ -270,3 +275,59 @@ def run_reference_validators(x: np.ndarray, y: np.ndarray, sr: int, threshold_db
                                                                      level_percentile, anchor_band)
     return dict(states=states, levels=np.array(levels), freqs=freqs, c1_db=np.asarray(c1_db), c2_db=np.asarray(c2_db),
                 n_c1=n1, n_c2=n2, v2_c1_db=np.asarray(a1_db), v2_c2_db=np.asarray(a2_db), v2_n_c1=m1, v2_n_c2=m2)
+
+
+def run_reference_calibration(orig: np.ndarray, base: np.ndarray, sr: int, args=()) -> dict:
+    """Run the reference's calibration front end `main()` (src/calibrate_to_baseline_v2.py:130-313) on an original /
+    baseline-recording pair.  `args`: extra command-line words.  Returns dict(json = the file it saved, stdout, delay)."""
+    import json
+    assert reference_available(), "reference sources not present"
+    store = _Store()
+    store.inputs["orig.flac"] = (np.ascontiguousarray(orig, dtype=np.float32), sr)
+    store.inputs["base.flac"] = (np.ascontiguousarray(base, dtype=np.float32), sr)
+    mod = load_reference_module("calibrate", store)
+    fd, tmp = tempfile.mkstemp(suffix=".json")
+    os.close(fd)
+    argv = sys.argv
+    buf = io.StringIO()
+    try:
+        sys.argv = ["calibrate_to_baseline_v2.py", "--orig", "orig.flac", "--base", "base.flac", "--sr", str(sr),
+                    "--out_json", tmp] + [str(a) for a in args]
+        with contextlib.redirect_stdout(buf):
+            mod.main()
+        with open(tmp, "r", encoding="utf-8") as f:
+            out = json.load(f)
+    finally:
+        sys.argv = argv
+        os.unlink(tmp)
+    return dict(json=out, stdout=buf.getvalue(), module=mod)
+
+
+def run_reference_calibration_parts(orig: np.ndarray, base: np.ndarray, sr: int, delay: int, max_minutes: float = 6.0,
+                                    lo=(200, 1000), hi=(2000, 8000), ds_sr: int = 2000, chunk_sec: float = 25) -> dict:
+    """The intermediate arrays main() never returns, obtained by calling the reference's own functions the way main() does
+    (src/calibrate_to_baseline_v2.py:44-86 for the two decimated envelopes and their correlation, :166-196 for the frame
+    levels and tilts)."""
+    from scipy.signal import fftconvolve, resample_poly
+    assert reference_available(), "reference sources not present"
+    orig = np.ascontiguousarray(orig, dtype=np.float32)
+    base = np.ascontiguousarray(base, dtype=np.float32)
+    mod = load_reference_module("calibrate", _Store())
+    mid, half = int(0.5 * len(base)), int(0.5 * chunk_sec * sr)
+    s, e = max(0, mid - half), min(len(base), mid + half)
+    mb_ds = resample_poly(mod.power_mono(base[s:e]), ds_sr, sr).astype(np.float32)
+    mb_ds = mb_ds - np.mean(mb_ds)
+    mo_ds = resample_poly(mod.power_mono(orig).astype(np.float32), ds_sr, sr).astype(np.float32)
+    mo_ds = mo_ds - np.mean(mo_ds)
+    corr = fftconvolve(mo_ds, mb_ds[::-1], mode="valid")
+    base_start, orig_start = max(0, -delay), max(0, delay)
+    avail = min(len(base) - base_start, len(orig) - orig_start, int(max_minutes * 60 * sr))
+    xb, xo = base[base_start:base_start + avail], orig[orig_start:orig_start + avail]
+    n_frames = 1 + (avail - 4096) // 2048
+    ol, bl, tl = (np.zeros(n_frames, np.float32) for _ in range(3))
+    for i in range(n_frames):
+        st = i * 2048
+        ol[i] = mod.rms_dbfs_from_mono(mod.power_mono(xo[st:st + 4096, :]))
+        bl[i] = mod.rms_dbfs_from_mono(mod.power_mono(xb[st:st + 4096, :]))
+        tl[i] = mod.stft_band_tilt(xb[st:st + 4096, :], sr, 4096, lo=tuple(lo), hi=tuple(hi))
+    return dict(mo_ds=mo_ds, mb_ds=mb_ds, corr=corr, k=int(np.argmax(corr)), orig_level=ol, base_level=bl, tilts=tl)

@@ -127,3 +127,33 @@ def test_validators_restatement(sr, kw):
                                                              kw.get("level_percentile", 10), kw.get("anchor_band", (900, 1100)))
     assert (m1, m2) == (r["v2_n_c1"], r["v2_n_c2"]) and np.array_equal(a1, r["v2_c1_db"]) and np.array_equal(a2, r["v2_c2_db"])
     assert vo.find_stable_frames(st) == rh.load_reference_module("validate", rh._Store()).find_stable_frames(st)
+
+
+@pytest.mark.parametrize("sr,words,kw", [
+    (48000, ["--hyst_list", 1, 3, "--delay_list_ms", 0, 150], dict(hyst_list=[1, 3], delay_list_ms=[0, 150])),
+    (44100, ["--hyst_list", 2, "--delay_list_ms", 50, 100, "--tilt_medfilt", 4, "--max_minutes", 0.1, "--gain_step_db", 1.5],
+     dict(hyst_list=[2], delay_list_ms=[50, 100], tilt_medfilt=4, max_minutes=0.1, gain_step_db=1.5))])
+def test_calibration_restatement(sr, words, kw):
+    """oracle/calibrate_oracle.py against main() of src/calibrate_to_baseline_v2.py executed in place (saved JSON) and
+    against its functions called the way main() calls them (envelopes, levels, tilts): identical."""
+    from oracle import calibrate_oracle as co
+    x = synth.pcm16_to_float(synth.quantise_pcm16(synth.recipe_level_steps(9.0, sr, 83, min_s=0.25, max_s=0.8)))
+    d = 17891
+    y = orc.run("standard", x[d:d + 7 * sr], sr, gate_ui=50, up_delay_ms=100.0)["out"].astype(np.float32)
+    base = synth.pcm16_to_float(synth.quantise_pcm16(0.7 * y))
+    r = rh.run_reference_calibration(x, base, sr, words)
+    o = co.calibrate(x, base, sr, **kw)
+    assert {k: v for k, v in r["json"].items() if k not in ("orig", "base")} == o["json"]
+    assert abs(o["delay"] - d) <= sr // 2000 + 1
+    parts = rh.run_reference_calibration_parts(x, base, sr, o["delay"], max_minutes=kw.get("max_minutes", 6.0))
+    f = co.find_delay(x, base, sr=sr)
+    assert np.array_equal(f["mo_ds"], parts["mo_ds"]) and np.array_equal(f["mb_ds"], parts["mb_ds"]) and f["k"] == parts["k"]
+    for key in ("orig_level", "base_level", "tilts"):
+        assert np.array_equal(o[key], parts[key])
+    mod = r["module"]
+    st = (1 + (np.arange(50) // 2) % 2).astype(np.int32)
+    assert np.array_equal(co.debounce_state(st, 3), mod.debounce_state(st, 3))
+    lab_o, lab_r = co.kmeans2_1d(o["tilts_s"]), mod.kmeans2_1d(o["tilts_s"])
+    assert np.array_equal(lab_o[0], lab_r[0]) and lab_o[1:] == lab_r[1:]
+    lv, fs = o["orig_level"], o["starts"]
+    assert np.array_equal(co.simulate_state(lv, fs, sr, -40.0, 3.0, 120.0), mod.simulate_state(lv, fs, sr, -40.0, 3.0, 120.0))

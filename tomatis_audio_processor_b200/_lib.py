@@ -14,7 +14,7 @@ OK = 0
 FRAMING_STREAMING, FRAMING_WHOLEFILE, FRAMING_EQ_PAD, FRAMING_EQ_NOPAD = 0, 1, 2, 3
 GATE_UPDELAY, GATE_MINHOLD = 0, 1
 PCM_S16, PCM_S24 = 0, 1
-LEVELS_F64, LEVELS_MONO, LEVELS_HOPSUM_ONLY, LEVELS_MEANSQ_ONLY, LEVELS_LEFT, LEVELS_RIGHT = 1, 2, 8, 16, 32, 64
+LEVELS_F64, LEVELS_MONO, LEVELS_HOPSUM_ONLY, LEVELS_MEANSQ_ONLY, LEVELS_LEFT, LEVELS_RIGHT, LEVELS_POWER_EPS = 1, 2, 8, 16, 32, 64, 128
 (ARR_MEANSQ_F32, ARR_MEANSQ_F64, ARR_GATE_F64, ARR_STATE, ARR_ROW, ARR_C2_COUNT, ARR_CHUNK_PEAK,
  ARR_INPUT_PEAK, ARR_HOPSUM_F32, ARR_HOPSUM_F64) = range(10)
 
@@ -60,6 +60,10 @@ SIGNATURES = {
     "tmt_plan_edge_frames": (C.c_int, [_P, C.c_float, _P, _P, C.c_int, _P]),
     "tmt_plan_limiter": (C.c_int, [_P, C.c_float, _P]),
     "tmt_cond_spectrum": (C.c_int, [_P, _P, _P, C.c_int64, _P, C.c_int, C.c_int, C.c_int, _P, _P]),
+    "tmt_calib_envelope_decimate": (C.c_int, [_P, _P, C.c_int64, _P, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int64, _P, _P]),
+    "tmt_calib_xcorr_valid": (C.c_int, [_P, _P, C.c_int64, _P, C.c_int64, _P, _P]),
+    "tmt_calib_band_energies": (C.c_int, [_P, _P, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P]),
+    "tmt_calib_gate_grid": (C.c_int, [_P, _P, _P, _P, C.c_int, _P, _P, _P, C.c_int, _P, _P, _P, _P]),
     "tmt_plan_run_streaming": (C.c_int, [_P, C.c_double, C.c_double, C.c_int, C.c_int, C.c_float, C.c_float, _P]),
     "tmt_plan_launch_count": (C.c_int64, [_P]),
     "tmt_pcm_to_float": (C.c_int, [_P, C.c_int, C.c_int64, _P, _P]),

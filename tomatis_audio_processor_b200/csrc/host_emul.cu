@@ -6,6 +6,7 @@
 #include <cstring>
 #include "fft4096.cuh"
 #include "spectrum.cuh"
+#include "calib.cuh"
 #include "host_tables.hpp"
 
 using namespace tmt;
@@ -105,6 +106,55 @@ int tmt_emul_spectrum_ratio(const float* x_frame, const float* y_frame, const fl
         const float g = spec_anchor_gain(ratio_out, a0, a1);
         if (g > 0.f) for (int k = 0; k < kBins; ++k) ratio_out[k] = ratio_out[k] / g;
     }
+    return 0;
+}
+
+// calib.cuh on the CPU: the same per-thread functions the calibration kernels call.
+int tmt_emul_decimate(const float* x, long long n_in, const float* h, int len_h, int up, int down, long long n_pre_remove,
+                      long long n_out, float* out) {
+    for (long long j = 0; j < n_out; ++j)
+        out[j] = decimate_sample(reinterpret_cast<const float2*>(x), n_in, h, len_h, up, down, j + n_pre_remove);
+    return 0;
+}
+
+int tmt_emul_power_levels(const float* x, long long n, float* mono_out) {
+    for (long long i = 0; i < n; ++i) mono_out[i] = power_mono(reinterpret_cast<const float2*>(x)[i]);
+    return 0;
+}
+
+// one CTA of calib_band_kernel (plain radix-2 double FFT in place of fft4096_f64, like tmt_emul_spectrum_ratio)
+int tmt_emul_band_energies(const float* frame, const float* win, int lo0, int lo1, int hi0, int hi1, float* e_lo, float* e_hi) {
+    std::vector<cplx64> Z(kNfft);
+    const float2* src = reinterpret_cast<const float2*>(frame);
+    for (int n = 0; n < kNfft; ++n) {
+        int r = 0;
+        for (int b = 0; b < 12; ++b) r |= ((n >> b) & 1) << (11 - b);
+        Z[r] = cplx64{(double)(power_mono(src[n]) * win[n]), 0.0};
+    }
+    for (int len = 2; len <= kNfft; len <<= 1) {
+        const int half = len >> 1;
+        for (int i0 = 0; i0 < kNfft; i0 += len)
+            for (int p = 0; p < half; ++p) {
+                const double ang = -3.14159265358979323846 * (double)p / (double)half;
+                const double cs = std::cos(ang), sn = std::sin(ang);
+                const cplx64 u = Z[i0 + p], w = Z[i0 + p + half];
+                const cplx64 v = {w.x * cs - w.y * sn, w.x * sn + w.y * cs};
+                Z[i0 + p] = cplx64{u.x + v.x, u.y + v.y};
+                Z[i0 + p + half] = cplx64{u.x - v.x, u.y - v.y};
+            }
+    }
+    double a = 0.0, b = 0.0;
+    for (int k = lo0; k < lo1; ++k) a += (double)power_bin(Z.data(), k);
+    for (int k = hi0; k < hi1; ++k) b += (double)power_bin(Z.data(), k);
+    *e_lo = (float)a;
+    *e_hi = (float)b;
+    return 0;
+}
+
+int tmt_emul_gate_grid(const float* level, const long long* start, const unsigned char* want, int n, const float* on, const float* off,
+                       const long long* delay, int n_combos, int* mismatches, int* switches, unsigned char* states) {
+    for (int c = 0; c < n_combos; ++c)
+        gate_grid_combo(level, start, want, n, on[c], off[c], delay[c], &mismatches[c], &switches[c], states ? states + (size_t)c * n : nullptr);
     return 0;
 }
 

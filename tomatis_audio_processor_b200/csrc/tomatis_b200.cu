@@ -26,6 +26,7 @@
 #include "../../include/tomatis_b200.h"
 #include "fft4096.cuh"
 #include "spectrum.cuh"
+#include "calib.cuh"
 #include "host_tables.hpp"
 
 namespace {
@@ -136,6 +137,11 @@ template <> struct Arith<float> {
         const float mono = __fsqrt_rn(__fmul_rn(l, l));
         return __fmul_rn(mono, mono);
     }
+    // calibration front end: mono = sqrt(0.5*(l*l + r*r) + 1e-12) (src/calibrate_to_baseline_v2.py:8-15)
+    static __device__ __forceinline__ float msq_power(float2 x, float sc) {
+        const float mono = power_mono(make_float2(__fmul_rn(x.x, sc), __fmul_rn(x.y, sc)));
+        return __fmul_rn(mono, mono);
+    }
     // one channel on its own: np.mean(x_mono * x_mono) (src/analyze_stereo_state.py:16-19,112-113)
     static __device__ __forceinline__ float sq(float x, float sc) {
         const float v = __fmul_rn(x, sc);
@@ -154,6 +160,11 @@ template <> struct Arith<double> {
     static __device__ __forceinline__ double msq_mono(float2 x, float sc) {
         const double l = __dmul_rn((double)x.x, (double)sc);
         const double mono = __dsqrt_rn(__dmul_rn(l, l));
+        return __dmul_rn(mono, mono);
+    }
+    static __device__ __forceinline__ double msq_power(float2 x, float sc) {
+        const double l = __dmul_rn((double)x.x, (double)sc), r = __dmul_rn((double)x.y, (double)sc);
+        const double mono = __dsqrt_rn(__dadd_rn(__dmul_rn(0.5, __dadd_rn(__dmul_rn(l, l), __dmul_rn(r, r))), 1e-12));
         return __dmul_rn(mono, mono);
     }
     static __device__ __forceinline__ double sq(float x, float sc) {
@@ -211,6 +222,13 @@ levels_kernel(const TrackDev* __restrict__ tracks, const float* __restrict__ in_
             for (int i = 1; i < 16; ++i) {
                 a0 = Arith<T>::add(a0, Arith<T>::msq_mono(x0[i], sc));
                 a1 = Arith<T>::add(a1, Arith<T>::msq_mono(x1[i], sc));
+            }
+        } else if (mono == 4) {                      // power-average mono with the epsilon inside the root (calibration)
+            a0 = Arith<T>::msq_power(x0[0], sc); a1 = Arith<T>::msq_power(x1[0], sc);
+#pragma unroll
+            for (int i = 1; i < 16; ++i) {
+                a0 = Arith<T>::add(a0, Arith<T>::msq_power(x0[i], sc));
+                a1 = Arith<T>::add(a1, Arith<T>::msq_power(x1[i], sc));
             }
         } else {                                     // 2: left channel alone, 3: right channel alone
             const bool right = (mono == 3);
@@ -1259,6 +1277,118 @@ column_median_kernel(const float* __restrict__ ratio, int n, long long ld, float
     if (threadIdx.x == 0) med[blockIdx.x] = (n & 1) ? vals[0] : __fmul_rn(__fadd_rn(vals[0], vals[1]), 0.5f);
 }
 
+// ------------------------------------------------------------------------------------------------
+// N4 calibration front end (src/calibrate_to_baseline_v2.py); per-thread code in calib.cuh.
+__global__ void __launch_bounds__(256)
+calib_decimate_kernel(const float2* __restrict__ x, long long n_in, const float* __restrict__ h, int len_h, int up, int down,
+                      long long n_pre_remove, long long n_out, float* __restrict__ out) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < n_out; j += stride)
+        out[j] = decimate_sample(x, n_in, h, len_h, up, down, j + n_pre_remove);
+}
+
+constexpr int kSumBlocks = 1024;
+__global__ void __launch_bounds__(256) calib_partial_sum_kernel(const float* __restrict__ v, long long n, double* __restrict__ partial) {
+    __shared__ double red[256];
+    double acc = 0.0;
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)kSumBlocks * 256) acc += (double)v[i];
+    red[threadIdx.x] = acc;
+    __syncthreads();
+    for (int w = 128; w > 0; w >>= 1) {
+        if (threadIdx.x < w) red[threadIdx.x] += red[threadIdx.x + w];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) partial[blockIdx.x] = red[0];
+}
+__global__ void __launch_bounds__(256) calib_subtract_kernel(float* __restrict__ v, long long n, float mean) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) v[i] = __fsub_rn(v[i], mean);
+}
+
+// corr[k] = sum_j a[k + j] * b[j], k in [0, na - nb]: a CTA owns 1024 consecutive lags (4 per thread), b is walked in tiles
+// of 2048 staged in shared memory with the matching window of a; each thread slides an 8-value register window over a,
+// one 128-bit load per 16 multiply-adds; float32 partial sums are folded into double accumulators once per tile.
+constexpr int kXcLags = 1024, kXcTile = 2048;
+__global__ void __launch_bounds__(256)
+calib_xcorr_kernel(const float* __restrict__ a, long long na, const float* __restrict__ b, int nb, float* __restrict__ corr,
+                   long long n_lags) {
+    __shared__ __align__(16) float sa[kXcLags + kXcTile + 8];
+    __shared__ __align__(16) float sb[kXcTile];
+    const int t = threadIdx.x;
+    const long long k0 = (long long)blockIdx.x * kXcLags;
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int j0 = 0; j0 < nb; j0 += kXcTile) {
+        __syncthreads();
+        for (int i = t; i < kXcLags + kXcTile + 8; i += 256) {
+            const long long idx = k0 + j0 + i;
+            sa[i] = idx < na ? a[idx] : 0.f;
+        }
+        for (int i = t; i < kXcTile; i += 256) sb[i] = (j0 + i < nb) ? b[j0 + i] : 0.f;
+        __syncthreads();
+        float f0 = 0.f, f1 = 0.f, f2 = 0.f, f3 = 0.f;
+        float4 lo = *reinterpret_cast<const float4*>(&sa[4 * t]);
+#pragma unroll 4
+        for (int j = 0; j < kXcTile; j += 4) {
+            const float4 hi = *reinterpret_cast<const float4*>(&sa[4 * t + j + 4]);
+            const float4 bb = *reinterpret_cast<const float4*>(&sb[j]);
+            f0 = fmaf(lo.x, bb.x, f0); f1 = fmaf(lo.y, bb.x, f1); f2 = fmaf(lo.z, bb.x, f2); f3 = fmaf(lo.w, bb.x, f3);
+            f0 = fmaf(lo.y, bb.y, f0); f1 = fmaf(lo.z, bb.y, f1); f2 = fmaf(lo.w, bb.y, f2); f3 = fmaf(hi.x, bb.y, f3);
+            f0 = fmaf(lo.z, bb.z, f0); f1 = fmaf(lo.w, bb.z, f1); f2 = fmaf(hi.x, bb.z, f2); f3 = fmaf(hi.y, bb.z, f3);
+            f0 = fmaf(lo.w, bb.w, f0); f1 = fmaf(hi.x, bb.w, f1); f2 = fmaf(hi.y, bb.w, f2); f3 = fmaf(hi.z, bb.w, f3);
+            lo = hi;
+        }
+        acc[0] += (double)f0; acc[1] += (double)f1; acc[2] += (double)f2; acc[3] += (double)f3;
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const long long k = k0 + 4 * t + r;
+        if (k < n_lags) corr[k] = (float)acc[r];
+    }
+}
+
+// stft_band_tilt: energies of two bin ranges of |rfft(power_mono(frame) * hann)|^2, one CTA per frame (fp64 transform, rounded
+// to complex64 like NumPy's result); the band sums are accumulated in double in a fixed order and rounded to float32.
+__global__ void __launch_bounds__(256)
+calib_band_kernel(const float2* __restrict__ x, const float* __restrict__ win, int lo0, int lo1, int hi0, int hi1,
+                  float* __restrict__ e_lo, float* __restrict__ e_hi) {
+    extern __shared__ __align__(16) unsigned char band_smem[];
+    double2* sm = reinterpret_cast<double2*>(band_smem);
+    const int t = threadIdx.x;
+    const float2* src = x + (long long)blockIdx.x * kHop;
+    for (int n = t; n < kNfft; n += 256) sm[bitrev12(n)] = make_double2((double)__fmul_rn(power_mono(src[n]), win[n]), 0.0);
+    __syncthreads();
+    fft4096_f64(sm, t);
+    const int nb = spec_bins_of_thread(t);
+    float pw[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) pw[i] = (i < nb) ? power_bin(reinterpret_cast<const cplx64*>(sm), spec_bin(t, i)) : 0.f;
+    __syncthreads();
+    float* P = reinterpret_cast<float*>(band_smem);
+#pragma unroll
+    for (int i = 0; i < 9; ++i) if (i < nb) P[spec_bin(t, i)] = pw[i];
+    __syncthreads();
+    const int warp = t >> 5, lane = t & 31;
+    if (warp < 2) {
+        const int k0 = warp == 0 ? lo0 : hi0, k1 = warp == 0 ? lo1 : hi1;
+        double s = 0.0;
+        for (int k = k0 + lane; k < k1; k += 32) s += (double)P[k];
+        for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+        if (lane == 0) (warp == 0 ? e_lo : e_hi)[blockIdx.x] = (float)s;
+    }
+}
+
+__global__ void __launch_bounds__(128)
+calib_gate_grid_kernel(const float* __restrict__ level, const long long* __restrict__ start, const unsigned char* __restrict__ want,
+                       int n, const float* __restrict__ on, const float* __restrict__ off, const long long* __restrict__ delay,
+                       int n_combos, int* __restrict__ mismatches, int* __restrict__ switches, unsigned char* __restrict__ states) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_combos) return;
+    int mis, sw;
+    gate_grid_combo(level, start, want, n, on[c], off[c], delay[c], &mis, &sw, states ? states + (size_t)c * n : nullptr);
+    mismatches[c] = mis;
+    switches[c] = sw;
+}
+
 // ================================================================================================
 // host side
 template <typename T> struct DevBuf {
@@ -1864,10 +1994,12 @@ int tmt_plan_input_peaks(tmt_plan* p, void* stream) {
 
 int tmt_plan_levels(tmt_plan* p, int flags, const float* in_scale, void* stream) {
     const int use_f64 = flags & TMT_LEVELS_F64;
-    const int mono = (flags & TMT_LEVELS_MONO) ? 1 : (flags & TMT_LEVELS_LEFT) ? 2 : (flags & TMT_LEVELS_RIGHT) ? 3 : 0;
+    const int mono = (flags & TMT_LEVELS_MONO) ? 1 : (flags & TMT_LEVELS_LEFT) ? 2 : (flags & TMT_LEVELS_RIGHT) ? 3
+                     : (flags & TMT_LEVELS_POWER_EPS) ? 4 : 0;
     if (!p) return fail(TMT_ERR_INVALID, "plan is NULL");
-    if (((flags & TMT_LEVELS_MONO) != 0) + ((flags & TMT_LEVELS_LEFT) != 0) + ((flags & TMT_LEVELS_RIGHT) != 0) > 1)
-        return fail(TMT_ERR_INVALID, "TMT_LEVELS_MONO, _LEFT and _RIGHT exclude each other");
+    if (((flags & TMT_LEVELS_MONO) != 0) + ((flags & TMT_LEVELS_LEFT) != 0) + ((flags & TMT_LEVELS_RIGHT) != 0) +
+            ((flags & TMT_LEVELS_POWER_EPS) != 0) > 1)
+        return fail(TMT_ERR_INVALID, "TMT_LEVELS_MONO, _LEFT, _RIGHT and _POWER_EPS exclude each other");
     if (p->n_tracks == 0 || (p->max_hb == 0 && !(flags & TMT_LEVELS_MEANSQ_ONLY))) return TMT_OK;
     CUDA_TRY(cudaSetDevice(p->e->device));
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
@@ -2121,6 +2253,101 @@ int tmt_cond_spectrum(tmt_engine* e, const void* x, const void* y, int64_t total
     column_median_kernel<<<kBins, 256, 0, st>>>(d_ratio.p, n_frames, (long long)n_frames, d_med.p);
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaMemcpyAsync(median_out, d_med.p, sizeof(float) * kBins, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return TMT_OK;
+}
+
+int tmt_calib_envelope_decimate(tmt_engine* e, const void* x, int64_t n_in, const float* h, int len_h, int up, int down,
+                                int64_t n_pre_remove, int64_t n_out, float* out, void* stream) {
+    if (!e || !h || len_h <= 0 || up < 1 || down < 1 || n_in < 0 || n_out < 0 || n_pre_remove < 0) return fail(TMT_ERR_INVALID, "bad arguments");
+    if (n_out == 0) return TMT_OK;
+    if (!x || !out) return fail(TMT_ERR_INVALID, "NULL buffer");
+    CUDA_TRY(cudaSetDevice(e->device));
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    DevBuf<float> d_h;
+    DevBuf<double> d_part;
+    CUDA_TRY(d_h.alloc((size_t)len_h));
+    CUDA_TRY(d_part.alloc(kSumBlocks));
+    CUDA_TRY(cudaMemcpyAsync(d_h.p, h, sizeof(float) * (size_t)len_h, cudaMemcpyHostToDevice, st));
+    const int grid = (int)std::min<long long>((n_out + 255) / 256, 148LL * 16);
+    calib_decimate_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const float2*>(x), n_in, d_h.p, len_h, up, down, n_pre_remove, n_out, out);
+    CUDA_TRY(cudaGetLastError());
+    // x - np.mean(x): block partial sums in double, folded on the host in a fixed order
+    calib_partial_sum_kernel<<<kSumBlocks, 256, 0, st>>>(out, n_out, d_part.p);
+    CUDA_TRY(cudaGetLastError());
+    std::vector<double> part(kSumBlocks);
+    CUDA_TRY(cudaMemcpyAsync(part.data(), d_part.p, sizeof(double) * kSumBlocks, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    double sum = 0.0;
+    for (double v : part) sum += v;
+    calib_subtract_kernel<<<grid, 256, 0, st>>>(out, n_out, (float)(sum / (double)n_out));
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return TMT_OK;
+}
+
+int tmt_calib_xcorr_valid(tmt_engine* e, const float* a, int64_t na, const float* b, int64_t nb, float* corr, void* stream) {
+    if (!e || na < 0 || nb <= 0 || nb > na || nb > 0x7fffffffLL) return fail(TMT_ERR_INVALID, "need 0 < nb <= na");
+    if (!a || !b || !corr) return fail(TMT_ERR_INVALID, "NULL buffer");
+    CUDA_TRY(cudaSetDevice(e->device));
+    const long long n_lags = na - nb + 1;
+    calib_xcorr_kernel<<<(unsigned)((n_lags + kXcLags - 1) / kXcLags), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(a, na, b, (int)nb, corr, n_lags);
+    CUDA_TRY(cudaGetLastError());
+    return TMT_OK;
+}
+
+int tmt_calib_band_energies(tmt_engine* e, const void* x, int64_t total, int n_frames, int lo0, int lo1, int hi0, int hi1,
+                            float* e_lo, float* e_hi, void* stream) {
+    if (!e || n_frames < 0 || total < 0) return fail(TMT_ERR_INVALID, "bad arguments");
+    if (!e->have_win) return fail(TMT_ERR_INVALID, "engine window not set");
+    if (n_frames == 0) return TMT_OK;
+    if (!x || !e_lo || !e_hi) return fail(TMT_ERR_INVALID, "NULL buffer");
+    if ((long long)(n_frames - 1) * kHop + kNfft > total) return fail(TMT_ERR_INVALID, "%d frames do not fit into %lld sample-frames", n_frames, (long long)total);
+    if (lo0 < 0 || lo1 > kBins || hi0 < 0 || hi1 > kBins) return fail(TMT_ERR_INVALID, "band outside [0, %d]", kBins);
+    CUDA_TRY(cudaSetDevice(e->device));
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    CUDA_TRY(cudaFuncSetAttribute(calib_band_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSpecSmemBytes));
+    DevBuf<float> d_lo, d_hi;
+    CUDA_TRY(d_lo.alloc((size_t)n_frames));
+    CUDA_TRY(d_hi.alloc((size_t)n_frames));
+    calib_band_kernel<<<n_frames, 256, kSpecSmemBytes, st>>>(reinterpret_cast<const float2*>(x), e->win.p, lo0, lo1, hi0, hi1, d_lo.p, d_hi.p);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(e_lo, d_lo.p, sizeof(float) * (size_t)n_frames, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(e_hi, d_hi.p, sizeof(float) * (size_t)n_frames, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return TMT_OK;
+}
+
+int tmt_calib_gate_grid(tmt_engine* e, const float* level, const int64_t* start, const uint8_t* want, int n, const float* on,
+                        const float* off, const int64_t* delay, int n_combos, int32_t* mismatches, int32_t* switches, uint8_t* states,
+                        void* stream) {
+    if (!e || n < 0 || n_combos < 0) return fail(TMT_ERR_INVALID, "bad arguments");
+    if (n_combos == 0) return TMT_OK;
+    if ((n > 0 && (!level || !start || !want)) || !on || !off || !delay || !mismatches || !switches) return fail(TMT_ERR_INVALID, "NULL buffer");
+    CUDA_TRY(cudaSetDevice(e->device));
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    DevBuf<float> d_level, d_on, d_off;
+    DevBuf<long long> d_start, d_delay;
+    DevBuf<unsigned char> d_want, d_states;
+    DevBuf<int> d_mis, d_sw;
+    if (states && n > 0) CUDA_TRY(d_states.alloc((size_t)n * (size_t)n_combos));
+    CUDA_TRY(d_level.alloc((size_t)std::max(n, 1))); CUDA_TRY(d_start.alloc((size_t)std::max(n, 1))); CUDA_TRY(d_want.alloc((size_t)std::max(n, 1)));
+    CUDA_TRY(d_on.alloc((size_t)n_combos)); CUDA_TRY(d_off.alloc((size_t)n_combos)); CUDA_TRY(d_delay.alloc((size_t)n_combos));
+    CUDA_TRY(d_mis.alloc((size_t)n_combos)); CUDA_TRY(d_sw.alloc((size_t)n_combos));
+    if (n > 0) {
+        CUDA_TRY(cudaMemcpyAsync(d_level.p, level, sizeof(float) * (size_t)n, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(d_start.p, start, sizeof(long long) * (size_t)n, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(d_want.p, want, (size_t)n, cudaMemcpyHostToDevice, st));
+    }
+    CUDA_TRY(cudaMemcpyAsync(d_on.p, on, sizeof(float) * (size_t)n_combos, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(d_off.p, off, sizeof(float) * (size_t)n_combos, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(d_delay.p, delay, sizeof(long long) * (size_t)n_combos, cudaMemcpyHostToDevice, st));
+    calib_gate_grid_kernel<<<(n_combos + 127) / 128, 128, 0, st>>>(d_level.p, d_start.p, d_want.p, n, d_on.p, d_off.p, d_delay.p, n_combos, d_mis.p, d_sw.p,
+                                                                   (states && n > 0) ? d_states.p : nullptr);
+    CUDA_TRY(cudaGetLastError());
+    if (states && n > 0) CUDA_TRY(cudaMemcpyAsync(states, d_states.p, (size_t)n * (size_t)n_combos, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(mismatches, d_mis.p, sizeof(int) * (size_t)n_combos, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(switches, d_sw.p, sizeof(int) * (size_t)n_combos, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
     return TMT_OK;
 }

@@ -147,7 +147,8 @@ class Plan:
     def levels(self, use_f64: bool = False, in_scale: Optional[np.ndarray] = None, mono: bool = False, part: str = "all",
                channel: Optional[str] = None):
         """part: "all" | "hopsums" (hop-block sums only) | "meansq" (mean squares from the sums already in the plan);
-        channel: None (the mode's stereo / mono formula) | "left" | "right" (np.mean(x*x) of that channel alone)"""
+        channel: None (the mode's stereo / mono formula) | "left" | "right" (np.mean(x*x) of that channel alone) |
+        "power_eps" (the calibration front end's power-average mono, epsilon inside the root)"""
         ptr = None
         if in_scale is not None:
             in_scale = np.ascontiguousarray(in_scale, dtype=np.float32)
@@ -155,7 +156,7 @@ class Plan:
             ptr = in_scale.ctypes.data_as(C.c_void_p)
         flags = (int(bool(use_f64)) | (L.LEVELS_MONO if mono else 0)
                  | {"all": 0, "hopsums": L.LEVELS_HOPSUM_ONLY, "meansq": L.LEVELS_MEANSQ_ONLY}[part]
-                 | {None: 0, "left": L.LEVELS_LEFT, "right": L.LEVELS_RIGHT}[channel])
+                 | {None: 0, "left": L.LEVELS_LEFT, "right": L.LEVELS_RIGHT, "power_eps": L.LEVELS_POWER_EPS}[channel])
         L.check(self.lib.tmt_plan_levels(self.h, flags, ptr, _stream_ptr(_torch())),
                 "tmt_plan_levels")
 
@@ -564,6 +565,90 @@ def cond_spectrum_median(x, y, frames, anchor_bins=None, device: int = 0) -> np.
                                       frames.ctypes.data_as(C.c_void_p), int(frames.size), a0, a1,
                                       out.ctypes.data_as(C.c_void_p), _stream_ptr(torch)), "tmt_cond_spectrum")
     return out
+
+
+# ------------------------------------------------------------------------------------------- calibration (N4)
+def calib_envelope(x, lo: int, hi: int, up: int, down: int, device: int = 0):
+    """Envelope of x[lo:hi] for the delay estimate (src/calibrate_to_baseline_v2.py:57-61,71-74): power_mono, resample_poly
+    (up, down), mean removed.  x: float32 [N, 2] host array or device tensor.  Returns a float32 device tensor."""
+    torch = _torch()
+    eng = get_engine(device)
+    xd = _to_device(torch, [x], device)[0]
+    lo, hi = int(lo), int(hi)
+    if not 0 <= lo <= hi <= int(xd.shape[0]):
+        raise ValueError(f"range [{lo}, {hi}) outside the {int(xd.shape[0])} sample-frames of the file")
+    plan = tb.resample_poly_plan(hi - lo, up, down)
+    out = torch.empty(plan["n_out"], dtype=torch.float32, device=xd.device)
+    h = plan["h"] if plan["h"] is not None else np.ones(1, np.float32)          # up == down: resample_poly returns x itself
+    h = np.ascontiguousarray(h, dtype=np.float32)
+    L.check(eng.lib.tmt_calib_envelope_decimate(eng.h, C.c_void_p(xd.data_ptr() + 8 * lo), hi - lo,
+                                                h.ctypes.data_as(C.c_void_p), int(h.size), plan["up"], plan["down"],
+                                                plan["n_pre_remove"], plan["n_out"], C.c_void_p(out.data_ptr()),
+                                                _stream_ptr(torch)), "tmt_calib_envelope_decimate")
+    return out
+
+
+def calib_xcorr(a_dev, b_dev) -> np.ndarray:
+    """corr[k] = sum_j a[k + j] * b[j], k = 0 .. len(a) - len(b) (fftconvolve(a, b[::-1], "valid"), :77-78) -> host float32."""
+    torch = _torch()
+    eng = get_engine(a_dev.device.index or 0)
+    na, nb = int(a_dev.numel()), int(b_dev.numel())
+    if nb == 0 or nb > na:
+        raise ValueError(f"valid cross-correlation needs 0 < len(b) <= len(a), got {nb} and {na}")
+    corr = torch.empty(na - nb + 1, dtype=torch.float32, device=a_dev.device)
+    L.check(eng.lib.tmt_calib_xcorr_valid(eng.h, C.c_void_p(a_dev.data_ptr()), na, C.c_void_p(b_dev.data_ptr()), nb,
+                                          C.c_void_p(corr.data_ptr()), _stream_ptr(torch)), "tmt_calib_xcorr_valid")
+    return corr.cpu().numpy()
+
+
+def calib_frame_levels(x, device: int = 0) -> np.ndarray:
+    """rms_dbfs_from_mono(power_mono(frame)) (:8-15,193-194) of the frames [i*hop, i*hop + n_fft) that lie inside x -> float32."""
+    torch = _torch()
+    eng = get_engine(device)
+    xd = _to_device(torch, [x], device)[0]
+    n = int(xd.shape[0])
+    plan = Plan(eng, L.FRAMING_EQ_NOPAD, [L.TrackDesc(xd.data_ptr(), None, n, 0, n, 0, 0, 0, -1)])
+    try:
+        plan.levels(channel="power_eps")
+        return tb.levels_from_meansq(plan.read(L.ARR_MEANSQ_F32)).astype(np.float32)
+    finally:
+        plan.close()
+
+
+def calib_band_energies(x, n_frames: int, lo_bins, hi_bins, device: int = 0):
+    """Band energies of stft_band_tilt (:17-30) for the first n_frames frames of x: sums of |rfft(power_mono * hann)|^2 over
+    the bin ranges [lo_bins[0], lo_bins[1]) and [hi_bins[0], hi_bins[1]) -> (e_lo, e_hi) float32."""
+    torch = _torch()
+    eng = get_engine(device)
+    xd = _to_device(torch, [x], device)[0]
+    e_lo, e_hi = np.zeros(n_frames, np.float32), np.zeros(n_frames, np.float32)
+    L.check(eng.lib.tmt_calib_band_energies(eng.h, C.c_void_p(xd.data_ptr()), int(xd.shape[0]), int(n_frames),
+                                            int(lo_bins[0]), int(lo_bins[1]), int(hi_bins[0]), int(hi_bins[1]),
+                                            e_lo.ctypes.data_as(C.c_void_p), e_hi.ctypes.data_as(C.c_void_p),
+                                            _stream_ptr(torch)), "tmt_calib_band_energies")
+    return e_lo, e_hi
+
+
+def calib_gate_grid(level, start, want, on, off, delay, want_states: bool = False, device: int = 0):
+    """simulate_state (:88-112) for len(on) parameter sets over the same frames -> (mismatches, switches[, states])."""
+    torch = _torch()
+    eng = get_engine(device)
+    level = np.ascontiguousarray(level, dtype=np.float32)
+    start = np.ascontiguousarray(start, dtype=np.int64)
+    want = np.ascontiguousarray(want, dtype=np.uint8)
+    on, off = np.ascontiguousarray(on, dtype=np.float32), np.ascontiguousarray(off, dtype=np.float32)
+    delay = np.ascontiguousarray(delay, dtype=np.int64)
+    n, nc = int(level.size), int(on.size)
+    assert start.size == n and want.size == n and off.size == nc and delay.size == nc
+    mis, sw = np.zeros(nc, np.int32), np.zeros(nc, np.int32)
+    states = np.zeros((nc, n), np.uint8) if want_states else None
+    L.check(eng.lib.tmt_calib_gate_grid(eng.h, level.ctypes.data_as(C.c_void_p), start.ctypes.data_as(C.c_void_p),
+                                        want.ctypes.data_as(C.c_void_p), n, on.ctypes.data_as(C.c_void_p),
+                                        off.ctypes.data_as(C.c_void_p), delay.ctypes.data_as(C.c_void_p), nc,
+                                        mis.ctypes.data_as(C.c_void_p), sw.ctypes.data_as(C.c_void_p),
+                                        states.ctypes.data_as(C.c_void_p) if want_states else None, _stream_ptr(torch)),
+            "tmt_calib_gate_grid")
+    return (mis, sw, states) if want_states else (mis, sw)
 
 
 def run(mode: str, xs: Sequence, sr: int, **kw) -> List[dict]:

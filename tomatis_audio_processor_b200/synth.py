@@ -113,6 +113,28 @@ def recipe_threshold_ramps(seconds: float, sr: int, seed: int, t_on: float, t_of
     return x.astype(np.float32)
 
 
+def recipe_level_steps(seconds: float, sr: int, seed: int, lo_dbfs: float = -52.0, hi_dbfs: float = -28.0,
+                       min_s: float = 0.4, max_s: float = 1.8, edge_s: float = 0.02) -> np.ndarray:
+    """Calibration recipe: pink noise that alternates between a quiet and a loud plateau (each jittered by +-4 dB) held
+    for random durations in [min_s, max_s] -- an aperiodic envelope, so the envelope cross-correlation of
+    src/calibrate_to_baseline_v2.py:44-86 has one clear peak, and a bimodal level distribution for its gate fit."""
+    n = int(round(seconds * sr))
+    rng = np.random.default_rng(seed)
+    noise = pink_noise(n, 2, rng)
+    lev_db = np.empty(n, dtype=np.float64)
+    pos, loud = 0, False
+    while pos < n:
+        ln = int(rng.uniform(min_s, max_s) * sr)
+        lev_db[pos:pos + ln] = (hi_dbfs if loud else lo_dbfs) + rng.uniform(-4.0, 4.0)
+        pos += ln
+        loud = not loud
+    k = max(1, int(edge_s * sr))
+    lev_db = np.convolve(np.pad(lev_db, (k // 2, k - 1 - k // 2), mode="edge"), np.ones(k) / k, mode="valid")
+    x = noise * _db(lev_db)[:, None]
+    np.clip(x, -1.0, 1.0, out=x)
+    return x.astype(np.float32)
+
+
 def quantise_pcm16(x: np.ndarray) -> np.ndarray:
     """Round to the int16 grid (values stay float32 and exactly representable) so golden
     fixtures can store inputs as int16."""

@@ -294,3 +294,52 @@ def _flush_chunk_blocks_replay(n_frames: int, n_fft=N_FFT, hop=HOP):
     if flushed < n_frames + 1:
         out.append((flushed, n_frames + 1))
     return out
+
+
+# ------------------------------------------------------------------------------------------------ calibration (N4)
+def resample_poly_plan(n_in: int, up: int, down: int):
+    """What scipy.signal.resample_poly(x, up, down) does to a float32 signal of n_in samples, as tables: the Kaiser(5)
+    windowed-sinc low-pass of firwin (2*10*max(up, down) + 1 taps, cutoff 1/max(up, down), unit DC gain) cast to float32,
+    times up, zero-padded so the kept outputs are centred; y[j] = upfirdn(h, x, up, down)[j + n_pre_remove], j < n_out.
+    Returns dict(up, down, h float32, n_pre_remove, n_out) with up/down reduced; h is None when up == down (identity).
+    The reference reaches it through find_delay_by_corr (src/calibrate_to_baseline_v2.py:60,73)."""
+    import math
+    g = math.gcd(int(up), int(down))
+    up, down = int(up) // g, int(down) // g
+    if up == down == 1:
+        return dict(up=1, down=1, h=None, n_pre_remove=0, n_out=int(n_in))
+    n_out = n_in * up
+    n_out = n_out // down + bool(n_out % down)
+    max_rate = max(up, down)
+    f_c = 1.0 / max_rate
+    half_len = 10 * max_rate
+    numtaps = 2 * half_len + 1
+    m = np.arange(0, numtaps, dtype=np.float64) - 0.5 * (numtaps - 1)
+    h = f_c * np.sinc(f_c * m) * np.kaiser(numtaps, 5.0)
+    h /= np.sum(h)
+    h = h.astype(np.float32)
+    h *= up
+    n_pre_pad = down - half_len % down
+    n_post_pad = 0
+    n_pre_remove = (half_len + n_pre_pad) // down
+
+    def out_len(len_h):                      # scipy.signal._upfirdn._output_len
+        return (((n_in - 1) * up + len_h) - 1) // down + 1
+
+    while out_len(numtaps + n_pre_pad + n_post_pad) < n_out + n_pre_remove:
+        n_post_pad += 1
+    h = np.concatenate([np.zeros(n_pre_pad, np.float32), h, np.zeros(n_post_pad, np.float32)])
+    return dict(up=up, down=down, h=h, n_pre_remove=int(n_pre_remove), n_out=int(n_out))
+
+
+def medfilt_zero_padded(x: np.ndarray, kernel_size: int) -> np.ndarray:
+    """scipy.signal.medfilt on a 1-D array: sliding median of an odd window over the zero-extended signal
+    (src/calibrate_to_baseline_v2.py:209)."""
+    k = int(kernel_size)
+    assert k % 2 == 1
+    x = np.asarray(x)
+    if x.size == 0:
+        return x.copy()
+    pad = np.zeros(k // 2, dtype=x.dtype)
+    w = np.lib.stride_tricks.sliding_window_view(np.concatenate([pad, x, pad]), k)
+    return np.sort(w, axis=1)[:, k // 2]
