@@ -113,6 +113,10 @@ int tmt_plan_track_chunks(const tmt_plan* p, int track);
 int tmt_plan_track_chunk_base(const tmt_plan* p, int track);
 /* Limiter chunk c of `track`: file sample range [*s0, *s1) (already clipped to [0,total)). */
 int tmt_plan_chunk_range(const tmt_plan* p, int track, int c, int64_t* s0, int64_t* s1);
+/* The same geometry in bulk (one call per plan instead of one per track / chunk): per-track arrays of n_tracks int32 each
+ * (NULL skips one), and every chunk range of the plan as [total_chunks][2] int64 (s0, s1) in plan order. */
+int tmt_plan_geometry(const tmt_plan* p, int32_t* n_frames, int32_t* frame_base, int32_t* n_chunks, int32_t* chunk_base);
+int tmt_plan_chunk_ranges(const tmt_plan* p, int64_t* ranges);
 
 /* Copy `count` elements starting at `offset` of a plan array to/from `ptr` (host if is_device==0,
  * else device); synchronises `stream` for host copies. */

@@ -88,19 +88,20 @@ class Plan:
         self.total_frames = self.lib.tmt_plan_total_frames(h)
         self.total_chunks = self.lib.tmt_plan_total_chunks(h)
         self.total_units = self.lib.tmt_plan_total_units(h)
-        self.track_frames = [self.lib.tmt_plan_track_frames(h, t) for t in range(self.n_tracks)]
-        self.frame_base = [self.lib.tmt_plan_track_frame_base(h, t) for t in range(self.n_tracks)]
-        self.track_chunks = [self.lib.tmt_plan_track_chunks(h, t) for t in range(self.n_tracks)]
-        self.chunk_base = [self.lib.tmt_plan_track_chunk_base(h, t) for t in range(self.n_tracks)]
+        geo = np.zeros((4, max(1, self.n_tracks)), dtype=np.int32)            # one call instead of four per track
+        L.check(self.lib.tmt_plan_geometry(h, *(geo[i].ctypes.data_as(C.c_void_p) for i in range(4))), "tmt_plan_geometry")
+        self.track_frames, self.frame_base, self.track_chunks, self.chunk_base = (geo[i, :self.n_tracks].tolist() for i in range(4))
+        self._chunk_ranges = None
 
     # -- geometry
     def chunk_ranges(self, track: int):
-        out = []
-        s0, s1 = C.c_int64(), C.c_int64()
-        for c in range(self.track_chunks[track]):
-            L.check(self.lib.tmt_plan_chunk_range(self.h, track, c, C.byref(s0), C.byref(s1)))
-            out.append((s0.value, s1.value))
-        return out
+        """[(s0, s1)] of the track's limiter chunks, file sample ranges."""
+        if self._chunk_ranges is None:
+            r = np.zeros((max(1, self.total_chunks), 2), dtype=np.int64)
+            L.check(self.lib.tmt_plan_chunk_ranges(self.h, r.ctypes.data_as(C.c_void_p)), "tmt_plan_chunk_ranges")
+            self._chunk_ranges = r.tolist()
+        cb = self.chunk_base[track]
+        return [tuple(v) for v in self._chunk_ranges[cb:cb + self.track_chunks[track]]]
 
     # -- arrays
     def _count(self, which):
@@ -321,21 +322,22 @@ def run_streaming(mode: str, xs: Sequence, sr: int, device: int = 0, want_host: 
         states = plan.read(L.ARR_STATE)
         rows = plan.read(L.ARR_ROW)
         peaks = plan.read(L.ARR_CHUNK_PEAK)
+        levels_all = tb.levels_from_meansq(msq)                        # one vectorised pass for the whole batch
+        launches = plan.launch_count()
         res = []
         for t in range(plan.n_tracks):
             fb, nf = plan.frame_base[t], plan.track_frames[t]
             total = int(xd[t].shape[0])
             ranges = plan.chunk_ranges(t)
             cb = plan.chunk_base[t]
-            m = msq[fb:fb + nf]
             starts = -(n_fft // 2) + hop * np.arange(nf, dtype=np.int64)
             res.append(dict(
                 out=(yd[t].cpu().numpy() if want_host else yd[t]),
                 chunk_lengths=[int(b - a) for (a, b) in ranges if b > a],
                 chunk_ranges=ranges, chunk_peaks=peaks[cb:cb + len(ranges)].copy(),
-                meansq=m.copy(), levels=tb.levels_from_meansq(m), states=states[fb:fb + nf].copy(),
+                meansq=msq[fb:fb + nf].copy(), levels=levels_all[fb:fb + nf].copy(), states=states[fb:fb + nf].copy(),
                 rows=rows[fb:fb + nf].copy(), frame_starts=starts, csv_mask=(starts >= 0) & (starts < total),
-                xfade_frames=sp.xfade_frames, sr=sr, Ton=sp.Ton, Toff=sp.Toff, launches=plan.launch_count()))
+                xfade_frames=sp.xfade_frames, sr=sr, Ton=sp.Ton, Toff=sp.Toff, launches=launches))
         return res
     finally:
         plan.close()
