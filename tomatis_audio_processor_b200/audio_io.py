@@ -86,6 +86,24 @@ def _wav_info(path) -> AudioInfo:
     return AudioInfo(sr, ch, size // block, sub, "WAV")
 
 
+def _wav_decode(raw, subtype, n, dtype):
+    """n interleaved samples from the data chunk's bytes, scaled like libsndfile's float reads."""
+    if subtype == "PCM_16":
+        return raw[:2 * n].view("<i2").astype(dtype) / dtype(32768.0)
+    if subtype == "PCM_24":
+        b = raw[:3 * n].reshape(-1, 3).astype(np.int32)
+        v = (b[:, 0] | (b[:, 1] << 8) | (b[:, 2] << 16))
+        v = np.where(v & 0x800000, v - 0x1000000, v)
+        return v.astype(dtype) / dtype(8388608.0)
+    if subtype == "PCM_32":
+        return (raw[:4 * n].view("<i4").astype(np.float64) / 2147483648.0).astype(dtype)
+    if subtype == "PCM_U8":
+        return (raw[:n].astype(dtype) - dtype(128.0)) / dtype(128.0)
+    if subtype == "FLOAT":
+        return raw[:4 * n].view("<f4").astype(dtype)
+    return raw[:8 * n].view("<f8").astype(dtype)
+
+
 def _wav_read(path, dtype):
     info = _wav_info(path)
     _, offset, size = _wav_header(path)
@@ -93,22 +111,7 @@ def _wav_read(path, dtype):
     with open(path, "rb") as f:
         f.seek(offset)
         raw = np.frombuffer(f.read(size), dtype=np.uint8)
-    if info.subtype == "PCM_16":
-        x = raw[:2 * n].view("<i2").astype(dtype) / dtype(32768.0)
-    elif info.subtype == "PCM_24":
-        b = raw[:3 * n].reshape(-1, 3).astype(np.int32)
-        v = (b[:, 0] | (b[:, 1] << 8) | (b[:, 2] << 16))
-        v = np.where(v & 0x800000, v - 0x1000000, v)
-        x = v.astype(dtype) / dtype(8388608.0)
-    elif info.subtype == "PCM_32":
-        x = (raw[:4 * n].view("<i4").astype(np.float64) / 2147483648.0).astype(dtype)
-    elif info.subtype == "PCM_U8":
-        x = (raw[:n].astype(dtype) - dtype(128.0)) / dtype(128.0)
-    elif info.subtype == "FLOAT":
-        x = raw[:4 * n].view("<f4").astype(dtype)
-    else:
-        x = raw[:8 * n].view("<f8").astype(dtype)
-    return x.reshape(info.frames, info.channels), info.samplerate
+    return _wav_decode(raw, info.subtype, n, dtype).reshape(info.frames, info.channels), info.samplerate
 
 
 def quantise_pcm24(y: np.ndarray) -> np.ndarray:
@@ -168,6 +171,25 @@ def read(path, dtype="float32"):
     if _ext(path) != ".wav":
         raise AudioFormatUnavailable(f"reading {_ext(path) or 'this'} files needs the soundfile package (libsndfile)")
     return _wav_read(path, np.dtype(dtype).type)
+
+
+def read_range(path, start: int, stop: int, dtype="float32"):
+    """Sample-frames [start, stop) of a file, [stop - start, ch] -- what one rank of a time-sharded run loads
+    (fin.seek(start); fin.read(stop - start, always_2d=True))."""
+    start, stop = int(start), int(stop)
+    if _sf is not None:
+        x, _ = _sf.read(path, start=start, stop=stop, dtype=dtype, always_2d=True)
+        return x
+    if _ext(path) != ".wav":
+        raise AudioFormatUnavailable(f"reading {_ext(path) or 'this'} files needs the soundfile package (libsndfile)")
+    i = _wav_info(path)
+    (_, ch, _, block, _), offset, size = _wav_header(path)
+    start, stop = max(0, min(start, i.frames)), max(0, min(stop, i.frames))
+    stop = max(stop, start)
+    with open(path, "rb") as f:
+        f.seek(offset + start * block)
+        raw = np.frombuffer(f.read((stop - start) * block), dtype=np.uint8)
+    return _wav_decode(raw, i.subtype, (stop - start) * ch, np.dtype(dtype).type).reshape(stop - start, ch)
 
 
 def write(path, y, samplerate, subtype="PCM_24", format=None):
