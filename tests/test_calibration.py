@@ -58,8 +58,10 @@ class EmulatedKernels:
         return _HostTensor(out)
 
     def calib_xcorr(self, a, b):
-        if b.arr.size == 0 or b.arr.size > a.arr.size:
-            raise ValueError("valid cross-correlation needs 0 < len(b) <= len(a)")
+        if a.arr.size == 0 or b.arr.size == 0:
+            raise ValueError("cross-correlation of an empty envelope")
+        if b.arr.size > a.arr.size:                      # scipy swaps the operands of a "valid" convolution
+            return self.calib_xcorr(b, a)[::-1].copy()
         return np.correlate(a.arr.astype(np.float64), b.arr.astype(np.float64), mode="valid").astype(np.float32)
 
     def calib_frame_levels(self, x, device=0):
@@ -285,8 +287,13 @@ def test_calibration_gpu_kernels_against_numpy_and_emulation(emul):
         got = engine.calib_xcorr(torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda())
         ref = np.correlate(a.astype(np.float64), b.astype(np.float64), mode="valid")
         assert got.shape == ref.shape and np.abs(got - ref).max() <= 2e-5 * np.sqrt(nb) * 4
+    from scipy.signal import fftconvolve
+    a, b = rng.standard_normal(700).astype(np.float32), rng.standard_normal(1900).astype(np.float32)
+    got = engine.calib_xcorr(torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda())     # second operand longer: scipy's swap
+    ref = fftconvolve(a.astype(np.float64), b[::-1].astype(np.float64), mode="valid")
+    assert got.shape == ref.shape and np.abs(got - ref).max() <= 1e-3
     with pytest.raises(ValueError):
-        engine.calib_xcorr(torch.zeros(10).cuda(), torch.zeros(11).cuda())
+        engine.calib_xcorr(torch.zeros(10).cuda(), torch.zeros(0).cuda())
     # envelope + decimation against the emulated per-thread code (same arithmetic) and scipy
     from scipy.signal import resample_poly
     for n_in, up, down in ((48000, 2000, 48000), (44100, 2000, 44100), (999, 3, 7), (25, 1, 24), (4800, 1, 1)):
@@ -337,3 +344,38 @@ def test_calibration_gpu_cli_files(tmp_path):
     assert list(saved)[2:] == list(g["json"])
     assert prod.find_delay_by_corr(po, pb, sr=g["sr"]) == g["json"]["delay_samples_orig_minus_base"]
     assert os.path.getsize(pj) > 0
+
+
+def _pair(sr, secs, base_secs, seed, lead, up_ms=100.0):
+    """orig = x[lead:], base = the oracle's standard-mode output of the first base_secs of x: the baseline starts `lead`
+    samples EARLIER than the original (negative delay)."""
+    from oracle import tomatis_oracle as orc
+    from tomatis_audio_processor_b200 import synth
+    x = synth.pcm16_to_float(synth.quantise_pcm16(synth.recipe_level_steps(secs, sr, seed, min_s=0.25, max_s=0.8)))
+    y = orc.run("standard", x[:int(base_secs * sr)], sr, gate_ui=50, up_delay_ms=up_ms)["out"].astype(np.float32)
+    return np.ascontiguousarray(x[lead:]), synth.pcm16_to_float(synth.quantise_pcm16(0.9 * y))
+
+
+@pytest.mark.parametrize("sr,lead,kw", [(48000, 30007, dict(hyst_list=(2, 3), delay_list_ms=(50, 100))),
+                                        (44100, 12345, dict(hyst_list=(3,), delay_list_ms=(100,), max_minutes=0.08, tilt_medfilt=7))])
+def test_front_end_negative_delay_matches_oracle(emulated_engine, sr, lead, kw):
+    """The baseline leads the original (delay < 0: base_start = -delay, orig_start = 0, :168-169), short overlap cap.  The
+    baseline has to be longer than the 25 s chunk for that: its middle chunk must lie inside the original."""
+    orig, base = _pair(sr, 31.0, 29.0, 77, lead)
+    o = co.calibrate(orig, base, sr, **kw)
+    r = prod.calibrate(orig, base, sr, **kw)
+    assert o["delay"] < 0 and abs(o["delay"] + lead) <= sr // 2000 + 1
+    assert r["json"] == o["json"] and r["delay"] == o["delay"]
+    assert np.array_equal(r["orig_level"], o["orig_level"]) and np.array_equal(r["base_level"], o["base_level"])
+    assert np.array_equal(r["base_state"], o["base_state"]) and np.array_equal(r["music_mask"], o["music_mask"])
+    assert np.abs(r["tilts"] - o["tilts"]).max() < TILT_TOL_DB
+
+
+def test_front_end_baseline_chunk_longer_than_original(emulated_engine):
+    """scipy's "valid" convolution swaps its operands when the second is the longer one, so the reference does not fail on
+    an original shorter than the baseline chunk (:77-78): same (meaningless) delay, same JSON."""
+    orig, base = _pair(48000, 8.0, 8.0, 78, 30007)
+    assert len(base) > len(orig)
+    kw = dict(hyst_list=(3,), delay_list_ms=(100,))
+    o, r = co.calibrate(orig, base, 48000, **kw), prod.calibrate(orig, base, 48000, **kw)
+    assert r["delay"] == o["delay"] and r["json"] == o["json"]

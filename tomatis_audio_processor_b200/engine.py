@@ -591,12 +591,15 @@ def calib_envelope(x, lo: int, hi: int, up: int, down: int, device: int = 0):
 
 
 def calib_xcorr(a_dev, b_dev) -> np.ndarray:
-    """corr[k] = sum_j a[k + j] * b[j], k = 0 .. len(a) - len(b) (fftconvolve(a, b[::-1], "valid"), :77-78) -> host float32."""
+    """fftconvolve(a, b[::-1], "valid") (:77-78) -> host float32: corr[k] = sum_j a[k + j] * b[j], k = 0 .. len(a) - len(b).
+    Like scipy, a second operand longer than the first swaps the roles: the result is then sum_j a[j] * b[len(b) - len(a) - k + j]."""
     torch = _torch()
     eng = get_engine(a_dev.device.index or 0)
     na, nb = int(a_dev.numel()), int(b_dev.numel())
-    if nb == 0 or nb > na:
-        raise ValueError(f"valid cross-correlation needs 0 < len(b) <= len(a), got {nb} and {na}")
+    if na == 0 or nb == 0:
+        raise ValueError("cross-correlation of an empty envelope")
+    if nb > na:
+        return calib_xcorr(b_dev, a_dev)[::-1].copy()
     corr = torch.empty(na - nb + 1, dtype=torch.float32, device=a_dev.device)
     L.check(eng.lib.tmt_calib_xcorr_valid(eng.h, C.c_void_p(a_dev.data_ptr()), na, C.c_void_p(b_dev.data_ptr()), nb,
                                           C.c_void_p(corr.data_ptr()), _stream_ptr(torch)), "tmt_calib_xcorr_valid")

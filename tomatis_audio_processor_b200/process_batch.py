@@ -149,8 +149,10 @@ def reduce_table(table: np.ndarray, world: int, device: int) -> np.ndarray:
     import torch
     import torch.distributed as dist
     use_cuda = torch.cuda.is_available()
+    if use_cuda:
+        torch.cuda.set_device(device)
     if not dist.is_initialized():
-        dist.init_process_group("nccl" if use_cuda else "gloo")
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{device}")) if use_cuda else dist.init_process_group("gloo")
     t = torch.from_numpy(table.copy())
     if use_cuda:
         t = t.to(f"cuda:{device}")
