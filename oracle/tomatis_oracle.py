@@ -28,7 +28,6 @@ at the ill-conditioned edges, not as the default.
 """
 from __future__ import annotations
 
-import math
 
 import numpy as np
 

@@ -9,12 +9,7 @@ ranks needs no collective.
 """
 from __future__ import annotations
 
-from typing import Optional
-
-import numpy as np
-
 from . import _lib as L
-from . import tables as tb
 from .engine import Plan, get_engine, streaming_params, whole_track_desc, _torch
 
 
