@@ -157,3 +157,15 @@ def test_calibration_restatement(sr, words, kw):
     assert np.array_equal(lab_o[0], lab_r[0]) and lab_o[1:] == lab_r[1:]
     lv, fs = o["orig_level"], o["starts"]
     assert np.array_equal(co.simulate_state(lv, fs, sr, -40.0, 3.0, 120.0), mod.simulate_state(lv, fs, sr, -40.0, 3.0, 120.0))
+
+
+@pytest.mark.parametrize("n_fft,hop", [(2048, 1024), (1024, 512), (4096, 1024), (8192, 4096), (2048, 512)])
+def test_other_fft_sizes_restatement(n_fft, hop):
+    """The reference exposes --n_fft / --hop (src/process_tomatis.py:509-510); the GPU path implements 4096 / 2048 only, but
+    the oracle follows the reference for every size (frame counts, flush schedule, pairwise level sums, overlap factor 2 and
+    4): pinned here so that a general-size kernel path has its checker."""
+    xs = synth.pcm16_to_float(synth.quantise_pcm16(synth.recipe_gated_pink(2.5, 48000, 84, env_hz=1.5, hi_dbfs=-22.0)))
+    xa = synth.pcm16_to_float(synth.quantise_pcm16(synth.recipe_swept_pink(2.5, 48000, 85, period_s=0.7, peak=0.5)))
+    _check("standard", xs, 48000, gate_ui=50, up_delay_ms=80.0, n_fft=n_fft, hop=hop)
+    _check("xfade", xs, 48000, gate_ui=60, xfade_ms=120.0, up_delay_ms=40.0, n_fft=n_fft, hop=hop)
+    _check("adaptive", xa, 48000, min_hold_ms=100.0, xfade_ms=200.0, n_fft=n_fft, hop=hop)
