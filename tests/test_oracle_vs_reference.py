@@ -169,3 +169,36 @@ def test_other_fft_sizes_restatement(n_fft, hop):
     _check("standard", xs, 48000, gate_ui=50, up_delay_ms=80.0, n_fft=n_fft, hop=hop)
     _check("xfade", xs, 48000, gate_ui=60, xfade_ms=120.0, up_delay_ms=40.0, n_fft=n_fft, hop=hop)
     _check("adaptive", xa, 48000, min_hold_ms=100.0, xfade_ms=200.0, n_fft=n_fft, hop=hop)
+
+
+def test_random_parameter_sweep_restatement():
+    """Seeded sweep over the whole parameter surface of the three process() signatures (gate maps, hysteresis, delays, tilt
+    corners and slopes, crossfade lengths, output gain, head-room margin, sample rates, ragged lengths): the oracle equals the
+    executed reference in every case -- output samples, chunk lengths and CSV text."""
+    rng = np.random.default_rng(2024)
+    for case in range(12):
+        sr = int(rng.choice([44100, 48000, 96000]))
+        n = int(rng.integers(3000, 90000))
+        tilt = dict(fc=float(rng.choice([500.0, 1000.0, 2000.0])), slope=float(rng.choice([6.0, 12.0, 18.0])),
+                    c1_low=float(rng.choice([5.0, 15.0])), c1_high=float(rng.choice([-15.0, -8.0])),
+                    c2_low=float(rng.choice([-15.0, -5.0])), c2_high=float(rng.choice([15.0, 10.0])))
+        mode = ("standard", "xfade", "adaptive")[case % 3]
+        if mode == "adaptive":
+            x = synth.recipe_swept_pink(n / sr + 0.01, sr, 300 + case, period_s=float(rng.uniform(0.2, 0.8)),
+                                        peak=float(rng.choice([0.08, 0.5, 0.95])))[:n]
+            kw = dict(tilt, target_c2=float(rng.choice([0.3, 0.5, 0.7])), hyst_db=float(rng.choice([1.0, 3.0, 6.0])),
+                      min_hold_ms=float(rng.choice([0.0, 60.0, 250.0])), xfade_ms=float(rng.choice([0.0, 100.0, 500.0])),
+                      headroom_margin=float(rng.choice([0.0, 2.0, 6.0])))
+        else:
+            x = synth.recipe_gated_pink(n / sr + 0.01, sr, 300 + case, env_hz=float(rng.uniform(1.0, 4.0)),
+                                        lo_dbfs=float(rng.uniform(-70, -50)), hi_dbfs=float(rng.uniform(-35, -10)))[:n]
+            kw = dict(tilt, gate_ui=float(rng.uniform(35, 65)), hysteresis_db=float(rng.choice([0.0, 3.0, 8.0])),
+                      up_delay_ms=float(rng.choice([0.0, 30.0, 250.0])), gate_scale=float(rng.choice([1.0, 0.8])),
+                      gate_offset=float(rng.choice([-100, -90])))
+            if mode == "standard":
+                kw.update(gate_mode=str(rng.choice(["linear", "log_percent"])), dynamic_range=float(rng.choice([60.0, 80.0])),
+                          output_gain_db=float(rng.choice([0.0, -6.0, 3.0])))
+            else:
+                kw.update(xfade_ms=float(rng.choice([0.0, 50.0, 400.0])))
+        x = synth.pcm16_to_float(synth.quantise_pcm16(x))
+        _check(mode, x, sr, **kw)
