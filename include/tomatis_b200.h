@@ -240,6 +240,28 @@ int tmt_calib_gate_grid(tmt_engine* e, const float* level, const int64_t* start,
                         const float* off, const int64_t* delay, int n_combos, int32_t* mismatches, int32_t* switches,
                         uint8_t* states, void* stream);
 
+/* ---- general FFT sizes (EXPERIMENTAL: parity on hardware not yet verified, the Python front ends use it only with
+ * TMT_GENERIC_FFT=1).  The reference exposes --n_fft / --hop (src/process_tomatis.py:509-510, _adaptive.py:396-397,
+ * _xfade.py:388-389); the fused kernels implement 4096 / 2048.  Plain path for power-of-two n_fft in [128, 8192], hop in
+ * [1, n_fft]: frame k covers [first_start + k*hop, + n_fft), zeros outside [0, total).  All pointers device.
+ * flavour: 0 streaming (standard / xfade), 1 adaptive float32 pipeline, 2 adaptive float64 pipeline. */
+/* np.mean(mono*mono) per frame in NumPy's pairwise order (src/process_tomatis.py:370,51; _adaptive.py:74-76); out: float32 or
+ * float64 [n_frames]. */
+int tmt_generic_meansq(tmt_engine* e, const void* x, int64_t total, int64_t first_start, int n_fft, int hop, int n_frames, int use_f64,
+                       float in_scale, int mono_file, void* meansq_out, void* stream);
+/* window -> FFT -> gain row rows[k] -> IFFT -> window per frame (src/process_tomatis.py:394-398, _adaptive.py:307-313), double
+ * precision with the reference's float32 roundings around it; frames_out: float2 (flavours 0, 1) or double2 (2) [n_frames][n_fft]. */
+int tmt_generic_frames(tmt_engine* e, const void* x, int64_t total, int64_t first_start, int n_fft, int hop, int n_frames, const float* win,
+                       const float* gains, const uint16_t* rows, float in_scale, int flavour, void* frames_out, void* stream);
+/* Overlap-add in the reference's frame order + window-energy normalisation (src/process_tomatis.py:400-406,422;
+ * _adaptive.py:316-332), times post_scale (output gain / restored pre-attenuation); y_out: float2 or double2 [total]. */
+int tmt_generic_overlap_add(tmt_engine* e, const void* frames, int flavour, int64_t total, int64_t first_start, int n_fft, int hop, int n_frames,
+                            const float* win, float post_scale, void* y_out, void* stream);
+/* write_clamped's limiter (src/process_tomatis.py:352-355; _adaptive.py:341-345) over the chunks bounds[c] = (s0, s1): peak per
+ * chunk into peaks_out (float32 / float64 [n_chunks]), chunks above `limit` scaled by limit / peak in place. */
+int tmt_generic_limit(tmt_engine* e, void* y, int use_f64, const int64_t* bounds, int n_chunks, double limit, void* peaks_out, void* stream);
+int tmt_generic_to_float(tmt_engine* e, const void* y_f64, int64_t n, void* out_f32, void* stream);
+
 /* Number of kernel launches issued by this plan since creation (bench.py's gpu_launches). */
 int64_t tmt_plan_launch_count(const tmt_plan* p);
 

@@ -30,7 +30,7 @@ def _stale(target: str, sources) -> bool:
 
 def build_library(force: bool = False, verbose: bool = False) -> str:
     """Compile csrc/tomatis_b200.cu -> csrc/libtomatis_b200.so for sm_100a."""
-    srcs = [os.path.join(CSRC, f) for f in ("tomatis_b200.cu", "fft4096.cuh", "spectrum.cuh", "calib.cuh", "host_tables.hpp")]
+    srcs = [os.path.join(CSRC, f) for f in ("tomatis_b200.cu", "fft4096.cuh", "spectrum.cuh", "calib.cuh", "generic.cuh", "host_tables.hpp")]
     srcs.append(os.path.join(os.path.dirname(HERE), "include", "tomatis_b200.h"))
     if force or _stale(LIB_PATH, srcs):
         cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH, srcs[0]]
@@ -44,7 +44,7 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
 
 def build_emulation(force: bool = False) -> str:
     """Host-only build of the FFT stage functions (csrc/host_emul.cu) for the CPU tests."""
-    srcs = [os.path.join(CSRC, f) for f in ("host_emul.cu", "fft4096.cuh", "spectrum.cuh", "calib.cuh", "host_tables.hpp")]
+    srcs = [os.path.join(CSRC, f) for f in ("host_emul.cu", "fft4096.cuh", "spectrum.cuh", "calib.cuh", "generic.cuh", "host_tables.hpp")]
     if force or _stale(EMUL_PATH, srcs):
         cmd = [_nvcc(), "-O2", "-std=c++17", "-Xcompiler", "-fPIC", "-shared", "-Wno-deprecated-gpu-targets",
                "-o", EMUL_PATH, srcs[0]]

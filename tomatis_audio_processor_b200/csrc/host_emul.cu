@@ -7,6 +7,7 @@
 #include "fft4096.cuh"
 #include "spectrum.cuh"
 #include "calib.cuh"
+#include "generic.cuh"
 #include "host_tables.hpp"
 
 using namespace tmt;
@@ -155,6 +156,86 @@ int tmt_emul_gate_grid(const float* level, const long long* start, const unsigne
                        const long long* delay, int n_combos, int* mismatches, int* switches, unsigned char* states) {
     for (int c = 0; c < n_combos; ++c)
         gate_grid_combo(level, start, want, n, on[c], off[c], delay[c], &mismatches[c], &switches[c], states ? states + (size_t)c * n : nullptr);
+    return 0;
+}
+
+// generic.cuh on the CPU: the per-thread functions of the general-FFT-size kernels; the cooperative transform of
+// gen_frame_kernel is replaced by a plain radix-2 double FFT (same butterflies, twiddles from cos / sin).
+int tmt_emul_gen_meansq(const float* x, long long total, long long first_start, int n_fft, int hop, int n_frames, int use_f64, float sc,
+                        int mono_file, void* out) {
+    const float2* src = reinterpret_cast<const float2*>(x);
+    for (int k = 0; k < n_frames; ++k) {
+        if (use_f64) reinterpret_cast<double*>(out)[k] = gen_frame_meansq<double>(src, total, first_start + (long long)k * hop, n_fft, sc, mono_file != 0);
+        else reinterpret_cast<float*>(out)[k] = gen_frame_meansq<float>(src, total, first_start + (long long)k * hop, n_fft, sc, mono_file != 0);
+    }
+    return 0;
+}
+
+static void emul_fft_pow2(std::vector<cplx64>& Z, int n) {       // in: bit-reversed order, out: natural order, forward
+    for (int len = 2; len <= n; len <<= 1) {
+        const int half = len >> 1;
+        for (int i0 = 0; i0 < n; i0 += len)
+            for (int p = 0; p < half; ++p) {
+                const double ang = -3.14159265358979323846 * (double)p / (double)half;
+                const double cs = std::cos(ang), sn = std::sin(ang);
+                const cplx64 u = Z[i0 + p], w = Z[i0 + p + half];
+                const cplx64 v = {w.x * cs - w.y * sn, w.x * sn + w.y * cs};
+                Z[i0 + p] = cplx64{u.x + v.x, u.y + v.y};
+                Z[i0 + p + half] = cplx64{u.x - v.x, u.y - v.y};
+            }
+    }
+}
+
+int tmt_emul_gen_frames(const float* x, long long total, long long first_start, int n_fft, int hop, int n_frames, const float* win,
+                        const float* gains, const unsigned short* rows, float sc, int flavour, void* frames_out) {
+    const float2* src = reinterpret_cast<const float2*>(x);
+    int log2n = 0;
+    while ((1 << log2n) < n_fft) ++log2n;
+    auto rev = [&](int v) { int r = 0; for (int b = 0; b < log2n; ++b) r |= ((v >> b) & 1) << (log2n - 1 - b); return r; };
+    std::vector<cplx64> Z(n_fft), Y(n_fft);
+    for (int k = 0; k < n_frames; ++k) {
+        const long long pos0 = first_start + (long long)k * hop;
+        for (int n = 0; n < n_fft; ++n) {
+            double re, im;
+            gen_input(gen_sample(src, total, pos0 + n), sc, win[n], flavour, &re, &im);
+            Z[rev(n)] = cplx64{re, im};
+        }
+        emul_fft_pow2(Z, n_fft);
+        const float* g = gains + (size_t)rows[k] * (n_fft / 2 + 1);
+        for (int q = 0; q < n_fft; ++q) {
+            const double gg = (double)g[q <= n_fft / 2 ? q : n_fft - q];
+            Y[rev(q)] = cplx64{Z[q].x * gg, -Z[q].y * gg};
+        }
+        emul_fft_pow2(Y, n_fft);
+        for (int n = 0; n < n_fft; ++n) {
+            const double yr = Y[n].x * (1.0 / n_fft), yi = -Y[n].y * (1.0 / n_fft);
+            const size_t o = (size_t)k * n_fft + n;
+            if (flavour == kGenAdaptiveF64) {
+                reinterpret_cast<double2*>(frames_out)[o] = make_double2(yr * (double)win[n], yi * (double)win[n]);
+            } else {
+                float ox, oy;
+                gen_output_f32(yr, yi, win[n], flavour, &ox, &oy);
+                reinterpret_cast<float2*>(frames_out)[o] = make_float2(ox, oy);
+            }
+        }
+    }
+    return 0;
+}
+
+int tmt_emul_gen_ola(const void* frames, int flavour, long long total, long long first_start, int n_fft, int hop, int n_frames,
+                     const float* win, float post, void* y_out) {
+    for (long long s = 0; s < total; ++s) {
+        if (flavour == kGenAdaptiveF64) {
+            double ox, oy;
+            gen_ola_sample<double, double2>(reinterpret_cast<const double2*>(frames), win, s, first_start, n_fft, hop, n_frames, true, &ox, &oy);
+            reinterpret_cast<double2*>(y_out)[s] = make_double2(ox * (double)post, oy * (double)post);
+        } else {
+            float ox, oy;
+            gen_ola_sample<float, float2>(reinterpret_cast<const float2*>(frames), win, s, first_start, n_fft, hop, n_frames,
+                                          flavour == kGenAdaptiveF32, &ox, &oy);
+            reinterpret_cast<float2*>(y_out)[s] = make_float2(ox * post, oy * post);
+        }
+    }
     return 0;
 }
 

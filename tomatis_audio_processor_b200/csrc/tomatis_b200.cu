@@ -27,6 +27,7 @@
 #include "fft4096.cuh"
 #include "spectrum.cuh"
 #include "calib.cuh"
+#include "generic.cuh"
 #include "host_tables.hpp"
 
 namespace {
@@ -1433,6 +1434,136 @@ calib_gate_grid_kernel(const float* __restrict__ level, const long long* __restr
     switches[c] = sw;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// General FFT sizes (EXPERIMENTAL; csrc/generic.cuh).  Coverage path, not the hot path.
+template <typename T>
+__global__ void __launch_bounds__(128)
+gen_meansq_kernel(const float2* __restrict__ x, long long total, long long first_start, int n_fft, int hop, int n_frames, float sc,
+                  int mono_file, T* __restrict__ out) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n_frames) out[k] = gen_frame_meansq<T>(x, total, first_start + (long long)k * hop, n_fft, sc, mono_file != 0);
+}
+
+__device__ void fft_pow2_f64(double2* sm, int n, int log2n, int t) {      // in: bit-reversed order, out: natural order, forward
+    for (int s = 1; s <= log2n; ++s) {
+        const int half = 1 << (s - 1);
+        for (int b = t; b < (n >> 1); b += 256) {
+            const int pos = b & (half - 1);
+            const int i = ((b >> (s - 1)) << s) + pos, j = i + half;
+            double sn, cs;
+            sincospi(-(double)pos / (double)half, &sn, &cs);
+            const double2 u = sm[i], v0 = sm[j];
+            const double2 v = make_double2(v0.x * cs - v0.y * sn, v0.x * sn + v0.y * cs);
+            sm[i] = make_double2(u.x + v.x, u.y + v.y);
+            sm[j] = make_double2(u.x - v.x, u.y - v.y);
+        }
+        __syncthreads();
+    }
+}
+
+struct GenFrameParams {
+    const float2* x;
+    long long total, first_start;
+    int n_fft, log2n, hop, n_frames;
+    const float* win;
+    const float* gains;      // [n_rows][n_fft/2 + 1]
+    const uint16_t* rows;    // [n_frames]
+    float in_scale;
+    int flavour;
+    void* frames;            // float2 (flavours 0, 1) or double2 (2) [n_frames][n_fft]
+};
+
+__global__ void __launch_bounds__(256) gen_frame_kernel(const GenFrameParams prm) {
+    extern __shared__ __align__(16) unsigned char gen_smem[];
+    double2* sm = reinterpret_cast<double2*>(gen_smem);
+    const int t = threadIdx.x, N = prm.n_fft, sh = 32 - prm.log2n;
+    const long long pos0 = prm.first_start + (long long)blockIdx.x * prm.hop;
+    for (int n = t; n < N; n += 256) {
+        double re, im;
+        gen_input(gen_sample(prm.x, prm.total, pos0 + n), prm.in_scale, prm.win[n], prm.flavour, &re, &im);
+        sm[__brev((unsigned)n) >> sh] = make_double2(re, im);
+    }
+    __syncthreads();
+    fft_pow2_f64(sm, N, prm.log2n, t);
+    const float* g = prm.gains + (size_t)prm.rows[blockIdx.x] * (N / 2 + 1);
+    for (int k = t; k < N; k += 256) {                   // real symmetric gain, conjugate for the inverse transform
+        const double gg = (double)g[k <= N / 2 ? k : N - k];
+        const double2 v = sm[k];
+        sm[k] = make_double2(v.x * gg, -v.y * gg);
+    }
+    __syncthreads();
+    for (int k = t; k < N; k += 256) {
+        const int r = (int)(__brev((unsigned)k) >> sh);
+        if (k < r) { const double2 a = sm[k]; sm[k] = sm[r]; sm[r] = a; }
+    }
+    __syncthreads();
+    fft_pow2_f64(sm, N, prm.log2n, t);                   // conj(FFT(conj(Y))) = N * IFFT(Y)
+    const double inv_n = 1.0 / (double)N;
+    for (int n = t; n < N; n += 256) {
+        const double2 v = sm[n];
+        const double yr = v.x * inv_n, yi = -v.y * inv_n;
+        const float w = prm.win[n];
+        const size_t o = (size_t)blockIdx.x * N + n;
+        if (prm.flavour == kGenAdaptiveF64) {
+            reinterpret_cast<double2*>(prm.frames)[o] = make_double2(yr * (double)w, yi * (double)w);
+        } else {
+            float ox, oy;
+            gen_output_f32(yr, yi, w, prm.flavour, &ox, &oy);
+            reinterpret_cast<float2*>(prm.frames)[o] = make_float2(ox, oy);
+        }
+    }
+}
+
+template <typename A, typename F, typename O>
+__global__ void __launch_bounds__(256)
+gen_ola_kernel(const F* __restrict__ frames, const float* __restrict__ win, long long total, long long first_start, int n_fft, int hop,
+               int n_frames, int clamp_norm, float post, O* __restrict__ out) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x; s < total; s += stride) {
+        A ox, oy;
+        gen_ola_sample<A, F>(frames, win, s, first_start, n_fft, hop, n_frames, clamp_norm != 0, &ox, &oy);
+        O o;
+        o.x = ox * (A)post;                               // output gain / restored pre-attenuation (1 = identity)
+        o.y = oy * (A)post;
+        out[s] = o;
+    }
+}
+
+__device__ __forceinline__ void gen_atomic_max(float* p, float v) { atomicMax(reinterpret_cast<int*>(p), __float_as_int(v)); }
+__device__ __forceinline__ void gen_atomic_max(double* p, double v) {
+    atomicMax(reinterpret_cast<unsigned long long*>(p), (unsigned long long)__double_as_longlong(v));
+}
+// per-chunk peak (non-negative values: the bit patterns order like the numbers) and the limiter of write_clamped
+template <typename V, typename T>
+__global__ void __launch_bounds__(256) gen_peak_kernel(const V* __restrict__ y, const long long* __restrict__ bounds, T* __restrict__ peaks) {
+    const long long s0 = bounds[2 * blockIdx.y], s1 = bounds[2 * blockIdx.y + 1];
+    T m = 0;
+    for (long long i = s0 + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < s1; i += (long long)gridDim.x * blockDim.x) {
+        const V v = y[i];
+        m = fmax(m, fmax(fabs(v.x), fabs(v.y)));
+    }
+    for (int o = 16; o; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0 && m > 0) gen_atomic_max(peaks + blockIdx.y, m);
+}
+template <typename V, typename T>
+__global__ void __launch_bounds__(256) gen_limit_kernel(V* __restrict__ y, const long long* __restrict__ bounds, const T* __restrict__ peaks, T limit) {
+    const T peak = peaks[blockIdx.y];
+    if (!(peak > limit)) return;
+    const T scale = limit / peak;
+    const long long s0 = bounds[2 * blockIdx.y], s1 = bounds[2 * blockIdx.y + 1];
+    for (long long i = s0 + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < s1; i += (long long)gridDim.x * blockDim.x) {
+        V v = y[i];
+        v.x = v.x * scale;
+        v.y = v.y * scale;
+        y[i] = v;
+    }
+}
+__global__ void __launch_bounds__(256) gen_to_float_kernel(const double2* __restrict__ y, float2* __restrict__ out, long long n) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = make_float2((float)y[i].x, (float)y[i].y);
+}
+
 // ================================================================================================
 // host side
 template <typename T> struct DevBuf {
@@ -2412,6 +2543,102 @@ int tmt_calib_gate_grid(tmt_engine* e, const float* level, const int64_t* start,
     CUDA_TRY(cudaMemcpyAsync(mismatches, d_mis.p, sizeof(int) * (size_t)n_combos, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaMemcpyAsync(switches, d_sw.p, sizeof(int) * (size_t)n_combos, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
+    return TMT_OK;
+}
+
+// ---- general FFT sizes (EXPERIMENTAL) ------------------------------------------------------------
+static int gen_check(tmt_engine* e, int n_fft, int hop, int n_frames, int* log2n) {
+    if (!e) return fail(TMT_ERR_INVALID, "engine is NULL");
+    int l = 0;
+    while ((1 << l) < n_fft) ++l;
+    if ((1 << l) != n_fft || n_fft < 128 || n_fft > 8192) return fail(TMT_ERR_UNSUPPORTED, "n_fft must be a power of two in [128, 8192], got %d", n_fft);
+    if (hop < 1 || hop > n_fft) return fail(TMT_ERR_UNSUPPORTED, "hop must lie in [1, n_fft], got %d", hop);
+    if (n_frames < 0) return fail(TMT_ERR_INVALID, "negative frame count");
+    *log2n = l;
+    return TMT_OK;
+}
+
+int tmt_generic_meansq(tmt_engine* e, const void* x, int64_t total, int64_t first_start, int n_fft, int hop, int n_frames, int use_f64,
+                       float in_scale, int mono_file, void* meansq_out, void* stream) {
+    int l2;
+    int rc = gen_check(e, n_fft, hop, n_frames, &l2);
+    if (rc) return rc;
+    if (n_frames == 0) return TMT_OK;
+    if (!x || !meansq_out || total < 0) return fail(TMT_ERR_INVALID, "bad buffers");
+    CUDA_TRY(cudaSetDevice(e->device));
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const int grid = (n_frames + 127) / 128;
+    if (use_f64)
+        gen_meansq_kernel<double><<<grid, 128, 0, st>>>(reinterpret_cast<const float2*>(x), total, first_start, n_fft, hop, n_frames, in_scale, mono_file, reinterpret_cast<double*>(meansq_out));
+    else
+        gen_meansq_kernel<float><<<grid, 128, 0, st>>>(reinterpret_cast<const float2*>(x), total, first_start, n_fft, hop, n_frames, in_scale, mono_file, reinterpret_cast<float*>(meansq_out));
+    CUDA_TRY(cudaGetLastError());
+    return TMT_OK;
+}
+
+int tmt_generic_frames(tmt_engine* e, const void* x, int64_t total, int64_t first_start, int n_fft, int hop, int n_frames, const float* win,
+                       const float* gains, const uint16_t* rows, float in_scale, int flavour, void* frames_out, void* stream) {
+    GenFrameParams prm;
+    int rc = gen_check(e, n_fft, hop, n_frames, &prm.log2n);
+    if (rc) return rc;
+    if (n_frames == 0) return TMT_OK;
+    if (!x || !win || !gains || !rows || !frames_out || total < 0 || flavour < kGenStreaming || flavour > kGenAdaptiveF64) return fail(TMT_ERR_INVALID, "bad arguments");
+    CUDA_TRY(cudaSetDevice(e->device));
+    prm.x = reinterpret_cast<const float2*>(x); prm.total = total; prm.first_start = first_start; prm.n_fft = n_fft; prm.hop = hop;
+    prm.n_frames = n_frames; prm.win = win; prm.gains = gains; prm.rows = rows; prm.in_scale = in_scale; prm.flavour = flavour; prm.frames = frames_out;
+    const int smem = n_fft * (int)sizeof(double2);
+    CUDA_TRY(cudaFuncSetAttribute(gen_frame_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    gen_frame_kernel<<<n_frames, 256, smem, reinterpret_cast<cudaStream_t>(stream)>>>(prm);
+    CUDA_TRY(cudaGetLastError());
+    return TMT_OK;
+}
+
+int tmt_generic_overlap_add(tmt_engine* e, const void* frames, int flavour, int64_t total, int64_t first_start, int n_fft, int hop, int n_frames,
+                            const float* win, float post_scale, void* y_out, void* stream) {
+    int l2;
+    int rc = gen_check(e, n_fft, hop, n_frames, &l2);
+    if (rc) return rc;
+    if (total <= 0) return TMT_OK;
+    if ((n_frames > 0 && !frames) || !win || !y_out || flavour < kGenStreaming || flavour > kGenAdaptiveF64) return fail(TMT_ERR_INVALID, "bad arguments");
+    CUDA_TRY(cudaSetDevice(e->device));
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const int grid = (int)std::min<long long>((total + 255) / 256, 16LL * e->n_sms);
+    if (flavour == kGenAdaptiveF64)
+        gen_ola_kernel<double, double2, double2><<<grid, 256, 0, st>>>(reinterpret_cast<const double2*>(frames), win, total, first_start, n_fft, hop, n_frames, 1, post_scale, reinterpret_cast<double2*>(y_out));
+    else
+        gen_ola_kernel<float, float2, float2><<<grid, 256, 0, st>>>(reinterpret_cast<const float2*>(frames), win, total, first_start, n_fft, hop, n_frames, flavour == kGenAdaptiveF32, post_scale, reinterpret_cast<float2*>(y_out));
+    CUDA_TRY(cudaGetLastError());
+    return TMT_OK;
+}
+
+int tmt_generic_limit(tmt_engine* e, void* y, int use_f64, const int64_t* bounds, int n_chunks, double limit, void* peaks_out, void* stream) {
+    if (!e || n_chunks < 0) return fail(TMT_ERR_INVALID, "bad arguments");
+    if (n_chunks == 0) return TMT_OK;
+    if (!y || !bounds || !peaks_out) return fail(TMT_ERR_INVALID, "NULL buffer");
+    CUDA_TRY(cudaSetDevice(e->device));
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const dim3 grid(4 * e->n_sms, n_chunks);
+    const long long* b = reinterpret_cast<const long long*>(bounds);
+    CUDA_TRY(cudaMemsetAsync(peaks_out, 0, (use_f64 ? sizeof(double) : sizeof(float)) * (size_t)n_chunks, st));
+    if (use_f64) {
+        gen_peak_kernel<double2, double><<<grid, 256, 0, st>>>(reinterpret_cast<const double2*>(y), b, reinterpret_cast<double*>(peaks_out));
+        gen_limit_kernel<double2, double><<<grid, 256, 0, st>>>(reinterpret_cast<double2*>(y), b, reinterpret_cast<const double*>(peaks_out), limit);
+    } else {
+        gen_peak_kernel<float2, float><<<grid, 256, 0, st>>>(reinterpret_cast<const float2*>(y), b, reinterpret_cast<float*>(peaks_out));
+        gen_limit_kernel<float2, float><<<grid, 256, 0, st>>>(reinterpret_cast<float2*>(y), b, reinterpret_cast<const float*>(peaks_out), (float)limit);
+    }
+    CUDA_TRY(cudaGetLastError());
+    return TMT_OK;
+}
+
+int tmt_generic_to_float(tmt_engine* e, const void* y_f64, int64_t n, void* out_f32, void* stream) {
+    if (!e || n < 0) return fail(TMT_ERR_INVALID, "bad arguments");
+    if (n == 0) return TMT_OK;
+    if (!y_f64 || !out_f32) return fail(TMT_ERR_INVALID, "NULL buffer");
+    CUDA_TRY(cudaSetDevice(e->device));
+    const int grid = (int)std::min<long long>((n + 255) / 256, 16LL * e->n_sms);
+    gen_to_float_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(reinterpret_cast<const double2*>(y_f64), reinterpret_cast<float2*>(out_f32), n);
+    CUDA_TRY(cudaGetLastError());
     return TMT_OK;
 }
 

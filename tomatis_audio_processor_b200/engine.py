@@ -286,6 +286,10 @@ def streaming_params(mode: str, sr: int, *, gate_ui=50, gate_mode="log_percent",
                            m_on=tb.meansq_threshold_on(Ton), m_off=tb.meansq_threshold_off(Toff))
 
 
+def _host_array(x) -> np.ndarray:
+    return x if isinstance(x, np.ndarray) else x.cpu().numpy()
+
+
 def _to_device(torch, xs, device):
     out = []
     for x in xs:
@@ -310,6 +314,9 @@ def run_streaming(mode: str, xs: Sequence, sr: int, device: int = 0, want_host: 
     eng = get_engine(device)
     n_fft, hop = params.get("n_fft", tb.N_FFT), params.get("hop", tb.HOP)
     if n_fft != eng.n_fft or hop != eng.hop:
+        from . import generic
+        if generic.enabled():                                         # experimental general-size path (TMT_GENERIC_FFT=1)
+            return generic.run_streaming(mode, [_host_array(x) for x in xs], sr, device=device, **params)
         raise NotImplementedError(f"GPU path implements n_fft={eng.n_fft}, hop={eng.hop}; got {n_fft}/{hop}")
     sp = streaming_params(mode, sr, **params)
     eng.set_gain_rows(sp.rows, key=sp.rows_key)
@@ -361,6 +368,12 @@ def run_adaptive(xs: Sequence, sr: int, device: int = 0, want_host: bool = True,
     torch = _torch()
     eng = get_engine(device)
     if n_fft != eng.n_fft or hop != eng.hop:
+        from . import generic
+        if generic.enabled():                                         # experimental general-size path (TMT_GENERIC_FFT=1)
+            return generic.run_adaptive([_host_array(x) for x in xs], sr, device=device, fc=fc, slope=slope, c1_low=c1_low,
+                                        c1_high=c1_high, c2_low=c2_low, c2_high=c2_high, target_c2=target_c2, hyst_db=hyst_db,
+                                        min_hold_ms=min_hold_ms, xfade_ms=xfade_ms, headroom_margin=headroom_margin,
+                                        n_fft=n_fft, hop=hop)
         raise NotImplementedError(f"GPU path implements n_fft={eng.n_fft}, hop={eng.hop}; got {n_fft}/{hop}")
     hold, xf = tb.adaptive_frame_counts(sr, min_hold_ms, xfade_ms, hop)
     c1_db, c2_db = tb.tilt_curves_db(sr, n_fft, fc, slope, c1_low, c1_high, c2_low, c2_high)
