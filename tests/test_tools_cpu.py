@@ -29,3 +29,19 @@ def test_tensor_core_feasibility_model():
     assert verdict["tf32 x1 (plain TF32 GEMM)"] == "FAILS" and verdict["bf16 x3"] == "FAILS"
     assert verdict["tf32 x3 (Fh*xh + Fh*xl + Fl*xh)"] == "ok" and verdict["fp16 x3, per-frame scale"] == "ok"
     assert verdict["float32 butterflies (what stft_kernel does now)"] == "ok"
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside ours): one JSON line with the contract's keys, timing
+    the oracle port on the host cores -- runs without a GPU."""
+    import json
+    p = _run("bench.py", "--impl", "reference", "--steps", "1", "--warmup", "3", "--cpu-tracks", "2", "--cpu-workers", "2")
+    assert p.returncode == 0, p.stdout + p.stderr
+    line = json.loads(p.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["metric"] == "audio_seconds_per_second" and line["unit"] == "audio-s/s"
+    assert line["higher_is_better"] is True and line["vs_baseline"] is None and line["data"] == "synthetic" and line["dtype"] == "f32"
+    assert line["value"] > 0 and line["ms_per_step"] > 0 and line["steps"] == 1 and line["warmup"] >= 3 and line["n_gpus"] == 1
+    assert "workload" in line["config"] and "model" not in line["config"]
+    cb, e2e = line["cpu_baseline"], line["e2e"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == line["value"] and cb["unit"] == line["unit"] and cb["sample"]
+    assert e2e == {"value": line["value"], "unit": line["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
