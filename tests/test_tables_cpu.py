@@ -58,3 +58,41 @@ def test_flush_schedule_closed_form_equals_the_frame_by_frame_replay():
     for nf, hp in ((2048, 1024), (8192, 4096), (4096, 1024), (4096, 4096)):
         for n in (0, 1, 100, 500, 1000, 5000):
             assert tb.flush_chunk_blocks(n, nf, hp) == tb._flush_chunk_blocks_replay(n, nf, hp), (nf, hp, n)
+
+
+def test_random_geometry_and_resampler_tables():
+    """Seeded sweeps of the host tables against their checkers: limiter chunk ranges of the general-size path and both frame
+    layouts against the oracle's frame-by-frame versions, the polyphase resampler plan against scipy's own output length and
+    filter, the up-delay run length against a direct replay of the reference's arming rule."""
+    from scipy.signal import firwin, resample_poly
+    from oracle import tomatis_oracle as orc
+    from tomatis_audio_processor_b200 import generic
+    rng = np.random.default_rng(99)
+    for _ in range(60):
+        n_fft = int(2 ** rng.integers(7, 14))
+        hop = int(rng.integers(1, n_fft + 1))
+        total = int(rng.integers(0, 900000))
+        _, _, starts = orc.frame_layout_streaming(total, n_fft, hop)
+        first, nf = generic.streaming_layout(total, n_fft, hop)
+        assert nf == len(starts)
+        want = [(max(0, a), min(total, b)) for a, b in orc.flush_schedule(nf, n_fft, hop) if min(total, b) > max(0, a)]
+        assert generic.flush_sample_ranges(nf, total, n_fft, hop) == want
+    for _ in range(40):
+        n_in, up, down = int(rng.integers(1, 5000)), int(rng.integers(1, 12)), int(rng.integers(1, 60))
+        plan = tb.resample_poly_plan(n_in, up, down)
+        x = rng.standard_normal(n_in).astype(np.float32)
+        assert plan["n_out"] == len(resample_poly(x, up, down))
+        if plan["h"] is not None:
+            m = max(plan["up"], plan["down"])
+            h = firwin(2 * 10 * m + 1, 1.0 / m, window=("kaiser", 5.0)).astype(np.float32) * plan["up"]
+            core = plan["h"][np.flatnonzero(plan["h"])[0]:np.flatnonzero(plan["h"])[-1] + 1]
+            ref = h[np.flatnonzero(h)[0]:np.flatnonzero(h)[-1] + 1]
+            assert core.shape == ref.shape and np.allclose(core, ref, rtol=2e-6, atol=1e-9)
+    for _ in range(200):
+        sr, ms, hop = int(rng.choice([44100, 48000, 96000])), float(rng.uniform(0, 400)), int(rng.choice([256, 512, 1024, 2048, 3000]))
+        d = int(sr * ms / 1000.0)
+        # replay: every frame is loud; frame j (0-based) starts at j*hop, armed at frame 0 with pending = d
+        j = 0
+        while j * hop < d:
+            j += 1
+        assert tb.updelay_run_frames(sr, ms, hop) == j + 1
