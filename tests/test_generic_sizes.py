@@ -1,9 +1,9 @@
-"""General FFT sizes (generic.py + csrc/generic.cuh; EXPERIMENTAL, off by default).  CPU: frame geometry and limiter chunks
+"""General FFT sizes (generic.py + csrc/generic.cuh).  CPU: frame geometry and limiter chunks
 against the oracle, and the whole path for n_fft / hop other than 4096 / 2048 with the kernels' per-thread code run on the CPU
 (csrc/host_emul.cu) against the oracle, which tests/test_oracle_vs_reference.py pins to the executed reference for these
 sizes -- mean squares bit-exact, states / rows / chunk lengths exact, PCM within 1e-5 of the float64-FFT evaluation everywhere
-and of the float32-FFT reference wherever that is well-conditioned.  GPU: the same through the C ABI, run only with
-TMT_GENERIC_FFT=1 (the launch path has not been on hardware yet)."""
+and of the float32-FFT reference wherever that is well-conditioned.  GPU: the same through the C ABI (engine.run with
+n_fft / hop keywords, the way the command lines call it)."""
 import ctypes as C
 import os
 
@@ -170,8 +170,10 @@ def test_emulated_general_path_matches_oracle(emul, n_fft, hop):
         _compare("adaptive", o, orc.run("adaptive", xa, sr, fft_dtype="float64", **kw), r)
 
 
-def test_general_path_is_off_by_default_and_checks_sizes(monkeypatch):
+def test_general_path_is_on_by_default_and_checks_sizes(monkeypatch):
     monkeypatch.delenv("TMT_GENERIC_FFT", raising=False)
+    assert generic.enabled()
+    monkeypatch.setenv("TMT_GENERIC_FFT", "0")
     assert not generic.enabled()
     for bad in ((100, 50), (16384, 8192), (3000, 1500), (2048, 0), (2048, 4096)):
         with pytest.raises(NotImplementedError):
@@ -179,9 +181,8 @@ def test_general_path_is_off_by_default_and_checks_sizes(monkeypatch):
     generic.check_sizes(2048, 1024)
 
 
-# ------------------------------------------------------------------------------------------------ GPU (opt-in)
+# ------------------------------------------------------------------------------------------------ GPU
 @pytest.mark.gpu
-@pytest.mark.skipif(os.environ.get("TMT_GENERIC_FFT", "0") != "1", reason="experimental general-size path: set TMT_GENERIC_FFT=1")
 @pytest.mark.parametrize("n_fft,hop", SIZES)
 def test_general_path_gpu_matches_oracle(n_fft, hop):
     from tomatis_audio_processor_b200 import engine

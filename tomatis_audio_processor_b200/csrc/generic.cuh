@@ -1,4 +1,4 @@
-// General FFT sizes (EXPERIMENTAL, not enabled by default: TMT_GENERIC_FFT=1).  The reference exposes --n_fft / --hop
+// General FFT sizes.  The reference exposes --n_fft / --hop
 // (src/process_tomatis.py:509-510); the fused kernels are specialised for 4096 / 2048.  This is the plain path for every
 // other power-of-two n_fft in [128, 8192] and any hop in [1, n_fft]: per-frame levels in NumPy's pairwise order, one CTA per
 // frame for window -> FFT -> gain -> IFFT -> window in double precision with the reference's float32 roundings on either side

@@ -315,7 +315,7 @@ def run_streaming(mode: str, xs: Sequence, sr: int, device: int = 0, want_host: 
     n_fft, hop = params.get("n_fft", tb.N_FFT), params.get("hop", tb.HOP)
     if n_fft != eng.n_fft or hop != eng.hop:
         from . import generic
-        if generic.enabled():                                         # experimental general-size path (TMT_GENERIC_FFT=1)
+        if generic.enabled():                                         # general-size path (csrc/generic.cuh)
             return generic.run_streaming(mode, [_host_array(x) for x in xs], sr, device=device, **params)
         raise NotImplementedError(f"GPU path implements n_fft={eng.n_fft}, hop={eng.hop}; got {n_fft}/{hop}")
     sp = streaming_params(mode, sr, **params)
@@ -369,7 +369,7 @@ def run_adaptive(xs: Sequence, sr: int, device: int = 0, want_host: bool = True,
     eng = get_engine(device)
     if n_fft != eng.n_fft or hop != eng.hop:
         from . import generic
-        if generic.enabled():                                         # experimental general-size path (TMT_GENERIC_FFT=1)
+        if generic.enabled():                                         # general-size path (csrc/generic.cuh)
             return generic.run_adaptive([_host_array(x) for x in xs], sr, device=device, fc=fc, slope=slope, c1_low=c1_low,
                                         c1_high=c1_high, c2_low=c2_low, c2_high=c2_high, target_c2=target_c2, hyst_db=hyst_db,
                                         min_hold_ms=min_hold_ms, xfade_ms=xfade_ms, headroom_margin=headroom_margin,

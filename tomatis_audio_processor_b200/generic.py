@@ -1,4 +1,4 @@
-"""General FFT sizes -- EXPERIMENTAL, off by default (set TMT_GENERIC_FFT=1).
+"""General FFT sizes: every `--n_fft` / `--hop` other than the fused kernels' 4096 / 2048 (TMT_GENERIC_FFT=0 turns it off).
 
 The reference exposes `--n_fft` / `--hop` (`src/process_tomatis.py:509-510`, `_adaptive.py:396-397`, `_xfade.py:388-389`);
 the fused kernels implement the defaults 4096 / 2048 and everything else raises NotImplementedError.  This module is the
@@ -6,8 +6,8 @@ plain path for the other sizes (power-of-two n_fft in [128, 8192], any hop in [1
 points of the C ABI (csrc/generic.cuh): per-frame levels in NumPy's pairwise order, the gate automata of the main path (run
 on an audio-less plan over the frames), one CTA per frame for window -> FFT -> gain -> IFFT -> window in double precision
 with the reference's float32 roundings around it, gather overlap-add in the reference's frame order, limiter.  Coverage, not
-speed.  Status: the per-thread arithmetic is checked on the CPU against the oracle (tests/test_generic_sizes.py, through
-csrc/host_emul.cu); the CUDA launch path has NOT been run on hardware yet, which is why it is not enabled by default.
+speed.  The per-thread arithmetic is checked on the CPU against the oracle (tests/test_generic_sizes.py, through
+csrc/host_emul.cu) and the CUDA path on the B200 (same file, -m gpu; first hardware run: profiles/r02/generic_first_run.md).
 """
 from __future__ import annotations
 
@@ -24,7 +24,7 @@ STREAMING, ADAPTIVE_F32, ADAPTIVE_F64 = 0, 1, 2          # kGenStreaming / kGenA
 
 
 def enabled() -> bool:
-    return os.environ.get("TMT_GENERIC_FFT", "0") == "1"
+    return os.environ.get("TMT_GENERIC_FFT", "1") != "0"
 
 
 def check_sizes(n_fft: int, hop: int):
