@@ -3,15 +3,25 @@
 // The reference does, per STFT frame and per channel, rfft -> real gain -> irfft
 // (/root/reference/src/process_tomatis.py:394-398).  Here the stereo pair is packed as one
 // complex signal z = L + iR (the gain is real and symmetric, so IFFT(g*FFT(z)) = yL + i*yR),
-// and N = 4096 = 16*16*16 is done as three register-resident radix-16 stages with two
-// shared-memory exchanges per direction.  Index split
+// and N = 4096 = 16*16*16 is done as three register-resident radix-16 stages.  Index split
 //     n = 256*n1 + 16*n2 + n3          k = k1 + 16*k2 + 256*k3
-// forward:  A (threads (n2,n3), DFT over n1, twiddle W4096^((16*n2+n3)*k1))  -> smem E1
-//           B (threads (k1,n3), DFT over n2, twiddle W256^(n3*k2)) -> smem E2
+// forward:  A (threads (n2,n3), DFT over n1, twiddle W4096^((16*n2+n3)*k1))  -> exchange E1 (shared memory)
+//           B (threads (k1,n3), DFT over n2, twiddle W256^(n3*k2)) -> exchange E2 (TENSOR MEMORY, see below)
 //           C (threads (k1,k2), DFT over n3)  -> X[k1+16*k2+256*k3] in registers
 // inverse:  exactly the mirror (C' B' A') with conjugate twiddles applied on stage inputs, so
 // the spectrum never leaves registers between forward and inverse and the time-domain result
 // lands in the same thread/register layout the input was loaded in (n = 256*j + t).
+//
+// E2 swaps the 4-bit register index k2 with the 4-bit thread index n3 inside groups of 16 threads.  All 16 threads of such
+// a group sit in one warp (lane = 2*n3 + (k1 & 1)), so the exchange can use the warp's own 32 lanes of tensor memory instead
+// of shared memory: a tcgen05.st in the .32x32b shape (lane i, column c <-> thread i, register c) followed by a tcgen05.ld in
+// the .16x256b shape (lane r, column c <-> thread 4*(r%8) + (c%8)/2, register 4*(c/8) + 2*(r/8) + c%2) moves two thread bits
+// into the register index and two register bits into the thread index.  Two such round trips make the 4-bit exchange; the
+// radix-16 butterfly of stage C is split into its two radix-4 layers and one round trip sits on either side of the first
+// layer (n3 = 4a + b: bits a arrive with the first trip, bits b with the second), so every round trip is adjacent to
+// arithmetic and costs no register moves.  The inverse path runs the two trips backwards (st .16x256b, ld .32x32b).
+// Measured on B200 (tools/mb_tmem_xpose.cu): 41 SM-cycles per warp-level exchange on the tensor-memory pipe against 64
+// wavefront-cycles on the shared-memory pipe that co-limits this kernel; same latency (~200 cycles).
 //
 // Everything here is __host__ __device__ so tests/ can run the same code on the CPU
 // (csrc/host_emul.cu) -- there is no GPU in the build container.
@@ -25,9 +35,9 @@ namespace tmt {
 constexpr int kNfft = 4096;
 constexpr int kHop = 2048;
 constexpr int kThreads = 256;       // one frame per CTA pass, 16 points per thread
-constexpr int kRowPad = 18;         // E2 row stride in float2 (16 + 2): rows stay 16-byte aligned, so the C side moves two
-                                    // points per 128-bit access (8 instead of 16 instructions); conflict-free both ways
-constexpr int kExchFloat2 = 256 * kRowPad;   // the E2 exchange buffer (36 864 B)
+constexpr int kE1Row = 264;         // E1 row stride in float2 (256 + 8): the B side reads rows k1 and k1 + 1 from the two lane
+                                    // parities of a warp, the 64-byte skew keeps every half warp on 32 distinct banks
+constexpr int kE1Float2 = 16 * kE1Row;       // the E1 exchange buffer (33 792 B)
 
 // Complex arithmetic on float2.  On the device every operation is a packed FP32x2 instruction
 // (FADD2 / FMUL2 / FFMA2, new on sm_100): re/im live in one 64-bit register pair, and the swap,
@@ -166,13 +176,21 @@ TMT_HD void dft16_inv_tw(float2 (&v)[16], const float2 (&p)[16]) {
     dft16_layer2<true>(v);
 }
 
-// ---- shared-memory exchange layouts (float2 units) -------------------------------------
-// E1 (linear):  idx = k1*256 + n2*16 + n3        A side: j*256 + t       B side: (t>>4)*256 + j*16 + (t&15)
-// E2 (padded):  idx = (k1*16 + k2)*18 + n3       B side: ((t>>4)*16 + j)*18 + (t&15)    C side: t*18 + j
-TMT_HD int e1_a(int t, int j) { return j * 256 + t; }
-TMT_HD int e1_b(int t, int j) { return (t >> 4) * 256 + j * 16 + (t & 15); }
-TMT_HD int e2_b(int t, int j) { return ((t >> 4) * 16 + j) * kRowPad + (t & 15); }
-TMT_HD int e2_c(int t, int j) { return t * kRowPad + j; }
+// ---- thread maps ------------------------------------------------------------------------------
+// A side (and the time domain): thread t holds n = 256*j + t, i.e. (n2, n3) = (t >> 4, t & 15).
+// B side: warp w = t >> 5 owns k1 in {2w, 2w + 1}; lane = 2*n3 + (k1 & 1).
+// C side (after the tensor-memory exchange): k1 unchanged per warp, lane = 16*(k1 & 1) + 8*q1 + 4*q0 + 2*q3 + q2 for
+// k2 = (q3 q2 q1 q0), i.e. k1 = t >> 4 and k2 = 4*(t & 3) + ((t >> 2) & 3).
+TMT_HD int b_k1(int t) { return 2 * (t >> 5) + (t & 1); }
+TMT_HD int b_n3(int t) { return (t & 31) >> 1; }
+TMT_HD int c_k1(int t) { return t >> 4; }
+TMT_HD int c_k2(int t) { return 4 * (t & 3) + ((t >> 2) & 3); }
+// bin held in register j of thread t after stage C (and expected by stage C')
+TMT_HD int bin_of(int t, int j) { return c_k1(t) + 16 * c_k2(t) + 256 * j; }
+
+// ---- shared-memory exchange E1 (float2 units):  idx = k1*264 + n2*16 + n3 ----------------------
+TMT_HD int e1_a(int t, int j) { return j * kE1Row + t; }
+TMT_HD int e1_b(int t, int j) { return b_k1(t) * kE1Row + j * 16 + b_n3(t); }
 
 // Twiddles.  Both twiddle stages have the form v[k] *= b^k with a PER-THREAD base:
 //   stage A (thread t = 16*n2 + n3, output k1):  W256^(n2*k1) * W4096^(n3*k1) = (W4096^t)^k1
@@ -207,84 +225,116 @@ TMT_HD void tw_table(float2 (&p)[16], const TwBase w) {
     p[12] = b12; p[13] = cmul(b12, b1); p[14] = cmul(b12, b2); p[15] = cmul(b12, b3);
 }
 
-// ---- exchange pieces -----------------------------------------------------------------------
+// ---- exchange pieces (E1) -----------------------------------------------------------------------
 TMT_HD void st_e1a(const float2 (&v)[16], int t, float2* buf) {
 #pragma unroll
     for (int j = 0; j < 16; ++j) buf[e1_a(t, j)] = v[j];
 }
 TMT_HD void ld_e1b(float2 (&v)[16], int t, const float2* buf) {
+    const float2* p = buf + e1_b(t, 0);
 #pragma unroll
-    for (int j = 0; j < 16; ++j) v[j] = buf[e1_b(t, j)];
-}
-TMT_HD void st_e2b(const float2 (&v)[16], int t, float2* buf) {
-#pragma unroll
-    for (int j = 0; j < 16; ++j) buf[e2_b(t, j)] = v[j];
-}
-TMT_HD void ld_e2c(float2 (&v)[16], int t, const float2* buf) {
-    const float4* row = reinterpret_cast<const float4*>(buf + e2_c(t, 0));
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        const float4 x = row[j];
-        v[2 * j] = make_float2(x.x, x.y);
-        v[2 * j + 1] = make_float2(x.z, x.w);
-    }
-}
-TMT_HD void st_e2c(const float2 (&v)[16], int t, float2* buf) {
-    float4* row = reinterpret_cast<float4*>(buf + e2_c(t, 0));
-#pragma unroll
-    for (int j = 0; j < 8; ++j) row[j] = make_float4(v[2 * j].x, v[2 * j].y, v[2 * j + 1].x, v[2 * j + 1].y);
-}
-TMT_HD void ld_e2b(float2 (&v)[16], int t, const float2* buf) {
-#pragma unroll
-    for (int j = 0; j < 16; ++j) v[j] = buf[e2_b(t, j)];
+    for (int j = 0; j < 16; ++j) v[j] = p[j * 16];
 }
 TMT_HD void st_e1b(const float2 (&v)[16], int t, float2* buf) {
+    float2* p = buf + e1_b(t, 0);
 #pragma unroll
-    for (int j = 0; j < 16; ++j) buf[e1_b(t, j)] = v[j];
+    for (int j = 0; j < 16; ++j) p[j * 16] = v[j];
 }
 TMT_HD void ld_e1a(float2 (&v)[16], int t, const float2* buf) {
 #pragma unroll
     for (int j = 0; j < 16; ++j) v[j] = buf[e1_a(t, j)];
 }
 
-// ---- composite forward stages (in: v[j] = windowed z[256*j + t]) ---------------------------
-TMT_HD void fwd_a(float2 (&v)[16], int t, const TwBase wa, float2* bufP) {
-    dft16<false>(v);
-    tw_pow<false>(v, wa);
-    st_e1a(v, t, bufP);
+// ---- exchange E2 through tensor memory: register naming around the four round trips -------------
+// A round trip works on the raw 32-register image of a thread.  "Column order" is what .32x32b stores / loads
+// (register c <-> column c: float2 index c/2, component c%2); "row order" is what .16x256b loads / stores
+// (register 16*I + 4*g + 2*h + e <-> lane 16*I + 8*h + T/4, column 8*g + 2*(T%4) + e of thread T).
+TMT_HD int row_reg(int hi2, int g) { return 16 * (hi2 >> 1) + 4 * g + 2 * (hi2 & 1); }   // float2 (2-bit arrival index hi2, column group g)
+
+// forward trip 1, send: B outputs v[k2] in column order
+TMT_HD void x_fwd1_pack(const float2 (&v)[16], float (&r)[32]) {
+#pragma unroll
+    for (int q = 0; q < 16; ++q) { r[2 * q] = v[q].x; r[2 * q + 1] = v[q].y; }
 }
-TMT_HD void fwd_b(float2 (&v)[16], int t, const TwBase wb, const float2* bufP, float2* bufQ) {
-    ld_e1b(v, t, bufP);
-    dft16<false>(v);
-    tw_pow<false>(v, wb);
-    st_e2b(v, t, bufQ);
+// forward, between the trips: r (row order) holds x[a][g] (a = n3 >> 2 just arrived, g = k2 >> 2 still here);
+// first radix-4 layer of stage C over a, result x[c][g] packed in column order at float2 column 4*c + g
+template <bool INV>
+TMT_HD void x_layer_a(const float (&r)[32], float (&s)[32]) {
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+        float2 x[4];
+#pragma unroll
+        for (int a = 0; a < 4; ++a) x[a] = make_float2(r[row_reg(a, g)], r[row_reg(a, g) + 1]);
+        radix4<INV>(x[0], x[1], x[2], x[3]);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) { s[2 * (4 * c + g)] = x[c].x; s[2 * (4 * c + g) + 1] = x[c].y; }
+    }
 }
-// out: v[j] = Z[(t>>4) + 16*(t&15) + 256*j]
-TMT_HD void fwd_c(float2 (&v)[16], int t, const float2* bufQ) {
-    ld_e2c(v, t, bufQ);
-    dft16<false>(v);
+// forward trip 2, receive: s (row order) holds y[b][c] (b = n3 & 3 just arrived, c = column group); second layer of stage C
+// (twiddles W16^(b*c) fused) -> v[k3] natural
+TMT_HD void x_fwd2_finish(const float (&s)[32], float2 (&v)[16]) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) v[4 * c + b] = make_float2(s[row_reg(b, c)], s[row_reg(b, c) + 1]);
+    dft16_layer2<false>(v);
 }
-// ---- composite inverse stages (unnormalised; the 1/4096 is folded into the gain table) ------
-TMT_HD void inv_c(float2 (&v)[16], int t, float2* bufP) {
-    dft16<true>(v);
-    st_e2c(v, t, bufP);
+// conj(W16^M) * v for the inverse transform's inner twiddles (M = b*c)
+template <int M>
+TMT_HD float2 mul_w16c(float2 v) {
+    if (M == 0) return v;
+    if (M == 4) return make_float2(-v.y, v.x);                  // conj(-i) = +i
+    if (M == 1) return cmulc(v, w16<1>());
+    if (M == 2) return cmulc(v, w16<2>());
+    if (M == 3) return cmulc(v, w16<3>());
+    if (M == 6) return cmulc(v, w16<6>());
+    return cmulc(v, w16<9>());
 }
-TMT_HD void inv_b(float2 (&v)[16], int t, const TwBase wb, const float2* bufP, float2* bufQ) {
-    ld_e2b(v, t, bufP);
-    float2 p[16];
-    tw_table(p, wb);
-    dft16_inv_tw(v, p);
-    st_e1b(v, t, bufQ);
+// inverse trip 1 (undoes forward trip 2), send: first layer of stage C' over d (k3 = c + 4d) gives b = n3 & 3, inner
+// twiddles conj(W16^(b*c)) applied while both indices are still in registers; packed in row order with b as the index that leaves
+TMT_HD void x_inv1_pack(float2 (&v)[16], float (&r)[32]) {
+    radix4<true>(v[0], v[4], v[8], v[12]);
+    radix4<true>(v[1], v[5], v[9], v[13]);
+    radix4<true>(v[2], v[6], v[10], v[14]);
+    radix4<true>(v[3], v[7], v[11], v[15]);                      // now v[4b + c]
+#define TMT_XW(b, c) { const float2 y = mul_w16c<(b) * (c)>(v[4 * (b) + (c)]); r[row_reg(b, c)] = y.x; r[row_reg(b, c) + 1] = y.y; }
+    TMT_XW(0, 0) TMT_XW(0, 1) TMT_XW(0, 2) TMT_XW(0, 3)
+    TMT_XW(1, 0) TMT_XW(1, 1) TMT_XW(1, 2) TMT_XW(1, 3)
+    TMT_XW(2, 0) TMT_XW(2, 1) TMT_XW(2, 2) TMT_XW(2, 3)
+    TMT_XW(3, 0) TMT_XW(3, 1) TMT_XW(3, 2) TMT_XW(3, 3)
+#undef TMT_XW
 }
-// out: v[j] = 4096 * y[256*j + t]
-TMT_HD void inv_a(float2 (&v)[16], int t, const TwBase wa, const float2* bufQ) {
-    ld_e1a(v, t, bufQ);
-    float2 p[16];
-    tw_table(p, wa);
-    dft16_inv_tw(v, p);
+// inverse, between the trips: r (column order) holds x[c][g] at float2 column 4*c + g (g = k2 >> 2 is back); second layer
+// of stage C' over c gives a = n3 >> 2, packed in row order with a as the index that leaves
+TMT_HD void x_layer_c_inv(const float (&r)[32], float (&s)[32]) {
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+        float2 x[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) x[c] = make_float2(r[2 * (4 * c + g)], r[2 * (4 * c + g) + 1]);
+        radix4<true>(x[0], x[1], x[2], x[3]);
+#pragma unroll
+        for (int a = 0; a < 4; ++a) { s[row_reg(a, g)] = x[a].x; s[row_reg(a, g) + 1] = x[a].y; }
+    }
+}
+// inverse trip 2, receive: column order = v[k2] natural
+TMT_HD void x_inv2_unpack(const float (&s)[32], float2 (&v)[16]) {
+#pragma unroll
+    for (int q = 0; q < 16; ++q) v[q] = make_float2(s[2 * q], s[2 * q + 1]);
 }
 
-// bin held in register j of thread t after fwd_c (and expected by inv_c)
-TMT_HD int bin_of(int t, int j) { return (t >> 4) + 16 * (t & 15) + 256 * j; }
+// The data movement of the round trips, for the CPU emulation (csrc/host_emul.cu): src/dst index a warp's 32 x 32 register image.
+// forward trip (st .32x32b, ld .16x256b): thread T register 16*I + 4*g + 2*h + e  <-  thread (16*I + 8*h + T/4) register 8*g + 2*(T%4) + e
+inline void emul_trip_fwd(const float* src, float* dst) {
+    for (int T = 0; T < 32; ++T)
+        for (int I = 0; I < 2; ++I) for (int g = 0; g < 4; ++g) for (int h = 0; h < 2; ++h) for (int e = 0; e < 2; ++e)
+            dst[T * 32 + 16 * I + 4 * g + 2 * h + e] = src[(16 * I + 8 * h + T / 4) * 32 + 8 * g + 2 * (T % 4) + e];
+}
+// inverse trip (st .16x256b, ld .32x32b): the inverse permutation
+inline void emul_trip_inv(const float* src, float* dst) {
+    for (int T = 0; T < 32; ++T)
+        for (int I = 0; I < 2; ++I) for (int g = 0; g < 4; ++g) for (int h = 0; h < 2; ++h) for (int e = 0; e < 2; ++e)
+            dst[(16 * I + 8 * h + T / 4) * 32 + 8 * g + 2 * (T % 4) + e] = src[T * 32 + 16 * I + 4 * g + 2 * h + e];
+}
 
 }  // namespace tmt

@@ -14,63 +14,89 @@ using namespace tmt;
 
 extern "C" {
 
-// z_in: 4096 complex (interleaved re,im); spec_out: 4096 complex in NATURAL bin order (forward only)
-int tmt_emul_forward(const float* z_in, float* spec_out) {
+// The stage sequence of stft_kernel for one frame, thread by thread, with the tensor-memory round trips of exchange E2 replaced
+// by their data movement (emul_trip_fwd / emul_trip_inv, verified on hardware by tools/mb_tmem_xpose.cu).
+// spec: if non-null, receives the spectrum in NATURAL bin order (before the gain); g_half: natural-order half-spectrum gain or
+// null (forward only).
+static void emul_frame(const float* z_in, const float* g_half, float* spec, float* z_out) {
     auto tb = build_tw_bases();
     auto WA = [&](int t) { return TwBase{tb[4 * t], tb[4 * t + 1]}; };
     auto WB = [&](int t) { return TwBase{tb[4 * t + 2], tb[4 * t + 3]}; };
-    std::vector<float2> P(kExchFloat2), Q(kExchFloat2);
-    std::vector<float2> regs(256 * 16);
+    std::vector<float> gperm(4096, 1.0f);
+    if (g_half) permute_gain_row(g_half, gperm.data());
+    std::vector<float2> P(kE1Float2);
+    std::vector<float> R(256 * 32), S(256 * 32);
     float2 v[16];
-    for (int t = 0; t < 256; ++t) {
+    for (int t = 0; t < 256; ++t) {                                   // A
         for (int j = 0; j < 16; ++j) v[j] = make_float2(z_in[2 * (256 * j + t)], z_in[2 * (256 * j + t) + 1]);
-        fwd_a(v, t, WA(t), P.data());
+        dft16<false>(v);
+        tw_pow<false>(v, WA(t));
+        st_e1a(v, t, P.data());
     }
-    for (int t = 0; t < 256; ++t) fwd_b(v, t, WB(t), P.data(), Q.data());
-    for (int t = 0; t < 256; ++t) {
-        fwd_c(v, t, Q.data());
-        for (int j = 0; j < 16; ++j) {
-            const int k = bin_of(t, j);
-            spec_out[2 * k] = v[j].x;
-            spec_out[2 * k + 1] = v[j].y;
-        }
+    for (int t = 0; t < 256; ++t) {                                   // B
+        ld_e1b(v, t, P.data());
+        dft16<false>(v);
+        tw_pow<false>(v, WB(t));
+        float r[32];
+        x_fwd1_pack(v, r);
+        for (int c = 0; c < 32; ++c) R[t * 32 + c] = r[c];
     }
+    for (int w = 0; w < 8; ++w) emul_trip_fwd(R.data() + w * 1024, S.data() + w * 1024);
+    for (int t = 0; t < 256; ++t) {                                   // first layer of C
+        float r[32], s[32];
+        for (int c = 0; c < 32; ++c) r[c] = S[t * 32 + c];
+        x_layer_a<false>(r, s);
+        for (int c = 0; c < 32; ++c) R[t * 32 + c] = s[c];
+    }
+    for (int w = 0; w < 8; ++w) emul_trip_fwd(R.data() + w * 1024, S.data() + w * 1024);
+    for (int t = 0; t < 256; ++t) {                                   // second layer of C, gain, first layer of C'
+        float s[32], r[32];
+        for (int c = 0; c < 32; ++c) s[c] = S[t * 32 + c];
+        x_fwd2_finish(s, v);
+        if (spec)
+            for (int j = 0; j < 16; ++j) { spec[2 * bin_of(t, j)] = v[j].x; spec[2 * bin_of(t, j) + 1] = v[j].y; }
+        if (!z_out) continue;
+        for (int j = 0; j < 16; ++j) { v[j].x *= gperm[t * 16 + j]; v[j].y *= gperm[t * 16 + j]; }
+        x_inv1_pack(v, r);
+        for (int c = 0; c < 32; ++c) R[t * 32 + c] = r[c];
+    }
+    if (!z_out) return;
+    for (int w = 0; w < 8; ++w) emul_trip_inv(R.data() + w * 1024, S.data() + w * 1024);
+    for (int t = 0; t < 256; ++t) {                                   // second layer of C'
+        float r[32], s[32];
+        for (int c = 0; c < 32; ++c) r[c] = S[t * 32 + c];
+        x_layer_c_inv(r, s);
+        for (int c = 0; c < 32; ++c) R[t * 32 + c] = s[c];
+    }
+    for (int w = 0; w < 8; ++w) emul_trip_inv(R.data() + w * 1024, S.data() + w * 1024);
+    for (int t = 0; t < 256; ++t) {                                   // B'
+        float s[32];
+        for (int c = 0; c < 32; ++c) s[c] = S[t * 32 + c];
+        x_inv2_unpack(s, v);
+        float2 p[16];
+        tw_table(p, WB(t));
+        dft16_inv_tw(v, p);
+        st_e1b(v, t, P.data());
+    }
+    for (int t = 0; t < 256; ++t) {                                   // A'
+        ld_e1a(v, t, P.data());
+        float2 p[16];
+        tw_table(p, WA(t));
+        dft16_inv_tw(v, p);
+        for (int j = 0; j < 16; ++j) { z_out[2 * (256 * j + t)] = v[j].x; z_out[2 * (256 * j + t) + 1] = v[j].y; }
+    }
+}
+
+// z_in: 4096 complex (interleaved re,im); spec_out: 4096 complex in NATURAL bin order (forward only)
+int tmt_emul_forward(const float* z_in, float* spec_out) {
+    emul_frame(z_in, nullptr, spec_out, nullptr);
     return 0;
 }
 
 // Full per-frame operator: out = IFFT(gain * FFT(z_in)) with gain given as a natural-order
 // half spectrum g[0..2048] (the 1/4096 is applied through the permuted gain row, as on the GPU).
 int tmt_emul_filter(const float* z_in, const float* g_half, float* z_out) {
-    auto tb = build_tw_bases();
-    auto WA = [&](int t) { return TwBase{tb[4 * t], tb[4 * t + 1]}; };
-    auto WB = [&](int t) { return TwBase{tb[4 * t + 2], tb[4 * t + 3]}; };
-    std::vector<float> gperm(4096);
-    permute_gain_row(g_half, gperm.data());
-    std::vector<float2> P(kExchFloat2), Q(kExchFloat2);
-    std::vector<float2> regs(256 * 16);
-    float2 v[16];
-    for (int t = 0; t < 256; ++t) {
-        for (int j = 0; j < 16; ++j) v[j] = make_float2(z_in[2 * (256 * j + t)], z_in[2 * (256 * j + t) + 1]);
-        fwd_a(v, t, WA(t), P.data());
-    }
-    for (int t = 0; t < 256; ++t) fwd_b(v, t, WB(t), P.data(), Q.data());
-    for (int t = 0; t < 256; ++t) {           // C, gain, C' : registers only; C' writes P (padded layout)
-        fwd_c(v, t, Q.data());
-        for (int j = 0; j < 16; ++j) {
-            const float g = gperm[t * 16 + j];
-            v[j].x *= g;
-            v[j].y *= g;
-        }
-        inv_c(v, t, P.data());
-    }
-    for (int t = 0; t < 256; ++t) inv_b(v, t, WB(t), P.data(), Q.data());
-    for (int t = 0; t < 256; ++t) {
-        inv_a(v, t, WA(t), Q.data());
-        for (int j = 0; j < 16; ++j) {
-            z_out[2 * (256 * j + t)] = v[j].x;
-            z_out[2 * (256 * j + t) + 1] = v[j].y;
-        }
-    }
+    emul_frame(z_in, g_half, nullptr, z_out);
     return 0;
 }
 

@@ -519,12 +519,13 @@ __global__ void gate_kernel(const TrackDev* __restrict__ tracks, const T* __rest
 // Register budget.  The three radix-16 stages want ~190 registers when the per-thread constants
 // (analysis window 16, synthesis window x normalisation 16, overlap-add carry 16) also live in registers;
 // at 128 (two CTAs per SM) ptxas spilled 43 of them to local memory, and those spills were 48 % of the
-// L1 data-pipe wavefronts of v1 (profiles/r01).  All three are strictly thread-private, so they are
-// parked in TENSOR MEMORY: each warp owns a 32-lane quarter of the CTA's TMEM allocation and moves 16
-// values per thread with one tcgen05.st / tcgen05.ld (.32x32b.x16).  TMEM is otherwise idle in this
-// kernel (no MMA), its datapath is separate from the L1/shared-memory pipe the exchanges saturate, and
-// nothing stays resident in registers across the butterflies.  kStore == 1 is the shared-memory
-// fall-back of the same structure (A/B comparison; selected with TMT_STFT_STORE=smem).
+// L1 data-pipe wavefronts of v1 (profiles/r01).  Everything thread-private is therefore parked in TENSOR
+// MEMORY: each warp owns a 32-lane x 128-column region of the CTA's allocation and moves 16 values per thread
+// with one tcgen05.st / tcgen05.ld (.32x32b.x16).  TMEM is otherwise idle in this kernel (no MMA), its
+// datapath is separate from the L1/shared-memory pipe, and nothing stays resident in registers across the
+// butterflies.  The same region also carries the E2 exchange of the FFT (fft4096.cuh): the 16 x 16 transposes
+// between stages B and C run as tcgen05.st/.ld round trips in two different shapes instead of through shared
+// memory, which halves the shared-memory wavefronts of a frame (the pipe that limited v7, profiles/r01).
 struct StftParams {
     const TrackDev* tracks;
     const UnitDev* units;
@@ -543,32 +544,65 @@ struct StftParams {
     float limit;
 };
 
-constexpr int kTmemWarpCols = 112;                   // analysis window 16 | synthesis window 16 | carry 16 | raw input halves 2 x 16 | stage-A twiddles 32
-constexpr int kTmemCols = 256;                       // per CTA: 2 warps per lane quarter x 80 columns, rounded to a power of two (2 CTAs = all 512)
-constexpr int kStftSmemTmem = (4096 + kExchFloat2) * (int)sizeof(float2) + 64;
-constexpr int kStftSmemSmem = kStftSmemTmem + 2 * kNfft * (int)sizeof(float) + kHop * (int)sizeof(float2);
+// tensor-memory columns of a warp: synthesis window 16 | carry 16 | raw input halves 2 x 16 | stage-A twiddles 32 | E2 exchange 32
+constexpr int kTmemWarpCols = 128;
+constexpr int kTcSwin = 0, kTcCarry = 16, kTcHalf = 32, kTcTwA = 64, kTcXchg = 96;
+constexpr int kTmemCols = 256;                       // per CTA: 2 warps per lane quarter x 128 columns (2 CTAs = all 512)
+// shared memory: E1 exchange buffer | analysis window, thread-private float4 quads [4][256] | tail (TMEM slot, reduction, queue)
+constexpr int kStftSmemE1 = kE1Float2 * (int)sizeof(float2);
+constexpr int kStftSmemWin = kNfft * (int)sizeof(float);
+constexpr int kStftSmem = kStftSmemE1 + kStftSmemWin + 64;
 
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
+#define TMT_OPS16_IN(r, o) "f"(r[o+0]), "f"(r[o+1]), "f"(r[o+2]), "f"(r[o+3]), "f"(r[o+4]), "f"(r[o+5]), "f"(r[o+6]), "f"(r[o+7]), \
+                           "f"(r[o+8]), "f"(r[o+9]), "f"(r[o+10]), "f"(r[o+11]), "f"(r[o+12]), "f"(r[o+13]), "f"(r[o+14]), "f"(r[o+15])
+#define TMT_OPS16_OUT(r, o) "=f"(r[o+0]), "=f"(r[o+1]), "=f"(r[o+2]), "=f"(r[o+3]), "=f"(r[o+4]), "=f"(r[o+5]), "=f"(r[o+6]), "=f"(r[o+7]), \
+                            "=f"(r[o+8]), "=f"(r[o+9]), "=f"(r[o+10]), "=f"(r[o+11]), "=f"(r[o+12]), "=f"(r[o+13]), "=f"(r[o+14]), "=f"(r[o+15])
 __device__ __forceinline__ void tmem_st16(uint32_t taddr, const float (&r)[16]) {
     asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
-                 ::"r"(taddr), "f"(r[0]), "f"(r[1]), "f"(r[2]), "f"(r[3]), "f"(r[4]), "f"(r[5]), "f"(r[6]), "f"(r[7]),
-                   "f"(r[8]), "f"(r[9]), "f"(r[10]), "f"(r[11]), "f"(r[12]), "f"(r[13]), "f"(r[14]), "f"(r[15]) : "memory");
+                 ::"r"(taddr), TMT_OPS16_IN(r, 0) : "memory");
 }
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&r)[16]) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-                 : "=f"(r[0]), "=f"(r[1]), "=f"(r[2]), "=f"(r[3]), "=f"(r[4]), "=f"(r[5]), "=f"(r[6]), "=f"(r[7]),
-                   "=f"(r[8]), "=f"(r[9]), "=f"(r[10]), "=f"(r[11]), "=f"(r[12]), "=f"(r[13]), "=f"(r[14]), "=f"(r[15])
-                 : "r"(taddr) : "memory");
+                 : TMT_OPS16_OUT(r, 0) : "r"(taddr) : "memory");
 }
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
-// Thread-private parking space: kStore 0 = tensor memory, 1 = shared memory.
-template <int kStore> struct Park;
-template <> struct Park<0> {
-    uint32_t base;       // TMEM address of this warp's 48 columns (lane quarter in bits 31:16)
-    __device__ __forceinline__ void init(unsigned char* smem_tail, int t, const float* win, const float* swin, const float2* tw_a, float post_gain) {
+// E2 round trips (fft4096.cuh).  forward: thread-major store (.32x32b), row-major load (.16x256b, lanes 0-15 then 16-31 of the
+// warp's quarter); inverse: the same two shapes the other way round.  In place on the thread's 32-register image.
+__device__ __forceinline__ void tmem_trip_fwd(uint32_t a, float (&r)[32]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+                 ::"r"(a), TMT_OPS16_IN(r, 0) : "memory");
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+                 ::"r"(a + 16), TMT_OPS16_IN(r, 16) : "memory");
+    tmem_wait_st();
+    asm volatile("tcgen05.ld.sync.aligned.16x256b.x4.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                 : TMT_OPS16_OUT(r, 0) : "r"(a) : "memory");
+    asm volatile("tcgen05.ld.sync.aligned.16x256b.x4.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                 : TMT_OPS16_OUT(r, 16) : "r"(a + (16u << 16)) : "memory");
+    tmem_wait_ld();
+}
+__device__ __forceinline__ void tmem_trip_inv(uint32_t a, float (&r)[32]) {
+    asm volatile("tcgen05.st.sync.aligned.16x256b.x4.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+                 ::"r"(a), TMT_OPS16_IN(r, 0) : "memory");
+    asm volatile("tcgen05.st.sync.aligned.16x256b.x4.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+                 ::"r"(a + (16u << 16)), TMT_OPS16_IN(r, 16) : "memory");
+    tmem_wait_st();
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                 : TMT_OPS16_OUT(r, 0) : "r"(a) : "memory");
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                 : TMT_OPS16_OUT(r, 16) : "r"(a + 16) : "memory");
+    tmem_wait_ld();
+}
+
+// Thread-private parking space in tensor memory (+ the analysis window in shared memory).
+struct Park {
+    uint32_t base;       // TMEM address of this warp's 128 columns (lane quarter in bits 31:16)
+    const float4* aw;    // this thread's analysis-window quads in shared memory: aw[256 * g] = w[256 * (4g + 0..3) + t]
+    __device__ __forceinline__ void init(unsigned char* smem_win, unsigned char* smem_tail, int t, const float* win, const float* swin,
+                                         const float2* tw_a, float post_gain) {
         uint32_t* slot = reinterpret_cast<uint32_t*>(smem_tail);
         if ((t >> 5) == 0) {
             asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
@@ -580,17 +614,20 @@ template <> struct Park<0> {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const int warp = t >> 5;
         base = *slot + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((warp >> 2) * kTmemWarpCols);
-        fill_tables(t, win, swin, tw_a, post_gain);
+        float4* awr = reinterpret_cast<float4*>(smem_win) + t;
+#pragma unroll
+        for (int g = 0; g < 4; ++g)
+            awr[256 * g] = make_float4(__ldg(win + 256 * (4 * g) + t), __ldg(win + 256 * (4 * g + 1) + t), __ldg(win + 256 * (4 * g + 2) + t),
+                                       __ldg(win + 256 * (4 * g + 3) + t));
+        aw = awr;
+        fill_tables(t, swin, tw_a, post_gain);
     }
-    // thread-private constants -> this region's columns: analysis window | synthesis window x normalisation x output gain | stage-A twiddles
-    __device__ __forceinline__ void fill_tables(int t, const float* win, const float* swin, const float2* tw_a, float post_gain) const {
+    // thread-private constants -> this region's columns: synthesis window x normalisation x output gain | stage-A twiddles
+    __device__ __forceinline__ void fill_tables(int t, const float* swin, const float2* tw_a, float post_gain) const {
         float r[16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) r[j] = __ldg(win + 256 * j + t);
-        tmem_st16(base, r);
-#pragma unroll
         for (int j = 0; j < 16; ++j) r[j] = __ldg(swin + 256 * j + t) * post_gain;   // output gain folded into the synthesis window
-        tmem_st16(base + 16, r);
+        tmem_st16(base + kTcSwin, r);
         const float4* ta = reinterpret_cast<const float4*>(tw_a + 16 * t);
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
@@ -599,43 +636,26 @@ template <> struct Park<0> {
                 const float4 x = __ldg(ta + 4 * h + q);
                 r[4 * q] = x.x; r[4 * q + 1] = x.y; r[4 * q + 2] = x.z; r[4 * q + 3] = x.w;
             }
-            tmem_st16(base + 80 + 16 * h, r);
+            tmem_st16(base + kTcTwA + 16 * h, r);
         }
         tmem_wait_st();
     }
-    // v[k] *= p^k (CONJ: conj(p^k)), p = W4096^t, powers read from tensor memory
-    template <bool CONJ>
-    __device__ __forceinline__ void twiddle_a(float2 (&v)[16], const TwBase) const {
-        float a[16], b[16];
-        tmem_ld16(base + 80, a);
-        tmem_ld16(base + 96, b);
-        tmem_wait_ld();
-#pragma unroll
-        for (int k = 1; k < 8; ++k) {
-            const float2 p = make_float2(a[2 * k], a[2 * k + 1]);
-            v[k] = CONJ ? cmulc(v[k], p) : cmul(v[k], p);
-        }
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            const float2 p = make_float2(b[2 * k], b[2 * k + 1]);
-            v[k + 8] = CONJ ? cmulc(v[k + 8], p) : cmul(v[k + 8], p);
-        }
-    }
-    // inverse stage-A twiddles plus the operands of the frame's tail (synthesis window, carry) in one batch of tensor-memory
-    // loads: a single wait, and the tail's loads complete under the last butterflies
-    __device__ __forceinline__ void twiddle_a_fwd(float2 (&v)[16], const TwBase, const float (&a)[16], const float (&b)[16]) const {
+    // forward stage-A twiddles (powers of W4096^t read from tensor memory)
+    __device__ __forceinline__ void twiddle_a_fwd(float2 (&v)[16], const float (&a)[16], const float (&b)[16]) const {
 #pragma unroll
         for (int k = 1; k < 8; ++k) v[k] = cmul(v[k], make_float2(a[2 * k], a[2 * k + 1]));
 #pragma unroll
         for (int k = 0; k < 8; ++k) v[k + 8] = cmul(v[k + 8], make_float2(b[2 * k], b[2 * k + 1]));
     }
-    __device__ __forceinline__ void inv_fetch_issue(float (&a)[16], float (&b)[16], float (&s)[16], float (&cr)[16], int) const {
-        tmem_ld16(base + 80, a);           // issued before the CTA barrier that precedes stage A': the loads fly while the
-        tmem_ld16(base + 96, b);           // warp waits for the slower warps
-        tmem_ld16(base + 16, s);
-        tmem_ld16(base + 32, cr);
+    // inverse stage-A twiddles plus the operands of the frame's tail (synthesis window, carry) in one batch of tensor-memory
+    // loads: a single wait, and the tail's loads complete under the last butterflies
+    __device__ __forceinline__ void inv_fetch_issue(float (&a)[16], float (&b)[16], float (&s)[16], float (&cr)[16]) const {
+        tmem_ld16(base + kTcTwA, a);           // issued before the CTA barrier that precedes stage A': the loads fly while the
+        tmem_ld16(base + kTcTwA + 16, b);      // warp waits for the slower warps
+        tmem_ld16(base + kTcSwin, s);
+        tmem_ld16(base + kTcCarry, cr);
     }
-    __device__ __forceinline__ void inv_fetch_apply(float2 (&v)[16], const TwBase, const float (&a)[16], const float (&b)[16],
+    __device__ __forceinline__ void inv_fetch_apply(float2 (&v)[16], const float (&a)[16], const float (&b)[16],
                                                     const float (&cr)[16], float2 (&c)[8]) const {
         tmem_wait_ld();
         float2 p[16];
@@ -654,37 +674,37 @@ template <> struct Park<0> {
             asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(a), "n"(kTmemCols) : "memory");
         }
     }
-    __device__ __forceinline__ void load_awin(float (&w)[16], int) const { tmem_ld16(base, w); tmem_wait_ld(); }
-    __device__ __forceinline__ void load_tail(float (&s)[16], float2 (&c)[8], int) const {
+    __device__ __forceinline__ void load_tail(float (&s)[16], float2 (&c)[8]) const {
         float cr[16];
-        tmem_ld16(base + 16, s);
-        tmem_ld16(base + 32, cr);
+        tmem_ld16(base + kTcSwin, s);
+        tmem_ld16(base + kTcCarry, cr);
         tmem_wait_ld();
 #pragma unroll
         for (int j = 0; j < 8; ++j) c[j] = make_float2(cr[2 * j], cr[2 * j + 1]);
     }
-    __device__ __forceinline__ void store_carry(const float2 (&c)[8], int) const {
+    __device__ __forceinline__ void store_carry(const float2 (&c)[8]) const {
         float cr[16];
 #pragma unroll
         for (int j = 0; j < 8; ++j) { cr[2 * j] = c[j].x; cr[2 * j + 1] = c[j].y; }
-        tmem_st16(base + 32, cr);
+        tmem_st16(base + kTcCarry, cr);
     }
     // raw (unwindowed) input half frames, two slots
     __device__ __forceinline__ void stage_put(int slot, const float2 (&x)[8]) const {
         float r[16];
 #pragma unroll
         for (int j = 0; j < 8; ++j) { r[2 * j] = x[j].x; r[2 * j + 1] = x[j].y; }
-        tmem_st16(base + 48 + 16 * slot, r);
+        tmem_st16(base + kTcHalf + 16 * slot, r);
     }
     // v = [half `slot`, half `slot ^ 1`] x analysis window
     __device__ __forceinline__ void stage_get_windowed(int slot, float2 (&v)[16], float (&ta)[16], float (&tb2)[16]) const {
-        float a[16], b[16], w[16];
-        tmem_ld16(base + 48 + 16 * slot, a);
-        tmem_ld16(base + 48 + 16 * (slot ^ 1), b);
-        tmem_ld16(base, w);
-        tmem_ld16(base + 80, ta);          // stage-A twiddles ride along: one wait for the whole frame prologue
-        tmem_ld16(base + 96, tb2);
+        float a[16], b[16];
+        tmem_ld16(base + kTcHalf + 16 * slot, a);
+        tmem_ld16(base + kTcHalf + 16 * (slot ^ 1), b);
+        tmem_ld16(base + kTcTwA, ta);          // stage-A twiddles ride along: one wait for the whole frame prologue
+        tmem_ld16(base + kTcTwA + 16, tb2);
+        const float4 w0 = aw[0], w1 = aw[256], w2 = aw[512], w3 = aw[768];
         tmem_wait_ld();
+        const float w[16] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w, w2.x, w2.y, w2.z, w2.w, w3.x, w3.y, w3.z, w3.w};
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             v[j] = cscale(make_float2(a[2 * j], a[2 * j + 1]), w[j]);
@@ -692,52 +712,8 @@ template <> struct Park<0> {
         }
     }
     __device__ __forceinline__ void sync_stores() const { tmem_wait_st(); }
-};
-template <> struct Park<1> {
-    float* aw;        // [4096]
-    float* sw;        // [4096]
-    float2* cy;       // [2048]
-    __device__ __forceinline__ void init(unsigned char* smem_tail, int t, const float* win, const float* swin, const float2*, float post_gain) {
-        aw = reinterpret_cast<float*>(smem_tail + 64);
-        sw = aw + kNfft;
-        cy = reinterpret_cast<float2*>(sw + kNfft);
-#pragma unroll
-        for (int j = 0; j < 16; ++j) { aw[256 * j + t] = __ldg(win + 256 * j + t); sw[256 * j + t] = __ldg(swin + 256 * j + t) * post_gain; }
-        __syncthreads();
-    }
-    __device__ __forceinline__ void fini(unsigned char*, int) {}
-    __device__ __forceinline__ void load_awin(float (&w)[16], int t) const {
-#pragma unroll
-        for (int j = 0; j < 16; ++j) w[j] = aw[256 * j + t];
-    }
-    __device__ __forceinline__ void load_tail(float (&s)[16], float2 (&c)[8], int t) const {
-#pragma unroll
-        for (int j = 0; j < 16; ++j) s[j] = sw[256 * j + t];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) c[j] = cy[256 * j + t];
-    }
-    __device__ __forceinline__ void store_carry(const float2 (&c)[8], int t) const {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) cy[256 * j + t] = c[j];
-    }
-    template <bool CONJ>
-    __device__ __forceinline__ void twiddle_a(float2 (&v)[16], const TwBase wa) const { tw_pow<CONJ>(v, wa); }
-    __device__ __forceinline__ void twiddle_a_fwd(float2 (&v)[16], const TwBase wa, const float (&)[16], const float (&)[16]) const { tw_pow<false>(v, wa); }
-    __device__ __forceinline__ void inv_fetch_issue(float (&)[16], float (&)[16], float (&s)[16], float (&cr)[16], int t) const {
-#pragma unroll
-        for (int j = 0; j < 16; ++j) s[j] = sw[256 * j + t];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) { const float2 x = cy[256 * j + t]; cr[2 * j] = x.x; cr[2 * j + 1] = x.y; }
-    }
-    __device__ __forceinline__ void inv_fetch_apply(float2 (&v)[16], const TwBase wa, const float (&)[16], const float (&)[16],
-                                                    const float (&cr)[16], float2 (&c)[8]) const {
-        float2 p[16];
-        tw_table(p, wa);
-        dft16_inv_tw(v, p);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) c[j] = make_float2(cr[2 * j], cr[2 * j + 1]);
-    }
-    __device__ __forceinline__ void sync_stores() const {}
+    __device__ __forceinline__ void trip_fwd(float (&r)[32]) const { tmem_trip_fwd(base + kTcXchg, r); }
+    __device__ __forceinline__ void trip_inv(float (&r)[32]) const { tmem_trip_inv(base + kTcXchg, r); }
 };
 
 // End of a work unit: publish the unit's peak; with the fused limiter, the CTA that completes a chunk's last unit rescales it.
@@ -806,23 +782,16 @@ __device__ __forceinline__ void unit_epilogue(const StftParams& prm, int chunk, 
     }
 }
 
-__device__ __forceinline__ void park_put(const Park<0>& p, int slot, const float2 (&x)[8]) { p.stage_put(slot, x); }
-__device__ __forceinline__ void park_put(const Park<1>&, int, const float2 (&)[8]) {}
-
-template <int kStore>
 __global__ void __launch_bounds__(kThreads, 2) stft_kernel(const StftParams prm) {
     extern __shared__ __align__(16) unsigned char smraw[];
-    float2* bufP = reinterpret_cast<float2*>(smraw);         // E1 layout only (linear, 32 KB)
-    float2* bufQ = bufP + 4096;                              // E2 layout only (padded rows)
-    unsigned char* tail = reinterpret_cast<unsigned char*>(bufQ + kExchFloat2);
+    float2* bufP = reinterpret_cast<float2*>(smraw);         // E1 exchange (padded rows, 33 KB)
+    unsigned char* tail = smraw + kStftSmemE1 + kStftSmemWin;
     float* red = reinterpret_cast<float*>(tail + 16);
     const int t = threadIdx.x;
 
-    Park<kStore> park;
-    park.init(tail, t, prm.win, prm.swin, prm.tw_a, prm.post_gain);
-    const float4* tb4 = reinterpret_cast<const float4*>(prm.tw_bases) + 2 * t;
-    const float4 ba = __ldg(tb4), bb = __ldg(tb4 + 1);
-    const TwBase wa = {make_float2(ba.x, ba.y), make_float2(ba.z, ba.w)};
+    Park park;
+    park.init(smraw + kStftSmemE1, tail, t, prm.win, prm.swin, prm.tw_a, prm.post_gain);
+    const float4 bb = __ldg(reinterpret_cast<const float4*>(prm.tw_bases) + 2 * t + 1);
     const TwBase wb = {make_float2(bb.x, bb.y), make_float2(bb.z, bb.w)};
 
     // Work units are claimed from a global counter: unit lengths are deliberately uneven (see tmt_plan_create), so the
@@ -849,7 +818,7 @@ __global__ void __launch_bounds__(kThreads, 2) stft_kernel(const StftParams prm)
             float2 z[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) z[j] = make_float2(0.f, 0.f);
-            park.store_carry(z, t);
+            park.store_carry(z);
         }
         float peak = 0.f;
         const int last = un.b1 - un.b0;                    // frames of this unit: i = 0 .. last  (f = b0 - 1 + i)
@@ -869,13 +838,16 @@ __global__ void __launch_bounds__(kThreads, 2) stft_kernel(const StftParams prm)
                 }
             }
         };
-        if constexpr (kStore == 0) {       // prologue: halves 0 and 1 of the unit -> staging slots 0 and 1
+        {                                  // prologue: halves 0 and 1 of the unit -> staging slots 0 and 1
             float2 x[8];
             load_half(0, x);
             park.stage_put(0, x);
             load_half(1, x);
             park.stage_put(1, x);
         }
+        // gain-row index of the next frame, fetched one frame ahead (it heads a dependent chain: index -> row address -> gains)
+        auto row_of = [&](int f) { return (f >= 0 && f < n_frames) ? (int)__ldg(rows + f) : 0; };
+        int row_next = row_of(un.b0 - 1);
 
         for (int i = 0; i <= last; ++i) {
             const int f = un.b0 - 1 + i;
@@ -883,66 +855,49 @@ __global__ void __launch_bounds__(kThreads, 2) stft_kernel(const StftParams prm)
             const bool have = (f >= 0) && (f < n_frames);
             const int rel = i * kHop;                          // frame start relative to the unit
             park.sync_stores();
-            // kStore 0: every input sample is read from global memory exactly once, one frame ahead of its
-            // first use, and waits in tensor memory; the loads below belong to frame i+1 and complete under
-            // this frame's butterflies
+            // every input sample is read from global memory exactly once, one frame ahead of its first use, and waits in
+            // tensor memory; the loads below belong to frame i+1 and complete under this frame's butterflies
             float2 pf[8];
-            float fa[16], fb[16];                                  // forward stage-A twiddles (tensor-memory variant)
             float s[16];                                           // synthesis window x normalisation (x output gain)
             float2 c[8];                                           // carried half frame
-            const bool do_pf = (kStore == 0) && (i < last);
+            const bool do_pf = (i < last);
+            const int row = row_next;
+            row_next = row_of(f + 1);
             if (have) {
-                if constexpr (kStore == 0) {
+                {
+                    float fa[16], fb[16];                          // forward stage-A twiddles
                     park.stage_get_windowed(i & 1, v, fa, fb);
                     if (do_pf) load_half(i + 2, pf);
-                } else {
-                    const float2* src = in_u + rel;
-                    if (rel >= in_lo && rel + kNfft + kHop <= in_hi) {
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) v[j] = ld_stream(src + 256 * j);
-                        if ((t & 15) == 0) {           // next frame's new half -> L2 (one 128-B line per 16 lanes)
-#pragma unroll
-                            for (int j = 16; j < 24; ++j) prefetch_l2(src + 256 * j);
-                        }
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) {
-                            const int p = rel + 256 * j + t;
-                            v[j] = (p >= in_lo && p < in_hi) ? __ldg(src + 256 * j) : make_float2(0.f, 0.f);
-                        }
-                    }
-                    float w[16];
-                    park.load_awin(w, t);
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) v[j] = cscale(v[j], w[j]);       // analysis window
+                    dft16<false>(v);                                                  // A
+                    park.twiddle_a_fwd(v, fa, fb);
                 }
-                const int row = rows[f];
-                // tilt gain x crossfade weight: one real row per frame, register order; issued a whole stage ahead so the
-                // L1/L2 latency is long gone when stage C needs it
-                const float4* g4 = reinterpret_cast<const float4*>(prm.gperm + (size_t)row * kNfft + t * 16);
-                dft16<false>(v);                                                  // A
-                park.twiddle_a_fwd(v, wa, fa, fb);
                 st_e1a(v, t, bufP);
-                const float4 g0 = __ldg(g4), g1 = __ldg(g4 + 1), g2 = __ldg(g4 + 2), g3 = __ldg(g4 + 3);
                 __syncthreads();
                 ld_e1b(v, t, bufP);
                 dft16<false>(v);                                                  // B
                 tw_pow<false>(v, wb);
-                st_e2b(v, t, bufQ);
-                // E2 rows k1*16 .. k1*16+15 are written and read only by the 16 threads with t>>4 == k1 (one half
-                // warp), in B, C/C' and B' alike: the E2 exchanges need warp-level ordering only
-                __syncwarp();
-                if (do_pf) park_put(park, i & 1, pf);          // slot of the half this frame no longer needs
-                ld_e2c(v, t, bufQ);
-                dft16<false>(v);                                                  // C
+                // E2: the 16 x 16 transposes between stages B and C run through tensor memory, one round trip on either side
+                // of C's first radix-4 layer (fft4096.cuh); no shared-memory traffic, no barrier
+                float r[32], q[32];
+                if (do_pf) park.stage_put(i & 1, pf);          // slot of the half this frame no longer needs
+                x_fwd1_pack(v, r);
+                park.trip_fwd(r);
+                // tilt gain x crossfade weight: one real row per frame, register order; issued before the second round trip
+                // (the few rows in use stay in L1), in the registers the staged input half has just left
+                const float4* g4 = reinterpret_cast<const float4*>(prm.gperm + (size_t)row * kNfft + t * 16);
+                const float4 g0 = __ldg(g4), g1 = __ldg(g4 + 1), g2 = __ldg(g4 + 2), g3 = __ldg(g4 + 3);
+                x_layer_a<false>(r, q);                                           // C, first layer
+                park.trip_fwd(q);
+                x_fwd2_finish(q, v);                                              // C, second layer
                 v[0] = cscale(v[0], g0.x); v[1] = cscale(v[1], g0.y); v[2] = cscale(v[2], g0.z); v[3] = cscale(v[3], g0.w);
                 v[4] = cscale(v[4], g1.x); v[5] = cscale(v[5], g1.y); v[6] = cscale(v[6], g1.z); v[7] = cscale(v[7], g1.w);
                 v[8] = cscale(v[8], g2.x); v[9] = cscale(v[9], g2.y); v[10] = cscale(v[10], g2.z); v[11] = cscale(v[11], g2.w);
                 v[12] = cscale(v[12], g3.x); v[13] = cscale(v[13], g3.y); v[14] = cscale(v[14], g3.z); v[15] = cscale(v[15], g3.w);
-                dft16<true>(v);                                                   // C'
-                st_e2c(v, t, bufQ);            // same rows this thread just read: no barrier needed in between
-                __syncwarp();
-                ld_e2b(v, t, bufQ);
+                x_inv1_pack(v, r);                                                // C', first layer + inner twiddles
+                park.trip_inv(r);
+                x_layer_c_inv(r, q);                                              // C', second layer
+                park.trip_inv(q);
+                x_inv2_unpack(q, v);
                 {
                     float2 pw[16];
                     tw_table(pw, wb);
@@ -950,15 +905,15 @@ __global__ void __launch_bounds__(kThreads, 2) stft_kernel(const StftParams prm)
                 }
                 st_e1b(v, t, bufP);            // the very words this thread read in ld_e1b: no hazard with slower warps still in B
                 float ta[16], tb2[16], cr[16];
-                park.inv_fetch_issue(ta, tb2, s, cr, t);
+                park.inv_fetch_issue(ta, tb2, s, cr);
                 __syncthreads();
                 ld_e1a(v, t, bufP);            // next frame's st_e1a overwrites exactly the words this thread reads here
-                park.inv_fetch_apply(v, wa, ta, tb2, cr, c);                    // A' (twiddles fused into the first butterflies)
+                park.inv_fetch_apply(v, ta, tb2, cr, c);                        // A' (twiddles fused into the first butterflies)
             } else {
 #pragma unroll
                 for (int j = 0; j < 16; ++j) v[j] = make_float2(0.f, 0.f);
-                if (do_pf) { load_half(i + 2, pf); park_put(park, i & 1, pf); }
-                park.load_tail(s, c, t);
+                if (do_pf) { load_half(i + 2, pf); park.stage_put(i & 1, pf); }
+                park.load_tail(s, c);
             }
 
             // synthesis window, overlap-add with the carried half, interior normalisation (folded into swin)
@@ -986,7 +941,7 @@ __global__ void __launch_bounds__(kThreads, 2) stft_kernel(const StftParams prm)
             }
 #pragma unroll
             for (int j = 0; j < 8; ++j) c[j] = cscale(v[j + 8], s[j + 8]);
-            park.store_carry(c, t);
+            park.store_carry(c);
         }
         unit_epilogue(prm, un.chunk, trp, peak, t, red);
         __syncthreads();
@@ -1604,7 +1559,6 @@ struct tmt_engine {
     std::mutex arena_mu;                    // plans of one engine may be created / destroyed from several host threads
     unsigned char* spare_arena = nullptr;   // arena of the last destroyed plan, reused by the next plan that fits
     size_t spare_arena_size = 0;
-    int stft_store = 0;       // 0: thread-private constants + carry in tensor memory, 1: in shared memory
     int gate_nseg = 0;        // > 0: force this many gate-scan segments per track (TMT_GATE_NSEG, tests)
     DevBuf<float2> tw_bases;  // [256][4]
     DevBuf<float2> tw_a;      // [256][16]
@@ -1826,10 +1780,8 @@ int tmt_engine_create(tmt_engine** out, int device, int n_fft, int hop) {
     }
     cudaMemcpy(e->tw_bases.p, twb.data(), sizeof(float2) * twb.size(), cudaMemcpyHostToDevice);
     cudaMemcpy(e->tw_a.p, twa.data(), sizeof(float2) * twa.size(), cudaMemcpyHostToDevice);
-    ce = cudaFuncSetAttribute(stft_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStftSmemTmem);
-    if (ce == cudaSuccess) ce = cudaFuncSetAttribute(stft_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStftSmemSmem);
+    ce = cudaFuncSetAttribute(stft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kStftSmem);
     if (ce != cudaSuccess) { delete e; return fail(TMT_ERR_CUDA, "cudaFuncSetAttribute(stft_kernel): %s", cudaGetErrorString(ce)); }
-    if (const char* sv = getenv("TMT_STFT_STORE")) e->stft_store = (strcmp(sv, "smem") == 0) ? 1 : 0;
     if (const char* sv = getenv("TMT_GATE_NSEG")) e->gate_nseg = atoi(sv);
 
     ce = cudaFuncSetAttribute(edge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kEdgeSmemBytes);
@@ -2263,8 +2215,7 @@ static int launch_stft(tmt_plan* p, float post_gain, float limit, cudaStream_t s
     prm.limit = limit;
     CUDA_TRY(cudaMemsetAsync(p->unit_counter.p, 0, sizeof(int), st));
     const int grid = std::min(p->n_units, 2 * e->n_sms);            // persistent: two CTAs per SM
-    if (e->stft_store == 0) stft_kernel<0><<<grid, kThreads, kStftSmemTmem, st>>>(prm);
-    else stft_kernel<1><<<grid, kThreads, kStftSmemSmem, st>>>(prm);
+    stft_kernel<<<grid, kThreads, kStftSmem, st>>>(prm);
     p->launches++;
     CUDA_TRY(cudaGetLastError());
     return TMT_OK;
