@@ -130,6 +130,31 @@ def cpu_baseline_single(n_tracks=3):
                       f"restatement of src/process_tomatis.py, float32 pocketfft), one process"}
 
 
+def parity_vs_oracle(x0, y0, states0, chunk_peaks0):
+    """GPU track 0 of the timed batch against the oracle on the same samples (checker only): PCM max-abs error against the
+    float64-FFT evaluation of the reference source (the north star's yardstick) and against its float32-FFT output, gate
+    mismatches, limiter chunks that differ in their over-the-limit decision."""
+    import numpy as np
+    from oracle import tomatis_oracle as orc
+    o32 = orc.process_standard(x0, SR, gate_ui=50)
+    o64 = orc.run("standard", x0, SR, gate_ui=50, fft_dtype="float64")
+    y = y0.astype(np.float64)
+    d64 = np.abs(y - o64["out"].astype(np.float64)).max(axis=1)
+    d32 = np.abs(y - o32["out"].astype(np.float64)).max(axis=1)
+    self_noise = np.abs(o32["out"].astype(np.float64) - o64["out"].astype(np.float64)).max(axis=1)
+    lens = np.asarray(o32["chunk_lengths"])
+    ends = np.cumsum(lens)
+    o_over = np.array([float(np.abs(o32["out"][e - n:e]).max()) >= 0.999 - 1e-6 for n, e in zip(lens, ends)])
+    return {"parity_max_abs": float(d64.max()), "parity_max_abs_vs_f32_fft": float(d32.max()),
+            "parity_pointwise_ok": bool(np.all(d32 <= 1e-5 + self_noise)),
+            "oracle_self_noise": float(self_noise.max()),
+            "gate_mismatches": int((np.asarray(states0) != np.asarray(o32["states"])).sum()),
+            "gate_frames": int(len(o32["states"])),
+            "limited_chunks_gpu": int((np.asarray(chunk_peaks0) > np.float32(0.999)).sum()), "limited_chunks_oracle": int(o_over.sum()),
+            "parity_sample": "track 0 of the timed batch (13 230 000 sample-frames) against oracle.process_standard on the same samples; "
+                             "parity_max_abs is against the float64-FFT evaluation of the reference source, bar 1e-5"}
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -253,6 +278,10 @@ def run_gpu_arm(args):
     lim_frac = float((peaks > np.float32(0.999)).mean())
     out_peak = float(y.abs().max())
     finite = bool(torch.isfinite(y[0]).all())
+    parity_in = None
+    if rank == 0 and not args.no_cpu:          # track 0 of the LAST timed step goes to the oracle below (checker leg, not timed)
+        nf0, nc0 = db.plan.track_frames[0], db.plan.track_chunks[0]
+        parity_in = (x[0].cpu().numpy(), y[0].cpu().numpy(), states[:nf0].copy(), peaks[:nc0].copy())
     db.close()
 
     # ---- end to end through the host-buffer API (pinned host memory, copies inside the timed region)
@@ -265,7 +294,7 @@ def run_gpu_arm(args):
         h_in = torch.empty((Te, N_SAMPLES, 2), dtype=torch.float32, pin_memory=True)
         h_out = torch.empty((Te, N_SAMPLES, 2), dtype=torch.float32, pin_memory=True)
         h_in.copy_(x[:Te])
-        del y
+        y = None
         pipe = HostBatchPipeline(N_SAMPLES, SR, "standard", device=local, wave_tracks=args.wave_tracks,
                                  unit_blocks=args.unit_blocks, gate_ui=50)
         for _ in range(max(1, min(args.warmup, 2))):
@@ -318,6 +347,19 @@ def run_gpu_arm(args):
         else:
             del h_in, h_out
 
+    # ---- the second named scaling target in the same line: one 2-hour 96 kHz file (BASELINE configs[4]), strong scaling
+    lf = None
+    if not args.no_longfile:
+        x = y = None
+        torch.cuda.empty_cache()
+        if world == 1 and not dist.is_initialized():
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            os.environ.setdefault("MASTER_PORT", "29533")
+            dist.init_process_group("nccl", rank=0, world_size=1, device_id=torch.device(dev))
+        lf = longfile_measure(args, dist, rank, world, local, args.steps, False)
+        for k in ("metric", "unit", "higher_is_better", "vs_baseline", "dtype", "data", "warmup"):
+            lf.pop(k, None)
+
     if rank == 0:
         peak_gbs, peak_src = measured_peak()
         achieved = ALG_BYTES_PER_SF * sf_rank / (stft_ms * 1e-3) / 1e9
@@ -337,10 +379,14 @@ def run_gpu_arm(args):
             "checks": {"c2_fraction": c2_frac, "chunks_over_limit": lim_frac, "output_peak": out_peak,
                        "finite": finite},
         }
+        if parity_in is not None:
+            line["checks"].update(parity_vs_oracle(*parity_in))
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_baseline_single(args.cpu_tracks)
+        if lf is not None:
+            line["longfile"] = lf
         print(json.dumps(line), flush=True)
-    if world > 1:
+    if dist.is_initialized():
         dist.barrier()
         dist.destroy_process_group()
 
@@ -393,20 +439,14 @@ def run_longfile_reference_arm(args):
     print(json.dumps(line), flush=True)
 
 
-def run_longfile_arm(args):
+def longfile_measure(args, dist, rank, world, local, steps, want_cpu):
+    """One 2-hour 96 kHz file, time-chunk sharded over the ranks of the (already initialised) process group; every rank
+    returns the record (only rank 0's is printed).  Timed like the batch arm: barrier + synchronize on both sides, CUDA
+    events, max over ranks."""
     import numpy as np
     import torch
-    import torch.distributed as dist
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
     dev = f"cuda:{local}"
-    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-    os.environ.setdefault("MASTER_PORT", "29531")
-    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device(dev))
-
     from tomatis_audio_processor_b200 import sharded, synth, _lib as L
     total = args.lf_total
     comm = sharded.Comm(None, dev)
@@ -428,12 +468,12 @@ def run_longfile_arm(args):
         sampler.start()
         time.sleep(0.3)
     l0 = plan.launch_count()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     t0 = time.time()
     e0.record()
-    for k in range(args.steps):
+    for k in range(steps):
         sess.step(ev[k])
     e1.record()
     barrier()
@@ -449,11 +489,12 @@ def run_longfile_arm(args):
     tmax = torch.tensor([ms_total, stft_ms], device=dev, dtype=torch.float64)
     dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
     ms_total, stft_ms = float(tmax[0]), float(tmax[1])
-    value = total / LF_SR * args.steps / (ms_total * 1e-3)
+    value = total / LF_SR * steps / (ms_total * 1e-3)
     states = plan.read(L.ARR_STATE)
     peaks = plan.read(L.ARR_CHUNK_PEAK)
     out_peak = float(sess.out.abs().max()) if sess.out.numel() else 0.0
     comm_bytes = comm.bytes_sent
+    n_passes = args.warmup + steps + 1
 
     # ---- end to end: the rank's own range from pinned host memory and back, copies inside the timed region
     e2e = None
@@ -483,31 +524,46 @@ def run_longfile_arm(args):
                "api": "sharded.StreamingShardSession.step with each rank's own range copied from / to pinned host float32 buffers",
                "host_peak_out": float(h_out.abs().max()) if n_own else 0.0}
         del h_in, h_out
+        n_passes += args.e2e_steps + 1
 
-    if rank == 0:
-        peak_gbs, peak_src = measured_peak()
-        sf_rank = me.own_hi - me.own_lo
-        achieved = ALG_BYTES_PER_SF * sf_rank / (stft_ms * 1e-3) / 1e9
-        traffic = ncu_traffic()
-        line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic", "config": longfile_config(world, total), "clocks": clocks, "e2e": e2e,
-            "gpu_launches": int(launches), "comm_bytes_per_step_rank0": int(comm_bytes // max(1, args.warmup + args.steps + 1 + (0 if args.no_e2e else args.e2e_steps + 1))),
-            "roofline": {"bound": "hbm", "kernel": "stft_kernel (fused gather+window+FFT+gain+IFFT+window+OLA+peak), rank 0 shard",
-                         "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs, "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": ALG_BYTES_PER_SF * sf_rank, "kernel_ms": stft_ms,
-                         "kernel_share_of_step": stft_ms * args.steps / ms_total,
-                         "traffic": (traffic or {}).get("dram_bytes_per_sf", None) and (traffic["dram_bytes_per_sf"] * sf_rank),
-                         "traffic_source": (traffic or {}).get("source")},
-            "phase_ms_rank0": breakdown,
-            "checks": {"c2_fraction": float((states == 2).mean()), "chunks_over_limit": float((peaks > np.float32(0.999)).mean()),
-                       "output_peak": out_peak, "frames": int(states.size)},
-        }
-        if world == 1 and not args.no_cpu:
-            line["cpu_baseline"] = cpu_baseline_longfile(args.lf_cpu_seconds)
-        print(json.dumps(line), flush=True)
+    peak_gbs, peak_src = measured_peak()
+    sf_rank = me.own_hi - me.own_lo
+    achieved = ALG_BYTES_PER_SF * sf_rank / (stft_ms * 1e-3) / 1e9
+    rec = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": args.warmup,
+        "ms_per_step": ms_total / steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "config": longfile_config(world, total), "clocks": clocks, "e2e": e2e,
+        "gpu_launches": int(launches), "comm_bytes_per_step_rank0": int(comm_bytes // max(1, n_passes)),
+        "roofline": {"bound": "hbm", "kernel": "stft_kernel (fused gather+window+FFT+gain+IFFT+window+OLA+peak), rank 0 shard",
+                     "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs, "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": ALG_BYTES_PER_SF * sf_rank, "kernel_ms": stft_ms,
+                     "kernel_share_of_step": stft_ms * steps / ms_total},
+        "phase_ms_rank0": breakdown,
+        "checks": {"c2_fraction": float((states == 2).mean()), "chunks_over_limit": float((peaks > np.float32(0.999)).mean()),
+                   "output_peak": out_peak, "frames": int(states.size)},
+    }
+    if want_cpu and rank == 0:
+        rec["cpu_baseline"] = cpu_baseline_longfile(args.lf_cpu_seconds)
     sess.close()
+    del own, sess
+    torch.cuda.empty_cache()
+    return rec
+
+
+def run_longfile_arm(args):
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    os.environ.setdefault("MASTER_PORT", "29531")
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device(f"cuda:{local}"))
+    rec = longfile_measure(args, dist, rank, world, local, args.steps, world == 1 and not args.no_cpu)
+    if rank == 0:
+        print(json.dumps(rec), flush=True)
     dist.barrier()
     dist.destroy_process_group()
 
@@ -532,6 +588,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-e2e-pcm", dest="no_e2e_pcm", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-longfile", dest="no_longfile", action="store_true", help="skip the long-file sub-record of the default line")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3                       # timing rule: at least 3 warm-up steps

@@ -94,6 +94,13 @@ __device__ __forceinline__ float4 ld_stream4(const float4* p) {
                  : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
     return r;
 }
+// read-only table load that stays where it is written (volatile: the compiler would hoist a plain __ldg to the top of the stage and
+// hold its 4 registers across all of it)
+__device__ __forceinline__ float4 ld_table4(const float4* p) {
+    float4 r;
+    asm volatile("ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+    return r;
+}
 __device__ __forceinline__ void st_stream(float2* p, float2 v) {
     asm volatile("st.global.L1::no_allocate.v2.f32 [%0], {%1,%2};" ::"l"(p), "f"(v.x), "f"(v.y) : "memory");
 }
@@ -548,10 +555,11 @@ struct StftParams {
 constexpr int kTmemWarpCols = 128;
 constexpr int kTcSwin = 0, kTcCarry = 16, kTcHalf = 32, kTcTwA = 64, kTcXchg = 96;
 constexpr int kTmemCols = 256;                       // per CTA: 2 warps per lane quarter x 128 columns (2 CTAs = all 512)
-// shared memory: E1 exchange buffer | analysis window, thread-private float4 quads [4][256] | tail (TMEM slot, reduction, queue)
-constexpr int kStftSmemE1 = kE1Float2 * (int)sizeof(float2);
+// shared memory: two E1 exchange buffers | analysis window, thread-private float4 quads [4][256] | tail (TMEM slot, reduction,
+// two mbarriers, queue)
+constexpr int kStftSmemE1 = 2 * kE1Float2 * (int)sizeof(float2);     // two frames in flight (frame pipeline of stft_kernel)
 constexpr int kStftSmemWin = kNfft * (int)sizeof(float);
-constexpr int kStftSmem = kStftSmemE1 + kStftSmemWin + 64;
+constexpr int kStftSmem = kStftSmemE1 + kStftSmemWin + 96;
 
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
@@ -647,21 +655,29 @@ struct Park {
 #pragma unroll
         for (int k = 0; k < 8; ++k) v[k + 8] = cmul(v[k + 8], make_float2(b[2 * k], b[2 * k + 1]));
     }
-    // inverse stage-A twiddles plus the operands of the frame's tail (synthesis window, carry) in one batch of tensor-memory
-    // loads: a single wait, and the tail's loads complete under the last butterflies
-    __device__ __forceinline__ void inv_fetch_issue(float (&a)[16], float (&b)[16], float (&s)[16], float (&cr)[16]) const {
-        tmem_ld16(base + kTcTwA, a);           // issued before the CTA barrier that precedes stage A': the loads fly while the
-        tmem_ld16(base + kTcTwA + 16, b);      // warp waits for the slower warps
+    // inverse stage-A twiddles are issued before the hand-off wait that precedes stage A' (the loads fly while the warp waits);
+    // the operands of the frame's tail (synthesis window, carry) are issued after A's first butterfly layer, when the twiddle
+    // registers are free again, and complete under the second layer
+    __device__ __forceinline__ void inv_fetch_issue(float (&a)[16], float (&b)[16]) const {
+        tmem_ld16(base + kTcTwA, a);
+        tmem_ld16(base + kTcTwA + 16, b);
+    }
+    __device__ __forceinline__ void inv_fetch_apply(float2 (&v)[16], const float (&a)[16], const float (&b)[16], float (&s)[16], float2 (&c)[8]) const {
+        tmem_wait_ld();
+        {
+            float2 p[16];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) { p[k] = make_float2(a[2 * k], a[2 * k + 1]); p[k + 8] = make_float2(b[2 * k], b[2 * k + 1]); }
+            radix4_tw<true, true, false>(v[0], v[4], v[8], v[12], p[0], p[4], p[8], p[12]);      // stage A', first layer with its twiddles fused in
+            radix4_tw<true, true, true>(v[1], v[5], v[9], v[13], p[1], p[5], p[9], p[13]);
+            radix4_tw<true, true, true>(v[2], v[6], v[10], v[14], p[2], p[6], p[10], p[14]);
+            radix4_tw<true, true, true>(v[3], v[7], v[11], v[15], p[3], p[7], p[11], p[15]);
+        }
+        float cr[16];
         tmem_ld16(base + kTcSwin, s);
         tmem_ld16(base + kTcCarry, cr);
-    }
-    __device__ __forceinline__ void inv_fetch_apply(float2 (&v)[16], const float (&a)[16], const float (&b)[16],
-                                                    const float (&cr)[16], float2 (&c)[8]) const {
+        dft16_layer2<true>(v);
         tmem_wait_ld();
-        float2 p[16];
-#pragma unroll
-        for (int k = 0; k < 8; ++k) { p[k] = make_float2(a[2 * k], a[2 * k + 1]); p[k + 8] = make_float2(b[2 * k], b[2 * k + 1]); }
-        dft16_inv_tw(v, p);                                                       // stage A' with its twiddles fused in
 #pragma unroll
         for (int j = 0; j < 8; ++j) c[j] = make_float2(cr[2 * j], cr[2 * j + 1]);
     }
@@ -782,9 +798,17 @@ __device__ __forceinline__ void unit_epilogue(const StftParams& prm, int chunk, 
     }
 }
 
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile("{\n\t.reg .pred p;\n\tTMT_MBAR_WAIT:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@!p bra TMT_MBAR_WAIT;\n\t}"
+                 ::"r"(bar), "r"(parity) : "memory");
+}
+
 __global__ void __launch_bounds__(kThreads, 2) stft_kernel(const StftParams prm) {
     extern __shared__ __align__(16) unsigned char smraw[];
-    float2* bufP = reinterpret_cast<float2*>(smraw);         // E1 exchange (padded rows, 33 KB)
+    float2* bufP = reinterpret_cast<float2*>(smraw);         // E1 exchange (padded rows, 2 x 33 KB: frames i and i+1)
     unsigned char* tail = smraw + kStftSmemE1 + kStftSmemWin;
     float* red = reinterpret_cast<float*>(tail + 16);
     const int t = threadIdx.x;
@@ -797,6 +821,15 @@ __global__ void __launch_bounds__(kThreads, 2) stft_kernel(const StftParams prm)
     // Work units are claimed from a global counter: unit lengths are deliberately uneven (see tmt_plan_create), so the
     // CTAs drift out of lock step and the chunk rescales of the fused limiter do not hit HBM all at once.
     int* next_unit = reinterpret_cast<int*>(tail + 56);
+    // split-phase hand-offs of the frame pipeline: bar_y = "stage A stored" (R -> Q), bar_x = "stage B' stored" (Q -> P)
+    const uint32_t bar_y = (uint32_t)__cvta_generic_to_shared(tail + 64), bar_x = (uint32_t)__cvta_generic_to_shared(tail + 72);
+    if (t == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar_y), "n"(kThreads) : "memory");
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar_x), "n"(kThreads) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    uint32_t px = 0, py = 0;                                 // phase parities (uniform)
     for (;;) {
         if (t == 0) *next_unit = atomicAdd(prm.unit_counter, 1);
         __syncthreads();
@@ -848,44 +881,63 @@ __global__ void __launch_bounds__(kThreads, 2) stft_kernel(const StftParams prm)
         // gain-row index of the next frame, fetched one frame ahead (it heads a dependent chain: index -> row address -> gains)
         auto row_of = [&](int f) { return (f >= 0 && f < n_frames) ? (int)__ldg(rows + f) : 0; };
         int row_next = row_of(un.b0 - 1);
+        auto have_frame = [&](int i) { const int f = un.b0 - 1 + i; return (f >= 0) && (f < n_frames); };
+
+        // Frame pipeline.  Per frame: R = window + stage A -> E1 buffer (A layout); Q = stages B, C, gain, C', B' on the same buffer
+        // (B layout, in place); P = stage A' + overlap-add + output.  The loop runs Q(i), R(i+1), P(i) with frames i and i+1 in
+        // the two E1 buffers: the stores of Q(i) are separated from their readers in P(i) by the whole of R(i+1), and the stores of
+        // R(i+1) from their readers in Q(i+1) by the whole of P(i).  Both hand-offs are split-phase mbarriers (arrive after the
+        // stores, wait before the loads), so a warp that is ahead does not stop, and the warps of a CTA drift out of lock step
+        // instead of hitting the FP32 pipe and the exchanges all at the same time.  Hazards: R(i+2) overwrites exactly the words
+        // this thread read in P(i); Q rewrites the words it read; everything else is ordered by the two barriers.
+        auto stage_r = [&](int i) {                 // window + A of frame i -> buf[i & 1]
+            float2 v[16];
+            float fa[16], fb[16];                   // forward stage-A twiddles
+            park.sync_stores();
+            park.stage_get_windowed(i & 1, v, fa, fb);
+            dft16<false>(v);                                                      // A
+            park.twiddle_a_fwd(v, fa, fb);
+            st_e1a(v, t, bufP + (i & 1) * kE1Float2);
+            mbar_arrive(bar_y);
+        };
+        if (have_frame(0)) stage_r(0);
 
         for (int i = 0; i <= last; ++i) {
             const int f = un.b0 - 1 + i;
-            float2 v[16];
-            const bool have = (f >= 0) && (f < n_frames);
+            const bool have = have_frame(i);
             const int rel = i * kHop;                          // frame start relative to the unit
-            park.sync_stores();
-            // every input sample is read from global memory exactly once, one frame ahead of its first use, and waits in
-            // tensor memory; the loads below belong to frame i+1 and complete under this frame's butterflies
+            float2* buf = bufP + (i & 1) * kE1Float2;
+            // every input sample is read from global memory exactly once, ahead of its first use, and waits in tensor memory;
+            // the loads below belong to frame i+1 (its second half) and complete under this frame's butterflies
             float2 pf[8];
-            float s[16];                                           // synthesis window x normalisation (x output gain)
-            float2 c[8];                                           // carried half frame
             const bool do_pf = (i < last);
             const int row = row_next;
             row_next = row_of(f + 1);
-            if (have) {
-                {
-                    float fa[16], fb[16];                          // forward stage-A twiddles
-                    park.stage_get_windowed(i & 1, v, fa, fb);
-                    if (do_pf) load_half(i + 2, pf);
-                    dft16<false>(v);                                                  // A
-                    park.twiddle_a_fwd(v, fa, fb);
+            if (do_pf) load_half(i + 2, pf);
+            if (i + 1 < last && (t & 15) == 0) {               // half i+3 -> L2 (one 128-byte line per 16 lanes), so that next frame's loads are short
+                const int p0 = (i + 3) * kHop;
+                if (p0 >= in_lo && p0 + kHop <= in_hi) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) prefetch_l2(in_u + p0 + 256 * j);
                 }
-                st_e1a(v, t, bufP);
-                __syncthreads();
-                ld_e1b(v, t, bufP);
+            }
+            if (have) {                                                           // ---- Q(i)
+                float2 v[16];
+                mbar_wait(bar_y, py);
+                py ^= 1;
+                ld_e1b(v, t, buf);
                 dft16<false>(v);                                                  // B
                 tw_pow<false>(v, wb);
                 // E2: the 16 x 16 transposes between stages B and C run through tensor memory, one round trip on either side
                 // of C's first radix-4 layer (fft4096.cuh); no shared-memory traffic, no barrier
                 float r[32], q[32];
-                if (do_pf) park.stage_put(i & 1, pf);          // slot of the half this frame no longer needs
+                if (do_pf) park.stage_put(i & 1, pf);          // slot of the half frame i no longer needs (its stage A is long done)
                 x_fwd1_pack(v, r);
                 park.trip_fwd(r);
                 // tilt gain x crossfade weight: one real row per frame, register order; issued before the second round trip
-                // (the few rows in use stay in L1), in the registers the staged input half has just left
+                // (the few rows in use stay in L1)
                 const float4* g4 = reinterpret_cast<const float4*>(prm.gperm + (size_t)row * kNfft + t * 16);
-                const float4 g0 = __ldg(g4), g1 = __ldg(g4 + 1), g2 = __ldg(g4 + 2), g3 = __ldg(g4 + 3);
+                const float4 g0 = ld_table4(g4), g1 = ld_table4(g4 + 1), g2 = ld_table4(g4 + 2), g3 = ld_table4(g4 + 3);
                 x_layer_a<false>(r, q);                                           // C, first layer
                 park.trip_fwd(q);
                 x_fwd2_finish(q, v);                                              // C, second layer
@@ -903,16 +955,27 @@ __global__ void __launch_bounds__(kThreads, 2) stft_kernel(const StftParams prm)
                     tw_table(pw, wb);
                     dft16_inv_tw(v, pw);                                          // B' (twiddles fused into the first butterflies)
                 }
-                st_e1b(v, t, bufP);            // the very words this thread read in ld_e1b: no hazard with slower warps still in B
-                float ta[16], tb2[16], cr[16];
-                park.inv_fetch_issue(ta, tb2, s, cr);
-                __syncthreads();
-                ld_e1a(v, t, bufP);            // next frame's st_e1a overwrites exactly the words this thread reads here
-                park.inv_fetch_apply(v, ta, tb2, cr, c);                        // A' (twiddles fused into the first butterflies)
+                st_e1b(v, t, buf);             // the very words this thread read in ld_e1b
+                mbar_arrive(bar_x);
+            }
+            if (do_pf) {
+                if (!have) park.stage_put(i & 1, pf);
+                if (have_frame(i + 1)) stage_r(i + 1);                           // ---- R(i+1)
+            }
+            float2 v[16];                                                         // ---- P(i)
+            float s[16];                                           // synthesis window x normalisation (x output gain)
+            float2 c[8];                                           // carried half frame
+            park.sync_stores();
+            if (have) {
+                float ta[16], tb2[16];
+                park.inv_fetch_issue(ta, tb2);
+                mbar_wait(bar_x, px);
+                px ^= 1;
+                ld_e1a(v, t, buf);             // stage A of frame i+2 overwrites exactly the words this thread reads here
+                park.inv_fetch_apply(v, ta, tb2, s, c);                         // A' (twiddles fused into the first butterflies)
             } else {
 #pragma unroll
                 for (int j = 0; j < 16; ++j) v[j] = make_float2(0.f, 0.f);
-                if (do_pf) { load_half(i + 2, pf); park.stage_put(i & 1, pf); }
                 park.load_tail(s, c);
             }
 
