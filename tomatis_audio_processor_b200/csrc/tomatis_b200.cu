@@ -840,8 +840,8 @@ __global__ void __launch_bounds__(kThreads, 2) stft_kernel(const StftParams prm)
         const TrackDev* trp = prm.tracks + un.track;
         const int n_frames = trp->n_frames;
         const long long upos = trp->first_start + (long long)(un.b0 - 1) * kHop;     // position of frame b0-1
-        const float2* in_u = trp->in + (upos - trp->in_origin) + t;                 // thread's sample 0 of frame b0-1
-        float2* out_u = trp->out + (upos - trp->out_origin) + t;
+        const float2* in_u = trp->in + (upos - trp->in_origin);                     // sample 0 of frame b0-1 (uniform; the thread adds t)
+        float2* out_u = trp->out + (upos - trp->out_origin);
         const long long span = (long long)(un.b1 - un.b0 + 2) * kHop + kNfft;
         const int in_lo = (int)max(-span, min(span, trp->in_lo - upos)), in_hi = (int)max(-span, min(span, trp->in_hi - upos));
         const int out_lo = (int)max(-span, min(span, trp->out_lo - upos)), out_hi = (int)max(-span, min(span, trp->out_hi - upos));
@@ -859,7 +859,7 @@ __global__ void __launch_bounds__(kThreads, 2) stft_kernel(const StftParams prm)
         // raw half frame h of the unit = positions [h*hop, (h+1)*hop) relative to the unit, zero outside the file
         auto load_half = [&](int h, float2 (&x)[8]) {
             const int p0 = h * kHop;
-            const float2* src = in_u + p0;
+            const float2* src = in_u + p0 + t;
             if (p0 >= in_lo && p0 + kHop <= in_hi) {
 #pragma unroll
                 for (int j = 0; j < 8; ++j) x[j] = ld_stream(src + 256 * j);
@@ -918,7 +918,7 @@ __global__ void __launch_bounds__(kThreads, 2) stft_kernel(const StftParams prm)
                 const int p0 = (i + 3) * kHop;
                 if (p0 >= in_lo && p0 + kHop <= in_hi) {
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) prefetch_l2(in_u + p0 + 256 * j);
+                    for (int j = 0; j < 8; ++j) prefetch_l2(in_u + p0 + t + 256 * j);
                 }
             }
             if (have) {                                                           // ---- Q(i)
@@ -982,7 +982,7 @@ __global__ void __launch_bounds__(kThreads, 2) stft_kernel(const StftParams prm)
             // synthesis window, overlap-add with the carried half, interior normalisation (folded into swin)
             const bool edge_blk = (f == 0 && edge_lo) || (f == n_frames && edge_hi);   // single-frame blocks: edge_kernel
             if (f >= un.b0 && !edge_blk) {       // emit output block f
-                float2* dst = out_u + rel;
+                float2* dst = out_u + rel + t;
                 if ((rel >= out_lo) && (rel + kHop <= out_hi)) {          // whole block inside the output window
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
