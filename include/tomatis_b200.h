@@ -57,6 +57,10 @@ extern "C" {
 #define TMT_ARR_INPUT_PEAK 7   /* float  [tracks]  max |x|                                        */
 #define TMT_ARR_HOPSUM_F32 8   /* float  [frames + tracks] pairwise sum of each hop block         */
 #define TMT_ARR_HOPSUM_F64 9   /* double [frames + tracks]                                        */
+#define TMT_ARR_BISECT_T 10        /* double [tracks]       threshold found by tmt_plan_bisect                     */
+#define TMT_ARR_BISECT_ITERS 11    /* int32  [tracks]       search steps taken                                     */
+#define TMT_ARR_BISECT_TRACE_T 12  /* double [tracks * 32]  T_mid of each step                                     */
+#define TMT_ARR_BISECT_TRACE_C2 13 /* int32  [tracks * 32]  C2 frame count of each step                            */
 
 typedef struct tmt_engine tmt_engine; /* per device: window, twiddles, gain rows */
 typedef struct tmt_plan tmt_plan;     /* per batch of tracks (or file shard): geometry + scratch */
@@ -121,6 +125,10 @@ int tmt_plan_chunk_ranges(const tmt_plan* p, int64_t* ranges);
 /* Copy `count` elements starting at `offset` of a plan array to/from `ptr` (host if is_device==0,
  * else device); synchronises `stream` for host copies. */
 int tmt_plan_read(tmt_plan* p, int which, int64_t offset, int64_t count, void* ptr, int is_device, void* stream);
+/* Several whole arrays in one call: n array ids, n host destinations (each large enough for its array); device-to-host copies are
+ * queued behind the plan's work on `stream` and the call waits once.  A single-file call of the streaming modes needs four
+ * arrays back (mean squares, states, rows, chunk peaks): one wait instead of four. */
+int tmt_plan_read_many(tmt_plan* p, int n, const int32_t* which, void* const* dst, void* stream);
 int tmt_plan_write(tmt_plan* p, int which, int64_t offset, int64_t count, const void* ptr, int is_device,
                    void* stream);
 
@@ -147,7 +155,7 @@ int tmt_plan_levels(tmt_plan* p, int flags, const float* in_scale, void* stream)
 /* K2b.  Gate automaton + crossfade counter as a block-level scan over frames.
  * gate_input: TMT_ARR_MEANSQ_F32, TMT_ARR_MEANSQ_F64 or TMT_ARR_GATE_F64.  Frame is "hi" when
  * value >= on[track], "lo" when value <= off[track] (host arrays of n_tracks doubles; thresholds in the
- * domain of the gate input).  param = consecutive hi frames needed to switch up (UPDELAY:
+ * domain of the gate input; both NULL: keep the thresholds already on the device).  param = consecutive hi frames needed to switch up (UPDELAY:
  * ceil(up_delay_samples/hop)+1) or min_hold_frames (MINHOLD).  xfade_frames = 0 -> hard switching.
  * alpha_init_to_target != 0: the counter starts at the first frame's target (adaptive,
  * src/process_tomatis_adaptive.py:257) instead of 0 (xfade, _xfade.py:171).
@@ -155,6 +163,16 @@ int tmt_plan_levels(tmt_plan* p, int flags, const float* in_scale, void* stream)
  * src/process_tomatis_adaptive.py:136-152). */
 int tmt_plan_gate(tmt_plan* p, int automaton, int gate_input, const double* on, const double* off, int param,
                   int xfade_frames, int alpha_init_to_target, int count_only, void* stream);
+
+/* find_optimal_threshold (src/process_tomatis_adaptive.py:124-154) in one launch: per track, up to max_iter (<= 32; the reference
+ * uses 30) bisection steps between t_low and t_high (host arrays of n_tracks doubles: the 5th / 95th percentile of the valid levels),
+ * each step a count-only TMT_GATE_MINHOLD scan of TMT_ARR_GATE_F64 with thresholds T_mid +- hyst_db / 2; `start` is the reference's
+ * initial best_T (the median), `active[t] == 0` skips the search for a track (no valid level) and keeps start[t].  All scalar
+ * arithmetic is float64 in the reference's order.  The thresholds best_T +- hyst_db / 2 are left in the plan's device-side on / off
+ * arrays: follow with tmt_plan_gate(..., on = NULL, off = NULL, ...) for the final states.  Results: TMT_ARR_BISECT_*.
+ * Tracks of more than 16384 frames: TMT_ERR_UNSUPPORTED (drive tmt_plan_gate(count_only) from the host instead). */
+int tmt_plan_bisect(tmt_plan* p, const double* t_low, const double* t_high, const double* start, const int32_t* active,
+                    double hyst_db, double target_c2, int hold_frames, int max_iter, void* stream);
 
 /* K1+K3+K4 fused: frame gather + Hann window + 4096-pt FFT (stereo packed as L+iR) + gain row +
  * inverse FFT + synthesis window + overlap-add (each output sample written exactly once, no atomics)

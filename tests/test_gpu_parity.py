@@ -311,3 +311,24 @@ def test_many_short_tracks_one_plan_and_no_leak():
     torch.cuda.empty_cache()
     free1 = torch.cuda.mem_get_info()[0]
     assert free0 - free1 < 64 * 1024 * 1024, (free0, free1)
+
+
+@pytest.mark.parametrize("generic", [False, True])
+def test_adaptive_threshold_search_in_kernel(generic, monkeypatch):
+    """find_optimal_threshold as one launch (tmt_plan_bisect): register-resident fast path (<= 16 states) and the generic
+    shared-memory path, over hysteresis 0 (a level can be hi and lo at once), hold 0, long holds, off-centre targets, ragged
+    batches -- optimal_T, the whole (T_mid, ratio) trace and the states must equal the oracle's."""
+    from tomatis_audio_processor_b200 import synth
+    if generic:
+        monkeypatch.setenv("TMT_BISECT_GENERIC", "1")
+    orc, eng = _oracle(), _engine()
+    xs = [synth.recipe_swept_pink(s, 48000, 70 + i, period_s=0.7 + 0.3 * i, peak=0.5) for i, s in enumerate([6.0, 2.5, 9.0])]
+    for hyst_db, hold_ms, target, xfade_ms in ((3.0, 250.0, 0.5, 500.0), (0.0, 0.0, 0.5, 0.0), (1.0, 100.0, 0.2, 120.0),
+                                                 (6.0, 40.0, 0.8, 60.0), (3.0, 330.0, 0.65, 200.0)):
+        kw = dict(hyst_db=hyst_db, min_hold_ms=hold_ms, target_c2=target, xfade_ms=xfade_ms)
+        rs = eng.run("adaptive", xs, 48000, **kw)
+        for x, r in zip(xs, rs):
+            o = orc.run("adaptive", x, 48000, **kw)
+            assert r["optimal_T"] == o["optimal_T"], (kw, r["optimal_T"], o["optimal_T"])
+            assert r["trace"] == o["trace"], kw
+            assert np.array_equal(r["states"], o["states"]), kw

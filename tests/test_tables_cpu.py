@@ -96,3 +96,21 @@ def test_random_geometry_and_resampler_tables():
         while j * hop < d:
             j += 1
         assert tb.updelay_run_frames(sr, ms, hop) == j + 1
+
+
+def test_fast_percentiles_equal_numpy_bit_for_bit():
+    """engine._percentile_thresholds (one sort, NumPy's lerp restated) against np.percentile / np.median on level-like data of
+    many sizes, float32-valued and float64-valued, with ties."""
+    from tomatis_audio_processor_b200.engine import _percentile_thresholds
+    rng = np.random.default_rng(11)
+    for n in list(range(1, 40)) + [100, 101, 1291, 14062, 14063]:
+        for kind in range(3):
+            v = rng.standard_normal(n) * 12.0 - 40.0
+            if kind == 1:
+                v = v.astype(np.float32).astype(np.float64)          # float32-valued levels (the float32 branch)
+            elif kind == 2:
+                v = np.round(v)                                       # many ties
+            got = _percentile_thresholds(v, np.ones(n, bool))
+            want = (np.percentile(v, 5), np.percentile(v, 95), np.median(v))
+            assert all(float(a) == float(b) for a, b in zip(got, want)), (n, kind, got, want)
+    assert _percentile_thresholds(np.zeros(3), np.zeros(3, bool)) is None

@@ -11,12 +11,15 @@ import os
 from .build import LIB_PATH
 
 OK = 0
+ERR_UNSUPPORTED = -3
 FRAMING_STREAMING, FRAMING_WHOLEFILE, FRAMING_EQ_PAD, FRAMING_EQ_NOPAD = 0, 1, 2, 3
 GATE_UPDELAY, GATE_MINHOLD = 0, 1
 PCM_S16, PCM_S24 = 0, 1
 LEVELS_F64, LEVELS_MONO, LEVELS_HOPSUM_ONLY, LEVELS_MEANSQ_ONLY, LEVELS_LEFT, LEVELS_RIGHT, LEVELS_POWER_EPS = 1, 2, 8, 16, 32, 64, 128
 (ARR_MEANSQ_F32, ARR_MEANSQ_F64, ARR_GATE_F64, ARR_STATE, ARR_ROW, ARR_C2_COUNT, ARR_CHUNK_PEAK,
- ARR_INPUT_PEAK, ARR_HOPSUM_F32, ARR_HOPSUM_F64) = range(10)
+ ARR_INPUT_PEAK, ARR_HOPSUM_F32, ARR_HOPSUM_F64, ARR_BISECT_T, ARR_BISECT_ITERS, ARR_BISECT_TRACE_T,
+ ARR_BISECT_TRACE_C2) = range(14)
+BISECT_MAX_ITER = 32
 
 
 class TrackDesc(C.Structure):
@@ -50,10 +53,12 @@ SIGNATURES = {
     "tmt_plan_track_chunk_base": (C.c_int, [_P, C.c_int]),
     "tmt_plan_chunk_range": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "tmt_plan_read": (C.c_int, [_P, C.c_int, C.c_int64, C.c_int64, _P, C.c_int, _P]),
+    "tmt_plan_read_many": (C.c_int, [_P, C.c_int, _P, _P, _P]),
     "tmt_plan_write": (C.c_int, [_P, C.c_int, C.c_int64, C.c_int64, _P, C.c_int, _P]),
     "tmt_plan_input_peaks": (C.c_int, [_P, _P]),
     "tmt_plan_levels": (C.c_int, [_P, C.c_int, _P, _P]),
     "tmt_plan_gate": (C.c_int, [_P, C.c_int, C.c_int, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
+    "tmt_plan_bisect": (C.c_int, [_P, _P, _P, _P, _P, C.c_double, C.c_double, C.c_int, C.c_int, _P]),
     "tmt_plan_stft": (C.c_int, [_P, C.c_float, C.c_int, _P]),
     "tmt_plan_stft_limited": (C.c_int, [_P, C.c_float, C.c_float, _P]),
     "tmt_plan_clear_peaks": (C.c_int, [_P, _P]),

@@ -41,6 +41,7 @@ class DeviceBatch:
         self.plan.stft_limited(self.sp.post_gain)
 
     def step(self):
+        self.eng.set_gain_rows(self.sp.rows, key=self.sp.rows_key)     # no-op unless another caller replaced the engine's table
         self.levels(); self.gate(); self.edges(); self.stft()
 
     def close(self):
@@ -97,6 +98,7 @@ class HostBatchPipeline:
 
     def process(self, host_in, host_out):
         torch, sp = self.torch, self.sp
+        self.eng.set_gain_rows(sp.rows, key=sp.rows_key)               # no-op unless another caller replaced the engine's table
         T = host_in.shape[0]
         if T % self.W:
             raise ValueError(f"track count {T} must be a multiple of the wave size {self.W}")

@@ -514,6 +514,228 @@ __global__ void gate_kernel(const TrackDev* __restrict__ tracks, const T* __rest
 }
 
 // ------------------------------------------------------------------------------------------------
+// Threshold search of adaptive mode (src/process_tomatis_adaptive.py:124-154) as ONE launch: one CTA per track runs the whole
+// <= 30-step bisection, every step a count-only scan of the min-hold automaton over the track's levels (same map composition as
+// gate_kernel, single segment).  The scalar bookkeeping is the reference's float64 arithmetic, operation for operation:
+// T_mid = (T_low + T_high) / 2, thresholds T_mid +- hyst_db / 2, c2_ratio = count / n (a correctly rounded quotient like Python's
+// int / int), diff = |c2_ratio - target|, best kept on strict improvement, stop below 0.01, halve towards the target.  The percentiles
+// that start it (p5 / p95 / median of the valid levels) stay on the host, computed once.  Results: the final thresholds go straight
+// into the plan's device-side on / off arrays for the final gate launch; best T, step count and the (T_mid, count) trace are read
+// back with the other results -- no host round trip per step.
+constexpr int kBisectMaxIter = 32;
+struct BisectParams {
+    const TrackDev* tracks;
+    const double* levels;     // TMT_ARR_GATE_F64
+    const double* t_low;      // [tracks] p5 of the valid levels
+    const double* t_high;     // [tracks] p95
+    const double* best0;      // [tracks] median (the answer when the search never improves on it, or the track is not searched)
+    const int* active;        // [tracks] 0: no valid level / no frame -> best0 is the answer
+    double half_hyst, target;
+    int hold, S, max_iter;
+    double* von;
+    double* voff;
+    double* best_T;           // [tracks]
+    int* n_iter;              // [tracks]
+    double* trace_T;          // [tracks][kBisectMaxIter]
+    int* trace_c2;            // [tracks][kBisectMaxIter]
+};
+
+// Fast path of the search for automata of at most 16 states (min-hold up to 7 frames: the reference default is 6): a transition
+// map is 16 nibbles in one 64-bit register, a thread's levels stay in registers across the steps, and the scan by map composition
+// runs on warp shuffles (gate_kernel's shared-memory maps cost 25 us per step on a 10-minute track, this costs ~3).
+__device__ __forceinline__ unsigned long long nib_compose(unsigned long long a, unsigned long long b, int S) {   // s -> b[a[s]]
+    unsigned long long r = 0;
+    for (int s = 0; s < S; ++s) {
+        const unsigned x = (unsigned)(a >> (4 * s)) & 15u;
+        r |= ((b >> (4 * x)) & 15ull) << (4 * s);
+    }
+    return r;
+}
+constexpr int kBisectFastFrames = 16;        // frames per thread held in registers (1024 threads x 16 = the single-segment limit)
+
+__global__ void __launch_bounds__(1024) bisect_fast_kernel(const BisectParams prm) {
+    __shared__ unsigned long long wtot[32];
+    __shared__ int red[33];
+    const int i = threadIdx.x, w = i >> 5, lane = i & 31;
+    const int S = prm.S, param = prm.hold;
+    const int track = blockIdx.x;
+    const TrackDev tr = prm.tracks[track];
+    const int F = tr.n_frames;
+    const double* v = prm.levels + tr.frame_base;
+    const int L = (F + 1023) / 1024;                      // <= kBisectFastFrames (checked by the host)
+    const int f0 = min(F, i * L), nf = min(F, f0 + L) - f0;
+    double x[kBisectFastFrames];
+#pragma unroll
+    for (int k = 0; k < kBisectFastFrames; ++k) x[k] = (k < nf) ? v[f0 + k] : 0.0;
+    // the four per-frame transition maps (class = hi | 2 * lo; both at once only when the hysteresis is zero) and the identity
+    unsigned long long mc[4] = {0, 0, 0, 0}, ident = 0;
+    for (int s = 0; s < S; ++s) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) mc[c] |= (unsigned long long)gate_next<TMT_GATE_MINHOLD>(s, (c & 1) != 0, (c & 2) != 0, param) << (4 * s);
+        ident |= (unsigned long long)s << (4 * s);
+    }
+    auto map_of = [&](unsigned c) { return c == 0u ? mc[0] : (c == 1u ? mc[1] : (c == 2u ? mc[2] : mc[3])); };
+    double T_low = prm.t_low[track], T_high = prm.t_high[track], best_T = prm.best0[track], best_diff = 1.0;
+    int iters = 0;
+    if (prm.active[track] && F > 0) {
+        for (int it = 0; it < prm.max_iter; ++it) {
+            const double T_mid = __dmul_rn(__dadd_rn(T_low, T_high), 0.5);
+            const double on = __dadd_rn(T_mid, prm.half_hyst), off = __dsub_rn(T_mid, prm.half_hyst);
+            // this thread's segment map
+            unsigned long long seg = ident;
+            unsigned cls = 0;                               // 2 bits per frame: hi | 2 * lo
+#pragma unroll
+            for (int k = 0; k < kBisectFastFrames; ++k) {
+                if (k < nf) {
+                    const unsigned c = ((x[k] >= on) ? 1u : 0u) | ((x[k] <= off) ? 2u : 0u);
+                    cls |= c << (2 * k);
+                    seg = nib_compose(seg, map_of(c), S);
+                }
+            }
+            // inclusive scan of the maps over the warp, then over the warps
+            unsigned long long inc = seg;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned long long prev = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane >= o) inc = nib_compose(prev, inc, S);
+            }
+            if (lane == 31) wtot[w] = inc;
+            __syncthreads();
+            if (w == 0) {
+                unsigned long long t = wtot[lane];
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const unsigned long long prev = __shfl_up_sync(0xffffffffu, t, o);
+                    if (lane >= o) t = nib_compose(prev, t, S);
+                }
+                wtot[lane] = t;                              // inclusive over warps
+            }
+            __syncthreads();
+            // start state of this thread: frames_since_switch starts at min_hold_frames in C1 (:100-103) = state `param`
+            unsigned long long excl = __shfl_up_sync(0xffffffffu, inc, 1);
+            if (lane == 0) excl = ident;
+            int cur = param;
+            if (w > 0) cur = (int)((wtot[w - 1] >> (4 * cur)) & 15ull);
+            cur = (int)((excl >> (4 * cur)) & 15ull);
+            int c2 = 0;
+#pragma unroll
+            for (int k = 0; k < kBisectFastFrames; ++k) {
+                if (k < nf) {
+                    const unsigned long long m = map_of((cls >> (2 * k)) & 3u);
+                    cur = (int)((m >> (4 * cur)) & 15ull);
+                    c2 += (cur > param) ? 1 : 0;
+                }
+            }
+#pragma unroll
+            for (int o = 16; o; o >>= 1) c2 += __shfl_xor_sync(0xffffffffu, c2, o);
+            if (lane == 0) red[w] = c2;
+            __syncthreads();
+            if (w == 0) {
+                int tsum = red[lane];
+#pragma unroll
+                for (int o = 16; o; o >>= 1) tsum += __shfl_xor_sync(0xffffffffu, tsum, o);
+                if (lane == 0) red[32] = tsum;
+            }
+            __syncthreads();
+            const int total = red[32];
+            const double ratio = __ddiv_rn((double)total, (double)F);
+            if (i == 0) { prm.trace_T[track * kBisectMaxIter + it] = T_mid; prm.trace_c2[track * kBisectMaxIter + it] = total; }
+            const double diff = fabs(__dsub_rn(ratio, prm.target));
+            if (diff < best_diff) { best_diff = diff; best_T = T_mid; }
+            ++iters;
+            if (diff < 0.01) break;
+            if (ratio < prm.target) T_high = T_mid; else T_low = T_mid;
+        }
+    }
+    if (i == 0) {
+        prm.best_T[track] = best_T;
+        prm.n_iter[track] = iters;
+        prm.von[track] = __dadd_rn(best_T, prm.half_hyst);
+        prm.voff[track] = __dsub_rn(best_T, prm.half_hyst);
+    }
+}
+
+__global__ void bisect_kernel(const BisectParams prm) {
+    extern __shared__ __align__(16) unsigned char gsm[];
+    const int NT = blockDim.x, NW = NT >> 5;
+    const int i = threadIdx.x, w = i >> 5, lane = i & 31;
+    const int S = prm.S, param = prm.hold;
+    uint8_t* maps = gsm;                     // [S][NT]
+    uint8_t* wmap = maps + S * NT;           // [S][NW]
+    uint8_t* segstart = wmap + S * NW;       // [NT]
+    uint8_t* wstart = segstart + NT;         // [NW]
+    int* red = reinterpret_cast<int*>(gsm + ((S * NT + S * NW + NT + NW + 15) & ~15));   // [NW + 1]
+    const int track = blockIdx.x;
+    const TrackDev tr = prm.tracks[track];
+    const int F = tr.n_frames;
+    const double* v = prm.levels + tr.frame_base;
+    const int L = (F + NT - 1) / NT;
+    const int f0 = min(F, i * L), f1 = min(F, f0 + L);
+    double T_low = prm.t_low[track], T_high = prm.t_high[track], best_T = prm.best0[track], best_diff = 1.0;
+    int iters = 0;
+    if (prm.active[track] && F > 0) {
+        for (int it = 0; it < prm.max_iter; ++it) {
+            const double T_mid = __dmul_rn(__dadd_rn(T_low, T_high), 0.5);
+            const double on = __dadd_rn(T_mid, prm.half_hyst), off = __dsub_rn(T_mid, prm.half_hyst);
+            // count-only scan (phases 1-3 of gate_kernel, one segment)
+            for (int s = 0; s < S; ++s) maps[s * NT + i] = (uint8_t)s;
+            for (int f = f0; f < f1; ++f) {
+                const double x = v[f];
+                const bool hi = x >= on, lo = x <= off;
+                for (int s = 0; s < S; ++s) maps[s * NT + i] = (uint8_t)gate_next<TMT_GATE_MINHOLD>(maps[s * NT + i], hi, lo, param);
+            }
+            __syncthreads();
+            for (int s = lane; s < S; s += 32) {
+                int cur = s;
+                for (int j = 0; j < 32; ++j) cur = maps[cur * NT + w * 32 + j];
+                wmap[s * NW + w] = (uint8_t)cur;
+            }
+            __syncthreads();
+            if (i == 0) {
+                int cur = param;                                   // frames_since_switch starts at min_hold_frames, state C1 (:100-103)
+                for (int ww = 0; ww < NW; ++ww) { wstart[ww] = (uint8_t)cur; cur = wmap[cur * NW + ww]; }
+            }
+            __syncthreads();
+            if (lane == 0) {
+                int cur = wstart[w];
+                for (int j = 0; j < 32; ++j) { segstart[w * 32 + j] = (uint8_t)cur; cur = maps[cur * NT + w * 32 + j]; }
+            }
+            __syncthreads();
+            int c2 = 0, cur = segstart[i];
+            for (int f = f0; f < f1; ++f) {
+                const double x = v[f];
+                cur = gate_next<TMT_GATE_MINHOLD>(cur, x >= on, x <= off, param);
+                c2 += gate_is_c2<TMT_GATE_MINHOLD>(cur, param) ? 1 : 0;
+            }
+#pragma unroll
+            for (int o = 16; o; o >>= 1) c2 += __shfl_xor_sync(0xffffffffu, c2, o);
+            if (lane == 0) red[w] = c2;
+            __syncthreads();
+            if (i == 0) {
+                int tot = 0;
+                for (int ww = 0; ww < NW; ++ww) tot += red[ww];
+                red[NW] = tot;
+            }
+            __syncthreads();
+            const int total = red[NW];
+            const double ratio = __ddiv_rn((double)total, (double)F);
+            if (i == 0) { prm.trace_T[track * kBisectMaxIter + it] = T_mid; prm.trace_c2[track * kBisectMaxIter + it] = total; }
+            const double diff = fabs(__dsub_rn(ratio, prm.target));
+            if (diff < best_diff) { best_diff = diff; best_T = T_mid; }
+            ++iters;
+            if (diff < 0.01) break;
+            if (ratio < prm.target) T_high = T_mid; else T_low = T_mid;
+        }
+    }
+    if (i == 0) {
+        prm.best_T[track] = best_T;
+        prm.n_iter[track] = iters;
+        prm.von[track] = __dadd_rn(best_T, prm.half_hyst);
+        prm.voff[track] = __dsub_rn(best_T, prm.half_hyst);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // K1+K3+K4 fused STFT kernel.  See fft4096.cuh for the FFT decomposition.
 // Output block b of a track = positions [first_start + b*hop, +hop) = second half of frame b-1 plus
 // first half of frame b.  A CTA owns a run of blocks [b0,b1) (one limiter chunk or a slice of one),
@@ -1038,14 +1260,26 @@ constexpr int kEdgeSmemBytes = kNfft * (int)sizeof(double2);
 
 __device__ __forceinline__ int bitrev12(int x) { return (int)(__brev((unsigned)x) >> 20); }
 
+// exp(-i*pi*k/2048), k < 2048: filled once per device by tw64_init_kernel with the very sincospi values the butterflies used to
+// compute on the fly (bit-identical results; the trigonometry was 3/4 of edge_kernel's 87 us)
+__device__ double2 g_tw64[2048];
+__global__ void tw64_init_kernel() {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < 2048) {
+        double sn, cs;
+        sincospi(-(double)k / 2048.0, &sn, &cs);
+        g_tw64[k] = make_double2(cs, sn);
+    }
+}
+
 __device__ void fft4096_f64(double2* sm, int t) {      // in: bit-reversed order, out: natural order, forward
     for (int s = 1; s <= 12; ++s) {
         const int half = 1 << (s - 1);
         for (int b = t; b < 2048; b += 256) {
             const int pos = b & (half - 1);
             const int i = ((b >> (s - 1)) << s) + pos, j = i + half;
-            double sn, cs;
-            sincospi(-(double)pos / (double)half, &sn, &cs);
+            const double2 w = g_tw64[pos << (12 - s)];
+            const double cs = w.x, sn = w.y;
             const double2 u = sm[i], x = sm[j];
             const double2 v = make_double2(x.x * cs - x.y * sn, x.x * sn + x.y * cs);
             sm[i] = make_double2(u.x + v.x, u.y + v.y);
@@ -1619,6 +1853,9 @@ struct tmt_engine {
     int n_sms = 0;
     DevBuf<float> win;        // [4096]
     DevBuf<float> swin;       // [2][4096]  synthesis window x interior normalisation (eps | clamp)
+    std::mutex stage_mu;                    // pinned staging buffer of tmt_plan_read_many
+    unsigned char* stage = nullptr;
+    size_t stage_size = 0;
     std::mutex arena_mu;                    // plans of one engine may be created / destroyed from several host threads
     unsigned char* spare_arena = nullptr;   // arena of the last destroyed plan, reused by the next plan that fits
     size_t spare_arena_size = 0;
@@ -1648,6 +1885,7 @@ struct tmt_plan {
     int n_tracks = 0, total_frames = 0, total_chunks = 0, n_units = 0;
     int max_hb = 0, max_frames = 0;
     long long max_chunk_len = 0, max_in_len = 0;
+    long long total_blocks = 0;  // output hop blocks of all work units
     std::vector<HostTrack> ht;
     std::vector<TrackDev> tracks_h;
     Arena arena;
@@ -1671,6 +1909,12 @@ struct tmt_plan {
     int seg_cap = 0;            // segments available in the scratch (all tracks together)
     DevBuf<float> chunk_peaks, in_peaks, in_scale;
     DevBuf<double> von, voff;
+    DevBuf<double> bis_in;      // threshold search: [3][tracks] T_low, T_high, start value
+    DevBuf<int> bis_active;     // [tracks]
+    DevBuf<double> bis_T;       // [tracks] result
+    DevBuf<int> bis_iters;      // [tracks]
+    DevBuf<double> bis_trace_T; // [tracks][kBisectMaxIter]
+    DevBuf<int> bis_trace_c2;   // [tracks][kBisectMaxIter]
     int64_t launches = 0;
 };
 
@@ -1717,7 +1961,7 @@ void chunk_blocks(int framing, int n_frames, std::vector<std::pair<int, int>>& o
     if (flushed < n_blocks) out.push_back({flushed, n_blocks});
 }
 
-int build_tracks_dev(tmt_plan* p) {
+void fill_tracks_host(tmt_plan* p) {
     p->tracks_h.resize(p->n_tracks);
     for (int i = 0; i < p->n_tracks; ++i) {
         const HostTrack& h = p->ht[i];
@@ -1739,6 +1983,10 @@ int build_tracks_dev(tmt_plan* p) {
         t.chunk_base = h.chunk_base; t.n_chunks = h.n_chunks;
         t.edge_lo = h.edge_lo; t.edge_hi = h.edge_hi;
     }
+}
+
+int build_tracks_dev(tmt_plan* p) {
+    fill_tracks_host(p);
     if (p->n_tracks)
         CUDA_TRY(cudaMemcpy(p->tracks.p, p->tracks_h.data(), sizeof(TrackDev) * p->n_tracks, cudaMemcpyHostToDevice));
     return TMT_OK;
@@ -1797,6 +2045,10 @@ int arr_info(tmt_plan* p, int which, ArrInfo* a) {
         case TMT_ARR_INPUT_PEAK: *a = {p->in_peaks.p, 4, (size_t)p->n_tracks}; return TMT_OK;
         case TMT_ARR_HOPSUM_F32: *a = {p->hsum.p, 4, (size_t)(p->total_frames + p->n_tracks)}; return TMT_OK;
         case TMT_ARR_HOPSUM_F64: *a = {p->hsum.p, 8, (size_t)(p->total_frames + p->n_tracks)}; return TMT_OK;
+        case TMT_ARR_BISECT_T: *a = {p->bis_T.p, 8, (size_t)p->n_tracks}; return TMT_OK;
+        case TMT_ARR_BISECT_ITERS: *a = {p->bis_iters.p, 4, (size_t)p->n_tracks}; return TMT_OK;
+        case TMT_ARR_BISECT_TRACE_T: *a = {p->bis_trace_T.p, 8, (size_t)p->n_tracks * kBisectMaxIter}; return TMT_OK;
+        case TMT_ARR_BISECT_TRACE_C2: *a = {p->bis_trace_c2.p, 4, (size_t)p->n_tracks * kBisectMaxIter}; return TMT_OK;
     }
     return fail(TMT_ERR_INVALID, "unknown plan array %d", which);
 }
@@ -1843,6 +2095,9 @@ int tmt_engine_create(tmt_engine** out, int device, int n_fft, int hop) {
     }
     cudaMemcpy(e->tw_bases.p, twb.data(), sizeof(float2) * twb.size(), cudaMemcpyHostToDevice);
     cudaMemcpy(e->tw_a.p, twa.data(), sizeof(float2) * twa.size(), cudaMemcpyHostToDevice);
+    tw64_init_kernel<<<8, 256>>>();
+    ce = cudaDeviceSynchronize();           // one-time: later work may run on non-blocking streams that do not order after this launch
+    if (ce != cudaSuccess) { delete e; return fail(TMT_ERR_CUDA, "twiddle table initialisation: %s", cudaGetErrorString(ce)); }
     ce = cudaFuncSetAttribute(stft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kStftSmem);
     if (ce != cudaSuccess) { delete e; return fail(TMT_ERR_CUDA, "cudaFuncSetAttribute(stft_kernel): %s", cudaGetErrorString(ce)); }
     if (const char* sv = getenv("TMT_GATE_NSEG")) e->gate_nseg = atoi(sv);
@@ -1857,6 +2112,7 @@ int tmt_engine_destroy(tmt_engine* e) {
     if (!e) return TMT_OK;
     cudaSetDevice(e->device);
     if (e->spare_arena) cudaFree(e->spare_arena);
+    if (e->stage) cudaFreeHost(e->stage);
     delete e;
     return TMT_OK;
 }
@@ -2014,6 +2270,7 @@ int tmt_plan_create(tmt_engine* e, tmt_plan** out, int framing, int n_tracks, co
     p->total_chunks = (int)chunks.size();
     for (const ChunkDev& c : chunks) p->n_unfusable += (c.fusable || c.s1 <= c.s0) ? 0 : 1;
     p->n_units = (int)units.size();
+    for (const UnitDev& u : units) p->total_blocks += u.b1 - u.b0;
     p->n_edges = (int)edges.size();
     const size_t nf = (size_t)frames, nt = (size_t)n_tracks;
     // one arena for every per-plan device array: first pass sizes it, second pass hands out the slices
@@ -2042,6 +2299,12 @@ int tmt_plan_create(tmt_engine* e, tmt_plan** out, int framing, int n_tracks, co
         TMT_SLICE(p->in_scale, nt + 1);
         TMT_SLICE(p->von, nt + 1);
         TMT_SLICE(p->voff, nt + 1);
+        TMT_SLICE(p->bis_in, 3 * nt + 1);
+        TMT_SLICE(p->bis_active, nt + 1);
+        TMT_SLICE(p->bis_T, nt + 1);
+        TMT_SLICE(p->bis_iters, nt + 1);
+        TMT_SLICE(p->bis_trace_T, nt * kBisectMaxIter + 1);
+        TMT_SLICE(p->bis_trace_c2, nt * kBisectMaxIter + 1);
 #undef TMT_SLICE
         if (pass == 0) {
             const size_t need = a.used + 256;
@@ -2061,15 +2324,26 @@ int tmt_plan_create(tmt_engine* e, tmt_plan** out, int framing, int n_tracks, co
             }
         }
     }
-    cudaMemset(p->rows.p, 0, sizeof(uint16_t) * (nf + 1));
-    cudaMemset(p->state.p, 0, nf + 1);
-    cudaMemset(p->hsum.p, 0, sizeof(double) * (nf + nt + 1));
-    cudaMemset(p->msq.p, 0, sizeof(double) * (nf + 1));
-    if (!units.empty()) cudaMemcpy(p->units.p, units.data(), sizeof(UnitDev) * units.size(), cudaMemcpyHostToDevice);
-    if (!chunks.empty()) cudaMemcpy(p->chunks.p, chunks.data(), sizeof(ChunkDev) * chunks.size(), cudaMemcpyHostToDevice);
-    if (!edges.empty()) cudaMemcpy(p->edges.p, edges.data(), sizeof(EdgeDev) * edges.size(), cudaMemcpyHostToDevice);
-    int rc = build_tracks_dev(p);
-    if (rc != TMT_OK) { delete p; return rc; }
+    // the slices hsum | msq | gate_f64 | state | rows are adjacent in the arena: one clear instead of four
+    {
+        char* z0 = reinterpret_cast<char*>(p->hsum.p);
+        char* z1 = reinterpret_cast<char*>(p->rows.p + nf + 1);
+        cudaMemset(z0, 0, (size_t)(z1 - z0));
+    }
+    // descriptors: tracks | units | chunks | chunk_done | unit_counter | edges are adjacent as well -> one packed upload
+    fill_tracks_host(p);
+    {
+        char* d0 = reinterpret_cast<char*>(p->tracks.p);
+        char* d1 = reinterpret_cast<char*>(p->edges.p + std::max<size_t>(edges.size(), 1));
+        std::vector<char> blob((size_t)(d1 - d0), 0);
+        auto put = [&](const void* dev, const void* src, size_t bytes) { if (bytes) memcpy(blob.data() + (reinterpret_cast<const char*>(dev) - d0), src, bytes); };
+        put(p->tracks.p, p->tracks_h.data(), sizeof(TrackDev) * p->tracks_h.size());
+        put(p->units.p, units.data(), sizeof(UnitDev) * units.size());
+        put(p->chunks.p, chunks.data(), sizeof(ChunkDev) * chunks.size());
+        put(p->edges.p, edges.data(), sizeof(EdgeDev) * edges.size());
+        const cudaError_t ce = cudaMemcpy(d0, blob.data(), blob.size(), cudaMemcpyHostToDevice);
+        if (ce != cudaSuccess) { delete p; return fail(TMT_ERR_CUDA, "descriptor upload: %s", cudaGetErrorString(ce)); }
+    }
     *out = p;
     return TMT_OK;
 }
@@ -2173,6 +2447,39 @@ int tmt_plan_read(tmt_plan* p, int which, int64_t offset, int64_t count, void* p
     return TMT_OK;
 }
 
+int tmt_plan_read_many(tmt_plan* p, int n, const int32_t* which, void* const* dst, void* stream) {
+    if (!p || n < 0 || (n > 0 && (!which || !dst))) return fail(TMT_ERR_INVALID, "bad arguments");
+    if (n == 0) return TMT_OK;
+    tmt_engine* e = p->e;
+    std::vector<ArrInfo> info((size_t)n);
+    std::vector<size_t> off((size_t)n);
+    size_t need = 0;
+    for (int i = 0; i < n; ++i) {
+        int rc = arr_info(p, which[i], &info[i]);
+        if (rc) return rc;
+        if (!dst[i]) return fail(TMT_ERR_INVALID, "dst[%d] is NULL", i);
+        off[i] = need;
+        need += (info[i].elem * info[i].count + 255) & ~size_t(255);
+    }
+    CUDA_TRY(cudaSetDevice(e->device));
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    std::lock_guard<std::mutex> lock(e->stage_mu);      // one pinned staging buffer per engine
+    if (need > e->stage_size) {
+        if (e->stage) cudaFreeHost(e->stage);
+        e->stage = nullptr; e->stage_size = 0;
+        const size_t want = std::max<size_t>(need, size_t(1) << 20);
+        if (cudaMallocHost(reinterpret_cast<void**>(&e->stage), want) != cudaSuccess)
+            return fail(TMT_ERR_NOMEM, "pinned staging buffer of %zu bytes: %s", want, cudaGetErrorString(cudaGetLastError()));
+        e->stage_size = want;
+    }
+    for (int i = 0; i < n; ++i)
+        if (info[i].count) CUDA_TRY(cudaMemcpyAsync(e->stage + off[i], info[i].ptr, info[i].elem * info[i].count, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));                // the only host wait, whatever the number of arrays
+    for (int i = 0; i < n; ++i)
+        if (info[i].count) memcpy(dst[i], e->stage + off[i], info[i].elem * info[i].count);
+    return TMT_OK;
+}
+
 int tmt_plan_write(tmt_plan* p, int which, int64_t offset, int64_t count, const void* ptr, int is_device, void* stream) {
     if (!p || !ptr) return fail(TMT_ERR_INVALID, "bad arguments");
     ArrInfo a;
@@ -2234,7 +2541,7 @@ int tmt_plan_levels(tmt_plan* p, int flags, const float* in_scale, void* stream)
 
 int tmt_plan_gate(tmt_plan* p, int automaton, int gate_input, const double* on, const double* off, int param,
                   int xfade_frames, int alpha_init_to_target, int count_only, void* stream) {
-    if (!p || !on || !off) return fail(TMT_ERR_INVALID, "bad arguments");
+    if (!p || ((on == nullptr) != (off == nullptr))) return fail(TMT_ERR_INVALID, "bad arguments");
     if (param < 0 || xfade_frames < 0 || xfade_frames > 65534) return fail(TMT_ERR_INVALID, "bad gate parameters");
     if (p->n_tracks == 0) return TMT_OK;
     int S;
@@ -2244,8 +2551,10 @@ int tmt_plan_gate(tmt_plan* p, int automaton, int gate_input, const double* on, 
     if (S > kMaxGateStates) return fail(TMT_ERR_UNSUPPORTED, "gate automaton needs %d states (max %d): delay/hold too long for the GPU scan", S, kMaxGateStates);
     CUDA_TRY(cudaSetDevice(p->e->device));
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    CUDA_TRY(cudaMemcpyAsync(p->von.p, on, sizeof(double) * p->n_tracks, cudaMemcpyHostToDevice, st));
-    CUDA_TRY(cudaMemcpyAsync(p->voff.p, off, sizeof(double) * p->n_tracks, cudaMemcpyHostToDevice, st));
+    if (on) {               // NULL / NULL: keep the thresholds already on the device (left there by tmt_plan_bisect)
+        CUDA_TRY(cudaMemcpyAsync(p->von.p, on, sizeof(double) * p->n_tracks, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(p->voff.p, off, sizeof(double) * p->n_tracks, cudaMemcpyHostToDevice, st));
+    }
     const int X = xfade_frames, ai = alpha_init_to_target ? 1 : 0, co = count_only ? 1 : 0;
     if (gate_input == TMT_ARR_MEANSQ_F32) {
         const float* v = reinterpret_cast<const float*>(p->msq.p);
@@ -2256,6 +2565,43 @@ int tmt_plan_gate(tmt_plan* p, int automaton, int gate_input, const double* on, 
     if (!v) return fail(TMT_ERR_INVALID, "gate_input must be MEANSQ_F32, MEANSQ_F64 or GATE_F64");
     return automaton == TMT_GATE_UPDELAY ? launch_gate<double, TMT_GATE_UPDELAY>(p, v, param, S, X, ai, co, st)
                                          : launch_gate<double, TMT_GATE_MINHOLD>(p, v, param, S, X, ai, co, st);
+}
+
+int tmt_plan_bisect(tmt_plan* p, const double* t_low, const double* t_high, const double* start, const int32_t* active, double hyst_db,
+                    double target_c2, int hold_frames, int max_iter, void* stream) {
+    if (!p || !t_low || !t_high || !start || !active) return fail(TMT_ERR_INVALID, "bad arguments");
+    if (hold_frames < 0 || max_iter < 0 || max_iter > kBisectMaxIter) return fail(TMT_ERR_INVALID, "bad search parameters (max_iter <= %d)", kBisectMaxIter);
+    if (p->n_tracks == 0) return TMT_OK;
+    const int S = 2 * (hold_frames + 1);
+    if (S > kMaxGateStates) return fail(TMT_ERR_UNSUPPORTED, "gate automaton needs %d states (max %d): hold too long for the GPU scan", S, kMaxGateStates);
+    if (p->max_frames > 16384 || p->e->gate_nseg > 1)
+        return fail(TMT_ERR_UNSUPPORTED, "in-kernel threshold search covers tracks of up to 16384 frames (single-segment scan)");
+    CUDA_TRY(cudaSetDevice(p->e->device));
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const size_t nt = (size_t)p->n_tracks;
+    CUDA_TRY(cudaMemcpyAsync(p->bis_in.p, t_low, sizeof(double) * nt, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(p->bis_in.p + nt, t_high, sizeof(double) * nt, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(p->bis_in.p + 2 * nt, start, sizeof(double) * nt, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(p->bis_active.p, active, sizeof(int) * nt, cudaMemcpyHostToDevice, st));
+    int NT = 1024;
+    auto need = [&](int n) { return (size_t)((S * n + S * (n / 32) + n + n / 32 + 15) & ~15) + sizeof(int) * (size_t)(n / 32 + 1); };
+    while (NT > 32 && need(NT) > 96 * 1024) NT >>= 1;
+    const size_t smem = need(NT);
+    if (smem > 200 * 1024) return fail(TMT_ERR_UNSUPPORTED, "gate automaton with %d states needs %zu B of shared memory", S, smem);
+    CUDA_TRY(cudaFuncSetAttribute(bisect_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 48 * 1024)));
+    BisectParams prm;
+    prm.tracks = p->tracks.p; prm.levels = p->gate_f64.p;
+    prm.t_low = p->bis_in.p; prm.t_high = p->bis_in.p + nt; prm.best0 = p->bis_in.p + 2 * nt; prm.active = p->bis_active.p;
+    prm.half_hyst = hyst_db / 2; prm.target = target_c2; prm.hold = hold_frames; prm.S = S; prm.max_iter = max_iter;
+    prm.von = p->von.p; prm.voff = p->voff.p; prm.best_T = p->bis_T.p; prm.n_iter = p->bis_iters.p;
+    prm.trace_T = p->bis_trace_T.p; prm.trace_c2 = p->bis_trace_c2.p;
+    if (S <= 16 && p->max_frames <= 1024 * kBisectFastFrames && !getenv("TMT_BISECT_GENERIC"))
+        bisect_fast_kernel<<<p->n_tracks, 1024, 0, st>>>(prm);
+    else
+        bisect_kernel<<<p->n_tracks, NT, smem, st>>>(prm);
+    p->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return TMT_OK;
 }
 
 static int launch_stft(tmt_plan* p, float post_gain, float limit, cudaStream_t st) {
@@ -2317,14 +2663,18 @@ int tmt_plan_stft_limited(tmt_plan* p, float post_gain, float limit, void* strea
     if (!(limit > 0.f)) return fail(TMT_ERR_INVALID, "limit must be positive");
     CUDA_TRY(cudaSetDevice(e->device));
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    // Small jobs (a single short file): the kernel lasts a few frame times, every chunk finishes at its very end, and the in-kernel
+    // rescale -- one CTA per chunk, latency-bound -- would be a serial tail.  The separate limiter pass spreads the same bytes over
+    // all SMs and costs one launch.  Large jobs hide the rescale under the other CTAs' butterflies and keep it fused.
+    const bool fuse = p->total_blocks >= 48LL * e->n_sms;
     if (p->n_units) {
-        int rc = launch_stft(p, post_gain, limit, st);
+        int rc = launch_stft(p, post_gain, fuse ? limit : 0.f, st);
         if (rc) return rc;
     }
-    if (p->n_unfusable == 0 || p->max_chunk_len == 0) return TMT_OK;
+    if ((fuse && p->n_unfusable == 0) || p->max_chunk_len == 0) return TMT_OK;
     const long long per_cta = 256LL * 16;
     int gx = (int)std::min<long long>((p->max_chunk_len + per_cta - 1) / per_cta, 8LL * e->n_sms);
-    limiter_kernel<<<dim3(std::max(gx, 1), p->total_chunks), 256, 0, st>>>(p->tracks.p, p->chunks.p, p->chunk_peaks.p, limit, 1);
+    limiter_kernel<<<dim3(std::max(gx, 1), p->total_chunks), 256, 0, st>>>(p->tracks.p, p->chunks.p, p->chunk_peaks.p, limit, fuse ? 1 : 0);
     p->launches++;
     CUDA_TRY(cudaGetLastError());
     return TMT_OK;

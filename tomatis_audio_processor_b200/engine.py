@@ -71,7 +71,8 @@ class Engine:
 _ARR_DTYPES = {L.ARR_MEANSQ_F32: np.float32, L.ARR_MEANSQ_F64: np.float64, L.ARR_GATE_F64: np.float64,
                L.ARR_STATE: np.uint8, L.ARR_ROW: np.uint16, L.ARR_C2_COUNT: np.int32,
                L.ARR_CHUNK_PEAK: np.float32, L.ARR_INPUT_PEAK: np.float32,
-               L.ARR_HOPSUM_F32: np.float32, L.ARR_HOPSUM_F64: np.float64}
+               L.ARR_HOPSUM_F32: np.float32, L.ARR_HOPSUM_F64: np.float64, L.ARR_BISECT_T: np.float64,
+               L.ARR_BISECT_ITERS: np.int32, L.ARR_BISECT_TRACE_T: np.float64, L.ARR_BISECT_TRACE_C2: np.int32}
 
 
 class Plan:
@@ -105,8 +106,10 @@ class Plan:
 
     # -- arrays
     def _count(self, which):
-        if which in (L.ARR_C2_COUNT, L.ARR_INPUT_PEAK):
+        if which in (L.ARR_C2_COUNT, L.ARR_INPUT_PEAK, L.ARR_BISECT_T, L.ARR_BISECT_ITERS):
             return self.n_tracks
+        if which in (L.ARR_BISECT_TRACE_T, L.ARR_BISECT_TRACE_C2):
+            return self.n_tracks * L.BISECT_MAX_ITER
         if which == L.ARR_CHUNK_PEAK:
             return self.total_chunks
         if which in (L.ARR_HOPSUM_F32, L.ARR_HOPSUM_F64):
@@ -122,6 +125,15 @@ class Plan:
             L.check(self.lib.tmt_plan_read(self.h, which, offset, count, out.ctypes.data_as(C.c_void_p), 0,
                                            _stream_ptr(torch)), "tmt_plan_read")
         return out
+
+    def read_many(self, *which) -> list:
+        """Whole arrays, one host wait for all of them (tmt_plan_read_many)."""
+        torch = _torch()
+        outs = [np.empty(max(1, self._count(w)), dtype=_ARR_DTYPES[w]) for w in which]
+        ids = (C.c_int32 * len(which))(*which)
+        ptrs = (C.c_void_p * len(which))(*(o.ctypes.data for o in outs))
+        L.check(self.lib.tmt_plan_read_many(self.h, len(which), ids, ptrs, _stream_ptr(torch)), "tmt_plan_read_many")
+        return [o[:self._count(w)] for o, w in zip(outs, which)]
 
     def write(self, which: int, data: np.ndarray, offset: int = 0):
         torch = _torch()
@@ -163,11 +175,31 @@ class Plan:
 
     def gate(self, automaton: int, gate_input: int, on, off, param: int, xfade_frames: int,
              alpha_init_to_target: bool = False, count_only: bool = False):
-        on = np.ascontiguousarray(np.broadcast_to(np.asarray(on, dtype=np.float64), (max(1, self.n_tracks),)))
-        off = np.ascontiguousarray(np.broadcast_to(np.asarray(off, dtype=np.float64), (max(1, self.n_tracks),)))
-        L.check(self.lib.tmt_plan_gate(self.h, automaton, gate_input, on.ctypes.data_as(C.c_void_p),
-                                       off.ctypes.data_as(C.c_void_p), int(param), int(xfade_frames),
+        """on / off None: keep the thresholds already on the device (left there by bisect())."""
+        if on is None and off is None:
+            pon = poff = None
+        else:
+            on = np.ascontiguousarray(np.broadcast_to(np.asarray(on, dtype=np.float64), (max(1, self.n_tracks),)))
+            off = np.ascontiguousarray(np.broadcast_to(np.asarray(off, dtype=np.float64), (max(1, self.n_tracks),)))
+            pon, poff = on.ctypes.data_as(C.c_void_p), off.ctypes.data_as(C.c_void_p)
+        L.check(self.lib.tmt_plan_gate(self.h, automaton, gate_input, pon, poff, int(param), int(xfade_frames),
                                        int(alpha_init_to_target), int(count_only), _stream_ptr(_torch())), "tmt_plan_gate")
+
+    def can_bisect(self) -> bool:
+        """The in-kernel threshold search covers tracks the gate scan handles in one segment."""
+        return max(self.track_frames, default=0) <= 16384
+
+    def bisect(self, t_low, t_high, start, active, hyst_db: float, target_c2: float, hold: int, max_iter: int = 30):
+        """find_optimal_threshold for every track in one launch (tmt_plan_bisect); results in ARR_BISECT_*."""
+        n = max(1, self.n_tracks)
+        arrs = [np.ascontiguousarray(np.broadcast_to(np.asarray(a, dtype=np.float64), (n,))) for a in (t_low, t_high, start)]
+        act = np.ascontiguousarray(np.broadcast_to(np.asarray(active, dtype=np.int32), (n,)))
+        rc = self.lib.tmt_plan_bisect(self.h, *(a.ctypes.data_as(C.c_void_p) for a in arrs), act.ctypes.data_as(C.c_void_p),
+                                      float(hyst_db), float(target_c2), int(hold), int(max_iter), _stream_ptr(_torch()))
+        if rc == L.ERR_UNSUPPORTED:          # long tracks / forced multi-segment scan: the caller drives the search from the host
+            return False
+        L.check(rc, "tmt_plan_bisect")
+        return True
 
     def stft(self, post_gain: float = 1.0, skip_edges: bool = True):
         L.check(self.lib.tmt_plan_stft(self.h, float(post_gain), int(skip_edges), _stream_ptr(_torch())), "tmt_plan_stft")
@@ -263,10 +295,30 @@ class StreamingParams:
     m_off: float = field(default=0.0)
 
 
-def streaming_params(mode: str, sr: int, *, gate_ui=50, gate_mode="log_percent", dynamic_range=80.0, gate_scale=1.0,
-                     gate_offset=-100, hysteresis_db=3.0, fc=1000.0, slope=12.0, c1_low=+15.0, c1_high=-15.0,
-                     c2_low=-15.0, c2_high=+15.0, up_delay_ms=250.0, xfade_ms=0.0, n_fft=tb.N_FFT, hop=tb.HOP,
-                     output_gain_db=0.0) -> StreamingParams:
+_params_cache = {}
+
+
+def streaming_params(mode: str, sr: int, **kw) -> StreamingParams:
+    """Host-side preamble of standard / xfade, cached per parameter set: the tilt tables cost more host time than a whole
+    single-track call costs on the GPU (0.2 - 0.4 ms of NumPy against 0.25 ms of kernels for a 60 s file)."""
+    try:
+        key = (mode, sr, tuple(sorted(kw.items())))
+        hit = _params_cache.get(key)
+    except TypeError:                     # unhashable argument (array-valued): no caching
+        key, hit = None, None
+    if hit is None:
+        hit = _streaming_params(mode, sr, **kw)
+        if key is not None:
+            if len(_params_cache) > 64:
+                _params_cache.clear()
+            _params_cache[key] = hit
+    return hit
+
+
+def _streaming_params(mode: str, sr: int, *, gate_ui=50, gate_mode="log_percent", dynamic_range=80.0, gate_scale=1.0,
+                      gate_offset=-100, hysteresis_db=3.0, fc=1000.0, slope=12.0, c1_low=+15.0, c1_high=-15.0,
+                      c2_low=-15.0, c2_high=+15.0, up_delay_ms=250.0, xfade_ms=0.0, n_fft=tb.N_FFT, hop=tb.HOP,
+                      output_gain_db=0.0) -> StreamingParams:
     if mode == "standard" and gate_mode == "log_percent":
         T = tb.gate_threshold_log_percent(gate_ui, dynamic_range)
     else:
@@ -325,10 +377,7 @@ def run_streaming(mode: str, xs: Sequence, sr: int, device: int = 0, want_host: 
     plan = Plan(eng, L.FRAMING_STREAMING, [whole_track_desc(x, y) for x, y in zip(xd, yd)], unit_blocks)
     try:
         plan.run_streaming(sp.m_on, sp.m_off, sp.run_frames, sp.xfade_frames, sp.post_gain)
-        msq = plan.read(L.ARR_MEANSQ_F32)
-        states = plan.read(L.ARR_STATE)
-        rows = plan.read(L.ARR_ROW)
-        peaks = plan.read(L.ARR_CHUNK_PEAK)
+        msq, states, rows, peaks = plan.read_many(L.ARR_MEANSQ_F32, L.ARR_STATE, L.ARR_ROW, L.ARR_CHUNK_PEAK)
         levels_all = tb.levels_from_meansq(msq)                        # one vectorised pass for the whole batch
         launches = plan.launch_count()
         res = []
@@ -350,12 +399,33 @@ def run_streaming(mode: str, xs: Sequence, sr: int, device: int = 0, want_host: 
         plan.close()
 
 
+def _percentile_sorted(s: np.ndarray, q: float):
+    """np.percentile(s, q) (method "linear") of an already sorted float64 array, bit for bit: NumPy's virtual index
+    (n - 1) * (q / 100), its two neighbours and its two-sided lerp (a + (b - a) * g, or b - (b - a) * (1 - g) once g >= 0.5)."""
+    n = len(s)
+    vi = (n - 1) * np.true_divide(q, 100)
+    lo = int(np.floor(vi))
+    if vi >= n - 1:
+        lo = hi = n - 1
+    else:
+        hi = lo + 1
+    g = vi - lo
+    a, b = s[lo], s[hi]
+    d = b - a
+    return b - d * (1 - g) if g >= 0.5 else a + d * g
+
+
 def _percentile_thresholds(levels, valid):
+    """(p5, p95, median) of the valid levels (src/process_tomatis_adaptive.py:131-135).  One sort and three reads instead of
+    np.percentile + np.median (0.6 ms of host time per 10-minute track against 0.5 ms of kernels for the whole file); the
+    values are NumPy's own, bit for bit (tests/test_tables_cpu.py)."""
     vl = levels[valid]
-    if len(vl) == 0:
+    n = len(vl)
+    if n == 0:
         return None
-    p5, p95 = np.percentile(vl, [5, 95])          # same linear interpolation as two separate calls
-    return p5, p95, np.median(vl)
+    s = np.sort(vl)
+    med = s[n // 2] if n % 2 else (s[n // 2 - 1] + s[n // 2]) / 2.0
+    return _percentile_sorted(s, 5), _percentile_sorted(s, 95), med
 
 
 def run_adaptive(xs: Sequence, sr: int, device: int = 0, want_host: bool = True, outs=None, unit_blocks: int = 0,
@@ -376,9 +446,10 @@ def run_adaptive(xs: Sequence, sr: int, device: int = 0, want_host: bool = True,
                                         n_fft=n_fft, hop=hop)
         raise NotImplementedError(f"GPU path implements n_fft={eng.n_fft}, hop={eng.hop}; got {n_fft}/{hop}")
     hold, xf = tb.adaptive_frame_counts(sr, min_hold_ms, xfade_ms, hop)
-    c1_db, c2_db = tb.tilt_curves_db(sr, n_fft, fc, slope, c1_low, c1_high, c2_low, c2_high)
-    eng.set_gain_rows(tb.gain_rows_adaptive(c1_db, c2_db, xf),
-                      key=("adaptive", sr, fc, slope, c1_low, c1_high, c2_low, c2_high, xf, n_fft))
+    rows_key = ("adaptive", sr, fc, slope, c1_low, c1_high, c2_low, c2_high, xf, n_fft)
+    if eng._rows_key != rows_key:                 # the table build is host work worth skipping (see streaming_params)
+        c1_db, c2_db = tb.tilt_curves_db(sr, n_fft, fc, slope, c1_low, c1_high, c2_low, c2_high)
+        eng.set_gain_rows(tb.gain_rows_adaptive(c1_db, c2_db, xf), key=rows_key)
     # single-channel files (accepted by the reference, _adaptive.py:180-181) ride in the L lane with R = 0
     mono_in = [isinstance(x, np.ndarray) and (x.ndim == 1 or x.shape[1] == 1) for x in xs]
     if any(mono_in) and not all(mono_in):
@@ -430,30 +501,36 @@ def run_adaptive(xs: Sequence, sr: int, device: int = 0, want_host: bool = True,
                 else:
                     T_low[t], T_high[t], best_T[t] = pt
             traces = [[] for _ in range(nt)]
-            for _ in range(30):
-                if not active.any():
-                    break
-                T_mid = (T_low + T_high) / 2
-                plan.gate(L.GATE_MINHOLD, L.ARR_GATE_F64, T_mid + hyst_db / 2, T_mid - hyst_db / 2, hold, xf,
-                          alpha_init_to_target=True, count_only=True)
-                c2 = plan.read(L.ARR_C2_COUNT)
-                for t in range(nt):
-                    if not active[t]:
-                        continue
-                    ratio = int(c2[t]) / plan.track_frames[t]
-                    traces[t].append((float(T_mid[t]), ratio))
-                    diff = abs(ratio - target_c2)
-                    if diff < best_diff[t]:
-                        best_diff[t] = diff; best_T[t] = T_mid[t]
-                    if diff < 0.01:
-                        active[t] = False
-                        continue
-                    if ratio < target_c2:
-                        T_high[t] = T_mid[t]
-                    else:
-                        T_low[t] = T_mid[t]
-            plan.gate(L.GATE_MINHOLD, L.ARR_GATE_F64, best_T + hyst_db / 2, best_T - hyst_db / 2, hold, xf,
-                      alpha_init_to_target=True, count_only=False)
+            # the whole search in one launch when the tracks fit the single-segment scan; thresholds stay on the device for the
+            # final gate, results come back at the end
+            in_kernel = plan.can_bisect() and plan.bisect(T_low, T_high, best_T, active, hyst_db, target_c2, hold, 30)
+            if in_kernel:
+                plan.gate(L.GATE_MINHOLD, L.ARR_GATE_F64, None, None, hold, xf, alpha_init_to_target=True, count_only=False)
+            else:
+                for _ in range(30):
+                    if not active.any():
+                        break
+                    T_mid = (T_low + T_high) / 2
+                    plan.gate(L.GATE_MINHOLD, L.ARR_GATE_F64, T_mid + hyst_db / 2, T_mid - hyst_db / 2, hold, xf,
+                              alpha_init_to_target=True, count_only=True)
+                    c2 = plan.read(L.ARR_C2_COUNT)
+                    for t in range(nt):
+                        if not active[t]:
+                            continue
+                        ratio = int(c2[t]) / plan.track_frames[t]
+                        traces[t].append((float(T_mid[t]), ratio))
+                        diff = abs(ratio - target_c2)
+                        if diff < best_diff[t]:
+                            best_diff[t] = diff; best_T[t] = T_mid[t]
+                        if diff < 0.01:
+                            active[t] = False
+                            continue
+                        if ratio < target_c2:
+                            T_high[t] = T_mid[t]
+                        else:
+                            T_low[t] = T_mid[t]
+                plan.gate(L.GATE_MINHOLD, L.ARR_GATE_F64, best_T + hyst_db / 2, best_T - hyst_db / 2, hold, xf,
+                          alpha_init_to_target=True, count_only=False)
             plan.stft(1.0, skip_edges=True)
             if use_f64:
                 plan.edge_frames(1.0, None, None, pipeline_f64=True)
@@ -461,7 +538,13 @@ def run_adaptive(xs: Sequence, sr: int, device: int = 0, want_host: bool = True,
                 restore = np.array([np.float32(tb.db_to_lin_keep(branch[i][0])) for i in idx], dtype=np.float32)
                 plan.edge_frames(1.0, scale, restore, pipeline_f64=False)
             plan.limiter()
-            states = plan.read(L.ARR_STATE); rows = plan.read(L.ARR_ROW); peaks = plan.read(L.ARR_CHUNK_PEAK)
+            if in_kernel:
+                states, rows, peaks, best_T, iters, tr_T, tr_c = plan.read_many(
+                    L.ARR_STATE, L.ARR_ROW, L.ARR_CHUNK_PEAK, L.ARR_BISECT_T, L.ARR_BISECT_ITERS, L.ARR_BISECT_TRACE_T, L.ARR_BISECT_TRACE_C2)
+                tr_T, tr_c = tr_T.reshape(nt, L.BISECT_MAX_ITER), tr_c.reshape(nt, L.BISECT_MAX_ITER)
+                traces = [[(float(tr_T[t, k]), int(tr_c[t, k]) / plan.track_frames[t]) for k in range(int(iters[t]))] for t in range(nt)]
+            else:
+                states, rows, peaks = plan.read_many(L.ARR_STATE, L.ARR_ROW, L.ARR_CHUNK_PEAK)
             for t, i in enumerate(idx):
                 fb, nf = plan.frame_base[t], plan.track_frames[t]
                 results[i] = dict(
