@@ -288,11 +288,26 @@ def run_gpu_arm(args):
     e2e = None
     e2e_pcm = None
     if not args.no_e2e:
-        Te = min(T, args.e2e_tracks)
-        Te -= Te % args.wave_tracks
-        Te = max(Te, args.wave_tracks)
-        h_in = torch.empty((Te, N_SAMPLES, 2), dtype=torch.float32, pin_memory=True)
-        h_out = torch.empty((Te, N_SAMPLES, 2), dtype=torch.float32, pin_memory=True)
+        # same tracks per GPU as `value` on one GPU (27 GB of pinned host memory); with several ranks on one host the pinned
+        # footprint would be N x 27 GB, so the multi-GPU runs keep a 32-track sample per rank and say so
+        want = args.e2e_tracks if args.e2e_tracks > 0 else (T if world == 1 else 32)
+        e2e_note = None
+        while True:
+            Te = min(T, want)
+            Te -= Te % args.wave_tracks
+            Te = max(Te, args.wave_tracks)
+            try:
+                h_in = torch.empty((Te, N_SAMPLES, 2), dtype=torch.float32, pin_memory=True)
+                h_out = torch.empty((Te, N_SAMPLES, 2), dtype=torch.float32, pin_memory=True)
+                break
+            except RuntimeError as exc:         # not enough pinnable host memory on this box: smaller sample, stated in the line
+                if want <= 32:
+                    raise
+                e2e_note = f"pinned host allocation for {Te} tracks failed ({str(exc)[:80]}); 32-track sample"
+                want = 32
+        if Te != T and e2e_note is None:
+            e2e_note = (f"{Te}-track sample per rank ({world} ranks share one host: {T} tracks per rank would pin "
+                        f"{2 * T * N_SAMPLES * 8 * world / 1e9:.0f} GB)") if world > 1 else f"{Te}-track sample (--e2e-tracks)"
         h_in.copy_(x[:Te])
         y = None
         pipe = HostBatchPipeline(N_SAMPLES, SR, "standard", device=local, wave_tracks=args.wave_tracks,
@@ -316,7 +331,7 @@ def run_gpu_arm(args):
                "steps": args.e2e_steps, "ms_per_step": float(ms[0]) / args.e2e_steps,
                "api": "tomatis_audio_processor_b200.batch.HostBatchPipeline.process (pinned host float32 in/out, "
                       f"waves of {args.wave_tracks} tracks, H2D/compute/D2H on 3 streams)",
-               "host_peak_out": float(h_out.abs().max())}
+               "host_peak_out": max(float(h_out[i].abs().max()) for i in sorted({0, Te // 2, Te - 1})), "note": e2e_note}
         pipe.close()
         # same pipeline with integer PCM crossing PCIe (int16 in as decoded from a 16-bit source, PCM_24 out as the
         # reference's output files store it): informational, the headline e2e above moves float32 like the reference arm
@@ -474,16 +489,24 @@ def longfile_measure(args, dist, rank, world, local, steps, want_cpu):
     t0 = time.time()
     e0.record()
     for k in range(steps):
-        sess.step(ev[k])
+        sess.step()                         # CUDA-graph replay of the whole pass (kernels + collectives)
     e1.record()
     barrier()
     t1 = time.time()
     clocks = sampler.stop(t0, t1) if rank == 0 else None
     ms_total = e0.elapsed_time(e1)
+    launches_per_step = None
+    for k in range(steps):                  # the same pass run eagerly: STFT kernel time (roofline) and the launch count
+        lk = plan.launch_count()
+        sess.step(ev[k])
+        launches_per_step = plan.launch_count() - lk
+    torch.cuda.synchronize()
     stft_ms = float(np.mean([a.elapsed_time(b) for a, b in ev]))
-    launches = plan.launch_count() - l0
+    launches = (launches_per_step or 0) * steps
     marks = []
+    bytes0 = comm.bytes_sent
     sess.step(marks=marks)
+    comm_step_bytes = comm.bytes_sent - bytes0
     torch.cuda.synchronize()
     breakdown = {b[0]: round(a[1].elapsed_time(b[1]), 4) for a, b in zip(marks, marks[1:])}
     tmax = torch.tensor([ms_total, stft_ms], device=dev, dtype=torch.float64)
@@ -493,8 +516,6 @@ def longfile_measure(args, dist, rank, world, local, steps, want_cpu):
     states = plan.read(L.ARR_STATE)
     peaks = plan.read(L.ARR_CHUNK_PEAK)
     out_peak = float(sess.out.abs().max()) if sess.out.numel() else 0.0
-    comm_bytes = comm.bytes_sent
-    n_passes = args.warmup + steps + 1
 
     # ---- end to end: the rank's own range from pinned host memory and back, copies inside the timed region
     e2e = None
@@ -524,7 +545,6 @@ def longfile_measure(args, dist, rank, world, local, steps, want_cpu):
                "api": "sharded.StreamingShardSession.step with each rank's own range copied from / to pinned host float32 buffers",
                "host_peak_out": float(h_out.abs().max()) if n_own else 0.0}
         del h_in, h_out
-        n_passes += args.e2e_steps + 1
 
     peak_gbs, peak_src = measured_peak()
     sf_rank = me.own_hi - me.own_lo
@@ -533,12 +553,12 @@ def longfile_measure(args, dist, rank, world, local, steps, want_cpu):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": args.warmup,
         "ms_per_step": ms_total / steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic", "config": longfile_config(world, total), "clocks": clocks, "e2e": e2e,
-        "gpu_launches": int(launches), "comm_bytes_per_step_rank0": int(comm_bytes // max(1, n_passes)),
+        "gpu_launches": int(launches), "comm_bytes_per_step_rank0": int(comm_step_bytes),
         "roofline": {"bound": "hbm", "kernel": "stft_kernel (fused gather+window+FFT+gain+IFFT+window+OLA+peak), rank 0 shard",
                      "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": ALG_BYTES_PER_SF * sf_rank, "kernel_ms": stft_ms,
                      "kernel_share_of_step": stft_ms * steps / ms_total},
-        "phase_ms_rank0": breakdown,
+        "phase_ms_rank0": breakdown, "graph_replay": bool(getattr(sess, "_graph", None) is not None),
         "checks": {"c2_fraction": float((states == 2).mean()), "chunks_over_limit": float((peaks > np.float32(0.999)).mean()),
                    "output_peak": out_peak, "frames": int(states.size)},
     }
@@ -576,7 +596,7 @@ def main():
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--tracks-per-gpu", dest="tracks_per_gpu", type=int, default=128)
     ap.add_argument("--unit-blocks", dest="unit_blocks", type=int, default=0)
-    ap.add_argument("--e2e-tracks", dest="e2e_tracks", type=int, default=32)
+    ap.add_argument("--e2e-tracks", dest="e2e_tracks", type=int, default=0, help="0 = all tracks of the rank on one GPU, 32 per rank otherwise")
     ap.add_argument("--e2e-steps", dest="e2e_steps", type=int, default=3)
     ap.add_argument("--wave-tracks", dest="wave_tracks", type=int, default=2)
     ap.add_argument("--cpu-tracks", dest="cpu_tracks", type=int, default=3)

@@ -111,6 +111,9 @@ int tmt_plan_set_level_ranges(tmt_plan* p, int track, int hb_lo, int hb_hi, int 
 int tmt_plan_total_frames(const tmt_plan* p);  /* sum of n_frames over tracks                  */
 int tmt_plan_total_chunks(const tmt_plan* p);
 int tmt_plan_total_units(const tmt_plan* p);
+/* Limiter chunks the plan does not produce completely (a time shard that owns part of a chunk): their peaks have to be combined
+ * across shards before tmt_plan_limiter; 0 means tmt_plan_stft_limited alone finishes the job. */
+int tmt_plan_unfusable_chunks(const tmt_plan* p);
 int tmt_plan_track_frames(const tmt_plan* p, int track);      /* n_frames of one track          */
 int tmt_plan_track_frame_base(const tmt_plan* p, int track);  /* its offset in per-frame arrays */
 int tmt_plan_track_chunks(const tmt_plan* p, int track);

@@ -23,7 +23,11 @@ def main():
     cases = [("standard", 48000, synth.recipe_gated_pink(11.0, 48000, 30, env_hz=0.9, hi_dbfs=-22.0), dict(gate_ui=50)),
              ("xfade", 48000, synth.recipe_threshold_ramps(4.0, 48000, 3, t_on=-48.5, t_off=-51.5, period_s=1.3), dict(gate_ui=50, xfade_ms=300.0)),
              ("adaptive", 48000, synth.recipe_swept_pink(4.0, 48000, 4, period_s=1.1, peak=0.5), dict())]
+    def say(msg):
+        print(f"[rank {rank}] {msg}", flush=True)
+
     for mode, sr, x, kw in cases:
+        say(f"case {mode}")
         total = len(x)
         framing = sharded.WHOLEFILE if mode == "adaptive" else sharded.STREAMING
         me = sharded.plan_shards(total, world, framing)[rank]
@@ -50,8 +54,11 @@ def main():
     o = orc.run("standard", x, 48000, gate_ui=50)
     sess = sharded.StreamingShardSession("standard", torch.from_numpy(x[me.own_lo:me.own_hi].copy()).cuda(), 48000, total, comm,
                                          device_index=local, gate_ui=50)
-    for _ in range(2):
+    say(f"session created, unfusable chunks {sess.be.plan.unfusable_chunks}, graph {sess.use_graph}")
+    for k in range(3):
         sess.step()
+        torch.cuda.synchronize()
+        say(f"session step {k} done (graph replay: {sess._graph is not None})")
     y = sess.out.cpu().numpy().astype(np.float64)
     d = np.abs(y - o["out"][me.own_lo:me.own_hi]).max(axis=1)
     if rank == world - 1:

@@ -116,7 +116,7 @@ def test_nccl_two_gpus_torchrun():
         pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
            "--master-port", "29517", os.path.join(HERE, "run_sharded_nccl.py")]
-    p = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    p = subprocess.run(cmd, capture_output=True, text=True, timeout=240)
     assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-3000:]
     assert "SHARDED-NCCL-OK" in p.stdout
 

@@ -2268,7 +2268,15 @@ int tmt_plan_create(tmt_engine* e, tmt_plan** out, int framing, int n_tracks, co
     p->total_frames = (int)frames;
     p->seg_cap = kGateSegCap;
     p->total_chunks = (int)chunks.size();
-    for (const ChunkDev& c : chunks) p->n_unfusable += (c.fusable || c.s1 <= c.s0) ? 0 : 1;
+    // chunks this plan writes samples of (work units or an fp64 edge block) without producing them completely: their peaks must be
+    // combined across shards before limiting.  Chunks the plan does not touch at all (other shards' chunks) do not count.
+    {
+        std::vector<char> touched(chunks.size(), 0);
+        for (size_t c = 0; c < chunks.size(); ++c) touched[c] = chunks[c].n_units > 0;
+        for (const EdgeDev& ed : edges) if (ed.chunk >= 0 && (size_t)ed.chunk < chunks.size()) touched[ed.chunk] = 1;
+        for (size_t c = 0; c < chunks.size(); ++c)
+            p->n_unfusable += (chunks[c].fusable || chunks[c].s1 <= chunks[c].s0 || !touched[c]) ? 0 : 1;
+    }
     p->n_units = (int)units.size();
     for (const UnitDev& u : units) p->total_blocks += u.b1 - u.b0;
     p->n_edges = (int)edges.size();
@@ -2401,6 +2409,7 @@ int tmt_plan_set_level_ranges(tmt_plan* p, int track, int hb_lo, int hb_hi, int 
 int tmt_plan_total_frames(const tmt_plan* p) { return p ? p->total_frames : -1; }
 int tmt_plan_total_chunks(const tmt_plan* p) { return p ? p->total_chunks : -1; }
 int tmt_plan_total_units(const tmt_plan* p) { return p ? p->n_units : -1; }
+int tmt_plan_unfusable_chunks(const tmt_plan* p) { return p ? p->n_unfusable : -1; }
 int tmt_plan_track_frames(const tmt_plan* p, int t) { return (p && t >= 0 && t < p->n_tracks) ? p->ht[t].n_frames : -1; }
 int tmt_plan_track_frame_base(const tmt_plan* p, int t) { return (p && t >= 0 && t < p->n_tracks) ? p->ht[t].frame_base : -1; }
 int tmt_plan_track_chunks(const tmt_plan* p, int t) { return (p && t >= 0 && t < p->n_tracks) ? p->ht[t].n_chunks : -1; }

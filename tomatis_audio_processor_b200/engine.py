@@ -89,6 +89,7 @@ class Plan:
         self.total_frames = self.lib.tmt_plan_total_frames(h)
         self.total_chunks = self.lib.tmt_plan_total_chunks(h)
         self.total_units = self.lib.tmt_plan_total_units(h)
+        self.unfusable_chunks = self.lib.tmt_plan_unfusable_chunks(h)
         geo = np.zeros((4, max(1, self.n_tracks)), dtype=np.int32)            # one call instead of four per track
         L.check(self.lib.tmt_plan_geometry(h, *(geo[i].ctypes.data_as(C.c_void_p) for i in range(4))), "tmt_plan_geometry")
         self.track_frames, self.frame_base, self.track_chunks, self.chunk_base = (geo[i, :self.n_tracks].tolist() for i in range(4))

@@ -444,10 +444,13 @@ class StreamingShardSession:
     window and the output shard are created once; `step()` is one pass of the whole path -- halo hand-off, levels,
     level all-reduce, gate scan, STFT/OLA, edge frames, peak all-reduce, limiter -- with no host synchronisation."""
 
-    def __init__(self, mode: str, own, sr: int, total: int, comm: Comm, device_index: int = 0, unit_blocks: int = 0, **params):
+    def __init__(self, mode: str, own, sr: int, total: int, comm: Comm, device_index: int = 0, unit_blocks: int = 0,
+                 use_graph: bool = True, **params):
         from . import _lib as L
         from .engine import streaming_params
         self.L, self.comm, self.own = L, comm, own
+        # graph replay needs a capturable communicator: torch.distributed / NCCL (the in-process stand-ins of the tests are not)
+        self.use_graph, self._graph, self._thresholds_set = (use_graph and isinstance(comm, Comm)), None, False
         self.shards = plan_shards(total, comm.world, STREAMING, params.get("n_fft", tb.N_FFT), params.get("hop", tb.HOP))
         self.me = self.shards[comm.rank]
         assert own.shape[0] == self.me.own_hi - self.me.own_lo
@@ -457,8 +460,7 @@ class StreamingShardSession:
         # from here on the rank's samples live inside the window buffer: refresh them through this view
         self.own = window[self.me.own_lo - self.me.in_lo: self.me.own_hi - self.me.in_lo]
 
-    def step(self, stft_events=None, marks=None):
-        """marks: optional list that receives (label, torch.cuda.Event) after each phase (bench breakdown)."""
+    def _step_eager(self, stft_events=None, marks=None):
         comm, be, me, sp, L = self.comm, self.be, self.me, self.sp, self.L
 
         def mark(label):
@@ -472,12 +474,31 @@ class StreamingShardSession:
         mark("halo_issue")
         hsum = be.own_hop_sums()                                        # ... while the rank sums the hop blocks it owns
         mark("levels")
-        be.set_hop_sums(comm.allreduce(hsum, "sum"))                     # 2. every hop block has one owner: exact gather
+        if comm.world > 1:
+            hsum = comm.allreduce(hsum, "sum")                           # 2. every hop block has one owner: exact gather
+        be.set_hop_sums(hsum)
         mark("allreduce_levels")
-        be.gate(L.GATE_UPDELAY, L.ARR_MEANSQ_F32, sp.m_on, sp.m_off, sp.run_frames, sp.xfade_frames)
+        if not self._thresholds_set:                                     # thresholds go to the device once, not every pass
+            be.gate(L.GATE_UPDELAY, L.ARR_MEANSQ_F32, sp.m_on, sp.m_off, sp.run_frames, sp.xfade_frames)
+            self._thresholds_set = True
+        else:
+            be.gate(L.GATE_UPDELAY, L.ARR_MEANSQ_F32, None, None, sp.run_frames, sp.xfade_frames)
         mark("gate")
         comm.exchange_halos_end(pending, me, be.window)                  # the STFT is the first consumer of the halos
         mark("halo_wait")
+        if be.plan.unfusable_chunks == 0:
+            # every limiter chunk lies inside this rank's range (shards are cut on chunk boundaries): the per-chunk limiter runs
+            # inside the STFT kernel, no peak exchange, no separate pass (src/process_tomatis.py:331-357)
+            be.plan.clear_peaks()
+            be.edge_frames(sp.post_gain)
+            mark("edge")
+            if stft_events:
+                stft_events[0].record()
+            be.plan.stft_limited(sp.post_gain)
+            if stft_events:
+                stft_events[1].record()
+            mark("stft")
+            return
         if stft_events:
             stft_events[0].record()
         be.stft(sp.post_gain)
@@ -492,9 +513,37 @@ class StreamingShardSession:
         be.limiter()
         mark("limiter")
 
+    def step(self, stft_events=None, marks=None):
+        """One pass of the whole path over the rank's shard.  marks: optional list that receives (label, torch.cuda.Event)
+        after each phase (bench breakdown; runs eagerly).  Otherwise the launch sequence -- kernels and collectives -- is
+        captured into a CUDA graph on the first plain call and replayed afterwards: at 8 GPUs a pass lasts about a millisecond
+        and the host-side launch of three small collectives was a quarter of it."""
+        if marks is not None or stft_events is not None or not self.use_graph:
+            return self._step_eager(stft_events, marks)
+        import torch
+        if self._graph is None:
+            self._step_eager()                                           # warm-up outside capture (lazy initialisations)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            try:
+                with torch.cuda.graph(g):
+                    self._step_eager()
+                self._graph = g
+            except Exception as exc:                                     # capture not possible here: stay eager, say so once
+                import warnings
+                warnings.warn(f"StreamingShardSession: CUDA graph capture failed ({exc}); running eagerly")
+                self.use_graph = False
+                torch.cuda.synchronize()
+                return self._step_eager()
+        self._graph.replay()
+
     @property
     def out(self):
         return self.be.out
 
     def close(self):
+        if self._graph is not None:          # a live graph keeps the captured NCCL kernels' communicator busy: destroying the
+            import torch                     # process group with it still alive hangs
+            torch.cuda.synchronize()
+            self._graph = None
         self.be.close()
