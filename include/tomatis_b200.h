@@ -114,6 +114,9 @@ int tmt_plan_total_units(const tmt_plan* p);
 /* Limiter chunks the plan does not produce completely (a time shard that owns part of a chunk): their peaks have to be combined
  * across shards before tmt_plan_limiter; 0 means tmt_plan_stft_limited alone finishes the job. */
 int tmt_plan_unfusable_chunks(const tmt_plan* p);
+/* Dev counters of the fused limiter since the last reset: out2[0] = nanoseconds CTAs spent rescaling finished chunks (summed over
+ * CTAs), out2[1] = number of rescales.  Synchronises the device. */
+int tmt_plan_debug_counters(tmt_plan* p, uint64_t* out2, int reset);
 int tmt_plan_track_frames(const tmt_plan* p, int track);      /* n_frames of one track          */
 int tmt_plan_track_frame_base(const tmt_plan* p, int track);  /* its offset in per-frame arrays */
 int tmt_plan_track_chunks(const tmt_plan* p, int track);

@@ -48,6 +48,7 @@ SIGNATURES = {
     "tmt_plan_total_chunks": (C.c_int, [_P]),
     "tmt_plan_total_units": (C.c_int, [_P]),
     "tmt_plan_unfusable_chunks": (C.c_int, [_P]),
+    "tmt_plan_debug_counters": (C.c_int, [_P, _P, C.c_int]),
     "tmt_plan_track_frames": (C.c_int, [_P, C.c_int]),
     "tmt_plan_track_frame_base": (C.c_int, [_P, C.c_int]),
     "tmt_plan_track_chunks": (C.c_int, [_P, C.c_int]),

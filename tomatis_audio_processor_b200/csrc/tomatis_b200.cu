@@ -771,6 +771,7 @@ struct StftParams {
     int* chunk_done;
     int* unit_counter;      // dynamic work distribution (zeroed before every launch)
     float limit;
+    unsigned long long* dbg; // [2] dev counters: nanoseconds spent in chunk rescales (summed over CTAs), number of rescales
 };
 
 // tensor-memory columns of a warp: synthesis window 16 | carry 16 | raw input halves 2 x 16 | stage-A twiddles 32 | E2 exchange 32
@@ -985,14 +986,22 @@ __device__ __forceinline__ void unit_epilogue(const StftParams& prm, int chunk, 
             if (red[8] != 0.f) {
                 __threadfence();
                 const float pk = __int_as_float(atomicMax(reinterpret_cast<int*>(prm.chunk_peaks + chunk), 0));
+
+
                 if (pk > prm.limit) {
+                    unsigned long long t_begin = 0;
+                    if (t == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_begin));
                     const float sc = __fdiv_rn(prm.limit, pk);
                     const long long s0 = max(ch.s0, trp->out_lo), s1 = min(ch.s1, trp->out_hi);
                     float2* base = trp->out + (s0 - trp->out_origin);
                     const long long n = s1 - s0;
                     long long q = t;
                     if ((reinterpret_cast<uintptr_t>(base) & 15u) == 0) {
-                        // a single CTA is latency-bound: keep 64 KB in flight (16 x 16 B per thread)
+                        // 64 KB in flight per CTA (16 x 16 B per thread).  What this pass costs is its traffic, not the time the
+                        // CTA is held up (profiles/r02/limiter_study.md): 8 / 16 / 24 loads per thread in flight, the chunk
+                        // prefetched into L2 (per line or through the bulk-copy engine), streaming cache policies and a loop twice
+                        // as slow all leave the kernel time unchanged, while skipping the data movement alone makes the kernel
+                        // 13 % faster -- the extra 1.4 TB/s of mixed read / write traffic lengthens everybody's memory latency.
                         float4* b4 = reinterpret_cast<float4*>(base);
                         const long long n4 = n >> 1;
                         long long r = t;
@@ -1007,12 +1016,32 @@ __device__ __forceinline__ void unit_epilogue(const StftParams& prm, int chunk, 
                                 asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(b4 + r + j * kThreads),
                                              "f"(x[j].x * sc), "f"(x[j].y * sc), "f"(x[j].z * sc), "f"(x[j].w * sc) : "memory");
                         }
-                        q = 2 * (r - t) + t;          // samples [0, 2*(r-t)) are done; continue with the scalar tail
+                        {                        // the last, partial batch in the same shape (not a serial clean-up loop)
+                            float4 x[16];
+#pragma unroll
+                            for (int j = 0; j < 16; ++j)
+                                if (r + j * kThreads < n4)
+                                    asm volatile("ld.global.cg.v4.f32 {%0,%1,%2,%3}, [%4];"
+                                                 : "=f"(x[j].x), "=f"(x[j].y), "=f"(x[j].z), "=f"(x[j].w) : "l"(b4 + r + j * kThreads));
+#pragma unroll
+                            for (int j = 0; j < 16; ++j)
+                                if (r + j * kThreads < n4)
+                                    asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(b4 + r + j * kThreads),
+                                                 "f"(x[j].x * sc), "f"(x[j].y * sc), "f"(x[j].z * sc), "f"(x[j].w * sc) : "memory");
+                        }
+                        q = 2 * n4 + t;          // an odd last sample-frame is left to the scalar loop
                     }
                     for (; q < n; q += kThreads) {
                         float2 x;
                         asm volatile("ld.global.cg.v2.f32 {%0,%1}, [%2];" : "=f"(x.x), "=f"(x.y) : "l"(base + q));
                         st_stream(base + q, make_float2(x.x * sc, x.y * sc));
+                    }
+                    __syncthreads();
+                    if (t == 0) {
+                        unsigned long long t_end;
+                        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_end));
+                        atomicAdd(prm.dbg, t_end - t_begin);
+                        atomicAdd(prm.dbg + 1, 1ull);
                     }
                 }
             }
@@ -1894,6 +1923,7 @@ struct tmt_plan {
     DevBuf<ChunkDev> chunks;
     DevBuf<int> chunk_done;     // fused limiter: finished work units per chunk
     DevBuf<int> unit_counter;   // stft_kernel work queue head
+    DevBuf<unsigned long long> dbg;   // [2] dev counters of the fused limiter (see StftParams)
     int n_unfusable = 0;        // chunks the fused limiter must leave to limiter_kernel
     DevBuf<EdgeDev> edges;
     int n_edges = 0;
@@ -2291,6 +2321,7 @@ int tmt_plan_create(tmt_engine* e, tmt_plan** out, int framing, int n_tracks, co
         TMT_SLICE(p->chunks, std::max<size_t>(chunks.size(), 1));
         TMT_SLICE(p->chunk_done, chunks.size() + 1);
         TMT_SLICE(p->unit_counter, 1);
+        TMT_SLICE(p->dbg, 2);
         TMT_SLICE(p->edges, std::max<size_t>(edges.size(), 1));
         TMT_SLICE(p->edge_in_scale, nt + 1);
         TMT_SLICE(p->edge_out_scale, nt + 1);
@@ -2410,6 +2441,13 @@ int tmt_plan_total_frames(const tmt_plan* p) { return p ? p->total_frames : -1; 
 int tmt_plan_total_chunks(const tmt_plan* p) { return p ? p->total_chunks : -1; }
 int tmt_plan_total_units(const tmt_plan* p) { return p ? p->n_units : -1; }
 int tmt_plan_unfusable_chunks(const tmt_plan* p) { return p ? p->n_unfusable : -1; }
+int tmt_plan_debug_counters(tmt_plan* p, uint64_t* out2, int reset) {
+    if (!p || !out2) return fail(TMT_ERR_INVALID, "bad arguments");
+    CUDA_TRY(cudaSetDevice(p->e->device));
+    CUDA_TRY(cudaMemcpy(out2, p->dbg.p, 2 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    if (reset) CUDA_TRY(cudaMemset(p->dbg.p, 0, 2 * sizeof(uint64_t)));
+    return TMT_OK;
+}
 int tmt_plan_track_frames(const tmt_plan* p, int t) { return (p && t >= 0 && t < p->n_tracks) ? p->ht[t].n_frames : -1; }
 int tmt_plan_track_frame_base(const tmt_plan* p, int t) { return (p && t >= 0 && t < p->n_tracks) ? p->ht[t].frame_base : -1; }
 int tmt_plan_track_chunks(const tmt_plan* p, int t) { return (p && t >= 0 && t < p->n_tracks) ? p->ht[t].n_chunks : -1; }
@@ -2631,6 +2669,7 @@ static int launch_stft(tmt_plan* p, float post_gain, float limit, cudaStream_t s
     prm.chunk_done = p->chunk_done.p;
     prm.unit_counter = p->unit_counter.p;
     prm.limit = limit;
+    prm.dbg = p->dbg.p;
     CUDA_TRY(cudaMemsetAsync(p->unit_counter.p, 0, sizeof(int), st));
     const int grid = std::min(p->n_units, 2 * e->n_sms);            // persistent: two CTAs per SM
     stft_kernel<<<grid, kThreads, kStftSmem, st>>>(prm);
@@ -2675,7 +2714,8 @@ int tmt_plan_stft_limited(tmt_plan* p, float post_gain, float limit, void* strea
     // Small jobs (a single short file): the kernel lasts a few frame times, every chunk finishes at its very end, and the in-kernel
     // rescale -- one CTA per chunk, latency-bound -- would be a serial tail.  The separate limiter pass spreads the same bytes over
     // all SMs and costs one launch.  Large jobs hide the rescale under the other CTAs' butterflies and keep it fused.
-    const bool fuse = p->total_blocks >= 48LL * e->n_sms;
+    bool fuse = p->total_blocks >= 48LL * e->n_sms;
+    if (const char* fv = getenv("TMT_LIMITER_FUSED")) fuse = atoi(fv) != 0;        // dev switch: A/B of the two limiter placements
     if (p->n_units) {
         int rc = launch_stft(p, post_gain, fuse ? limit : 0.f, st);
         if (rc) return rc;
