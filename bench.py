@@ -212,6 +212,26 @@ def ncu_traffic():
         return None
 
 
+def fp32_secondary(sf_per_s, sm_mhz):
+    """Secondary ceiling: the kernel's FP32 work against the non-tensor FP32 peak.  Instruction counts are the
+    static SASS counts of the frame loop (profiles/stft_kernel_flops.json, tools/sass_count.py); the pipe executes 128 lanes per
+    clock and SM whether an instruction is an add, a multiply or a fused multiply-add, so `frac` is lane-ops against lane slots
+    (what bounds the kernel) and `achieved` the real flop rate (an FMA counts 2) against the 2-flop-per-slot peak."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "stft_kernel_flops.json")) as f:
+            c = json.load(f)
+    except Exception:
+        return None
+    mhz = float(sm_mhz or 1965.0)
+    slots = 128 * 148 * mhz * 1e6                        # FP32 lane slots per second
+    return {"bound": "fp32", "achieved": c["flop_per_sample_frame"] * sf_per_s / 1e12, "peak": 2 * slots / 1e12, "unit": "TFLOP/s",
+            "frac": c["lane_ops_per_sample_frame"] * sf_per_s / slots,
+            "flop_per_sample_frame": c["flop_per_sample_frame"], "lane_ops_per_sample_frame": c["lane_ops_per_sample_frame"],
+            "packed_fp32_instructions_per_thread_frame": c["packed_fp32_per_thread_frame"],
+            "peak_source": f"128 FP32 lanes x 148 SMs x {mhz:.0f} MHz (clock sampled during the run), 2 flop per lane slot",
+            "source": c["source"]}
+
+
 def run_gpu_arm(args):
     import numpy as np
     import torch
@@ -390,7 +410,8 @@ def run_gpu_arm(args):
                          "kernel_ms": stft_ms, "kernel_share_of_step": stft_ms * args.steps / ms_total,
                          "traffic": (traffic or {}).get("dram_bytes_per_sf", None) and
                                     (traffic["dram_bytes_per_sf"] * sf_rank),
-                         "traffic_source": (traffic or {}).get("source")},
+                         "traffic_source": (traffic or {}).get("source"),
+                         "secondary": fp32_secondary(sf_rank / (stft_ms * 1e-3), (clocks or {}).get("sm_mhz"))},
             "checks": {"c2_fraction": c2_frac, "chunks_over_limit": lim_frac, "output_peak": out_peak,
                        "finite": finite},
         }

@@ -332,3 +332,21 @@ def test_adaptive_threshold_search_in_kernel(generic, monkeypatch):
             assert r["optimal_T"] == o["optimal_T"], (kw, r["optimal_T"], o["optimal_T"])
             assert r["trace"] == o["trace"], kw
             assert np.array_equal(r["states"], o["states"]), kw
+
+
+def test_long_delay_and_hold_use_the_serial_gate():
+    """Up-delays / min-holds whose automaton has more than 255 states (beyond ~10.8 s / ~5.4 s at 48 kHz) leave the scan by map
+    composition and take the exact serial walk; the reference accepts any value (src/process_tomatis.py:285, _adaptive.py:190)."""
+    from tomatis_audio_processor_b200 import synth
+    orc, eng = _oracle(), _engine()
+    x = synth.recipe_gated_pink(40.0, 48000, 81, env_hz=0.02, hi_dbfs=-20.0, bursts=False)
+    kw = dict(gate_ui=50, up_delay_ms=12000.0)
+    r, o = eng.run("standard", [x], 48000, **kw)[0], orc.run("standard", x, 48000, **kw)
+    assert np.array_equal(r["states"], o["states"]) and (o["states"] == 2).any() and (o["states"] == 1).any()
+    assert r["chunk_lengths"] == o["chunk_lengths"]
+    xa = synth.recipe_swept_pink(30.0, 48000, 82, period_s=14.0, peak=0.5)
+    kw = dict(min_hold_ms=6000.0, xfade_ms=300.0)
+    r, o = eng.run("adaptive", [xa], 48000, **kw)[0], orc.run("adaptive", xa, 48000, **kw)
+    assert r["optimal_T"] == o["optimal_T"] and r["trace"] == o["trace"]
+    assert np.array_equal(r["states"], o["states"])
+    assert np.allclose(r["rows"] / max(r["xfade_frames"], 1), o["alphas"], atol=1e-9)

@@ -513,6 +513,35 @@ __global__ void gate_kernel(const TrackDev* __restrict__ tracks, const T* __rest
     }
 }
 
+// Fallback for automata with more states than the scan's byte-wide maps hold (up-delay beyond ~10 s, min-hold beyond ~5 s at
+// 48 kHz; the reference accepts any value): one thread per track walks the frames in order.  337 500 frames take a few
+// milliseconds -- a rarely used corner, kept exact rather than fast.
+template <typename T, int AUTO>
+__global__ void gate_serial_kernel(const TrackDev* __restrict__ tracks, const T* __restrict__ vals, const double* __restrict__ von,
+                                   const double* __restrict__ voff, int param, int X, int alpha_init, int count_only,
+                                   uint8_t* __restrict__ state, uint16_t* __restrict__ rows, int* __restrict__ c2_count) {
+    if (threadIdx.x != 0) return;
+    const int track = blockIdx.x;
+    const TrackDev tr = tracks[track];
+    const T* v = vals + tr.frame_base;
+    const T on = (T)von[track], off = (T)voff[track];
+    const int Xe = max(X, 1);
+    int cur = (AUTO == TMT_GATE_UPDELAY) ? 0 : param, k = 0, c2 = 0;
+    for (int f = 0; f < tr.n_frames; ++f) {
+        const T x = v[f];
+        cur = gate_next<AUTO>(cur, x >= on, x <= off, param);
+        const int t2 = gate_is_c2<AUTO>(cur, param) ? 1 : 0;
+        c2 += t2;
+        if (!count_only) {
+            state[tr.frame_base + f] = (uint8_t)(1 + t2);
+            if (alpha_init && f == 0) k = t2 * Xe;
+            else k = min(max(k + (t2 ? 1 : -1), 0), Xe);
+            rows[tr.frame_base + f] = (uint16_t)k;
+        }
+    }
+    c2_count[track] = c2;
+}
+
 // ------------------------------------------------------------------------------------------------
 // Threshold search of adaptive mode (src/process_tomatis_adaptive.py:124-154) as ONE launch: one CTA per track runs the whole
 // <= 30-step bisection, every step a count-only scan of the min-hold automaton over the track's levels (same map composition as
@@ -1016,18 +1045,22 @@ __device__ __forceinline__ void unit_epilogue(const StftParams& prm, int chunk, 
                                 asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(b4 + r + j * kThreads),
                                              "f"(x[j].x * sc), "f"(x[j].y * sc), "f"(x[j].z * sc), "f"(x[j].w * sc) : "memory");
                         }
-                        {                        // the last, partial batch in the same shape (not a serial clean-up loop)
-                            float4 x[16];
+                        for (; r + 3 * kThreads < n4; r += 4 * kThreads) {       // the rest of the chunk, four loads in flight
+                            float4 x[4];
 #pragma unroll
-                            for (int j = 0; j < 16; ++j)
-                                if (r + j * kThreads < n4)
-                                    asm volatile("ld.global.cg.v4.f32 {%0,%1,%2,%3}, [%4];"
-                                                 : "=f"(x[j].x), "=f"(x[j].y), "=f"(x[j].z), "=f"(x[j].w) : "l"(b4 + r + j * kThreads));
+                            for (int j = 0; j < 4; ++j)
+                                asm volatile("ld.global.cg.v4.f32 {%0,%1,%2,%3}, [%4];"
+                                             : "=f"(x[j].x), "=f"(x[j].y), "=f"(x[j].z), "=f"(x[j].w) : "l"(b4 + r + j * kThreads));
 #pragma unroll
-                            for (int j = 0; j < 16; ++j)
-                                if (r + j * kThreads < n4)
-                                    asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(b4 + r + j * kThreads),
-                                                 "f"(x[j].x * sc), "f"(x[j].y * sc), "f"(x[j].z * sc), "f"(x[j].w * sc) : "memory");
+                            for (int j = 0; j < 4; ++j)
+                                asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(b4 + r + j * kThreads),
+                                             "f"(x[j].x * sc), "f"(x[j].y * sc), "f"(x[j].z * sc), "f"(x[j].w * sc) : "memory");
+                        }
+                        for (; r < n4; r += kThreads) {
+                            float4 x;
+                            asm volatile("ld.global.cg.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(x.x), "=f"(x.y), "=f"(x.z), "=f"(x.w) : "l"(b4 + r));
+                            asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(b4 + r),
+                                         "f"(x.x * sc), "f"(x.y * sc), "f"(x.z * sc), "f"(x.w * sc) : "memory");
                         }
                         q = 2 * n4 + t;          // an odd last sample-frame is left to the scalar loop
                     }
@@ -1186,7 +1219,7 @@ __global__ void __launch_bounds__(kThreads, 2) stft_kernel(const StftParams prm)
                 x_fwd1_pack(v, r);
                 park.trip_fwd(r);
                 // tilt gain x crossfade weight: one real row per frame, register order; issued before the second round trip
-                // (the few rows in use stay in L1)
+                // (the few rows in use stay in L1; one trip earlier measured the same)
                 const float4* g4 = reinterpret_cast<const float4*>(prm.gperm + (size_t)row * kNfft + t * 16);
                 const float4 g0 = ld_table4(g4), g1 = ld_table4(g4 + 1), g2 = ld_table4(g4 + 2), g3 = ld_table4(g4 + 3);
                 x_layer_a<false>(r, q);                                           // C, first layer
@@ -2024,6 +2057,13 @@ int build_tracks_dev(tmt_plan* p) {
 
 template <typename T, int AUTO>
 int launch_gate(tmt_plan* p, const T* vals, int param, int S, int X, int alpha_init, int count_only, cudaStream_t st) {
+    if (S > kMaxGateStates) {            // more states than the scan's byte maps hold: exact serial walk (see gate_serial_kernel)
+        gate_serial_kernel<T, AUTO><<<p->n_tracks, 32, 0, st>>>(p->tracks.p, vals, p->von.p, p->voff.p, param, X, alpha_init, count_only,
+                                                               p->state.p, p->rows.p, p->c2.p);
+        p->launches++;
+        CUDA_TRY(cudaGetLastError());
+        return TMT_OK;
+    }
     // long tracks: cut into segments of >= 8 frames per thread so the scan spreads over the whole GPU
     int nseg = 1;
     if (p->max_frames > 16384) nseg = std::min(2 * p->e->n_sms, std::max(1, p->max_frames / 2048));
@@ -2595,7 +2635,6 @@ int tmt_plan_gate(tmt_plan* p, int automaton, int gate_input, const double* on, 
     if (automaton == TMT_GATE_UPDELAY) { if (param < 1) return fail(TMT_ERR_INVALID, "run_frames must be >= 1"); S = param + 1; }
     else if (automaton == TMT_GATE_MINHOLD) S = 2 * (param + 1);
     else return fail(TMT_ERR_INVALID, "unknown automaton %d", automaton);
-    if (S > kMaxGateStates) return fail(TMT_ERR_UNSUPPORTED, "gate automaton needs %d states (max %d): delay/hold too long for the GPU scan", S, kMaxGateStates);
     CUDA_TRY(cudaSetDevice(p->e->device));
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     if (on) {               // NULL / NULL: keep the thresholds already on the device (left there by tmt_plan_bisect)

@@ -47,9 +47,21 @@ def process_sharded(mode: str, in_path: str, out_path: str, comm, device_index: 
         raise NotImplementedError(f"the sharded adaptive path takes stereo files, got {ch} channel(s); use one GPU")
     if total == 0:
         raise ValueError("empty input file")
+    n_fft, hop = params.get("n_fft", tb.N_FFT), params.get("hop", tb.HOP)
+    if (n_fft, hop) != (tb.N_FFT, tb.HOP):                 # checked BEFORE any collective: every rank takes the same exit
+        raise NotImplementedError(f"the time-sharded path implements n_fft={tb.N_FFT}, hop={tb.HOP} (got {n_fft}/{hop}); "
+                                  f"other sizes run on one GPU (process_tomatis*.py)")
     framing = sharded.WHOLEFILE if mode == "adaptive" else sharded.STREAMING
-    me = sharded.plan_shards(total, comm.world, framing, params.get("n_fft", tb.N_FFT), params.get("hop", tb.HOP))[comm.rank]
-    own = torch.from_numpy(np.ascontiguousarray(audio_io.read_range(in_path, me.own_lo, me.own_hi, dtype="float32"))).to(comm.device)
+    me = sharded.plan_shards(total, comm.world, framing, n_fft, hop)[comm.rank]
+    # a rank whose read fails must not leave the others waiting in the first collective: agree on success first
+    own, err = None, None
+    try:
+        own = torch.from_numpy(np.ascontiguousarray(audio_io.read_range(in_path, me.own_lo, me.own_hi, dtype="float32"))).to(comm.device)
+    except Exception as e:                                  # noqa: BLE001 - re-raised on every rank below
+        err = e
+    n_bad = int(comm.allreduce(np.array([0.0 if err is None else 1.0], np.float32), "sum")[0])
+    if n_bad:
+        raise RuntimeError(f"{n_bad} rank(s) could not read their sample range of {in_path}" + (f": {err}" if err is not None else ""))
     log(f"samples [{me.own_lo}, {me.own_hi}) of {total} ({(me.own_hi - me.own_lo) / sr:.1f} s of {total / sr:.1f} s), "
         f"output blocks [{me.block_lo}, {me.block_hi})")
     run = sharded.run_adaptive_sharded if mode == "adaptive" else (lambda *a, **k: sharded.run_streaming_sharded(mode, *a, **k))

@@ -1,0 +1,64 @@
+"""Static instruction counts of stft_kernel's frame loop from the built library (here, no GPU): python tools/sass_count.py [--json out].
+
+The frame loop is the innermost backward branch around at least 400 packed FP32 instructions.  Packed FP32 instructions (FFMA2 / FMUL2 / FADD2,
+two lanes each) inside it, minus the duplicated output variant (whole block / clipped block: 8 FFMA2 each, one executes), give
+the per-thread, per-frame count the bench's secondary (FP32) roofline uses."""
+import json
+import os
+import re
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LIB = os.path.join(ROOT, "tomatis_audio_processor_b200", "csrc", "libtomatis_b200.so")
+
+
+def kernel_sass(name="stft_kernel"):
+    out = subprocess.run(["cuobjdump", "-sass", LIB], capture_output=True, text=True).stdout
+    lines, on = [], False
+    for ln in out.splitlines():
+        if "Function :" in ln:
+            on = name in ln
+            continue
+        m = re.match(r"\s+/\*([0-9a-f]{4,6})\*/\s+(.*?);", ln)
+        if on and m:
+            lines.append((int(m.group(1), 16), m.group(2).strip()))
+    return lines
+
+
+def main():
+    sass = kernel_sass()
+    addr = [a for a, _ in sass]
+    packed = [a for a, t in sass if re.search(r"\b(FFMA2|FMUL2|FADD2)\b", t)]
+    loop = None
+    for a, t in sass:
+        m = re.search(r"BRA\S*\s+(?:\S+,\s*)?0x([0-9a-f]+)", t)
+        if m:
+            tgt = int(m.group(1), 16)
+            if tgt < a and sum(tgt <= w <= a for w in packed) >= 400:          # a backward branch around (at least) a whole frame
+                if loop is None or (a - tgt) < (loop[1] - loop[0]):
+                    loop = (tgt, a)
+    body = [t for a, t in sass if loop and loop[0] <= a <= loop[1]]
+    def cnt(pat, where):
+        return sum(1 for t in where if re.search(pat, t))
+    res = {"kernel_instructions": len(sass), "loop_instructions": len(body)}
+    for k, pat in (("FFMA2", r"\bFFMA2\b"), ("FMUL2", r"\bFMUL2\b"), ("FADD2", r"\bFADD2\b"), ("FFMA", r"\bFFMA\b"), ("FMUL", r"\bFMUL\b"),
+                   ("FADD", r"\bFADD\b"), ("LDS", r"\bLDS"), ("STS", r"\bSTS"), ("LDTM", r"\bLDTM"), ("STTM", r"\bSTTM"), ("LDG", r"\bLDG"),
+                   ("STG", r"\bSTG"), ("LDL", r"\bLDL"), ("STL", r"\bSTL"), ("MOV", r"\bMOV\b"), ("SYNCS", r"\bSYNCS"), ("BAR", r"\bBAR\b")):
+        res[k] = cnt(pat, body)
+    dup_out = 8                                         # the clipped-block variant of the output FFMA2s
+    ffma2 = res["FFMA2"] - dup_out
+    res["packed_fp32_per_thread_frame"] = ffma2 + res["FMUL2"] + res["FADD2"]
+    res["flop_per_thread_frame"] = 4 * ffma2 + 2 * (res["FMUL2"] + res["FADD2"]) + 2 * res["FFMA"] + res["FMUL"] + res["FADD"]
+    res["flop_per_sample_frame"] = res["flop_per_thread_frame"] * 256 / 2048
+    res["lane_ops_per_sample_frame"] = 2 * res["packed_fp32_per_thread_frame"] * 256 / 2048
+    res["source"] = ("static SASS count of stft_kernel's frame loop (tools/sass_count.py on the built library): packed FP32 "
+                     "instructions per thread and frame, 256 threads per frame, 2048 new sample-frames per frame")
+    print(json.dumps(res, indent=1))
+    if "--json" in sys.argv:
+        with open(sys.argv[sys.argv.index("--json") + 1], "w") as f:
+            json.dump(res, f, indent=1)
+
+
+if __name__ == "__main__":
+    main()
