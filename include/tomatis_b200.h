@@ -158,6 +158,18 @@ int tmt_plan_input_peaks(tmt_plan* p, void* stream);
 #define TMT_LEVELS_POWER_EPS 128 /* mono = sqrt(0.5*(l*l + r*r) + 1e-12): calibration front end (src/calibrate_to_baseline_v2.py:8-15) */
 int tmt_plan_levels(tmt_plan* p, int flags, const float* in_scale, void* stream);
 
+/* Files with more than two channels (adaptive mode: the reference's `for c in range(ch)` loop, src/process_tomatis_adaptive.py:
+ * 307-313).  The caller cuts the file into channel pairs (tmt_channels_split), makes every pair a track of one plan and runs the
+ * stereo path on them; this entry point computes the level that all of them share -- mono = sqrt(mean(frame**2, axis=1)) over ALL
+ * channels (:74; NumPy's pairwise order along the channel axis, sum / channels in the array's dtype) -- from the interleaved file
+ * x (device, float32 [total][channels]) and stores the hop-block sums / mean squares into every track of the plan.  Tracks must
+ * have identical geometry.  flags: TMT_LEVELS_F64, TMT_LEVELS_HOPSUM_ONLY.  in_scale: as tmt_plan_levels (entry 0 is used). */
+int tmt_plan_levels_multichannel(tmt_plan* p, int flags, const float* in_scale, const float* x, int channels, void* stream);
+/* interleaved float32 [total][channels] -> ceil(channels / 2) stereo planes [pair][total][2] (an odd last channel gets a silent
+ * partner), and back (the partner is dropped).  Device pointers. */
+int tmt_channels_split(const float* in, int64_t total, int channels, float* pairs, void* stream);
+int tmt_channels_merge(const float* pairs, int64_t total, int channels, float* out, void* stream);
+
 /* K2b.  Gate automaton + crossfade counter as a block-level scan over frames.
  * gate_input: TMT_ARR_MEANSQ_F32, TMT_ARR_MEANSQ_F64 or TMT_ARR_GATE_F64.  Frame is "hi" when
  * value >= on[track], "lo" when value <= off[track] (host arrays of n_tracks doubles; thresholds in the

@@ -61,6 +61,24 @@ def cases():
     # adaptive 44.1 kHz, total % hop == hop-1 (tail reaches the window end)
     x = synth.recipe_swept_pink(2.0, 44100, 19, period_s=0.8, peak=0.4)
     c.append(("adaptive_44k1_tail", "adaptive", 44100, _q(x)[:2048 * 30 + 2047], dict(min_hold_ms=90.0, xfade_ms=150.0)))
+    c.extend(multichannel_cases())
+    return c
+
+
+def multichannel_cases():
+    """adaptive mode on files with more than two channels (the reference loops over channels, _adaptive.py:307-313)."""
+    c = []
+    # three channels (odd: the last one has no partner), float32 branch; the channels differ in level so that the all-channel
+    # level, the input peak and the output peak each come from a different place
+    a = synth.recipe_swept_pink(1.6, 48000, 31, period_s=0.7, peak=0.5)
+    b = synth.recipe_swept_pink(1.6, 48000, 32, period_s=0.9, peak=0.3)
+    c.append(("adaptive_48k_3ch", "adaptive", 48000, _q(np.concatenate([a, b[:, :1]], axis=1)), dict(min_hold_ms=100.0, xfade_ms=200.0)))
+    # 5.1 layout, float64 branch (input peak <= 0.141), 44.1 kHz, ragged length
+    parts = [synth.recipe_swept_pink(1.4, 44100, 33 + k, period_s=0.5 + 0.1 * k, peak=0.1 - 0.02 * k) for k in range(3)]
+    c.append(("adaptive_44k1_6ch_f64", "adaptive", 44100, _q(np.concatenate(parts, axis=1))[:2048 * 25 + 777], dict(xfade_ms=300.0)))
+    # nine channels: NumPy's mean over the channel axis switches to its 8-accumulator pairwise order from 8 channels on
+    parts = [synth.recipe_swept_pink(1.2, 48000, 40 + k, period_s=0.45 + 0.05 * k, peak=0.45 - 0.05 * k) for k in range(5)]
+    c.append(("adaptive_48k_9ch", "adaptive", 48000, _q(np.concatenate(parts, axis=1)[:, :9]), dict(min_hold_ms=80.0, xfade_ms=150.0)))
     return c
 
 
@@ -196,11 +214,13 @@ def main():
         return make_chan()
     if "--only-val" in sys.argv:
         return make_val()
-    make_chan()
-    make_val()
-    make_cal()
-    make_eq()
-    for name, mode, sr, x, kw in cases():
+    only_multi = "--only-multichannel" in sys.argv
+    if not only_multi:
+        make_chan()
+        make_val()
+        make_cal()
+        make_eq()
+    for name, mode, sr, x, kw in (multichannel_cases() if only_multi else cases()):
         r = rh.run_reference(mode, x, sr, **kw)
         q = synth.quantise_pcm16(x)
         assert np.array_equal(synth.pcm16_to_float(q), x)

@@ -87,6 +87,31 @@ def test_adaptive_process_files(tmp_path, capsys):
     capsys.readouterr()
 
 
+def test_adaptive_four_channel_file(tmp_path, capsys):
+    """More than two channels (the reference loops over channels, src/process_tomatis_adaptive.py:307-313): the pairs share
+    input peak, level, gate and limiter scale."""
+    from tomatis_audio_processor_b200 import process_tomatis_adaptive as pa
+    a = synth.recipe_swept_pink(3.0, 48000, 61, period_s=0.9, peak=0.5)
+    b = synth.recipe_swept_pink(3.0, 48000, 62, period_s=0.6, peak=0.35)
+    x = np.concatenate([a, b], axis=1)
+    p = str(tmp_path / "in.wav")
+    audio_io.write(p, x, 48000, subtype="PCM_24")
+    xq, _ = audio_io.read(p, dtype="float32")
+    assert xq.shape[1] == 4
+    out = str(tmp_path / "out.wav")
+    csv_path = str(tmp_path / "state.csv")
+    assert pa.process(p, out, state_csv_path=csv_path, min_hold_ms=120.0) == 0
+    y, sr = audio_io.read(out, dtype="float32")
+    o = _oracle().run("adaptive", xq, 48000, min_hold_ms=120.0)
+    o64 = _oracle().run("adaptive", xq, 48000, min_hold_ms=120.0, fft_dtype="float64")
+    assert sr == 48000 and y.shape == o["out"].shape == (len(x), 4)
+    d = np.abs(y.astype(np.float64) - o["out"].astype(np.float64)).max(axis=1)
+    d64 = np.abs(y.astype(np.float64) - o64["out"].astype(np.float64)).max(axis=1)
+    assert float(d[256:-256].max()) <= 1e-5 + Q24 and float(d64.max()) <= 1e-5 + Q24
+    assert _read_csv(csv_path) == _oracle().csv_rows("adaptive", o)
+    capsys.readouterr()
+
+
 def test_44k1_needs_any_sr_extension(tmp_path, capsys):
     from tomatis_audio_processor_b200 import process_tomatis as pt
     x = synth.recipe_gated_pink(2.0, 44100, 24, env_hz=2.0, hi_dbfs=-28.0)

@@ -59,6 +59,9 @@ SIGNATURES = {
     "tmt_plan_write": (C.c_int, [_P, C.c_int, C.c_int64, C.c_int64, _P, C.c_int, _P]),
     "tmt_plan_input_peaks": (C.c_int, [_P, _P]),
     "tmt_plan_levels": (C.c_int, [_P, C.c_int, _P, _P]),
+    "tmt_plan_levels_multichannel": (C.c_int, [_P, C.c_int, _P, _P, C.c_int, _P]),
+    "tmt_channels_split": (C.c_int, [_P, C.c_int64, C.c_int, _P, _P]),
+    "tmt_channels_merge": (C.c_int, [_P, C.c_int64, C.c_int, _P, _P]),
     "tmt_plan_gate": (C.c_int, [_P, C.c_int, C.c_int, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "tmt_plan_bisect": (C.c_int, [_P, _P, _P, _P, _P, C.c_double, C.c_double, C.c_int, C.c_int, _P]),
     "tmt_plan_stft": (C.c_int, [_P, C.c_float, C.c_int, _P]),

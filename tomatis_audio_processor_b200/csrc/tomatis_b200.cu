@@ -294,6 +294,110 @@ meansq_kernel(const TrackDev* __restrict__ tracks, const T* __restrict__ hsum, T
 }
 
 // ------------------------------------------------------------------------------------------------
+// More than two channels (adaptive mode only: the reference loops `for c in range(ch)`, src/process_tomatis_adaptive.py:307-313).
+// The file is cut into channel pairs, each pair is one track of the plan and runs through the stereo kernels (an odd last
+// channel rides with a silent partner); the level that drives the one shared gate comes from all channels:
+//     mono = np.sqrt(np.mean(frame**2, axis=1))      (src/process_tomatis_adaptive.py:74)
+// np.mean over the channel axis adds the squares in NumPy's pairwise order -- a plain left-to-right sum below 8 channels,
+// 8 strided accumulators combined as ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)) plus a sequential remainder from 8 to 128 --
+// and divides by the channel count in the array's dtype.
+template <typename T> struct ArithX;
+template <> struct ArithX<float> {
+    static __device__ __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b); }
+    static __device__ __forceinline__ float root(float a) { return __fsqrt_rn(a); }
+};
+template <> struct ArithX<double> {
+    static __device__ __forceinline__ double mul(double a, double b) { return __dmul_rn(a, b); }
+    static __device__ __forceinline__ double root(double a) { return __dsqrt_rn(a); }
+};
+template <typename T>
+__device__ __forceinline__ T msq_multi(const float* __restrict__ xs, int ch, float sc) {
+    auto sq = [&](int c) { const T v = ArithX<T>::mul((T)__ldg(xs + c), (T)sc); return ArithX<T>::mul(v, v); };
+    T s;
+    if (ch < 8) {
+        s = sq(0);
+        for (int c = 1; c < ch; ++c) s = Arith<T>::add(s, sq(c));
+    } else {
+        T r[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) r[j] = sq(j);
+        int i = 8;
+        for (; i < ch - (ch % 8); i += 8) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) r[j] = Arith<T>::add(r[j], sq(i + j));
+        }
+        s = Arith<T>::add(Arith<T>::add(Arith<T>::add(r[0], r[1]), Arith<T>::add(r[2], r[3])),
+                          Arith<T>::add(Arith<T>::add(r[4], r[5]), Arith<T>::add(r[6], r[7])));
+        for (; i < ch; ++i) s = Arith<T>::add(s, sq(i));
+    }
+    const T mono = ArithX<T>::root(Arith<T>::div(s, (T)ch));
+    return ArithX<T>::mul(mono, mono);
+}
+
+// Hop-block sums of the all-channel level, same lane layout and summation order as levels_kernel; x = the interleaved file
+// [total][ch]; the geometry is track 0's (every pair track of the plan has the same), the sums go to every track's slots.
+template <typename T>
+__global__ void __launch_bounds__(kLevelWarps * 32)
+levels_multi_kernel(const TrackDev* __restrict__ tracks, int n_tracks, const float* __restrict__ in_scale, const float* __restrict__ x,
+                    int ch, T* __restrict__ hsum) {
+    const TrackDev tr = tracks[0];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int q = tr.hb_lo + blockIdx.x * kLevelWarps + warp;
+    if (q >= tr.hb_hi) return;
+    const float sc = in_scale ? in_scale[0] : 1.0f;
+    const long long start = tr.first_start + (long long)q * kHop;
+    const int pr = lane & 3, leaf = lane >> 2;
+    T tot[2];
+#pragma unroll
+    for (int ps = 0; ps < 2; ++ps) {
+        const long long base = start + (ps * 8 + leaf) * 128 + 2 * pr;
+        T a0 = (T)0, a1 = (T)0;
+        for (int i = 0; i < 16; ++i) {
+            const long long p0 = base + 8 * i, p1 = p0 + 1;
+            const T m0 = (p0 >= tr.in_lo && p0 < tr.in_hi) ? msq_multi<T>(x + (p0 - tr.in_origin) * ch, ch, sc) : (T)0;
+            const T m1 = (p1 >= tr.in_lo && p1 < tr.in_hi) ? msq_multi<T>(x + (p1 - tr.in_origin) * ch, ch, sc) : (T)0;
+            a0 = i ? Arith<T>::add(a0, m0) : m0;
+            a1 = i ? Arith<T>::add(a1, m1) : m1;
+        }
+        T s = Arith<T>::add(a0, a1);
+        s = Arith<T>::add(s, __shfl_xor_sync(0xffffffffu, s, 1));
+        s = Arith<T>::add(s, __shfl_xor_sync(0xffffffffu, s, 2));
+        s = Arith<T>::add(s, __shfl_xor_sync(0xffffffffu, s, 4));
+        s = Arith<T>::add(s, __shfl_xor_sync(0xffffffffu, s, 8));
+        s = Arith<T>::add(s, __shfl_xor_sync(0xffffffffu, s, 16));
+        tot[ps] = s;
+    }
+    if (lane == 0) {
+        const T h = Arith<T>::add(tot[0], tot[1]);
+        for (int k = 0; k < n_tracks; ++k) hsum[tracks[k].hs_base + q] = h;
+    }
+}
+
+// [total][ch] interleaved -> ceil(ch/2) stereo planes [pair][total][2] (a missing partner is silence), and back
+__global__ void __launch_bounds__(256) channels_split_kernel(const float* __restrict__ in, long long total, int ch, float2* __restrict__ pairs) {
+    const int np = (ch + 1) / 2;
+    const long long n = total * np;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const long long s = i / np;
+        const int p = (int)(i - s * np);
+        const float* src = in + s * ch + 2 * p;
+        pairs[(long long)p * total + s] = make_float2(src[0], (2 * p + 1 < ch) ? src[1] : 0.f);
+    }
+}
+__global__ void __launch_bounds__(256) channels_merge_kernel(const float2* __restrict__ pairs, long long total, int ch, float* __restrict__ out) {
+    const int np = (ch + 1) / 2;
+    const long long n = total * np;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const long long s = i / np;
+        const int p = (int)(i - s * np);
+        const float2 v = pairs[(long long)p * total + s];
+        float* dst = out + s * ch + 2 * p;
+        dst[0] = v.x;
+        if (2 * p + 1 < ch) dst[1] = v.y;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // K2b gate.  Both automata are finite-state machines driven by two bits per frame
 // (hi: value >= on, lo: value <= off), so a run of frames is a map on the state set and maps compose
 // associatively.  One CTA per track; each thread owns a contiguous segment of frames, builds the
@@ -1017,7 +1121,11 @@ __device__ __forceinline__ void unit_epilogue(const StftParams& prm, int chunk, 
                 const float pk = __int_as_float(atomicMax(reinterpret_cast<int*>(prm.chunk_peaks + chunk), 0));
 
 
+#ifdef TMT_AB_NORESCALE
+                if (pk > 1e30f) {
+#else
                 if (pk > prm.limit) {
+#endif
                     unsigned long long t_begin = 0;
                     if (t == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_begin));
                     const float sc = __fdiv_rn(prm.limit, pk);
@@ -1144,10 +1252,22 @@ __global__ void __launch_bounds__(kThreads, 2) stft_kernel(const StftParams prm)
         auto load_half = [&](int h, float2 (&x)[8]) {
             const int p0 = h * kHop;
             const float2* src = in_u + p0 + t;
+#ifdef TMT_AB_NOLOAD       // timing study only (wrong output): the input never touches memory
+            if (p0 >= in_lo && p0 + kHop <= in_hi) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) x[j] = make_float2(__int_as_float(0x3c000000 + p0 + j + t), 0.25f);
+            } else {
+#elif defined(TMT_AB_L2LOAD)     // timing study only: every half frame comes from the same 16 KB (always an L2 hit)
+            if (p0 >= in_lo && p0 + kHop <= in_hi) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) x[j] = ld_stream(trp->in + 256 * j + t);
+            } else {
+#else
             if (p0 >= in_lo && p0 + kHop <= in_hi) {
 #pragma unroll
                 for (int j = 0; j < 8; ++j) x[j] = ld_stream(src + 256 * j);
             } else {
+#endif
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     const int p = p0 + 256 * j + t;
@@ -1198,7 +1318,11 @@ __global__ void __launch_bounds__(kThreads, 2) stft_kernel(const StftParams prm)
             const int row = row_next;
             row_next = row_of(f + 1);
             if (do_pf) load_half(i + 2, pf);
+#if defined(TMT_AB_NOLOAD) || defined(TMT_AB_L2LOAD)
+            if (false) {
+#else
             if (i + 1 < last && (t & 15) == 0) {               // half i+3 -> L2 (one 128-byte line per 16 lanes), so that next frame's loads are short
+#endif
                 const int p0 = (i + 3) * kHop;
                 if (p0 >= in_lo && p0 + kHop <= in_hi) {
 #pragma unroll
@@ -1271,7 +1395,11 @@ __global__ void __launch_bounds__(kThreads, 2) stft_kernel(const StftParams prm)
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
                         const float2 o = __ffma2_rn(v[j], make_float2(s[j], s[j]), c[j]);
+#ifdef TMT_AB_NOSTORE      // timing study only: the output never touches memory (one unlikely store keeps the arithmetic alive)
+                        if (o.x == 123.456f) st_stream(dst + 256 * j, o);
+#else
                         st_stream(dst + 256 * j, o);
+#endif
                         peak = fmaxf(peak, fmaxf(fabsf(o.x), fabsf(o.y)));
                     }
                 } else {
@@ -2622,6 +2750,58 @@ int tmt_plan_levels(tmt_plan* p, int flags, const float* in_scale, void* stream)
         if (do_msq) meansq_kernel<float><<<g2, 256, 0, st>>>(p->tracks.p, reinterpret_cast<const float*>(p->hsum.p), reinterpret_cast<float*>(p->msq.p));
     }
     p->launches += (do_sums ? 1 : 0) + (do_msq ? 1 : 0);
+    CUDA_TRY(cudaGetLastError());
+    return TMT_OK;
+}
+
+int tmt_plan_levels_multichannel(tmt_plan* p, int flags, const float* in_scale, const float* x, int channels, void* stream) {
+    if (!p || !x) return fail(TMT_ERR_INVALID, "bad arguments");
+    if (channels < 1 || channels > 128) return fail(TMT_ERR_INVALID, "channels must lie in [1, 128], got %d", channels);
+    if (flags & ~(TMT_LEVELS_F64 | TMT_LEVELS_HOPSUM_ONLY)) return fail(TMT_ERR_INVALID, "flags: TMT_LEVELS_F64 and TMT_LEVELS_HOPSUM_ONLY only");
+    if (p->n_tracks == 0 || p->max_hb == 0) return TMT_OK;
+    const HostTrack& h0 = p->ht[0];
+    for (const HostTrack& h : p->ht)
+        if (h.n_frames != h0.n_frames || h.hb_lo != h0.hb_lo || h.hb_hi != h0.hb_hi || h.d.total != h0.d.total || h.d.in_origin != h0.d.in_origin ||
+            h.d.in_len != h0.d.in_len)
+            return fail(TMT_ERR_INVALID, "the channel pairs of one file must be tracks of identical geometry");
+    CUDA_TRY(cudaSetDevice(p->e->device));
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const float* sc = nullptr;
+    if (in_scale) {
+        CUDA_TRY(cudaMemcpyAsync(p->in_scale.p, in_scale, sizeof(float) * p->n_tracks, cudaMemcpyHostToDevice, st));
+        sc = p->in_scale.p;
+    }
+    const dim3 g1(ceil_div(std::max(p->max_hb, 1), kLevelWarps));
+    const dim3 g2(ceil_div(std::max(p->max_frames, 1), 256), p->n_tracks);
+    const bool do_msq = !(flags & TMT_LEVELS_HOPSUM_ONLY);
+    if (flags & TMT_LEVELS_F64) {
+        levels_multi_kernel<double><<<g1, kLevelWarps * 32, 0, st>>>(p->tracks.p, p->n_tracks, sc, x, channels, p->hsum.p);
+        if (do_msq) meansq_kernel<double><<<g2, 256, 0, st>>>(p->tracks.p, p->hsum.p, p->msq.p);
+    } else {
+        levels_multi_kernel<float><<<g1, kLevelWarps * 32, 0, st>>>(p->tracks.p, p->n_tracks, sc, x, channels, reinterpret_cast<float*>(p->hsum.p));
+        if (do_msq) meansq_kernel<float><<<g2, 256, 0, st>>>(p->tracks.p, reinterpret_cast<const float*>(p->hsum.p), reinterpret_cast<float*>(p->msq.p));
+    }
+    p->launches += 1 + (do_msq ? 1 : 0);
+    CUDA_TRY(cudaGetLastError());
+    return TMT_OK;
+}
+
+int tmt_channels_split(const float* in, int64_t total, int channels, float* pairs, void* stream) {
+    if (!in || !pairs || total < 0 || channels < 1) return fail(TMT_ERR_INVALID, "bad arguments");
+    if (total == 0) return TMT_OK;
+    const long long n = total * ((channels + 1) / 2);
+    channels_split_kernel<<<(int)std::min<long long>((n + 255) / 256, 148 * 16), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        in, total, channels, reinterpret_cast<float2*>(pairs));
+    CUDA_TRY(cudaGetLastError());
+    return TMT_OK;
+}
+
+int tmt_channels_merge(const float* pairs, int64_t total, int channels, float* out, void* stream) {
+    if (!out || !pairs || total < 0 || channels < 1) return fail(TMT_ERR_INVALID, "bad arguments");
+    if (total == 0) return TMT_OK;
+    const long long n = total * ((channels + 1) / 2);
+    channels_merge_kernel<<<(int)std::min<long long>((n + 255) / 256, 148 * 16), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<const float2*>(pairs), total, channels, out);
     CUDA_TRY(cudaGetLastError());
     return TMT_OK;
 }

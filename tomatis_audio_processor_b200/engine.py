@@ -174,6 +174,16 @@ class Plan:
         L.check(self.lib.tmt_plan_levels(self.h, flags, ptr, _stream_ptr(_torch())),
                 "tmt_plan_levels")
 
+    def levels_multichannel(self, x_dev, channels: int, use_f64: bool = False, in_scale: Optional[np.ndarray] = None):
+        """The level all channel pairs of one file share (tmt_plan_levels_multichannel): x_dev = the interleaved file [N, channels]."""
+        ptr = None
+        if in_scale is not None:
+            in_scale = np.ascontiguousarray(in_scale, dtype=np.float32)
+            assert in_scale.size == self.n_tracks
+            ptr = in_scale.ctypes.data_as(C.c_void_p)
+        L.check(self.lib.tmt_plan_levels_multichannel(self.h, int(bool(use_f64)), ptr, C.c_void_p(x_dev.data_ptr()), int(channels),
+                                                      _stream_ptr(_torch())), "tmt_plan_levels_multichannel")
+
     def gate(self, automaton: int, gate_input: int, on, off, param: int, xfade_frames: int,
              alpha_init_to_target: bool = False, count_only: bool = False):
         """on / off None: keep the thresholds already on the device (left there by bisect())."""
@@ -431,13 +441,26 @@ def _percentile_thresholds(levels, valid):
 
 def run_adaptive(xs: Sequence, sr: int, device: int = 0, want_host: bool = True, outs=None, unit_blocks: int = 0,
                  fc=1000.0, slope=12.0, c1_low=15.0, c1_high=-15.0, c2_low=-15.0, c2_high=15.0, target_c2=0.5,
-                 hyst_db=3.0, min_hold_ms=250.0, xfade_ms=500.0, headroom_margin=2.0, n_fft=tb.N_FFT, hop=tb.HOP) -> List[dict]:
+                 hyst_db=3.0, min_hold_ms=250.0, xfade_ms=500.0, headroom_margin=2.0, n_fft=tb.N_FFT, hop=tb.HOP,
+                 _linked=None) -> List[dict]:
     """adaptive mode on a batch of tracks (src/process_tomatis_adaptive.py:157-373).
 
     Host: scalars, percentiles and the bisection bookkeeping.  Device: input peaks, levels, every gate
-    simulation of the bisection (count-only scans), the final gate + crossfade counter, STFT, limiter."""
+    simulation of the bisection (count-only scans), the final gate + crossfade counter, STFT, limiter.
+
+    A host array with more than two channels is one file whose channel pairs share the gate (run_adaptive_multichannel);
+    `_linked` = (interleaved device tensor, channels) is that function's hook: the tracks are the channel pairs of one file,
+    so input peak, level and output peak are taken over all of them."""
     torch = _torch()
     eng = get_engine(device)
+    if _linked is None and any(isinstance(x, np.ndarray) and x.ndim == 2 and x.shape[1] > 2 for x in xs):
+        if n_fft != eng.n_fft or hop != eng.hop:
+            raise NotImplementedError(f"files with more than two channels need n_fft={eng.n_fft}, hop={eng.hop}; got {n_fft}/{hop}")
+        kw = dict(device=device, want_host=want_host, unit_blocks=unit_blocks, fc=fc, slope=slope, c1_low=c1_low, c1_high=c1_high,
+                  c2_low=c2_low, c2_high=c2_high, target_c2=target_c2, hyst_db=hyst_db, min_hold_ms=min_hold_ms, xfade_ms=xfade_ms,
+                  headroom_margin=headroom_margin, n_fft=n_fft, hop=hop)
+        return [run_adaptive_multichannel(x, sr, **kw) if (isinstance(x, np.ndarray) and x.ndim == 2 and x.shape[1] > 2)
+                else run_adaptive([x], sr, **kw)[0] for x in xs]
     if n_fft != eng.n_fft or hop != eng.hop:
         from . import generic
         if generic.enabled():                                         # general-size path (csrc/generic.cuh)
@@ -467,6 +490,8 @@ def run_adaptive(xs: Sequence, sr: int, device: int = 0, want_host: bool = True,
     try:
         plan0.input_peaks()
         in_peaks = plan0.read(L.ARR_INPUT_PEAK)
+        if _linked is not None:                       # np.max(np.abs(x)) runs over every channel of the file (:201)
+            in_peaks = np.full_like(in_peaks, in_peaks.max() if len(in_peaks) else 0.0)
     except Exception:
         plan0.close()
         raise
@@ -482,7 +507,10 @@ def run_adaptive(xs: Sequence, sr: int, device: int = 0, want_host: bool = True,
         plan = plan0 if single_branch else Plan(eng, L.FRAMING_WHOLEFILE, [whole_track_desc(xd[i], yd[i]) for i in idx], unit_blocks)
         try:
             scale = np.array([np.float32(branch[i][1]) for i in idx], dtype=np.float32)
-            plan.levels(use_f64=use_f64, in_scale=scale, mono=mono)
+            if _linked is not None:
+                plan.levels_multichannel(_linked[0], _linked[1], use_f64=use_f64, in_scale=scale)
+            else:
+                plan.levels(use_f64=use_f64, in_scale=scale, mono=mono)
             msq = plan.read(L.ARR_MEANSQ_F64 if use_f64 else L.ARR_MEANSQ_F32)
             levels_all = tb.levels_from_meansq(msq)
             plan.write(L.ARR_GATE_F64, levels_all)
@@ -538,6 +566,9 @@ def run_adaptive(xs: Sequence, sr: int, device: int = 0, want_host: bool = True,
             else:      # restore_lin = db_to_lin(atten_db), float32 (src/process_tomatis_adaptive.py:335-337)
                 restore = np.array([np.float32(tb.db_to_lin_keep(branch[i][0])) for i in idx], dtype=np.float32)
                 plan.edge_frames(1.0, scale, restore, pipeline_f64=False)
+            if _linked is not None:                   # output_peak = np.max(np.abs(y)) over every channel (:340): one scale for all pairs
+                pk = plan.read(L.ARR_CHUNK_PEAK)
+                plan.write(L.ARR_CHUNK_PEAK, np.full_like(pk, pk.max() if len(pk) else 0.0))
             plan.limiter()
             if in_kernel:
                 states, rows, peaks, best_T, iters, tr_T, tr_c = plan.read_many(
@@ -560,6 +591,34 @@ def run_adaptive(xs: Sequence, sr: int, device: int = 0, want_host: bool = True,
         finally:
             plan.close()
     return results
+
+
+def run_adaptive_multichannel(x: np.ndarray, sr: int, device: int = 0, want_host: bool = True, **params) -> dict:
+    """adaptive mode on one file with more than two channels (the reference's `for c in range(ch)`,
+    src/process_tomatis_adaptive.py:307-313): the file is cut into channel pairs on the device, every pair is a track of one
+    plan of the stereo path, and what the reference computes over all channels -- input peak (:201), frame level (:74), output
+    peak (:340) -- is shared by the pairs, so that there is one gate, one pre-attenuation and one limiter scale."""
+    torch = _torch()
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    total, ch = x.shape
+    if ch > 128:
+        raise NotImplementedError(f"up to 128 channels, got {ch}")
+    npairs = (ch + 1) // 2
+    lib = L.load()
+    xd = torch.from_numpy(x).to(f"cuda:{device}")
+    pairs = torch.empty((npairs, max(1, total), 2), dtype=torch.float32, device=xd.device)
+    L.check(lib.tmt_channels_split(C.c_void_p(xd.data_ptr()), total, ch, C.c_void_p(pairs.data_ptr()), _stream_ptr(torch)), "tmt_channels_split")
+    outs = torch.empty_like(pairs)
+    res = run_adaptive([pairs[p, :total] for p in range(npairs)], sr, device=device, want_host=False,
+                       outs=[outs[p, :total] for p in range(npairs)], _linked=(xd, ch), **params)
+    yd = torch.empty_like(xd)
+    L.check(lib.tmt_channels_merge(C.c_void_p(outs.data_ptr()), total, ch, C.c_void_p(yd.data_ptr()), _stream_ptr(torch)), "tmt_channels_merge")
+    r = dict(res[0])
+    r["out"] = yd.cpu().numpy() if want_host else yd
+    r["output_peak"] = max(float(q["output_peak"]) for q in res)
+    r["launches"] = res[-1]["launches"] + 2
+    r["channels"] = ch
+    return r
 
 
 # ------------------------------------------------------------------------------ per-channel state analysis (N3)

@@ -7,9 +7,10 @@ reference).  Whole file in HBM; input peak, per-frame levels, every gate simulat
 bisection, the final gate + alpha counter, STFT/OLA, restore gain and the global limiter run on the device
 (engine.run_adaptive); percentiles and the bisection bookkeeping stay on the host.
 
-Mono files are accepted like in the reference (:180-181; they ride in the L lane of the stereo kernels).  Difference
-from the reference: more than two channels raise NotImplementedError -- the kernels pack a channel pair as one
-complex signal.
+Mono files are accepted like in the reference (:180-181; they ride in the L lane of the stereo kernels).  Files with more
+than two channels (the reference's `for c in range(ch)`, :307-313) are cut into channel pairs on the device; the pairs share
+input peak, frame level, gate and limiter scale, all taken over every channel like the reference does
+(engine.run_adaptive_multichannel; default n_fft / hop only).
 """
 from __future__ import annotations
 
@@ -49,8 +50,6 @@ def process(
     ch = x.shape[1]
     total = len(x)
     print(f"  sample rate: {sr} Hz\n  channels: {ch}\n  duration: {total / sr:.2f} s")
-    if ch > 2:
-        raise NotImplementedError(f"the B200 path processes mono and stereo files; got {ch} channels")
     if total == 0:
         raise ValueError("zero-size array to reduction operation maximum which has no identity")   # np.max(np.abs(x)), :201
 
