@@ -439,8 +439,10 @@ def longfile_config(n_gpus, total=LF_TOTAL):
                     f"--gate_ui 50, time-chunk sharded across {n_gpus} GPU(s) on limiter-chunk boundaries with one-hop halos",
         "mode": "standard", "gate_ui": 50, "sample_rate": LF_SR, "file_seconds": total / LF_SR, "n_fft": 4096, "hop": 2048,
         "l2_policy": f"inputs larger than L2 ({total * 8 / 1e9:.2f} GB in + out per pass, streamed once)",
-        "parallelism": f"time-chunk sharded x{n_gpus}: NCCL halo hand-off (2 x 16 KB per rank), all-reduce of per-frame mean squares "
-                       f"({total // 2048 * 4 / 1e6:.2f} MB) + redundant gate scan, all-reduce(max) of chunk peaks",
+        "parallelism": f"time-chunk sharded x{n_gpus} on limiter-chunk boundaries; per pass every rank's hop-block sums go to every rank "
+                       f"({total // 2048 * 4 / 1e6:.2f} MB assembled) for the redundant gate scan and one hop (16 KB) to each neighbour: "
+                       "peer-memory stores + flags over NVLink (CUDA IPC) when available, else NCCL all-gather + all-reduce; "
+                       "the per-chunk limiter is rank-local (fused in stft_kernel)",
     }
 
 
@@ -580,6 +582,9 @@ def longfile_measure(args, dist, rank, world, local, steps, want_cpu):
                      "algorithmic_bytes_per_launch": ALG_BYTES_PER_SF * sf_rank, "kernel_ms": stft_ms,
                      "kernel_share_of_step": stft_ms * steps / ms_total},
         "phase_ms_rank0": breakdown, "graph_replay": bool(getattr(sess, "_graph", None) is not None),
+        "exchange": ("none (one rank)" if world == 1 else "peer memory (publish / wait kernels, CUDA IPC over NVLink)"
+                     if getattr(sess, "peer", None) is not None else "NCCL collectives (all-gather + all-reduce)"),
+        "peer_status": (sess.peer.status() if getattr(sess, "peer", None) is not None else None),
         "checks": {"c2_fraction": float((states == 2).mean()), "chunks_over_limit": float((peaks > np.float32(0.999)).mean()),
                    "output_peak": out_peak, "frames": int(states.size)},
     }

@@ -276,8 +276,7 @@ int tmt_calib_gate_grid(tmt_engine* e, const float* level, const int64_t* start,
                         const float* off, const int64_t* delay, int n_combos, int32_t* mismatches, int32_t* switches,
                         uint8_t* states, void* stream);
 
-/* ---- general FFT sizes (EXPERIMENTAL: parity on hardware not yet verified, the Python front ends use it only with
- * TMT_GENERIC_FFT=1).  The reference exposes --n_fft / --hop (src/process_tomatis.py:509-510, _adaptive.py:396-397,
+/* ---- general FFT sizes (verified on hardware in round 2; on by default, TMT_GENERIC_FFT=0 turns it off).  The reference exposes --n_fft / --hop (src/process_tomatis.py:509-510, _adaptive.py:396-397,
  * _xfade.py:388-389); the fused kernels implement 4096 / 2048.  Plain path for power-of-two n_fft in [128, 8192], hop in
  * [1, n_fft]: frame k covers [first_start + k*hop, + n_fft), zeros outside [0, total).  All pointers device.
  * flavour: 0 streaming (standard / xfade), 1 adaptive float32 pipeline, 2 adaptive float64 pipeline. */
@@ -297,6 +296,29 @@ int tmt_generic_overlap_add(tmt_engine* e, const void* frames, int flavour, int6
  * chunk into peaks_out (float32 / float64 [n_chunks]), chunks above `limit` scaled by limit / peak in place. */
 int tmt_generic_limit(tmt_engine* e, void* y, int use_f64, const int64_t* bounds, int n_chunks, double limit, void* peaks_out, void* stream);
 int tmt_generic_to_float(tmt_engine* e, const void* y_f64, int64_t n, void* out_f32, void* stream);
+
+/* ---- one long file over several GPUs: the per-pass exchange through peer memory ------------------------
+ * The reference processes a file front to back in one process (src/process_tomatis.py:359-453); time shards need, per pass,
+ * every rank's hop-block sums on every rank (for the identical gate scan) and one hop of samples from each neighbour.  Instead
+ * of two collectives each rank owns an exchange buffer that the other ranks' processes map through CUDA IPC:
+ *   tmt_peer_alloc / tmt_peer_open / tmt_peer_close / tmt_peer_free   buffer of tmt_peer_bytes(n_hop_blocks) bytes + its 64-byte handle;
+ *   tmt_plan_peer_publish   after tmt_plan_levels(HOPSUM_ONLY): one kernel stores the rank's own hop sums into every rank's buffer,
+ *                           its first / last hop (device pointers, 2048 sample-frames each) into the neighbours' halo slots, and
+ *                           raises this rank's flag everywhere (system-scope release).  bases: host array of `world` device pointers
+ *                           (entry `rank` = the rank's own buffer);
+ *   tmt_plan_peer_wait      one kernel waits for all flags of the rank's own buffer (acquire; gives up after timeout_s and records
+ *                           1 + the missing rank in the status word, tmt_peer_status), then copies the assembled hop sums into the
+ *                           plan (TMT_ARR_HOPSUM_F32) and the halos into the first `left` / last `right` sample-frames of `window`.
+ * Every rank must call publish and wait once per pass, in that order.  One-track plans only. */
+size_t tmt_peer_bytes(int n_hop_blocks);
+int tmt_peer_alloc(int device, size_t bytes, void** ptr, unsigned char* handle64);
+int tmt_peer_open(int device, const unsigned char* handle64, void** ptr);
+int tmt_peer_close(int device, void* ptr);
+int tmt_peer_free(int device, void* ptr);
+int tmt_peer_status(int device, const void* base, int32_t* status);
+int tmt_plan_peer_publish(tmt_plan* p, int rank, int world, void* const* bases, const void* first_hop, const void* last_hop, void* stream);
+int tmt_plan_peer_wait(tmt_plan* p, int world, void* base, void* window, int64_t window_len, int left, int right, double timeout_s,
+                       void* stream);
 
 /* Number of kernel launches issued by this plan since creation (bench.py's gpu_launches). */
 int64_t tmt_plan_launch_count(const tmt_plan* p);

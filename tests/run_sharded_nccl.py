@@ -47,24 +47,39 @@ def main():
             print(f"{mode}: world {world}, {total} samples, interior err {d[256:-256].max():.2e}, vs fp64-FFT {d64:.2e}, "
                   f"comm {r['comm_bytes']} B")
         dist.barrier()
-    # the persistent session bench.py times: all-gather halo hand-off + hop-sum all-reduce, two passes
+    # the persistent session bench.py times, in both exchange flavours: peer memory (publish / wait kernels over CUDA IPC) and
+    # collectives (all-gather halo hand-off + hop-sum all-reduce).  Three passes on one input, then fresh samples in place and two
+    # more passes (a stale parity buffer or halo would show), each flavour against the oracle and against the other, bit for bit.
     x = cases[0][2]
+    x2 = synth.recipe_gated_pink(11.0, 48000, 77, env_hz=1.3, hi_dbfs=-20.0)
     total = len(x)
     me = sharded.plan_shards(total, world, sharded.STREAMING)[rank]
-    o = orc.run("standard", x, 48000, gate_ui=50)
-    sess = sharded.StreamingShardSession("standard", torch.from_numpy(x[me.own_lo:me.own_hi].copy()).cuda(), 48000, total, comm,
-                                         device_index=local, gate_ui=50)
-    say(f"session created, unfusable chunks {sess.be.plan.unfusable_chunks}, graph {sess.use_graph}")
-    for k in range(3):
-        sess.step()
-        torch.cuda.synchronize()
-        say(f"session step {k} done (graph replay: {sess._graph is not None})")
-    y = sess.out.cpu().numpy().astype(np.float64)
-    d = np.abs(y - o["out"][me.own_lo:me.own_hi]).max(axis=1)
-    if rank == world - 1:
-        d = d[:-256]
-    assert d.max() <= 1e-5, (rank, d.max())
-    sess.close()
+    outs = {}
+    for flavour in ("peer", "collectives"):
+        sess = sharded.StreamingShardSession("standard", torch.from_numpy(x[me.own_lo:me.own_hi].copy()).cuda(), 48000, total, comm,
+                                             device_index=local, gate_ui=50, use_peer=(flavour == "peer"))
+        say(f"{flavour}: session created, unfusable chunks {sess.be.plan.unfusable_chunks}, graph {sess.use_graph}, "
+            f"peer exchange {sess.peer is not None}")
+        assert (sess.peer is not None) == (flavour == "peer"), "peer-memory exchange not available on this box"
+        for src in (x, x2):
+            o = orc.run("standard", src, 48000, gate_ui=50)
+            sess.own.copy_(torch.from_numpy(src[me.own_lo:me.own_hi].copy()).cuda())
+            for k in range(3 if src is x else 2):
+                sess.step()
+                torch.cuda.synchronize()
+            say(f"{flavour}: passes done (graph replay: {sess._graph is not None})")
+            if sess.peer is not None:
+                assert sess.peer.status() == 0, sess.peer.status()
+            y = sess.out.cpu().numpy()
+            d = np.abs(y.astype(np.float64) - o["out"][me.own_lo:me.own_hi]).max(axis=1)
+            if rank == world - 1:
+                d = d[:-256]
+            assert d.max() <= 1e-5, (flavour, rank, d.max())
+            outs[(flavour, src is x)] = y.copy()
+        sess.close()
+        dist.barrier()
+    for key in (True, False):
+        assert np.array_equal(outs[("peer", key)], outs[("collectives", key)]), "peer-memory and collective exchange differ"
     dist.barrier()
     if rank == 0:
         print("SHARDED-NCCL-OK")

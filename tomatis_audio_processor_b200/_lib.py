@@ -63,6 +63,14 @@ SIGNATURES = {
     "tmt_channels_split": (C.c_int, [_P, C.c_int64, C.c_int, _P, _P]),
     "tmt_channels_merge": (C.c_int, [_P, C.c_int64, C.c_int, _P, _P]),
     "tmt_plan_gate": (C.c_int, [_P, C.c_int, C.c_int, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
+    "tmt_peer_bytes": (C.c_size_t, [C.c_int]),
+    "tmt_peer_alloc": (C.c_int, [C.c_int, C.c_size_t, _P, _P]),
+    "tmt_peer_open": (C.c_int, [C.c_int, _P, _P]),
+    "tmt_peer_close": (C.c_int, [C.c_int, _P]),
+    "tmt_peer_free": (C.c_int, [C.c_int, _P]),
+    "tmt_peer_status": (C.c_int, [C.c_int, _P, _P]),
+    "tmt_plan_peer_publish": (C.c_int, [_P, C.c_int, C.c_int, _P, _P, _P, _P]),
+    "tmt_plan_peer_wait": (C.c_int, [_P, C.c_int, _P, _P, C.c_int64, C.c_int, C.c_int, C.c_double, _P]),
     "tmt_plan_bisect": (C.c_int, [_P, _P, _P, _P, _P, C.c_double, C.c_double, C.c_int, C.c_int, _P]),
     "tmt_plan_stft": (C.c_int, [_P, C.c_float, C.c_int, _P]),
     "tmt_plan_stft_limited": (C.c_int, [_P, C.c_float, C.c_float, _P]),

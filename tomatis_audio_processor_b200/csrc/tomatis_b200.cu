@@ -398,6 +398,95 @@ __global__ void __launch_bounds__(256) channels_merge_kernel(const float2* __res
 }
 
 // ------------------------------------------------------------------------------------------------
+// Long file over several GPUs: the per-pass exchange through PEER MEMORY (NVLink) instead of collectives.
+// Each rank owns one "exchange buffer" (cudaMalloc, shared with the other ranks' processes through CUDA IPC), same layout
+// everywhere:   header (epoch, CTA counter, status) | flags[64] | halo staging [2 parities][2 sides][one hop] | hop sums [2][nb]
+// publish_kernel (after the rank summed its own hop blocks): stores these sums straight into EVERY rank's hop-sum array,
+// its first hop into the left neighbour's "from the right" slot and its last hop into the right neighbour's "from the left"
+// slot, then -- last CTA, after a system-scope fence -- raises flag[rank] = epoch in every rank's buffer (release).
+// wait_unpack_kernel (before the gate scan): spins until all flags of its own buffer reached the epoch (acquire), then copies
+// the assembled hop sums into the plan and the two halos into the rank's input window.
+// Two parities: a rank can be at most one pass ahead of a peer (it cannot leave pass k+1's wait before the peer published
+// pass k+1, i.e. finished reading pass k), so the data of pass k is never overwritten before it was read.
+constexpr int kPeerMaxWorld = 64;
+constexpr size_t kPeerOffFlags = 256, kPeerOffHalo = 512, kPeerHaloBytes = 2 * 2 * (size_t)kHop * sizeof(float2);
+constexpr size_t kPeerOffHsum = kPeerOffHalo + kPeerHaloBytes;
+__host__ __device__ inline size_t peer_nb_pad(int nb) { return ((size_t)nb + 63) & ~size_t(63); }
+
+struct PeerPublishParams {
+    unsigned char* bases[kPeerMaxWorld];   // every rank's exchange buffer as this process sees it (own one included)
+    int rank, world;
+    const float* hsum;                     // the plan's hop sums of this track (index = hop block)
+    int hb_lo, hb_hi, nb;
+    const float2* first_hop;               // own samples [0, hop) and [len - hop, len)
+    const float2* last_hop;
+};
+
+__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) { asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+__global__ void __launch_bounds__(256) peer_publish_kernel(const PeerPublishParams prm) {
+    __shared__ int is_last;
+    unsigned* hdr = reinterpret_cast<unsigned*>(prm.bases[prm.rank]);
+    const unsigned epoch = hdr[0] + 1u;                               // hdr[0] is only rewritten by the last CTA, below
+    const unsigned par = epoch & 1u;
+    const size_t nbp = peer_nb_pad(prm.nb);
+    const int gt = blockIdx.x * blockDim.x + threadIdx.x, gn = gridDim.x * blockDim.x;
+    for (int r = 0; r < prm.world; ++r) {
+        float* dst = reinterpret_cast<float*>(prm.bases[r] + kPeerOffHsum) + par * nbp;
+        for (int q = prm.hb_lo + gt; q < prm.hb_hi; q += gn) dst[q] = prm.hsum[q];
+    }
+    if (prm.rank + 1 < prm.world) {                                   // my last hop = the right neighbour's left halo
+        float2* dst = reinterpret_cast<float2*>(prm.bases[prm.rank + 1] + kPeerOffHalo) + (par * 2 + 0) * kHop;
+        for (int i = gt; i < kHop; i += gn) dst[i] = prm.last_hop[i];
+    }
+    if (prm.rank > 0) {                                               // my first hop = the left neighbour's right halo
+        float2* dst = reinterpret_cast<float2*>(prm.bases[prm.rank - 1] + kPeerOffHalo) + (par * 2 + 1) * kHop;
+        for (int i = gt; i < kHop; i += gn) dst[i] = prm.first_hop[i];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) is_last = (atomicAdd(hdr + 1, 1u) == gridDim.x - 1) ? 1 : 0;
+    __syncthreads();
+    if (is_last) {
+        __threadfence_system();
+        for (int r = threadIdx.x; r < prm.world; r += blockDim.x)
+            st_release_sys(reinterpret_cast<unsigned*>(prm.bases[r] + kPeerOffFlags) + prm.rank, epoch);
+        if (threadIdx.x == 0) { hdr[1] = 0u; hdr[0] = epoch; }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+peer_wait_unpack_kernel(unsigned char* base, int world, float* hsum_dst, int nb, float2* window, long long window_len, int left, int right,
+                        unsigned long long timeout_ns) {
+    unsigned* hdr = reinterpret_cast<unsigned*>(base);
+    const unsigned epoch = hdr[0];                                    // raised by this rank's publish_kernel earlier on the stream
+    if (threadIdx.x < world) {
+        const unsigned* flag = reinterpret_cast<const unsigned*>(base + kPeerOffFlags) + threadIdx.x;
+        unsigned long long t0;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        while ((int)(ld_acquire_sys(flag) - epoch) < 0) {
+            __nanosleep(200);
+            unsigned long long t1;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+            if (t1 - t0 > timeout_ns) { atomicExch(hdr + 2, 1u + threadIdx.x); break; }     // a peer never arrived: say which, do not hang
+        }
+    }
+    __syncthreads();
+    const unsigned par = epoch & 1u;
+    const int gt = blockIdx.x * blockDim.x + threadIdx.x, gn = gridDim.x * blockDim.x;
+    const float* src = reinterpret_cast<const float*>(base + kPeerOffHsum) + par * peer_nb_pad(nb);
+    for (int q = gt; q < nb; q += gn) hsum_dst[q] = __ldcg(src + q);
+    const float2* halo = reinterpret_cast<const float2*>(base + kPeerOffHalo) + (size_t)par * 2 * kHop;
+    for (int i = gt; i < left; i += gn) window[i] = __ldcg(halo + (kHop - left) + i);
+    for (int i = gt; i < right; i += gn) window[window_len - right + i] = __ldcg(halo + kHop + i);
+}
+
+// ------------------------------------------------------------------------------------------------
 // K2b gate.  Both automata are finite-state machines driven by two bits per frame
 // (hi: value >= on, lo: value <= off), so a run of frames is a map on the state set and maps compose
 // associatively.  One CTA per track; each thread owns a contiguous segment of frames, builds the
@@ -2802,6 +2891,85 @@ int tmt_channels_merge(const float* pairs, int64_t total, int channels, float* o
     const long long n = total * ((channels + 1) / 2);
     channels_merge_kernel<<<(int)std::min<long long>((n + 255) / 256, 148 * 16), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
         reinterpret_cast<const float2*>(pairs), total, channels, out);
+    CUDA_TRY(cudaGetLastError());
+    return TMT_OK;
+}
+
+// ---- peer-memory exchange of the sharded long file (see peer_publish_kernel) -------------------------------------------
+size_t tmt_peer_bytes(int n_hop_blocks) { return kPeerOffHsum + 2 * peer_nb_pad(std::max(n_hop_blocks, 0)) * sizeof(float); }
+
+int tmt_peer_alloc(int device, size_t bytes, void** ptr, unsigned char* handle64) {
+    if (!ptr || !handle64 || bytes < kPeerOffHsum) return fail(TMT_ERR_INVALID, "bad arguments");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    CUDA_TRY(cudaSetDevice(device));
+    void* p = nullptr;
+    CUDA_TRY(cudaMalloc(&p, bytes));
+    cudaError_t e = cudaMemset(p, 0, bytes);
+    cudaIpcMemHandle_t h;
+    if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) { cudaFree(p); return fail(TMT_ERR_CUDA, "exchange buffer: %s", cudaGetErrorString(e)); }
+    memcpy(handle64, &h, 64);
+    *ptr = p;
+    return TMT_OK;
+}
+int tmt_peer_open(int device, const unsigned char* handle64, void** ptr) {
+    if (!ptr || !handle64) return fail(TMT_ERR_INVALID, "bad arguments");
+    CUDA_TRY(cudaSetDevice(device));
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    CUDA_TRY(cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return TMT_OK;
+}
+int tmt_peer_close(int device, void* ptr) {
+    CUDA_TRY(cudaSetDevice(device));
+    if (ptr) CUDA_TRY(cudaIpcCloseMemHandle(ptr));
+    return TMT_OK;
+}
+int tmt_peer_free(int device, void* ptr) {
+    CUDA_TRY(cudaSetDevice(device));
+    if (ptr) CUDA_TRY(cudaFree(ptr));
+    return TMT_OK;
+}
+int tmt_peer_status(int device, const void* base, int32_t* status) {
+    if (!base || !status) return fail(TMT_ERR_INVALID, "bad arguments");
+    CUDA_TRY(cudaSetDevice(device));
+    unsigned v = 0;
+    CUDA_TRY(cudaMemcpy(&v, static_cast<const unsigned char*>(base) + 8, 4, cudaMemcpyDeviceToHost));
+    *status = (int32_t)v;
+    return TMT_OK;
+}
+
+int tmt_plan_peer_publish(tmt_plan* p, int rank, int world, void* const* bases, const void* first_hop, const void* last_hop, void* stream) {
+    if (!p || !bases || p->n_tracks != 1) return fail(TMT_ERR_INVALID, "peer exchange works on a one-track (one shard) plan");
+    if (world < 1 || world > kPeerMaxWorld || rank < 0 || rank >= world) return fail(TMT_ERR_INVALID, "bad rank / world (max %d ranks)", kPeerMaxWorld);
+    if ((rank > 0 && !first_hop) || (rank + 1 < world && !last_hop)) return fail(TMT_ERR_INVALID, "edge hops missing");
+    CUDA_TRY(cudaSetDevice(p->e->device));
+    const HostTrack& h = p->ht[0];
+    PeerPublishParams prm;
+    for (int r = 0; r < kPeerMaxWorld; ++r) prm.bases[r] = r < world ? static_cast<unsigned char*>(bases[r]) : nullptr;
+    prm.rank = rank; prm.world = world;
+    prm.hsum = reinterpret_cast<const float*>(p->hsum.p) + h.hs_base;
+    prm.hb_lo = h.hb_lo; prm.hb_hi = h.hb_hi; prm.nb = h.n_frames > 0 ? h.n_frames + 1 : 0;
+    prm.first_hop = static_cast<const float2*>(first_hop); prm.last_hop = static_cast<const float2*>(last_hop);
+    const int grid = std::max(1, std::min(32, ceil_div(std::max(h.hb_hi - h.hb_lo, kHop), 256)));
+    peer_publish_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(prm);
+    p->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return TMT_OK;
+}
+
+int tmt_plan_peer_wait(tmt_plan* p, int world, void* base, void* window, int64_t window_len, int left, int right, double timeout_s, void* stream) {
+    if (!p || !base || p->n_tracks != 1 || !window) return fail(TMT_ERR_INVALID, "bad arguments");
+    if (world < 1 || world > kPeerMaxWorld || left < 0 || right < 0 || left > kHop || right > kHop || left + right > window_len)
+        return fail(TMT_ERR_INVALID, "bad world / halo lengths");
+    CUDA_TRY(cudaSetDevice(p->e->device));
+    const HostTrack& h = p->ht[0];
+    const int nb = h.n_frames > 0 ? h.n_frames + 1 : 0;
+    const int grid = std::max(1, std::min(64, ceil_div(std::max(nb, kHop), 1024)));
+    peer_wait_unpack_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        static_cast<unsigned char*>(base), world, reinterpret_cast<float*>(p->hsum.p) + h.hs_base, nb, static_cast<float2*>(window), window_len,
+        left, right, (unsigned long long)(std::max(timeout_s, 0.001) * 1e9));
+    p->launches++;
     CUDA_TRY(cudaGetLastError());
     return TMT_OK;
 }

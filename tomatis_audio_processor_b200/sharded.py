@@ -216,6 +216,86 @@ class Comm:
         return None
 
 
+# ------------------------------------------------------------------------------------------------ peer-memory exchange
+class PeerExchange:
+    """The per-pass exchange of the persistent session through peer memory instead of collectives (include/tomatis_b200.h,
+    "peer memory"): every rank owns an exchange buffer, maps the other ranks' buffers through CUDA IPC (handles travel once, over
+    the process group), and a pass is two small kernels -- publish (own hop sums into every rank's buffer, edge hops into the
+    neighbours', flags raised) and wait + unpack -- instead of an all-gather, an all-reduce and the copies around them.
+    Construction is collective; `ok` is the same on every rank (False: some rank could not map a peer -> the session keeps
+    using the collectives)."""
+
+    def __init__(self, comm: "Comm", shard: Shard, device_index: int, timeout_s: float = 5.0):
+        import ctypes as C
+        from . import _lib as L
+        self.L, self.C, self.lib = L, C, L.load()
+        self.comm, self.shard, self.device, self.timeout_s = comm, shard, device_index, timeout_s
+        self.nb = shard.n_frames + 1 if shard.n_frames > 0 else 0
+        self.own_ptr, self.peers, self.ok = None, {}, False
+        torch, dist = comm.torch, comm.dist
+        handle = (C.c_ubyte * 64)()
+        ptr = C.c_void_p()
+        good = 1
+        try:
+            L.check(self.lib.tmt_peer_alloc(device_index, self.lib.tmt_peer_bytes(self.nb), C.byref(ptr), handle), "tmt_peer_alloc")
+            self.own_ptr = ptr.value
+        except Exception:
+            good = 0
+        mine = torch.tensor(list(bytes(handle)) + [good], dtype=torch.uint8, device=comm.device)
+        allh = torch.empty((comm.world, 65), dtype=torch.uint8, device=comm.device)
+        dist.all_gather_into_tensor(allh, mine, group=comm.group)
+        allh = allh.cpu().numpy()
+        good = int(allh[:, 64].min())
+        if good:
+            for r in range(comm.world):
+                if r == comm.rank:
+                    continue
+                q = C.c_void_p()
+                h = (C.c_ubyte * 64)(*allh[r, :64].tolist())
+                if self.lib.tmt_peer_open(device_index, h, C.byref(q)) != 0:
+                    good = 0
+                    break
+                self.peers[r] = q.value
+        flag = torch.tensor([good], dtype=torch.int32, device=comm.device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=comm.group)
+        self.ok = bool(int(flag.item()))
+        if not self.ok:
+            self.close()
+            return
+        self.bases = (C.c_void_p * comm.world)(*[(self.own_ptr if r == comm.rank else self.peers[r]) for r in range(comm.world)])
+
+    def publish(self, plan, own):
+        C, hop = self.C, tb.HOP
+        first = own.data_ptr() if self.shard.rank > 0 else None
+        last = own[own.shape[0] - hop:].data_ptr() if self.shard.rank + 1 < self.shard.world else None
+        from .engine import _stream_ptr
+        self.L.check(self.lib.tmt_plan_peer_publish(plan.h, self.shard.rank, self.shard.world, self.bases, C.c_void_p(first), C.c_void_p(last),
+                                                    _stream_ptr(self.comm.torch)), "tmt_plan_peer_publish")
+
+    def wait_unpack(self, plan, window):
+        C, s = self.C, self.shard
+        from .engine import _stream_ptr
+        self.L.check(self.lib.tmt_plan_peer_wait(plan.h, s.world, C.c_void_p(self.own_ptr), C.c_void_p(window.data_ptr()), int(window.shape[0]),
+                                                 s.own_lo - s.in_lo, s.in_hi - s.own_hi, float(self.timeout_s), _stream_ptr(self.comm.torch)),
+                     "tmt_plan_peer_wait")
+
+    def status(self) -> int:
+        """0, or 1 + the rank whose flag never arrived within the timeout (the pass that saw it produced garbage)."""
+        v = self.C.c_int32(0)
+        self.L.check(self.lib.tmt_peer_status(self.device, self.C.c_void_p(self.own_ptr), self.C.byref(v)), "tmt_peer_status")
+        return int(v.value)
+
+    def close(self):
+        for q in self.peers.values():
+            self.lib.tmt_peer_close(self.device, self.C.c_void_p(q))
+        self.peers = {}
+        if self.own_ptr:
+            if isinstance(self.comm, Comm) and self.comm.world > 1:
+                self.comm.dist.barrier(group=self.comm.group)      # nobody frees a buffer a peer still has mapped and may write to
+            self.lib.tmt_peer_free(self.device, self.C.c_void_p(self.own_ptr))
+            self.own_ptr = None
+
+
 # ------------------------------------------------------------------------------------------------ CUDA backend
 class CudaShardBackend:
     """engine.Plan over one shard: input window + owned output buffer on this rank's GPU."""
@@ -445,7 +525,8 @@ class StreamingShardSession:
     level all-reduce, gate scan, STFT/OLA, edge frames, peak all-reduce, limiter -- with no host synchronisation."""
 
     def __init__(self, mode: str, own, sr: int, total: int, comm: Comm, device_index: int = 0, unit_blocks: int = 0,
-                 use_graph: bool = True, **params):
+                 use_graph: bool = True, use_peer: Optional[bool] = None, **params):
+        import os
         from . import _lib as L
         from .engine import streaming_params
         self.L, self.comm, self.own = L, comm, own
@@ -459,6 +540,17 @@ class StreamingShardSession:
         self.be = CudaShardBackend(self.me, window, device_index, self.sp.rows, self.sp.rows_key, unit_blocks)
         # from here on the rank's samples live inside the window buffer: refresh them through this view
         self.own = window[self.me.own_lo - self.me.in_lo: self.me.own_hi - self.me.in_lo]
+        # per-pass exchange through peer memory (PeerExchange) when there is more than one rank, the communicator is a real
+        # process group and every halo is at most one hop from the adjacent rank; TMT_PEER_EXCHANGE=0 keeps the collectives
+        self.peer = None
+        if use_peer is None:
+            use_peer = os.environ.get("TMT_PEER_EXCHANGE", "1") != "0"
+        hop = tb.HOP
+        simple = all(s.own_hi - s.own_lo >= hop and s.own_lo - s.in_lo <= hop and s.in_hi - s.own_hi <= hop for s in self.shards)
+        if use_peer and comm.world > 1 and isinstance(comm, Comm) and comm.device.type == "cuda" and simple:
+            px = PeerExchange(comm, self.me, device_index)
+            if px.ok:
+                self.peer = px
 
     def _step_eager(self, stft_events=None, marks=None):
         comm, be, me, sp, L = self.comm, self.be, self.me, self.sp, self.L
@@ -470,6 +562,28 @@ class StreamingShardSession:
                 e.record()
                 marks.append((label, e))
         mark("start")
+        if self.peer is not None:
+            # hop sums of the blocks this rank owns -> published straight into every rank's exchange buffer together with the
+            # edge hops the neighbours need; then one kernel that waits for everybody's flag and unpacks sums and halos
+            s = me
+            nb = s.n_frames + 1 if s.n_frames > 0 else 0
+            if not getattr(be, "_ranges_set", False):
+                be.plan.set_level_ranges(0, min(s.block_lo, nb), min(s.block_hi, nb), 0, s.n_frames)
+                be._ranges_set = True
+            be.plan.levels(part="hopsums")
+            mark("levels")
+            self.peer.publish(be.plan, self.own)
+            mark("peer_publish")
+            self.peer.wait_unpack(be.plan, be.window)
+            mark("peer_wait")
+            be.plan.levels(part="meansq")
+            if not self._thresholds_set:
+                be.gate(L.GATE_UPDELAY, L.ARR_MEANSQ_F32, sp.m_on, sp.m_off, sp.run_frames, sp.xfade_frames)
+                self._thresholds_set = True
+            else:
+                be.gate(L.GATE_UPDELAY, L.ARR_MEANSQ_F32, None, None, sp.run_frames, sp.xfade_frames)
+            mark("gate")
+            return self._step_audio(stft_events, mark)
         pending = comm.exchange_halos_begin(self.own, me, self.shards)    # 1. halo hand-off starts (fresh data every pass) ...
         mark("halo_issue")
         hsum = be.own_hop_sums()                                        # ... while the rank sums the hop blocks it owns
@@ -486,6 +600,10 @@ class StreamingShardSession:
         mark("gate")
         comm.exchange_halos_end(pending, me, be.window)                  # the STFT is the first consumer of the halos
         mark("halo_wait")
+        return self._step_audio(stft_events, mark)
+
+    def _step_audio(self, stft_events, mark):
+        comm, be, sp = self.comm, self.be, self.sp
         if be.plan.unfusable_chunks == 0:
             # every limiter chunk lies inside this rank's range (shards are cut on chunk boundaries): the per-chunk limiter runs
             # inside the STFT kernel, no peak exchange, no separate pass (src/process_tomatis.py:331-357)
@@ -546,4 +664,9 @@ class StreamingShardSession:
             import torch                     # process group with it still alive hangs
             torch.cuda.synchronize()
             self._graph = None
+        if self.peer is not None:
+            import torch
+            torch.cuda.synchronize()
+            self.peer.close()
+            self.peer = None
         self.be.close()
