@@ -223,6 +223,12 @@ int tmt_plan_edge_frames(tmt_plan* p, float post_gain, const float* in_scale, co
  * (write_clamped, src/process_tomatis.py:352-355; global variant _adaptive.py:341-345). */
 int tmt_plan_limiter(tmt_plan* p, float limit, void* stream);
 
+/* tmt_plan_stft (chunk peaks cleared, no limiter) with the fp64 edge frames of tmt_plan_edge_frames running BESIDE the STFT kernel
+ * on the engine's side stream (forked from and joined back into `stream`): the two write disjoint blocks.  For jobs that limit in
+ * a separate pass anyway (adaptive mode, single short files), where the latency-bound edge kernel is a large part of the call. */
+int tmt_plan_stft_with_edges(tmt_plan* p, float post_gain, const float* in_scale, const float* out_scale, int pipeline_f64,
+                             void* stream);
+
 /* Convenience: levels (f32) -> gate -> edge frames -> stft with fused limiter on one stream, standard/xfade parameters. */
 int tmt_plan_run_streaming(tmt_plan* p, double m_on, double m_off, int run_frames, int xfade_frames,
                            float post_gain, float limit, void* stream);

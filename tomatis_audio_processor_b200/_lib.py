@@ -76,6 +76,7 @@ SIGNATURES = {
     "tmt_plan_stft_limited": (C.c_int, [_P, C.c_float, C.c_float, _P]),
     "tmt_plan_clear_peaks": (C.c_int, [_P, _P]),
     "tmt_plan_edge_frames": (C.c_int, [_P, C.c_float, _P, _P, C.c_int, _P]),
+    "tmt_plan_stft_with_edges": (C.c_int, [_P, C.c_float, _P, _P, C.c_int, _P]),
     "tmt_plan_limiter": (C.c_int, [_P, C.c_float, _P]),
     "tmt_cond_spectrum": (C.c_int, [_P, _P, _P, C.c_int64, _P, C.c_int, C.c_int, C.c_int, _P, _P]),
     "tmt_calib_envelope_decimate": (C.c_int, [_P, _P, C.c_int64, _P, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int64, _P, _P]),

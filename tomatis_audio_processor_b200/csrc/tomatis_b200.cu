@@ -765,13 +765,18 @@ struct BisectParams {
 // Fast path of the search for automata of at most 16 states (min-hold up to 7 frames: the reference default is 6): a transition
 // map is 16 nibbles in one 64-bit register, a thread's levels stay in registers across the steps, and the scan by map composition
 // runs on warp shuffles (gate_kernel's shared-memory maps cost 25 us per step on a 10-minute track, this costs ~3).
-__device__ __forceinline__ unsigned long long nib_compose(unsigned long long a, unsigned long long b, int S) {   // s -> b[a[s]]
-    unsigned long long r = 0;
-    for (int s = 0; s < S; ++s) {
-        const unsigned x = (unsigned)(a >> (4 * s)) & 15u;
-        r |= ((b >> (4 * x)) & 15ull) << (4 * s);
+// All 16 nibbles, fully unrolled on the two 32-bit halves (constant shifts, one funnel shift per look-up): nibbles of states >= S
+// carry values nobody reads (a valid state never maps to them).  The loop over S with run-time shifts was twice as long.
+__device__ __forceinline__ unsigned long long nib_compose(unsigned long long a, unsigned long long b, int /*S*/) {   // s -> b[a[s]]
+    const unsigned alo = (unsigned)a, ahi = (unsigned)(a >> 32);
+    unsigned rlo = 0, rhi = 0;
+#pragma unroll
+    for (int s = 0; s < 8; ++s) {
+        const unsigned x = (alo >> (4 * s)) & 15u, y = (ahi >> (4 * s)) & 15u;
+        rlo |= ((unsigned)(b >> (4 * x)) & 15u) << (4 * s);
+        rhi |= ((unsigned)(b >> (4 * y)) & 15u) << (4 * s);
     }
-    return r;
+    return ((unsigned long long)rhi << 32) | rlo;
 }
 constexpr int kBisectFastFrames = 16;        // frames per thread held in registers (1024 threads x 16 = the single-segment limit)
 
@@ -797,6 +802,13 @@ __global__ void __launch_bounds__(1024) bisect_fast_kernel(const BisectParams pr
         ident |= (unsigned long long)s << (4 * s);
     }
     auto map_of = [&](unsigned c) { return c == 0u ? mc[0] : (c == 1u ? mc[1] : (c == 2u ? mc[2] : mc[3])); };
+    // The maps of four consecutive frames, one per combination of their classes (256 of them, fixed for the whole search): a
+    // thread's segment map then costs one table read and one composition per four frames instead of four compositions -- the
+    // compositions (S dependent nibble look-ups each) are what a search step is made of.
+    __shared__ unsigned long long quad[256];
+    if (i < 256)
+        quad[i] = nib_compose(nib_compose(nib_compose(map_of(i & 3u), map_of((i >> 2) & 3u), S), map_of((i >> 4) & 3u), S), map_of((i >> 6) & 3u), S);
+    __syncthreads();
     double T_low = prm.t_low[track], T_high = prm.t_high[track], best_T = prm.best0[track], best_diff = 1.0;
     int iters = 0;
     if (prm.active[track] && F > 0) {
@@ -808,10 +820,17 @@ __global__ void __launch_bounds__(1024) bisect_fast_kernel(const BisectParams pr
             unsigned cls = 0;                               // 2 bits per frame: hi | 2 * lo
 #pragma unroll
             for (int k = 0; k < kBisectFastFrames; ++k) {
-                if (k < nf) {
-                    const unsigned c = ((x[k] >= on) ? 1u : 0u) | ((x[k] <= off) ? 2u : 0u);
-                    cls |= c << (2 * k);
-                    seg = nib_compose(seg, map_of(c), S);
+                if (k < nf) cls |= (((x[k] >= on) ? 1u : 0u) | ((x[k] <= off) ? 2u : 0u)) << (2 * k);
+            }
+#pragma unroll
+            for (int k = 0; k < kBisectFastFrames; k += 4) {
+                if (k + 4 <= nf) {
+                    const unsigned long long q = quad[(cls >> (2 * k)) & 255u];
+                    seg = k ? nib_compose(seg, q, S) : q;
+                } else {
+#pragma unroll
+                    for (int j = k; j < k + 4; ++j)
+                        if (j < nf) seg = nib_compose(seg, map_of((cls >> (2 * j)) & 3u), S);
                 }
             }
             // inclusive scan of the maps over the warp, then over the warps
@@ -1065,7 +1084,10 @@ struct Park {
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncthreads();
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const int warp = t >> 5;
+        // the shuffle tells the compiler that the warp index is warp-uniform: the tensor-memory addresses then live in uniform
+        // registers for the whole kernel instead of being converted (R2UR) in front of every access (-21 instructions per frame,
+        // -0.6 .. -1.3 % kernel time, profiles/r02/ab_uniform_base.txt)
+        const int warp = __shfl_sync(0xffffffffu, t >> 5, 0);
         base = *slot + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((warp >> 2) * kTmemWarpCols);
         float4* awr = reinterpret_cast<float4*>(smem_win) + t;
 #pragma unroll
@@ -1536,6 +1558,7 @@ struct EdgeParams {
 };
 
 constexpr int kEdgeSmemBytes = kNfft * (int)sizeof(double2);
+constexpr int kEdgeKernelSmemBytes = kEdgeSmemBytes + (kNfft / 2) * (int)sizeof(double2);     // edge_kernel: + the twiddle table
 
 __device__ __forceinline__ int bitrev12(int x) { return (int)(__brev((unsigned)x) >> 20); }
 
@@ -1551,13 +1574,15 @@ __global__ void tw64_init_kernel() {
     }
 }
 
-__device__ void fft4096_f64(double2* sm, int t) {      // in: bit-reversed order, out: natural order, forward
+// tw: the twiddle table, g_tw64 itself or a shared-memory copy of it (edge_kernel: a table read from global memory per
+// stage was a third of that latency-bound kernel)
+__device__ void fft4096_f64(double2* sm, int t, const double2* tw = g_tw64) {      // in: bit-reversed order, out: natural order, forward
     for (int s = 1; s <= 12; ++s) {
         const int half = 1 << (s - 1);
         for (int b = t; b < 2048; b += 256) {
             const int pos = b & (half - 1);
             const int i = ((b >> (s - 1)) << s) + pos, j = i + half;
-            const double2 w = g_tw64[pos << (12 - s)];
+            const double2 w = tw[pos << (12 - s)];
             const double cs = w.x, sn = w.y;
             const double2 u = sm[i], x = sm[j];
             const double2 v = make_double2(x.x * cs - x.y * sn, x.x * sn + x.y * cs);
@@ -1578,6 +1603,8 @@ __global__ void __launch_bounds__(256) edge_kernel(const EdgeParams prm) {
     const long long pos0 = tr.first_start + (long long)ed.frame * kHop;
     const float sc = prm.in_scale ? prm.in_scale[ed.track] : 1.0f;
     const float osc = prm.out_scale ? prm.out_scale[ed.track] : 1.0f;
+    double2* tw = sm + kNfft;                              // twiddles staged once per CTA (same values, same arithmetic)
+    for (int k = t; k < kNfft / 2; k += 256) tw[k] = g_tw64[k];
     for (int n = t; n < kNfft; n += 256) {
         const long long p = pos0 + n;
         float2 x = (p >= tr.in_lo && p < tr.in_hi) ? tr.in[p - tr.in_origin] : make_float2(0.f, 0.f);
@@ -1591,7 +1618,7 @@ __global__ void __launch_bounds__(256) edge_kernel(const EdgeParams prm) {
         sm[bitrev12(n)] = z;
     }
     __syncthreads();
-    fft4096_f64(sm, t);
+    fft4096_f64(sm, t, tw);
     {   // gain (real, symmetric), conjugate for the inverse transform, then bit-reverse in place
         const float* g = prm.gnat + (size_t)prm.rows[tr.frame_base + ed.frame] * (kNfft / 2 + 1);
         for (int k = t; k < kNfft; k += 256) {
@@ -1606,7 +1633,7 @@ __global__ void __launch_bounds__(256) edge_kernel(const EdgeParams prm) {
         }
         __syncthreads();
     }
-    fft4096_f64(sm, t);      // conj(FFT(conj(Y))) = N * IFFT(Y)
+    fft4096_f64(sm, t, tw);  // conj(FFT(conj(Y))) = N * IFFT(Y)
     float peak = 0.f;
     const int blk = ed.frame + ed.half;
     const long long out0 = tr.first_start + (long long)blk * kHop;
@@ -2145,6 +2172,11 @@ struct tmt_engine {
     DevBuf<float> gnat;       // [n_rows][2049] natural order (fp64 edge frames)
     int n_rows = 0;
     bool have_win = false;
+    // fork / join of the fp64 edge frames beside the STFT kernel (see launch_edges_beside): one side stream per engine, events
+    // recycled through a small pool (a plan takes a pair at its first fork and returns it when it is destroyed)
+    cudaStream_t side = nullptr;
+    std::mutex ev_mu;
+    std::vector<cudaEvent_t> ev_pool;
 };
 
 struct HostTrack {
@@ -2167,6 +2199,7 @@ struct tmt_plan {
     long long total_blocks = 0;  // output hop blocks of all work units
     std::vector<HostTrack> ht;
     std::vector<TrackDev> tracks_h;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     Arena arena;
     DevBuf<TrackDev> tracks;
     DevBuf<UnitDev> units;
@@ -2389,7 +2422,7 @@ int tmt_engine_create(tmt_engine** out, int device, int n_fft, int hop) {
     if (ce != cudaSuccess) { delete e; return fail(TMT_ERR_CUDA, "cudaFuncSetAttribute(stft_kernel): %s", cudaGetErrorString(ce)); }
     if (const char* sv = getenv("TMT_GATE_NSEG")) e->gate_nseg = atoi(sv);
 
-    ce = cudaFuncSetAttribute(edge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kEdgeSmemBytes);
+    ce = cudaFuncSetAttribute(edge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kEdgeKernelSmemBytes);
     if (ce != cudaSuccess) { delete e; return fail(TMT_ERR_CUDA, "cudaFuncSetAttribute(edge_kernel): %s", cudaGetErrorString(ce)); }
     *out = e;
     return TMT_OK;
@@ -2400,6 +2433,8 @@ int tmt_engine_destroy(tmt_engine* e) {
     cudaSetDevice(e->device);
     if (e->spare_arena) cudaFree(e->spare_arena);
     if (e->stage) cudaFreeHost(e->stage);
+    for (cudaEvent_t ev : e->ev_pool) cudaEventDestroy(ev);
+    if (e->side) cudaStreamDestroy(e->side);
     delete e;
     return TMT_OK;
 }
@@ -2459,18 +2494,46 @@ int tmt_plan_create(tmt_engine* e, tmt_plan** out, int framing, int n_tracks, co
     p->e = e;
     p->framing = framing;
     p->n_tracks = n_tracks;
+    bool jitter = true;
     if (unit_blocks <= 0) {
-        // default unit length: a unit costs one redundant warm-up frame (1/u of its work), and the dynamic queue leaves about
-        // one unit of idle time per CTA at the end (u * CTAs / blocks of the work); the sum is smallest at
-        // u = sqrt(blocks / CTAs).  59 (half a limiter chunk) is the cap: 128 tracks x 5 min gives 53.
+        // Default unit length.  Small jobs first: when the whole plan fits ONE wave of the persistent grid (2 CTAs per SM), the
+        // shortest units that still give every CTA at most one of them finish earliest -- the time of the launch is the longest
+        // unit plus its warm-up frame -- and uneven lengths would only lengthen it (a 10-minute file: 293 units of 48 blocks
+        // instead of 1 758 of 8 with a frame of warm-up each; a 60 s file: 264 units of 5 instead of 165 of 8).
+        // Otherwise: a unit costs one redundant warm-up frame (1/u of its work), and the dynamic queue leaves about one unit of
+        // idle time per CTA at the end (u * CTAs / blocks of the work); the sum is smallest at u = sqrt(blocks / CTAs).  59 (half
+        // a limiter chunk) is the cap: 128 tracks x 5 min gives 53.
         long long blocks = 0;
+        std::vector<int> lens;
+        std::vector<std::pair<int, int>> cbs;
         for (int i = 0; i < n_tracks; ++i) {
-            const long long nb = count_frames(framing, tracks[i].total) + 1;
+            const int nfr = count_frames(framing, tracks[i].total);
+            const long long nb = nfr > 0 ? nfr + 1 : 0;
             const long long lo = std::max<long long>(0, tracks[i].block_lo), hi = tracks[i].block_hi < 0 ? nb : std::min<long long>(nb, tracks[i].block_hi);
             blocks += std::max<long long>(0, hi - lo);
+            chunk_blocks(framing, nfr, cbs);
+            for (const auto& c : cbs) {
+                const long long a = std::max<long long>(c.first, lo), b = std::min<long long>(c.second, hi);
+                if (b > a) lens.push_back((int)(b - a));
+            }
         }
-        unit_blocks = (int)std::lround(std::sqrt((double)blocks / (2.0 * e->n_sms)));
-        unit_blocks = std::max(8, std::min(59, unit_blocks));
+        // an SM that hosts an fp64 edge CTA (running beside the STFT kernel) has room for one STFT CTA only
+        const long long slots = 2LL * e->n_sms - std::min<long long>(2LL * n_tracks, e->n_sms / 2);
+        int one_wave = 0;
+        if (blocks > 0 && blocks <= 59LL * slots && (long long)lens.size() <= slots) {
+            for (int u = (int)std::max<long long>(1, (blocks + slots - 1) / slots); u <= 59 && !one_wave; ++u) {
+                long long n = 0;
+                for (int len : lens) n += (len + u - 1) / u;
+                if (n <= slots) one_wave = u;
+            }
+        }
+        if (one_wave) {
+            unit_blocks = one_wave;
+            jitter = false;
+        } else {
+            unit_blocks = (int)std::lround(std::sqrt((double)blocks / (2.0 * e->n_sms)));
+            unit_blocks = std::max(8, std::min(59, unit_blocks));
+        }
     }
     std::vector<UnitDev> units;
     std::vector<ChunkDev> chunks;
@@ -2522,7 +2585,7 @@ int tmt_plan_create(tmt_engine* e, tmt_plan** out, int framing, int n_tracks, co
             // number of units and of redundant warm-up frames, but uneven lengths, so the persistent CTAs de-synchronise
             std::vector<int> cut(n_sub + 1);
             for (int s = 0; s <= n_sub; ++s) cut[s] = u0 + (int)((long long)(u1 - u0) * s / n_sub);
-            for (int s = 1; s < n_sub; ++s) {
+            for (int s = 1; s < n_sub && jitter; ++s) {
                 const uint32_t hsh = (uint32_t)(chunks.size() * 2654435761u + (uint32_t)s * 40503u) * 2246822519u;
                 const int span = std::min(cut[s] - cut[s - 1], cut[s + 1] - cut[s]);
                 cut[s] += (int)(((int)((hsh >> 12) & 1023) - 512) * (long long)(span * 3 / 10) / 512);
@@ -2648,6 +2711,12 @@ int tmt_plan_destroy(tmt_plan* p) {
     if (!p) return TMT_OK;
     tmt_engine* e = p->e;
     cudaSetDevice(e->device);
+    if (p->ev_fork) {
+        std::lock_guard<std::mutex> lock(e->ev_mu);
+        e->ev_pool.push_back(p->ev_fork);
+        e->ev_pool.push_back(p->ev_join);
+        p->ev_fork = p->ev_join = nullptr;
+    }
     if (p->arena.base) {
         // work queued on the plan's arrays may still be running: the next owner only touches the arena through stream-ordered
         // calls on the same device after a device-wide synchronisation here (cudaFree would have implied the same)
@@ -3091,6 +3160,12 @@ int tmt_plan_stft(tmt_plan* p, float post_gain, int skip_edges, void* stream) {
     return TMT_OK;
 }
 
+static bool stft_fused_limiter(const tmt_plan* p) {
+    bool fuse = p->total_blocks >= 48LL * p->e->n_sms;
+    if (const char* fv = getenv("TMT_LIMITER_FUSED")) fuse = atoi(fv) != 0;        // dev switch: A/B of the two limiter placements
+    return fuse;
+}
+
 int tmt_plan_stft_limited(tmt_plan* p, float post_gain, float limit, void* stream) {
     if (!p) return fail(TMT_ERR_INVALID, "plan is NULL");
     tmt_engine* e = p->e;
@@ -3101,8 +3176,7 @@ int tmt_plan_stft_limited(tmt_plan* p, float post_gain, float limit, void* strea
     // Small jobs (a single short file): the kernel lasts a few frame times, every chunk finishes at its very end, and the in-kernel
     // rescale -- one CTA per chunk, latency-bound -- would be a serial tail.  The separate limiter pass spreads the same bytes over
     // all SMs and costs one launch.  Large jobs hide the rescale under the other CTAs' butterflies and keep it fused.
-    bool fuse = p->total_blocks >= 48LL * e->n_sms;
-    if (const char* fv = getenv("TMT_LIMITER_FUSED")) fuse = atoi(fv) != 0;        // dev switch: A/B of the two limiter placements
+    const bool fuse = stft_fused_limiter(p);
     if (p->n_units) {
         int rc = launch_stft(p, post_gain, fuse ? limit : 0.f, st);
         if (rc) return rc;
@@ -3116,14 +3190,13 @@ int tmt_plan_stft_limited(tmt_plan* p, float post_gain, float limit, void* strea
     return TMT_OK;
 }
 
-int tmt_plan_edge_frames(tmt_plan* p, float post_gain, const float* in_scale, const float* out_scale, int pipeline_f64,
-                         void* stream) {
-    if (!p) return fail(TMT_ERR_INVALID, "plan is NULL");
+// The fp64 edge frames (<= 2 CTAs per track, latency-bound: 45 - 60 us whatever the job) write blocks the STFT kernel skips
+// and only share the chunk-peak atomics with it, so the two can run side by side.  beside = true: the edge kernel goes to the
+// engine's side stream, forked from `st` here; the caller launches the STFT kernel on `st` and then calls join_edges.  A single
+// 60 s file spends more time in edge_kernel than in stft_kernel; this takes it off the critical path.
+static int launch_edges(tmt_plan* p, float post_gain, const float* in_scale, const float* out_scale, int pipeline_f64, cudaStream_t st,
+                        bool beside) {
     tmt_engine* e = p->e;
-    if (!e->have_win || e->n_rows == 0) return fail(TMT_ERR_INVALID, "engine window / gain rows not set");
-    if (p->n_edges == 0) return TMT_OK;
-    CUDA_TRY(cudaSetDevice(e->device));
-    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     EdgeParams prm;
     prm.tracks = p->tracks.p;
     prm.edges = p->edges.p;
@@ -3144,9 +3217,53 @@ int tmt_plan_edge_frames(tmt_plan* p, float post_gain, const float* in_scale, co
     prm.norm_clamp = (p->framing == TMT_FRAMING_WHOLEFILE) ? 1 : 0;
     prm.pipeline_f64 = pipeline_f64 ? 1 : 0;
     prm.post_gain = post_gain;
-    edge_kernel<<<p->n_edges, 256, kEdgeSmemBytes, st>>>(prm);
+    cudaStream_t where = st;
+    if (beside) {
+        if (!p->ev_fork) {
+            std::lock_guard<std::mutex> lock(e->ev_mu);
+            if (!e->side) CUDA_TRY(cudaStreamCreateWithFlags(&e->side, cudaStreamNonBlocking));
+            for (cudaEvent_t* ev : {&p->ev_fork, &p->ev_join}) {
+                if (!e->ev_pool.empty()) { *ev = e->ev_pool.back(); e->ev_pool.pop_back(); }
+                else CUDA_TRY(cudaEventCreateWithFlags(ev, cudaEventDisableTiming));
+            }
+        }
+        CUDA_TRY(cudaEventRecord(p->ev_fork, st));
+        CUDA_TRY(cudaStreamWaitEvent(e->side, p->ev_fork, 0));
+        where = e->side;
+    }
+    edge_kernel<<<p->n_edges, 256, kEdgeKernelSmemBytes, where>>>(prm);
     p->launches++;
     CUDA_TRY(cudaGetLastError());
+    if (beside) CUDA_TRY(cudaEventRecord(p->ev_join, e->side));
+    return TMT_OK;
+}
+static int join_edges(tmt_plan* p, cudaStream_t st) {
+    CUDA_TRY(cudaStreamWaitEvent(st, p->ev_join, 0));
+    return TMT_OK;
+}
+
+int tmt_plan_edge_frames(tmt_plan* p, float post_gain, const float* in_scale, const float* out_scale, int pipeline_f64,
+                         void* stream) {
+    if (!p) return fail(TMT_ERR_INVALID, "plan is NULL");
+    tmt_engine* e = p->e;
+    if (!e->have_win || e->n_rows == 0) return fail(TMT_ERR_INVALID, "engine window / gain rows not set");
+    if (p->n_edges == 0) return TMT_OK;
+    CUDA_TRY(cudaSetDevice(e->device));
+    return launch_edges(p, post_gain, in_scale, out_scale, pipeline_f64, reinterpret_cast<cudaStream_t>(stream), false);
+}
+
+int tmt_plan_stft_with_edges(tmt_plan* p, float post_gain, const float* in_scale, const float* out_scale, int pipeline_f64, void* stream) {
+    if (!p) return fail(TMT_ERR_INVALID, "plan is NULL");
+    tmt_engine* e = p->e;
+    if (!e->have_win || e->n_rows == 0) return fail(TMT_ERR_INVALID, "engine window / gain rows not set");
+    CUDA_TRY(cudaSetDevice(e->device));
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    int rc = tmt_plan_clear_peaks(p, stream);
+    if (rc) return rc;
+    const bool beside = p->n_edges > 0 && p->n_units > 0 && !getenv("TMT_EDGES_SERIAL");
+    if (p->n_edges) { rc = launch_edges(p, post_gain, in_scale, out_scale, pipeline_f64, st, beside); if (rc) return rc; }
+    if (p->n_units) { rc = launch_stft(p, post_gain, 0.f, st); if (rc) return rc; }
+    if (beside) return join_edges(p, st);
     return TMT_OK;
 }
 
@@ -3172,6 +3289,13 @@ int tmt_plan_run_streaming(tmt_plan* p, double m_on, double m_off, int run_frame
     std::vector<double> on((size_t)std::max(p->n_tracks, 1), m_on), off((size_t)std::max(p->n_tracks, 1), m_off);
     rc = tmt_plan_gate(p, TMT_GATE_UPDELAY, TMT_ARR_MEANSQ_F32, on.data(), off.data(), run_frames, xfade_frames, 0, 0, stream);
     if (rc) return rc;
+    if (!stft_fused_limiter(p)) {
+        // small job: separate limiter pass anyway, so the edge frames can run beside the STFT kernel
+        if (!(limit > 0.f)) return fail(TMT_ERR_INVALID, "limit must be positive");
+        rc = tmt_plan_stft_with_edges(p, post_gain, nullptr, nullptr, 0, stream);
+        if (rc) return rc;
+        return tmt_plan_limiter(p, limit, stream);
+    }
     rc = tmt_plan_clear_peaks(p, stream);
     if (rc) return rc;
     rc = tmt_plan_edge_frames(p, post_gain, nullptr, nullptr, 0, stream);      // edge blocks first: their samples and peaks

@@ -234,6 +234,18 @@ class Plan:
         L.check(self.lib.tmt_plan_edge_frames(self.h, float(post_gain), pi, po, int(pipeline_f64), _stream_ptr(_torch())),
                 "tmt_plan_edge_frames")
 
+    def stft_with_edges(self, post_gain: float = 1.0, in_scale=None, out_scale=None, pipeline_f64: bool = False):
+        """stft() + edge_frames() with the fp64 edge kernel running beside the STFT kernel (tmt_plan_stft_with_edges)."""
+        pi = po = None
+        if in_scale is not None:
+            in_scale = np.ascontiguousarray(in_scale, dtype=np.float32)
+            pi = in_scale.ctypes.data_as(C.c_void_p)
+        if out_scale is not None:
+            out_scale = np.ascontiguousarray(out_scale, dtype=np.float32)
+            po = out_scale.ctypes.data_as(C.c_void_p)
+        L.check(self.lib.tmt_plan_stft_with_edges(self.h, float(post_gain), pi, po, int(pipeline_f64), _stream_ptr(_torch())),
+                "tmt_plan_stft_with_edges")
+
     def limiter(self, limit: float = tb.PEAK_LIMIT):
         L.check(self.lib.tmt_plan_limiter(self.h, float(np.float32(limit)), _stream_ptr(_torch())), "tmt_plan_limiter")
 
@@ -560,12 +572,11 @@ def run_adaptive(xs: Sequence, sr: int, device: int = 0, want_host: bool = True,
                             T_low[t] = T_mid[t]
                 plan.gate(L.GATE_MINHOLD, L.ARR_GATE_F64, best_T + hyst_db / 2, best_T - hyst_db / 2, hold, xf,
                           alpha_init_to_target=True, count_only=False)
-            plan.stft(1.0, skip_edges=True)
             if use_f64:
-                plan.edge_frames(1.0, None, None, pipeline_f64=True)
+                plan.stft_with_edges(1.0, None, None, pipeline_f64=True)
             else:      # restore_lin = db_to_lin(atten_db), float32 (src/process_tomatis_adaptive.py:335-337)
                 restore = np.array([np.float32(tb.db_to_lin_keep(branch[i][0])) for i in idx], dtype=np.float32)
-                plan.edge_frames(1.0, scale, restore, pipeline_f64=False)
+                plan.stft_with_edges(1.0, scale, restore, pipeline_f64=False)
             if _linked is not None:                   # output_peak = np.max(np.abs(y)) over every channel (:340): one scale for all pairs
                 pk = plan.read(L.ARR_CHUNK_PEAK)
                 plan.write(L.ARR_CHUNK_PEAK, np.full_like(pk, pk.max() if len(pk) else 0.0))

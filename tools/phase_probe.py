@@ -63,6 +63,15 @@ def adaptive():
     serial = (time.perf_counter() - t) / reps
     unwrap(engine.Plan, saved)
     parts = ", ".join(f"{k} {v / reps * 1e3:.3f}" for k, v in acc.items())
+    if os.environ.get("TMT_PROFILE"):
+        import cProfile, pstats
+        pr = cProfile.Profile()
+        pr.enable()
+        for _ in range(50):
+            engine.run_adaptive(xs, sr, want_host=False, outs=outs)
+        torch.cuda.synchronize()
+        pr.disable()
+        pstats.Stats(pr).sort_stats("tottime").print_stats(28)
     print(f"adaptive 600 s @ 48 kHz: whole call {whole * 1e3:.3f} ms; with a synchronise after every phase {serial * 1e3:.3f} ms: {parts}; "
           f"host outside the plan methods {(serial - sum(acc.values()) / reps) * 1e3:.3f}")
 
@@ -90,5 +99,6 @@ def general(n_fft, hop):
 
 if __name__ == "__main__":
     adaptive()
-    for nf, hp in ((2048, 1024), (1024, 512), (4096, 1024)):
-        general(nf, hp)
+    if "--general" in sys.argv:
+        for nf, hp in ((2048, 1024), (1024, 512), (4096, 1024)):
+            general(nf, hp)
