@@ -226,9 +226,18 @@ TMT_HD void tw_table(float2 (&p)[16], const TwBase w) {
 }
 
 // ---- exchange pieces (E1) -----------------------------------------------------------------------
+// The device stores are spelled as PTX: written as plain C++ assignments, ptxas copied most of the values into one fixed register
+// pair in front of their STS.64 (36 MOVs per frame in the two store groups; -34 instructions, -1.5 % kernel time,
+// profiles/r02/ab_asm_sts.txt).
 TMT_HD void st_e1a(const float2 (&v)[16], int t, float2* buf) {
+#if defined(__CUDA_ARCH__)
+    const unsigned a = (unsigned)__cvta_generic_to_shared(buf + t);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(a + j * kE1Row * 8), "f"(v[j].x), "f"(v[j].y) : "memory");
+#else
 #pragma unroll
     for (int j = 0; j < 16; ++j) buf[e1_a(t, j)] = v[j];
+#endif
 }
 TMT_HD void ld_e1b(float2 (&v)[16], int t, const float2* buf) {
     const float2* p = buf + e1_b(t, 0);
@@ -237,8 +246,14 @@ TMT_HD void ld_e1b(float2 (&v)[16], int t, const float2* buf) {
 }
 TMT_HD void st_e1b(const float2 (&v)[16], int t, float2* buf) {
     float2* p = buf + e1_b(t, 0);
+#if defined(__CUDA_ARCH__)
+    const unsigned a = (unsigned)__cvta_generic_to_shared(p);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(a + j * 128), "f"(v[j].x), "f"(v[j].y) : "memory");
+#else
 #pragma unroll
     for (int j = 0; j < 16; ++j) p[j * 16] = v[j];
+#endif
 }
 TMT_HD void ld_e1a(float2 (&v)[16], int t, const float2* buf) {
 #pragma unroll

@@ -19,6 +19,7 @@
 #include <cstdlib>
 #include <cmath>
 #include <vector>
+#include <type_traits>
 #include <algorithm>
 #include <new>
 #include <mutex>
@@ -1232,11 +1233,7 @@ __device__ __forceinline__ void unit_epilogue(const StftParams& prm, int chunk, 
                 const float pk = __int_as_float(atomicMax(reinterpret_cast<int*>(prm.chunk_peaks + chunk), 0));
 
 
-#ifdef TMT_AB_NORESCALE
-                if (pk > 1e30f) {
-#else
                 if (pk > prm.limit) {
-#endif
                     unsigned long long t_begin = 0;
                     if (t == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_begin));
                     const float sc = __fdiv_rn(prm.limit, pk);
@@ -1363,22 +1360,10 @@ __global__ void __launch_bounds__(kThreads, 2) stft_kernel(const StftParams prm)
         auto load_half = [&](int h, float2 (&x)[8]) {
             const int p0 = h * kHop;
             const float2* src = in_u + p0 + t;
-#ifdef TMT_AB_NOLOAD       // timing study only (wrong output): the input never touches memory
-            if (p0 >= in_lo && p0 + kHop <= in_hi) {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) x[j] = make_float2(__int_as_float(0x3c000000 + p0 + j + t), 0.25f);
-            } else {
-#elif defined(TMT_AB_L2LOAD)     // timing study only: every half frame comes from the same 16 KB (always an L2 hit)
-            if (p0 >= in_lo && p0 + kHop <= in_hi) {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) x[j] = ld_stream(trp->in + 256 * j + t);
-            } else {
-#else
             if (p0 >= in_lo && p0 + kHop <= in_hi) {
 #pragma unroll
                 for (int j = 0; j < 8; ++j) x[j] = ld_stream(src + 256 * j);
             } else {
-#endif
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     const int p = p0 + 256 * j + t;
@@ -1417,27 +1402,39 @@ __global__ void __launch_bounds__(kThreads, 2) stft_kernel(const StftParams prm)
         };
         if (have_frame(0)) stage_r(0);
 
-        for (int i = 0; i <= last; ++i) {
+        // One frame of the pipeline.  STEADY = std::true_type for the interior iterations of a unit, where everything the general
+        // body has to ask is known: frames i and i+1 exist, half frames i+2 and i+3 lie inside the input window, the output block
+        // lies inside the output window and is no edge block.  The steady body has no branches besides the two hand-off waits.
+        auto frame_iter = [&](const int i, auto steady_tag) {
+            constexpr bool STEADY = decltype(steady_tag)::value;
             const int f = un.b0 - 1 + i;
-            const bool have = have_frame(i);
+            const bool have = STEADY ? true : have_frame(i);
             const int rel = i * kHop;                          // frame start relative to the unit
             float2* buf = bufP + (i & 1) * kE1Float2;
             // every input sample is read from global memory exactly once, ahead of its first use, and waits in tensor memory;
             // the loads below belong to frame i+1 (its second half) and complete under this frame's butterflies
             float2 pf[8];
-            const bool do_pf = (i < last);
+            const bool do_pf = STEADY ? true : (i < last);
             const int row = row_next;
-            row_next = row_of(f + 1);
-            if (do_pf) load_half(i + 2, pf);
-#if defined(TMT_AB_NOLOAD) || defined(TMT_AB_L2LOAD)
-            if (false) {
-#else
-            if (i + 1 < last && (t & 15) == 0) {               // half i+3 -> L2 (one 128-byte line per 16 lanes), so that next frame's loads are short
-#endif
-                const int p0 = (i + 3) * kHop;
-                if (p0 >= in_lo && p0 + kHop <= in_hi) {
+            if (STEADY) {
+                row_next = (int)__ldg(rows + f + 1);
+                const float2* src = in_u + (i + 2) * kHop + t;
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) prefetch_l2(in_u + p0 + t + 256 * j);
+                for (int j = 0; j < 8; ++j) pf[j] = ld_stream(src + 256 * j);
+                if (t < 32) {                                  // half i+3 -> L2: the first warp asks for all 128 lines of it
+                    const float2* q = in_u + (i + 3) * kHop + t * 16;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) prefetch_l2(q + 512 * j);
+                }
+            } else {
+                row_next = row_of(f + 1);
+                if (do_pf) load_half(i + 2, pf);
+                if (i + 1 < last && (t & 15) == 0) {           // half i+3 -> L2 (one 128-byte line per 16 lanes), so that next frame's loads are short
+                    const int p0 = (i + 3) * kHop;
+                    if (p0 >= in_lo && p0 + kHop <= in_hi) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) prefetch_l2(in_u + p0 + t + 256 * j);
+                    }
                 }
             }
             if (have) {                                                           // ---- Q(i)
@@ -1479,7 +1476,7 @@ __global__ void __launch_bounds__(kThreads, 2) stft_kernel(const StftParams prm)
             }
             if (do_pf) {
                 if (!have) park.stage_put(i & 1, pf);
-                if (have_frame(i + 1)) stage_r(i + 1);                           // ---- R(i+1)
+                if (STEADY || have_frame(i + 1)) stage_r(i + 1);                 // ---- R(i+1)
             }
             float2 v[16];                                                         // ---- P(i)
             float s[16];                                           // synthesis window x normalisation (x output gain)
@@ -1499,18 +1496,14 @@ __global__ void __launch_bounds__(kThreads, 2) stft_kernel(const StftParams prm)
             }
 
             // synthesis window, overlap-add with the carried half, interior normalisation (folded into swin)
-            const bool edge_blk = (f == 0 && edge_lo) || (f == n_frames && edge_hi);   // single-frame blocks: edge_kernel
-            if (f >= un.b0 && !edge_blk) {       // emit output block f
+            const bool edge_blk = STEADY ? false : ((f == 0 && edge_lo) || (f == n_frames && edge_hi));   // single-frame blocks: edge_kernel
+            if (STEADY || (f >= un.b0 && !edge_blk)) {       // emit output block f
                 float2* dst = out_u + rel + t;
-                if ((rel >= out_lo) && (rel + kHop <= out_hi)) {          // whole block inside the output window
+                if (STEADY || ((rel >= out_lo) && (rel + kHop <= out_hi))) {          // whole block inside the output window
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
                         const float2 o = __ffma2_rn(v[j], make_float2(s[j], s[j]), c[j]);
-#ifdef TMT_AB_NOSTORE      // timing study only: the output never touches memory (one unlikely store keeps the arithmetic alive)
-                        if (o.x == 123.456f) st_stream(dst + 256 * j, o);
-#else
                         st_stream(dst + 256 * j, o);
-#endif
                         peak = fmaxf(peak, fmaxf(fabsf(o.x), fabsf(o.y)));
                     }
                 } else {
@@ -1528,6 +1521,18 @@ __global__ void __launch_bounds__(kThreads, 2) stft_kernel(const StftParams prm)
 #pragma unroll
             for (int j = 0; j < 8; ++j) c[j] = cscale(v[j + 8], s[j + 8]);
             park.store_carry(c);
+        };
+        // steady interval [s_lo, s_hi) of this unit (all bounds are monotone in i; positions are relative to the unit)
+        int s_lo = max(1, 1 - un.b0 + (edge_lo ? 1 : 0)), s_hi = min(last - 1, n_frames - un.b0);
+        s_lo = max(s_lo, max(((in_lo + kHop - 1) >> 11) - 2, (out_lo + kHop - 1) >> 11));
+        s_hi = min(s_hi, min((in_hi >> 11) - 3, out_hi >> 11));
+        for (int i = 0; i <= last;) {                 // one copy of each body: general iterations around the steady run
+            if (i >= s_lo && i < s_hi) {
+                for (; i < s_hi; ++i) frame_iter(i, std::true_type{});
+            } else {
+                frame_iter(i, std::false_type{});
+                ++i;
+            }
         }
         unit_epilogue(prm, un.chunk, trp, peak, t, red);
         __syncthreads();

@@ -1,6 +1,7 @@
 """Static instruction counts of stft_kernel's frame loop from the built library (here, no GPU): python tools/sass_count.py [--json out].
 
-The frame loop is the innermost backward branch around at least 400 packed FP32 instructions.  Packed FP32 instructions (FFMA2 / FMUL2 / FADD2,
+The frame loop is the innermost backward branch around at least 400 packed FP32 instructions (since round 2's steady-state
+specialisation: the steady loop, which has no clipped-output variant).  Packed FP32 instructions (FFMA2 / FMUL2 / FADD2,
 two lanes each) inside it, minus the duplicated output variant (whole block / clipped block: 8 FFMA2 each, one executes), give
 the per-thread, per-frame count the bench's secondary (FP32) roofline uses."""
 import json
@@ -46,7 +47,7 @@ def main():
                    ("FADD", r"\bFADD\b"), ("LDS", r"\bLDS"), ("STS", r"\bSTS"), ("LDTM", r"\bLDTM"), ("STTM", r"\bSTTM"), ("LDG", r"\bLDG"),
                    ("STG", r"\bSTG"), ("LDL", r"\bLDL"), ("STL", r"\bSTL"), ("MOV", r"\bMOV\b"), ("SYNCS", r"\bSYNCS"), ("BAR", r"\bBAR\b")):
         res[k] = cnt(pat, body)
-    dup_out = 8                                         # the clipped-block variant of the output FFMA2s
+    dup_out = 8 if res["STG"] > 8 else 0                # the clipped-block variant of the output FFMA2s (absent from the steady-state loop)
     ffma2 = res["FFMA2"] - dup_out
     res["packed_fp32_per_thread_frame"] = ffma2 + res["FMUL2"] + res["FADD2"]
     res["flop_per_thread_frame"] = 4 * ffma2 + 2 * (res["FMUL2"] + res["FADD2"]) + 2 * res["FFMA"] + res["FMUL"] + res["FADD"]
