@@ -35,9 +35,18 @@ namespace tmt {
 constexpr int kNfft = 4096;
 constexpr int kHop = 2048;
 constexpr int kThreads = 256;       // one frame per CTA pass, 16 points per thread
+#ifdef TMT_E1_PADDED_ROWS             // the earlier layout: 16 padded rows, 64-bit accesses on both sides
 constexpr int kE1Row = 264;         // E1 row stride in float2 (256 + 8): the B side reads rows k1 and k1 + 1 from the two lane
                                     // parities of a warp, the 64-byte skew keeps every half warp on 32 distinct banks
 constexpr int kE1Float2 = 16 * kE1Row;       // the E1 exchange buffer (33 792 B)
+#else
+// Rows interleaved in pairs: element (k1, col) lives at (k1 >> 1) * 512 + 2 * col + (k1 & 1).  The A side (thread t = col, rows
+// j = 0..15) then moves rows 2jp and 2jp + 1 with ONE 128-bit access (a warp covers 512 contiguous bytes), the B side (a warp
+// owns exactly one row pair, lane = 2 * n3 + (k1 & 1)) reads 32 consecutive float2 per access: no padding, no bank conflicts,
+// 16 shared-memory instructions fewer per frame.
+constexpr int kE1Row = 256;
+constexpr int kE1Float2 = 16 * kE1Row;       // the E1 exchange buffer (32 768 B)
+#endif
 
 // Complex arithmetic on float2.  On the device every operation is a packed FP32x2 instruction
 // (FADD2 / FMUL2 / FFMA2, new on sm_100): re/im live in one 64-bit register pair, and the swap,
@@ -189,8 +198,13 @@ TMT_HD int c_k2(int t) { return 4 * (t & 3) + ((t >> 2) & 3); }
 TMT_HD int bin_of(int t, int j) { return c_k1(t) + 16 * c_k2(t) + 256 * j; }
 
 // ---- shared-memory exchange E1 (float2 units):  idx = k1*264 + n2*16 + n3 ----------------------
+#ifdef TMT_E1_PADDED_ROWS
 TMT_HD int e1_a(int t, int j) { return j * kE1Row + t; }
 TMT_HD int e1_b(int t, int j) { return b_k1(t) * kE1Row + j * 16 + b_n3(t); }
+#else
+TMT_HD int e1_a(int t, int j) { return (j >> 1) * 512 + 2 * t + (j & 1); }
+TMT_HD int e1_b(int t, int j) { return (b_k1(t) >> 1) * 512 + 2 * (j * 16 + b_n3(t)) + (b_k1(t) & 1); }     // = (t >> 5) * 512 + 32 * j + (t & 31)
+#endif
 
 // Twiddles.  Both twiddle stages have the form v[k] *= b^k with a PER-THREAD base:
 //   stage A (thread t = 16*n2 + n3, output k1):  W256^(n2*k1) * W4096^(n3*k1) = (W4096^t)^k1
@@ -226,9 +240,37 @@ TMT_HD void tw_table(float2 (&p)[16], const TwBase w) {
 }
 
 // ---- exchange pieces (E1) -----------------------------------------------------------------------
-// The device stores are spelled as PTX: written as plain C++ assignments, ptxas copied most of the values into one fixed register
+// The device accesses are spelled as PTX: written as plain C++ assignments, ptxas copied most of the values into one fixed register
 // pair in front of their STS.64 (36 MOVs per frame in the two store groups; -34 instructions, -1.5 % kernel time,
 // profiles/r02/ab_asm_sts.txt).
+#if defined(__CUDA_ARCH__) && !defined(TMT_E1_PADDED_ROWS)
+TMT_HD void st_e1a(const float2 (&v)[16], int t, float2* buf) {
+    const unsigned a = (unsigned)__cvta_generic_to_shared(buf + 2 * t);
+#pragma unroll
+    for (int jp = 0; jp < 8; ++jp)
+        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a + jp * 4096), "f"(v[2 * jp].x), "f"(v[2 * jp].y), "f"(v[2 * jp + 1].x),
+                     "f"(v[2 * jp + 1].y) : "memory");
+}
+TMT_HD void ld_e1a(float2 (&v)[16], int t, const float2* buf) {
+    const float4* p = reinterpret_cast<const float4*>(buf) + t;
+#pragma unroll
+    for (int jp = 0; jp < 8; ++jp) {
+        const float4 x = p[jp * 256];
+        v[2 * jp] = make_float2(x.x, x.y);
+        v[2 * jp + 1] = make_float2(x.z, x.w);
+    }
+}
+TMT_HD void ld_e1b(float2 (&v)[16], int t, const float2* buf) {
+    const float2* p = buf + e1_b(t, 0);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = p[j * 32];
+}
+TMT_HD void st_e1b(const float2 (&v)[16], int t, float2* buf) {
+    const unsigned a = (unsigned)__cvta_generic_to_shared(buf + e1_b(t, 0));
+#pragma unroll
+    for (int j = 0; j < 16; ++j) asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(a + j * 256), "f"(v[j].x), "f"(v[j].y) : "memory");
+}
+#else
 TMT_HD void st_e1a(const float2 (&v)[16], int t, float2* buf) {
 #if defined(__CUDA_ARCH__)
     const unsigned a = (unsigned)__cvta_generic_to_shared(buf + t);
@@ -240,25 +282,24 @@ TMT_HD void st_e1a(const float2 (&v)[16], int t, float2* buf) {
 #endif
 }
 TMT_HD void ld_e1b(float2 (&v)[16], int t, const float2* buf) {
-    const float2* p = buf + e1_b(t, 0);
 #pragma unroll
-    for (int j = 0; j < 16; ++j) v[j] = p[j * 16];
+    for (int j = 0; j < 16; ++j) v[j] = buf[e1_b(t, j)];
 }
 TMT_HD void st_e1b(const float2 (&v)[16], int t, float2* buf) {
-    float2* p = buf + e1_b(t, 0);
 #if defined(__CUDA_ARCH__)
-    const unsigned a = (unsigned)__cvta_generic_to_shared(p);
+    const unsigned a = (unsigned)__cvta_generic_to_shared(buf + e1_b(t, 0));
 #pragma unroll
     for (int j = 0; j < 16; ++j) asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(a + j * 128), "f"(v[j].x), "f"(v[j].y) : "memory");
 #else
 #pragma unroll
-    for (int j = 0; j < 16; ++j) p[j * 16] = v[j];
+    for (int j = 0; j < 16; ++j) buf[e1_b(t, j)] = v[j];
 #endif
 }
 TMT_HD void ld_e1a(float2 (&v)[16], int t, const float2* buf) {
 #pragma unroll
     for (int j = 0; j < 16; ++j) v[j] = buf[e1_a(t, j)];
 }
+#endif
 
 // ---- exchange E2 through tensor memory: register naming around the four round trips -------------
 // A round trip works on the raw 32-register image of a thread.  "Column order" is what .32x32b stores / loads

@@ -1024,7 +1024,8 @@ constexpr int kTmemCols = 256;                       // per CTA: 2 warps per lan
 // two mbarriers, queue)
 constexpr int kStftSmemE1 = 2 * kE1Float2 * (int)sizeof(float2);     // two frames in flight (frame pipeline of stft_kernel)
 constexpr int kStftSmemWin = kNfft * (int)sizeof(float);
-constexpr int kStftSmem = kStftSmemE1 + kStftSmemWin + 96;
+constexpr int kStftSmemWb = 0;
+constexpr int kStftSmem = kStftSmemE1 + kStftSmemWin + kStftSmemWb + 96;
 
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
@@ -1308,13 +1309,16 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 
 __global__ void __launch_bounds__(kThreads, 2) stft_kernel(const StftParams prm) {
     extern __shared__ __align__(16) unsigned char smraw[];
-    float2* bufP = reinterpret_cast<float2*>(smraw);         // E1 exchange (padded rows, 2 x 33 KB: frames i and i+1)
-    unsigned char* tail = smraw + kStftSmemE1 + kStftSmemWin;
+    float2* bufP = reinterpret_cast<float2*>(smraw);         // E1 exchange (row pairs interleaved, 2 x 32 KB: frames i and i+1)
+    unsigned char* tail = smraw + kStftSmemE1 + kStftSmemWin + kStftSmemWb;
     float* red = reinterpret_cast<float*>(tail + 16);
-    const int t = threadIdx.x;
+    int t;                                                    // read once and kept: the compiler otherwise re-reads %tid.x (S2R, a
+    asm volatile("mov.u32 %0, %%tid.x;" : "=r"(t));           // long-latency instruction) in front of several address computations per frame
 
     Park park;
     park.init(smraw + kStftSmemE1, tail, t, prm.win, prm.swin, prm.tw_a, prm.post_gain);
+    // stage-B twiddle bases stay in registers: the compiler hoists the powers b^k out of the frame loop; a 16 x 16 table in shared
+    // memory (16 more LDS.128 per frame, 38 register copies fewer) measured the same (profiles/r02/ab_twb_smem.txt)
     const float4 bb = __ldg(reinterpret_cast<const float4*>(prm.tw_bases) + 2 * t + 1);
     const TwBase wb = {make_float2(bb.x, bb.y), make_float2(bb.z, bb.w)};
 
