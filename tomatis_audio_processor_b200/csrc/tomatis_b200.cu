@@ -1394,14 +1394,14 @@ __global__ void __launch_bounds__(kThreads, 2) stft_kernel(const StftParams prm)
         // stores, wait before the loads), so a warp that is ahead does not stop, and the warps of a CTA drift out of lock step
         // instead of hitting the FP32 pipe and the exchanges all at the same time.  Hazards: R(i+2) overwrites exactly the words
         // this thread read in P(i); Q rewrites the words it read; everything else is ordered by the two barriers.
-        auto stage_r = [&](int i) {                 // window + A of frame i -> buf[i & 1]
+        auto stage_r = [&](int par) {               // window + A of a frame with parity par -> buf[par]
             float2 v[16];
             float fa[16], fb[16];                   // forward stage-A twiddles
             park.sync_stores();
-            park.stage_get_windowed(i & 1, v, fa, fb);
+            park.stage_get_windowed(par, v, fa, fb);
             dft16<false>(v);                                                      // A
             park.twiddle_a_fwd(v, fa, fb);
-            st_e1a(v, t, bufP + (i & 1) * kE1Float2);
+            st_e1a(v, t, bufP + par * kE1Float2);
             mbar_arrive(bar_y);
         };
         if (have_frame(0)) stage_r(0);
@@ -1409,12 +1409,16 @@ __global__ void __launch_bounds__(kThreads, 2) stft_kernel(const StftParams prm)
         // One frame of the pipeline.  STEADY = std::true_type for the interior iterations of a unit, where everything the general
         // body has to ask is known: frames i and i+1 exist, half frames i+2 and i+3 lie inside the input window, the output block
         // lies inside the output window and is no edge block.  The steady body has no branches besides the two hand-off waits.
-        auto frame_iter = [&](const int i, auto steady_tag) {
+        // PAR = the frame's parity (which E1 buffer, which staging slot) when it is known at compile time -- the steady loop runs two
+        // frames per iteration -- or -1.
+        auto frame_iter = [&](const int i, auto steady_tag, auto par_tag) {
             constexpr bool STEADY = decltype(steady_tag)::value;
+            constexpr int PAR = decltype(par_tag)::value;
+            const int par = PAR < 0 ? (i & 1) : PAR;
             const int f = un.b0 - 1 + i;
             const bool have = STEADY ? true : have_frame(i);
             const int rel = i * kHop;                          // frame start relative to the unit
-            float2* buf = bufP + (i & 1) * kE1Float2;
+            float2* buf = bufP + par * kE1Float2;
             // every input sample is read from global memory exactly once, ahead of its first use, and waits in tensor memory;
             // the loads below belong to frame i+1 (its second half) and complete under this frame's butterflies
             float2 pf[8];
@@ -1451,7 +1455,7 @@ __global__ void __launch_bounds__(kThreads, 2) stft_kernel(const StftParams prm)
                 // E2: the 16 x 16 transposes between stages B and C run through tensor memory, one round trip on either side
                 // of C's first radix-4 layer (fft4096.cuh); no shared-memory traffic, no barrier
                 float r[32], q[32];
-                if (do_pf) park.stage_put(i & 1, pf);          // slot of the half frame i no longer needs (its stage A is long done)
+                if (do_pf) park.stage_put(par, pf);            // slot of the half frame i no longer needs (its stage A is long done)
                 x_fwd1_pack(v, r);
                 park.trip_fwd(r);
                 // tilt gain x crossfade weight: one real row per frame, register order; issued before the second round trip
@@ -1479,8 +1483,8 @@ __global__ void __launch_bounds__(kThreads, 2) stft_kernel(const StftParams prm)
                 mbar_arrive(bar_x);
             }
             if (do_pf) {
-                if (!have) park.stage_put(i & 1, pf);
-                if (STEADY || have_frame(i + 1)) stage_r(i + 1);                 // ---- R(i+1)
+                if (!have) park.stage_put(par, pf);
+                if (STEADY || have_frame(i + 1)) stage_r(par ^ 1);               // ---- R(i+1)
             }
             float2 v[16];                                                         // ---- P(i)
             float s[16];                                           // synthesis window x normalisation (x output gain)
@@ -1530,11 +1534,18 @@ __global__ void __launch_bounds__(kThreads, 2) stft_kernel(const StftParams prm)
         int s_lo = max(1, 1 - un.b0 + (edge_lo ? 1 : 0)), s_hi = min(last - 1, n_frames - un.b0);
         s_lo = max(s_lo, max(((in_lo + kHop - 1) >> 11) - 2, (out_lo + kHop - 1) >> 11));
         s_hi = min(s_hi, min((in_hi >> 11) - 3, out_hi >> 11));
-        for (int i = 0; i <= last;) {                 // one copy of each body: general iterations around the steady run
-            if (i >= s_lo && i < s_hi) {
-                for (; i < s_hi; ++i) frame_iter(i, std::true_type{});
+        using Even = std::integral_constant<int, 0>;
+        using Odd = std::integral_constant<int, 1>;
+        using Any = std::integral_constant<int, -1>;
+        for (int i = 0; i <= last;) {                 // general iterations around the steady run, which starts on an even frame
+            if (i >= s_lo && i + 1 < s_hi && !(i & 1)) {
+                do {
+                    frame_iter(i, std::true_type{}, Even{});
+                    frame_iter(i + 1, std::true_type{}, Odd{});
+                    i += 2;
+                } while (i + 1 < s_hi);
             } else {
-                frame_iter(i, std::false_type{});
+                frame_iter(i, std::false_type{}, Any{});
                 ++i;
             }
         }
