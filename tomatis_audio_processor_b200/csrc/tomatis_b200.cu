@@ -1180,7 +1180,7 @@ struct Park {
         for (int j = 0; j < 8; ++j) { r[2 * j] = x[j].x; r[2 * j + 1] = x[j].y; }
         tmem_st16(base + kTcHalf + 16 * slot, r);
     }
-    // v = [half `slot`, half `slot ^ 1`] x analysis window
+    // v = stage A's 16-point DFTs of [half `slot`, half `slot ^ 1`] x analysis window
     __device__ __forceinline__ void stage_get_windowed(int slot, float2 (&v)[16], float (&ta)[16], float (&tb2)[16]) const {
         float a[16], b[16];
         tmem_ld16(base + kTcHalf + 16 * slot, a);
@@ -1190,11 +1190,13 @@ struct Park {
         const float4 w0 = aw[0], w1 = aw[256], w2 = aw[512], w3 = aw[768];
         tmem_wait_ld();
         const float w[16] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w, w2.x, w2.y, w2.z, w2.w, w3.x, w3.y, w3.z, w3.w};
+        // the window taps are fused into stage A's first butterflies (8 packed instructions fewer per frame)
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            v[j] = cscale(make_float2(a[2 * j], a[2 * j + 1]), w[j]);
-            v[j + 8] = cscale(make_float2(b[2 * j], b[2 * j + 1]), w[j + 8]);
+            v[j] = make_float2(a[2 * j], a[2 * j + 1]);
+            v[j + 8] = make_float2(b[2 * j], b[2 * j + 1]);
         }
+        dft16_scaled<false>(v, w);
     }
     __device__ __forceinline__ void sync_stores() const { tmem_wait_st(); }
     __device__ __forceinline__ void trip_fwd(float (&r)[32]) const { tmem_trip_fwd(base + kTcXchg, r); }
@@ -1398,8 +1400,7 @@ __global__ void __launch_bounds__(kThreads, 2) stft_kernel(const StftParams prm)
             float2 v[16];
             float fa[16], fb[16];                   // forward stage-A twiddles
             park.sync_stores();
-            park.stage_get_windowed(par, v, fa, fb);
-            dft16<false>(v);                                                      // A
+            park.stage_get_windowed(par, v, fa, fb);                              // window + A
             park.twiddle_a_fwd(v, fa, fb);
             st_e1a(v, t, bufP + par * kE1Float2);
             mbar_arrive(bar_y);
@@ -1465,11 +1466,10 @@ __global__ void __launch_bounds__(kThreads, 2) stft_kernel(const StftParams prm)
                 x_layer_a<false>(r, q);                                           // C, first layer
                 park.trip_fwd(q);
                 x_fwd2_finish(q, v);                                              // C, second layer
-                v[0] = cscale(v[0], g0.x); v[1] = cscale(v[1], g0.y); v[2] = cscale(v[2], g0.z); v[3] = cscale(v[3], g0.w);
-                v[4] = cscale(v[4], g1.x); v[5] = cscale(v[5], g1.y); v[6] = cscale(v[6], g1.z); v[7] = cscale(v[7], g1.w);
-                v[8] = cscale(v[8], g2.x); v[9] = cscale(v[9], g2.y); v[10] = cscale(v[10], g2.z); v[11] = cscale(v[11], g2.w);
-                v[12] = cscale(v[12], g3.x); v[13] = cscale(v[13], g3.y); v[14] = cscale(v[14], g3.z); v[15] = cscale(v[15], g3.w);
-                x_inv1_pack(v, r);                                                // C', first layer + inner twiddles
+                {       // the gains are fused into the first butterflies of C' (8 packed instructions fewer per frame)
+                    const float g[16] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w, g2.x, g2.y, g2.z, g2.w, g3.x, g3.y, g3.z, g3.w};
+                    x_inv1_pack(v, r, g);                                         // gain + C', first layer + inner twiddles
+                }
                 park.trip_inv(r);
                 x_layer_c_inv(r, q);                                              // C', second layer
                 park.trip_inv(q);
