@@ -191,6 +191,13 @@ int tmt_plan_gate(tmt_plan* p, int automaton, int gate_input, const double* on, 
  * Tracks of more than 16384 frames: TMT_ERR_UNSUPPORTED (drive tmt_plan_gate(count_only) from the host instead). */
 int tmt_plan_bisect(tmt_plan* p, const double* t_low, const double* t_high, const double* start, const int32_t* active,
                     double hyst_db, double target_c2, int hold_frames, int max_iter, void* stream);
+/* tmt_plan_bisect followed by the final gate with the thresholds found -- tmt_plan_gate(TMT_GATE_MINHOLD, TMT_ARR_GATE_F64, NULL, NULL,
+ * hold_frames, xfade_frames, alpha_init_to_target, 0) -- in the same launch where the search runs on the register-resident path
+ * (<= 16 automaton states), as a second launch otherwise: TMT_ARR_STATE, TMT_ARR_ROW and TMT_ARR_C2_COUNT are final on return
+ * (simulate_gate + the alpha follower, src/process_tomatis_adaptive.py:226,253-265). */
+int tmt_plan_bisect_gate(tmt_plan* p, const double* t_low, const double* t_high, const double* start, const int32_t* active,
+                         double hyst_db, double target_c2, int hold_frames, int max_iter, int xfade_frames, int alpha_init_to_target,
+                         void* stream);
 
 /* K1+K3+K4 fused: frame gather + Hann window + 4096-pt FFT (stereo packed as L+iR) + gain row +
  * inverse FFT + synthesis window + overlap-add (each output sample written exactly once, no atomics)

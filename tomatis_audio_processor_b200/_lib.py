@@ -72,6 +72,7 @@ SIGNATURES = {
     "tmt_plan_peer_publish": (C.c_int, [_P, C.c_int, C.c_int, _P, _P, _P, _P]),
     "tmt_plan_peer_wait": (C.c_int, [_P, C.c_int, _P, _P, C.c_int64, C.c_int, C.c_int, C.c_double, _P]),
     "tmt_plan_bisect": (C.c_int, [_P, _P, _P, _P, _P, C.c_double, C.c_double, C.c_int, C.c_int, _P]),
+    "tmt_plan_bisect_gate": (C.c_int, [_P, _P, _P, _P, _P, C.c_double, C.c_double, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "tmt_plan_stft": (C.c_int, [_P, C.c_float, C.c_int, _P]),
     "tmt_plan_stft_limited": (C.c_int, [_P, C.c_float, C.c_float, _P]),
     "tmt_plan_clear_peaks": (C.c_int, [_P, _P]),

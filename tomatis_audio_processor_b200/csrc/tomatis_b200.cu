@@ -761,6 +761,11 @@ struct BisectParams {
     int* n_iter;              // [tracks]
     double* trace_T;          // [tracks][kBisectMaxIter]
     int* trace_c2;            // [tracks][kBisectMaxIter]
+    // final gate with the thresholds found (tmt_plan_bisect_gate; emit = 0: search only)
+    int emit, X, alpha_init;
+    uint8_t* state;
+    uint16_t* rows;
+    int* c2_count;
 };
 
 // Fast path of the search for automata of at most 16 states (min-hold up to 7 frames: the reference default is 6): a transition
@@ -894,6 +899,119 @@ __global__ void __launch_bounds__(1024) bisect_fast_kernel(const BisectParams pr
         prm.n_iter[track] = iters;
         prm.von[track] = __dadd_rn(best_T, prm.half_hyst);
         prm.voff[track] = __dsub_rn(best_T, prm.half_hyst);
+    }
+    if (!prm.emit || F == 0) return;
+    // Final gate with the thresholds found (simulate_gate + the alpha follower, src/process_tomatis_adaptive.py:226,253-265): one
+    // more scan of the maps for the states, then a scan of the crossfade counter's clamp maps (gate_kernel's steps 3-5 on shuffles).
+    {
+        const double on = __dadd_rn(best_T, prm.half_hyst), off = __dsub_rn(best_T, prm.half_hyst);
+        unsigned long long seg = ident;
+        unsigned cls = 0;
+#pragma unroll
+        for (int k = 0; k < kBisectFastFrames; ++k) {
+            if (k < nf) cls |= (((x[k] >= on) ? 1u : 0u) | ((x[k] <= off) ? 2u : 0u)) << (2 * k);
+        }
+#pragma unroll
+        for (int k = 0; k < kBisectFastFrames; k += 4) {
+            if (k + 4 <= nf) {
+                const unsigned long long q = quad[(cls >> (2 * k)) & 255u];
+                seg = k ? nib_compose(seg, q, S) : q;
+            } else {
+#pragma unroll
+                for (int j = k; j < k + 4; ++j)
+                    if (j < nf) seg = nib_compose(seg, map_of((cls >> (2 * j)) & 3u), S);
+            }
+        }
+        unsigned long long inc = seg;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned long long prev = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc = nib_compose(prev, inc, S);
+        }
+        __syncthreads();                                   // the search's last readers of wtot / red are done
+        if (lane == 31) wtot[w] = inc;
+        __syncthreads();
+        if (w == 0) {
+            unsigned long long t = wtot[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned long long prev = __shfl_up_sync(0xffffffffu, t, o);
+                if (lane >= o) t = nib_compose(prev, t, S);
+            }
+            wtot[lane] = t;
+        }
+        __syncthreads();
+        unsigned long long excl = __shfl_up_sync(0xffffffffu, inc, 1);
+        if (lane == 0) excl = ident;
+        int cur = param;
+        if (w > 0) cur = (int)((wtot[w - 1] >> (4 * cur)) & 15ull);
+        cur = (int)((excl >> (4 * cur)) & 15ull);
+        // states of this thread's frames, C2 count, clamp map of the crossfade counter over them
+        const int Xe = max(prm.X, 1);
+        unsigned c2bits = 0;
+        int c2 = 0;
+        Clamp3 am = {0, 0, Xe};
+        uint8_t* st = prm.state + tr.frame_base + f0;
+#pragma unroll
+        for (int k = 0; k < kBisectFastFrames; ++k) {
+            if (k < nf) {
+                const unsigned long long m = map_of((cls >> (2 * k)) & 3u);
+                cur = (int)((m >> (4 * cur)) & 15ull);
+                const int t2 = (cur > param) ? 1 : 0;
+                c2 += t2;
+                c2bits |= (unsigned)t2 << k;
+                st[k] = (uint8_t)(1 + t2);
+                Clamp3 g;
+                if (prm.alpha_init && f0 + k == 0) { g.d = 0; g.lo = g.hi = t2 * Xe; }
+                else { g.d = t2 ? 1 : -1; g.lo = 0; g.hi = Xe; }
+                am = clamp3_then(am, g);
+            }
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) c2 += __shfl_xor_sync(0xffffffffu, c2, o);
+        __shared__ int cw[3 * 32];
+        // inclusive scan of the clamp maps over the warp, then over the warps
+        Clamp3 ci = am;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            Clamp3 pv;
+            pv.d = __shfl_up_sync(0xffffffffu, ci.d, o); pv.lo = __shfl_up_sync(0xffffffffu, ci.lo, o); pv.hi = __shfl_up_sync(0xffffffffu, ci.hi, o);
+            if (lane >= o) ci = clamp3_then(pv, ci);
+        }
+        __syncthreads();
+        if (lane == 0) red[w] = c2;
+        if (lane == 31) { cw[w] = ci.d; cw[32 + w] = ci.lo; cw[64 + w] = ci.hi; }
+        __syncthreads();
+        if (w == 0) {
+            Clamp3 t = {cw[lane], cw[32 + lane], cw[64 + lane]};
+            int tsum = red[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                Clamp3 pv;
+                pv.d = __shfl_up_sync(0xffffffffu, t.d, o); pv.lo = __shfl_up_sync(0xffffffffu, t.lo, o); pv.hi = __shfl_up_sync(0xffffffffu, t.hi, o);
+                if (lane >= o) t = clamp3_then(pv, t);
+            }
+#pragma unroll
+            for (int o = 16; o; o >>= 1) tsum += __shfl_xor_sync(0xffffffffu, tsum, o);
+            cw[lane] = t.d; cw[32 + lane] = t.lo; cw[64 + lane] = t.hi;
+            if (lane == 0) prm.c2_count[track] = tsum;
+        }
+        __syncthreads();
+        Clamp3 ce;
+        ce.d = __shfl_up_sync(0xffffffffu, ci.d, 1); ce.lo = __shfl_up_sync(0xffffffffu, ci.lo, 1); ce.hi = __shfl_up_sync(0xffffffffu, ci.hi, 1);
+        int kc = 0;                                         // the counter starts at 0 (alpha[0] = target_alpha[0] through alpha_init)
+        if (w > 0) kc = clamp3_apply(Clamp3{cw[w - 1], cw[32 + w - 1], cw[64 + w - 1]}, kc);
+        if (lane > 0) kc = clamp3_apply(ce, kc);
+        uint16_t* rw = prm.rows + tr.frame_base + f0;
+#pragma unroll
+        for (int k = 0; k < kBisectFastFrames; ++k) {
+            if (k < nf) {
+                const int t2 = (int)((c2bits >> k) & 1u);
+                if (prm.alpha_init && f0 + k == 0) kc = t2 * Xe;
+                else kc = min(max(kc + (t2 ? 1 : -1), 0), Xe);
+                rw[k] = (uint16_t)kc;
+            }
+        }
     }
 }
 
@@ -3090,8 +3208,8 @@ int tmt_plan_gate(tmt_plan* p, int automaton, int gate_input, const double* on, 
                                          : launch_gate<double, TMT_GATE_MINHOLD>(p, v, param, S, X, ai, co, st);
 }
 
-int tmt_plan_bisect(tmt_plan* p, const double* t_low, const double* t_high, const double* start, const int32_t* active, double hyst_db,
-                    double target_c2, int hold_frames, int max_iter, void* stream) {
+static int plan_bisect_impl(tmt_plan* p, const double* t_low, const double* t_high, const double* start, const int32_t* active, double hyst_db,
+                            double target_c2, int hold_frames, int max_iter, int emit, int xfade_frames, int alpha_init, void* stream) {
     if (!p || !t_low || !t_high || !start || !active) return fail(TMT_ERR_INVALID, "bad arguments");
     if (hold_frames < 0 || max_iter < 0 || max_iter > kBisectMaxIter) return fail(TMT_ERR_INVALID, "bad search parameters (max_iter <= %d)", kBisectMaxIter);
     if (p->n_tracks == 0) return TMT_OK;
@@ -3118,13 +3236,32 @@ int tmt_plan_bisect(tmt_plan* p, const double* t_low, const double* t_high, cons
     prm.half_hyst = hyst_db / 2; prm.target = target_c2; prm.hold = hold_frames; prm.S = S; prm.max_iter = max_iter;
     prm.von = p->von.p; prm.voff = p->voff.p; prm.best_T = p->bis_T.p; prm.n_iter = p->bis_iters.p;
     prm.trace_T = p->bis_trace_T.p; prm.trace_c2 = p->bis_trace_c2.p;
-    if (S <= 16 && p->max_frames <= 1024 * kBisectFastFrames && !getenv("TMT_BISECT_GENERIC"))
+    prm.emit = 0; prm.X = xfade_frames; prm.alpha_init = alpha_init ? 1 : 0;
+    prm.state = p->state.p; prm.rows = p->rows.p; prm.c2_count = p->c2.p;
+    const bool fast = S <= 16 && p->max_frames <= 1024 * kBisectFastFrames && !getenv("TMT_BISECT_GENERIC");
+    if (fast) {
+        prm.emit = (emit && !getenv("TMT_BISECT_NO_EMIT")) ? 1 : 0;      // the fast kernel also writes the final states and rows
         bisect_fast_kernel<<<p->n_tracks, 1024, 0, st>>>(prm);
-    else
+    } else {
         bisect_kernel<<<p->n_tracks, NT, smem, st>>>(prm);
+    }
     p->launches++;
     CUDA_TRY(cudaGetLastError());
+    if (emit && !prm.emit)                                                // generic search: the gate scan follows as its own launch
+        return tmt_plan_gate(p, TMT_GATE_MINHOLD, TMT_ARR_GATE_F64, nullptr, nullptr, hold_frames, xfade_frames, alpha_init, 0, stream);
     return TMT_OK;
+}
+
+int tmt_plan_bisect(tmt_plan* p, const double* t_low, const double* t_high, const double* start, const int32_t* active, double hyst_db,
+                    double target_c2, int hold_frames, int max_iter, void* stream) {
+    return plan_bisect_impl(p, t_low, t_high, start, active, hyst_db, target_c2, hold_frames, max_iter, 0, 0, 0, stream);
+}
+
+int tmt_plan_bisect_gate(tmt_plan* p, const double* t_low, const double* t_high, const double* start, const int32_t* active, double hyst_db,
+                         double target_c2, int hold_frames, int max_iter, int xfade_frames, int alpha_init_to_target, void* stream) {
+    if (xfade_frames < 0 || xfade_frames > 65534) return fail(TMT_ERR_INVALID, "bad gate parameters");
+    return plan_bisect_impl(p, t_low, t_high, start, active, hyst_db, target_c2, hold_frames, max_iter, 1, xfade_frames, alpha_init_to_target,
+                            stream);
 }
 
 static int launch_stft(tmt_plan* p, float post_gain, float limit, cudaStream_t st) {

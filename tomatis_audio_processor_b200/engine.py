@@ -200,13 +200,20 @@ class Plan:
         """The in-kernel threshold search covers tracks the gate scan handles in one segment."""
         return max(self.track_frames, default=0) <= 16384
 
-    def bisect(self, t_low, t_high, start, active, hyst_db: float, target_c2: float, hold: int, max_iter: int = 30):
-        """find_optimal_threshold for every track in one launch (tmt_plan_bisect); results in ARR_BISECT_*."""
+    def bisect(self, t_low, t_high, start, active, hyst_db: float, target_c2: float, hold: int, max_iter: int = 30, final_gate=None):
+        """find_optimal_threshold for every track in one launch (tmt_plan_bisect); results in ARR_BISECT_*.
+        final_gate = (xfade_frames, alpha_init_to_target): also run the final gate with the thresholds found
+        (tmt_plan_bisect_gate; states, rows and C2 counts are final afterwards)."""
         n = max(1, self.n_tracks)
         arrs = [np.ascontiguousarray(np.broadcast_to(np.asarray(a, dtype=np.float64), (n,))) for a in (t_low, t_high, start)]
         act = np.ascontiguousarray(np.broadcast_to(np.asarray(active, dtype=np.int32), (n,)))
-        rc = self.lib.tmt_plan_bisect(self.h, *(a.ctypes.data_as(C.c_void_p) for a in arrs), act.ctypes.data_as(C.c_void_p),
-                                      float(hyst_db), float(target_c2), int(hold), int(max_iter), _stream_ptr(_torch()))
+        if final_gate is not None:
+            rc = self.lib.tmt_plan_bisect_gate(self.h, *(a.ctypes.data_as(C.c_void_p) for a in arrs), act.ctypes.data_as(C.c_void_p),
+                                               float(hyst_db), float(target_c2), int(hold), int(max_iter), int(final_gate[0]),
+                                               int(bool(final_gate[1])), _stream_ptr(_torch()))
+        else:
+            rc = self.lib.tmt_plan_bisect(self.h, *(a.ctypes.data_as(C.c_void_p) for a in arrs), act.ctypes.data_as(C.c_void_p),
+                                          float(hyst_db), float(target_c2), int(hold), int(max_iter), _stream_ptr(_torch()))
         if rc == L.ERR_UNSUPPORTED:          # long tracks / forced multi-segment scan: the caller drives the search from the host
             return False
         L.check(rc, "tmt_plan_bisect")
@@ -544,10 +551,9 @@ def run_adaptive(xs: Sequence, sr: int, device: int = 0, want_host: bool = True,
             traces = [[] for _ in range(nt)]
             # the whole search in one launch when the tracks fit the single-segment scan; thresholds stay on the device for the
             # final gate, results come back at the end
-            in_kernel = plan.can_bisect() and plan.bisect(T_low, T_high, best_T, active, hyst_db, target_c2, hold, 30)
-            if in_kernel:
-                plan.gate(L.GATE_MINHOLD, L.ARR_GATE_F64, None, None, hold, xf, alpha_init_to_target=True, count_only=False)
-            else:
+            in_kernel = plan.can_bisect() and plan.bisect(T_low, T_high, best_T, active, hyst_db, target_c2, hold, 30,
+                                                          final_gate=(xf, True))
+            if not in_kernel:
                 for _ in range(30):
                     if not active.any():
                         break
