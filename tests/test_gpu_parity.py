@@ -350,3 +350,25 @@ def test_long_delay_and_hold_use_the_serial_gate():
     assert r["optimal_T"] == o["optimal_T"] and r["trace"] == o["trace"]
     assert np.array_equal(r["states"], o["states"])
     assert np.allclose(r["rows"] / max(r["xfade_frames"], 1), o["alphas"], atol=1e-9)
+
+
+def test_edges_beside_stft_and_fused_final_gate_equal_the_serial_launches(monkeypatch):
+    """Two launch-structure optimisations of round 2 against their plain forms, bit for bit: the fp64 edge frames running beside
+    the STFT kernel on the side stream (small streaming jobs, adaptive) vs one after the other (TMT_EDGES_SERIAL), and the final gate
+    inside the threshold-search launch vs its own launch (TMT_BISECT_NO_EMIT)."""
+    from tomatis_audio_processor_b200 import synth
+    eng = _engine()
+    x = synth.recipe_swept_pink(6.0, 48000, 91, period_s=0.8, peak=0.5)
+    xs = synth.recipe_gated_pink(7.0, 48000, 92, env_hz=1.1, hi_dbfs=-21.0)
+    kw = dict(min_hold_ms=100.0, xfade_ms=200.0)
+    a = eng.run("adaptive", [x], 48000, **kw)[0]
+    s = eng.run("standard", [xs], 48000, gate_ui=50)[0]
+    monkeypatch.setenv("TMT_EDGES_SERIAL", "1")
+    monkeypatch.setenv("TMT_BISECT_NO_EMIT", "1")
+    a2 = eng.run("adaptive", [x], 48000, **kw)[0]
+    s2 = eng.run("standard", [xs], 48000, gate_ui=50)[0]
+    assert a2["launches"] == a["launches"] + 1                       # the gate scan is a launch of its own again
+    for r, r2 in ((a, a2), (s, s2)):
+        assert np.array_equal(r["out"], r2["out"])
+        assert np.array_equal(r["states"], r2["states"]) and np.array_equal(r["rows"], r2["rows"])
+    assert a["optimal_T"] == a2["optimal_T"] and a["trace"] == a2["trace"]

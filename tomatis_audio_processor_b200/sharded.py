@@ -286,12 +286,17 @@ class PeerExchange:
         return int(v.value)
 
     def close(self):
+        """Collective (every rank calls it, also on the failure path of the constructor): unmap the peers, wait for everybody,
+        free the own buffer."""
+        if getattr(self, "_closed", False):
+            return
+        self._closed = True
         for q in self.peers.values():
             self.lib.tmt_peer_close(self.device, self.C.c_void_p(q))
         self.peers = {}
+        if self.comm.world > 1:
+            self.comm.dist.barrier(group=self.comm.group)          # nobody frees a buffer a peer still has mapped and may write to
         if self.own_ptr:
-            if isinstance(self.comm, Comm) and self.comm.world > 1:
-                self.comm.dist.barrier(group=self.comm.group)      # nobody frees a buffer a peer still has mapped and may write to
             self.lib.tmt_peer_free(self.device, self.C.c_void_p(self.own_ptr))
             self.own_ptr = None
 
