@@ -247,7 +247,8 @@ int tmt_plan_run_streaming(tmt_plan* p, double m_on, double m_off, int run_frame
  * (src/process_tomatis.py:434, _adaptive.py:179).  n_values = samples x channels. */
 int tmt_pcm_to_float(const void* pcm, int format, int64_t n_values, float* out, void* stream);
 /* float32 -> PCM_24 as the reference's output files store it (subtype='PCM_24', src/process_tomatis.py:243,
- * _adaptive.py:351): rint(x * 0x7FFFFF), clipped to 24 bits. */
+ * _adaptive.py:351) through python-soundfile, i.e. libsndfile's FLAC conversion with clipping on: lrintf(x * 2^23), pinned to
+ * [-2^23, 2^23 - 1] (libsndfile src/flac.c f2flac24_clip_array; a WAV PCM_24 file holds floor(x * 2^23) instead, src/pcm.c). */
 int tmt_float_to_pcm(const float* in, int format, int64_t n_values, void* pcm, void* stream);
 
 /* y = dequantise(quantise_PCM24(y)) * scale in place: the PCM_24 write / read round trip of the static EQ's gain-protect

@@ -30,8 +30,10 @@ def build_gain_per_bin(sr, n_fft, eq_freqs, eq_db):
 
 
 def pcm24_roundtrip(y):
-    """What soundfile returns (dtype float32) after writing `y` as PCM_24: rint(y * 0x7FFFFF) clipped, / 2^23."""
-    q = np.clip(np.rint(np.asarray(y, dtype=np.float64) * 8388607.0), -8388608, 8388607)
+    """What soundfile returns (dtype float32) after writing `y` as FLAC PCM_24 (the container of the gain-protect pass,
+    src/layer2_apply_eq.py:226): libsndfile's clipping conversion lrint(y * 2^23) pinned to [-2^23, 2^23 - 1]
+    (src/flac.c f2flac24_clip_array; python-soundfile switches clipping on), read back as value / 2^23."""
+    q = np.clip(np.rint(np.asarray(y, dtype=np.float64) * 8388608.0), -8388608, 8388607)
     return (q / 8388608.0).astype(np.float32)
 
 

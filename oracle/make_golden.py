@@ -214,6 +214,8 @@ def main():
         return make_chan()
     if "--only-val" in sys.argv:
         return make_val()
+    if "--only-eq" in sys.argv:
+        return make_eq()
     only_multi = "--only-multichannel" in sys.argv
     if not only_multi:
         make_chan()

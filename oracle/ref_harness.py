@@ -120,9 +120,10 @@ def make_soundfile_standin(store: _Store) -> types.ModuleType:
 
 
 def _as_written(y, subtype):
-    """Samples as a later read(dtype='float32') returns them: libsndfile's PCM_24 rule, see audio_io.quantise_pcm24."""
+    """Samples as a later read(dtype='float32') returns them: libsndfile's FLAC PCM_24 rule with clipping on
+    (lrint(y * 2^23) pinned to 24 bits), see audio_io.quantise_pcm24."""
     if subtype == "PCM_24":
-        q = np.clip(np.rint(np.asarray(y, dtype=np.float64) * 8388607.0), -8388608, 8388607)
+        q = np.clip(np.rint(np.asarray(y, dtype=np.float64) * 8388608.0), -8388608, 8388607)
         return (q / 8388608.0).astype(np.float32)
     return np.asarray(y, dtype=np.float32)
 

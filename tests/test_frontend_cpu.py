@@ -30,9 +30,15 @@ def test_wav_roundtrip(tmp_path, subtype, tol):
 
 
 def test_pcm24_quantiser_matches_libsndfile_rule():
-    y = np.array([0.0, 1.0, -1.0, 0.5, 1.5, -1.5, 0.999, 2.5 / 8388607.0, 3.5 / 8388607.0])
-    q = audio_io.quantise_pcm24(y)
-    assert q.tolist() == [0, 8388607, -8388607, 4194304, 8388607, -8388608, 8380218, 2, 4]   # round half to even, clip
+    """libsndfile's clipping conversions (python-soundfile switches clipping on): FLAC rounds x * 2^23 half to even and pins,
+    WAV keeps the top three bytes of lrint(x * 2^31), i.e. the floor."""
+    L = 1.0 / 8388608.0
+    y = np.array([0.0, 1.0, -1.0, 0.5, 1.5, -1.5, 0.999, 2.5 * L, 3.5 * L, -2.5 * L, -0.25 * L, 0.75 * L])
+    assert audio_io.quantise_pcm24(y).tolist() == [0, 8388607, -8388608, 4194304, 8388607, -8388608, 8380219, 2, 4, -2, 0, 1]
+    assert audio_io.quantise_pcm24(y, "WAV").tolist() == [0, 8388607, -8388608, 4194304, 8388607, -8388608, 8380219, 2, 3, -3, -1, 0]
+    y32 = np.float32([0.999, -0.999, 0.1])
+    assert audio_io.quantise_pcm24(y32).tolist() == [int(np.rint(float(v) * 8388608.0)) for v in y32]
+    assert audio_io.quantise_pcm16(np.array([0.5, -1.0, 1.0, 1.25 / 32768.0, -0.5 / 32768.0])).tolist() == [16384, -32768, 32767, 1, -1]
 
 
 def test_flac_without_libsndfile_raises_format_unavailable(tmp_path):

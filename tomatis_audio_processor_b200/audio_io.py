@@ -4,7 +4,8 @@
 `soundfile` (libsndfile) is used when it is importable, so FLAC in / FLAC PCM_24 out behave exactly
 as in the reference.  Where it is not installed (this build image has no libsndfile) a small
 built-in RIFF/WAVE codec covers WAV PCM_16/24/32 and IEEE float, with libsndfile's scaling
-conventions (read: int / 2^(bits-1); write PCM_24: lrint(x * 0x7FFFFF), clipped), and any FLAC
+conventions (read: int / 2^(bits-1); write: the clipping conversions of libsndfile's src/pcm.c that
+python-soundfile switches on, see `quantise_pcm24`), and any FLAC
 request raises `AudioFormatUnavailable` -- which the standard/xfade front ends turn into the
 reference's own "FLAC failed -> write .wav" fallback (src/process_tomatis.py:242-251).
 """
@@ -114,11 +115,36 @@ def _wav_read(path, dtype):
     return _wav_decode(raw, info.subtype, n, dtype).reshape(info.frames, info.channels), info.samplerate
 
 
-def quantise_pcm24(y: np.ndarray) -> np.ndarray:
-    """float -> int32 holding 24-bit samples, libsndfile's float->PCM_24 rule (scale 0x7FFFFF, round to
-    nearest even, clip)."""
-    v = np.rint(np.asarray(y, dtype=np.float64) * 8388607.0)
+def _scaled_int32(y) -> np.ndarray:
+    """lrint(x * 2^31) clipped to int32 -- the first half of libsndfile's f2le*_clip_array / d2le*_clip_array (src/pcm.c):
+    `scaled_value = src[i] * normfact` with normfact = 8.0 * 0x10000000, values >= 0x7FFFFFFF and <= -0x80000000 pinned."""
+    v = np.rint(np.asarray(y, dtype=np.float64) * 2147483648.0)            # exact for float32 data (a power-of-two scale)
+    return np.clip(v, -2147483648.0, 2147483647.0).astype(np.int64)
+
+
+def quantise_pcm24(y: np.ndarray, container: str = "FLAC") -> np.ndarray:
+    """float -> int32 holding 24-bit samples, as libsndfile 1.2.x writes them with clipping switched on -- python-soundfile
+    switches it on for every file it opens (`sf_command(SFC_SET_CLIPPING, SF_TRUE)` in `SoundFile.__init__`), and the
+    reference writes through python-soundfile (src/process_tomatis.py:243,357).
+
+    FLAC (src/flac.c, f2flac24_clip_array / d2flac24_clip_array): lrint(x * 2^23), round half to even; scaled values
+          >= 0x7FFFFF give 0x7FFFFF, <= -0x800000 give -0x800000.
+    WAV  (src/pcm.c, f2let_clip_array / d2let_clip_array): lrint(x * 2^31) clipped to int32, of which the top three bytes are
+          stored -- an arithmetic shift, i.e. floor(x * 2^23) for float32 data.
+    The two containers therefore differ by up to one step of 2^-23.  Restated from the library's published source; it could
+    not be checked against a binary (no libsndfile in this image): treat the PCM edge as "within 1 LSB" (DESIGN.md section 0)."""
+    if str(container).upper() == "WAV":
+        return (_scaled_int32(y) >> 8).astype(np.int32)
+    v = np.rint(np.asarray(y, dtype=np.float64) * 8388608.0)
     return np.clip(v, -8388608, 8388607).astype(np.int32)
+
+
+def quantise_pcm16(y: np.ndarray, container: str = "WAV") -> np.ndarray:
+    """float -> int16 the same way: WAV stores the top two bytes of lrint(x * 2^31) (f2les_clip_array), FLAC lrint(x * 2^15)
+    clipped (f2flac16_clip_array)."""
+    if str(container).upper() == "WAV":
+        return (_scaled_int32(y) >> 16).astype(np.int16)
+    return np.clip(np.rint(np.asarray(y, dtype=np.float64) * 32768.0), -32768, 32767).astype(np.int16)
 
 
 def _wav_write(path, y, sr, subtype):
@@ -127,14 +153,14 @@ def _wav_write(path, y, sr, subtype):
         y = y[:, None]
     frames, ch = y.shape
     if subtype == "PCM_24":
-        v = quantise_pcm24(y).reshape(-1)
+        v = quantise_pcm24(y, "WAV").reshape(-1)
         data = np.empty((v.size, 3), dtype=np.uint8)
         data[:, 0] = v & 0xFF
         data[:, 1] = (v >> 8) & 0xFF
         data[:, 2] = (v >> 16) & 0xFF
         tag, bits = _WAVE_FORMAT_PCM, 24
     elif subtype == "PCM_16":
-        data = np.clip(np.rint(y.astype(np.float64) * 32767.0), -32768, 32767).astype("<i2").reshape(-1)
+        data = quantise_pcm16(y, "WAV").astype("<i2").reshape(-1)
         tag, bits = _WAVE_FORMAT_PCM, 16
     elif subtype == "FLOAT":
         data = y.astype("<f4").reshape(-1)

@@ -59,7 +59,7 @@ class HostBatchPipeline:
     in_format / out_format select what crosses PCIe:
       "f32"  float32 [T, N, 2]                       8 B per sample-frame each way (what the reference holds in memory)
       "s16"  int16   [T, N, 2]  (input only)         4 B/sf; converted on the device as soundfile would (value / 32768)
-      "s24"  uint8   [T, N, 6]  packed PCM_24        6 B/sf; input value / 8388608, output rint(y * 0x7FFFFF) clipped --
+      "s24"  uint8   [T, N, 6]  packed PCM_24        6 B/sf; input value / 8388608, output lrint(y * 2^23) clipped (FLAC rule) --
                                                      the reference's output files are PCM_24 (src/process_tomatis.py:243)
     """
 

@@ -1898,9 +1898,11 @@ __global__ void __launch_bounds__(256) s24_to_float_kernel(const unsigned* __res
     }
 }
 
-// float -> PCM_24, libsndfile's rule as restated in audio_io.quantise_pcm24: rint(x * 0x7FFFFF) in double, clipped
+// float -> PCM_24 as libsndfile writes it into a FLAC with clipping switched on (what python-soundfile does; restated in
+// audio_io.quantise_pcm24 from src/flac.c f2flac24_clip_array): lrintf(x * 2^23), pinned to [-2^23, 2^23 - 1].  The scale is a
+// power of two, so the product is exact and the only rounding is the round-half-even conversion (which saturates).
 __device__ __forceinline__ int quant24(float x) {
-    const int v = __double2int_rn((double)x * 8388607.0);
+    const int v = __float2int_rn(__fmul_rn(x, 8388608.0f));
     return max(-8388608, min(8388607, v));
 }
 __global__ void __launch_bounds__(256) float_to_s24_kernel(const float4* __restrict__ in, unsigned* __restrict__ out, long long n4,
