@@ -39,3 +39,39 @@ def test_filter_operator_matches_numpy(emul):
     yr = np.fft.irfft(np.fft.rfft(r.astype(np.float64)) * g, 4096)
     scale = max(np.abs(yl).max(), np.abs(yr).max())
     assert np.abs(out.real - yl).max() / scale < 3e-6 and np.abs(out.imag - yr).max() / scale < 3e-6
+
+
+# ---- pair mode (n_fft = 2048): two frames as the even / odd samples of one 4096-wide pass ------------------------------------
+@pytest.fixture(scope="module")
+def emul_pair(emul):
+    emul.tmt_emul_forward_pair.argtypes = [C.c_void_p, C.c_void_p]
+    emul.tmt_emul_filter_pair.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    return emul
+
+
+def test_pair_forward_is_two_2048_point_ffts(emul_pair):
+    rng = np.random.default_rng(2)
+    f = (rng.standard_normal((2, 2048)) + 1j * rng.standard_normal((2, 2048))).astype(np.complex64)
+    z = np.empty(4096, np.complex64)
+    z[0::2], z[1::2] = f[0], f[1]
+    out = np.empty(4096, np.complex64)
+    assert emul_pair.tmt_emul_forward_pair(z.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p)) == 0
+    ref = np.fft.fft(f.astype(np.complex128), axis=1).reshape(-1)
+    err = np.abs(out - ref).max() / np.abs(ref).max()
+    assert err < 2e-6, err
+
+
+def test_pair_filter_applies_each_frames_own_gain_row(emul_pair):
+    """Each frame of the pair: IFFT(G_p * FFT(L_p + iR_p)) = the per-channel rfft * g_p * irfft of the reference with n_fft = 2048."""
+    rng = np.random.default_rng(3)
+    lr = rng.standard_normal((2, 2, 2048)).astype(np.float32)                 # [frame][channel][sample]
+    g = np.exp(rng.uniform(-1.5, 1.5, (2, 1025))).astype(np.float32)
+    z = np.empty(4096, np.complex64)
+    z[0::2], z[1::2] = lr[0, 0] + 1j * lr[0, 1], lr[1, 0] + 1j * lr[1, 1]
+    out = np.empty(4096, np.complex64)
+    assert emul_pair.tmt_emul_filter_pair(z.ctypes.data_as(C.c_void_p), g.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p)) == 0
+    for p in range(2):
+        y = out[p::2]
+        for ch, got in ((0, y.real), (1, y.imag)):
+            want = np.fft.irfft(np.fft.rfft(lr[p, ch].astype(np.float64)) * g[p], 2048)
+            assert np.abs(got - want).max() / np.abs(want).max() < 3e-6

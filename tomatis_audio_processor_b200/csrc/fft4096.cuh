@@ -32,9 +32,18 @@
 
 namespace tmt {
 
-constexpr int kNfft = 4096;
-constexpr int kHop = 2048;
-constexpr int kThreads = 256;       // one frame per CTA pass, 16 points per thread
+// The library is compiled once per supported frame size: TMT_NFFT = 4096 (default; hop 2048) or 2048 (hop 1024, "pair mode":
+// two consecutive 2048-point frames ride one 4096-wide pass of the same machinery as the even and odd samples of the packed
+// vector, see the pair-mode section below).  Everything that is not the FFT derives its geometry from kNfft / kHop.
+#ifndef TMT_NFFT
+#define TMT_NFFT 4096
+#endif
+static_assert(TMT_NFFT == 4096 || TMT_NFFT == 2048, "fused path: n_fft 4096 (hop 2048) or 2048 (hop 1024)");
+constexpr int kNfft = TMT_NFFT;
+constexpr int kHop = TMT_NFFT / 2;
+constexpr bool kPair = (TMT_NFFT == 2048);
+constexpr int kPassLen = 4096;      // complex points of one pass of the FFT machinery (one 4096-frame or two 2048-frames)
+constexpr int kThreads = 256;       // one pass per CTA, 16 points per thread
 #ifdef TMT_E1_PADDED_ROWS             // the earlier layout: 16 padded rows, 64-bit accesses on both sides
 constexpr int kE1Row = 264;         // E1 row stride in float2 (256 + 8): the B side reads rows k1 and k1 + 1 from the two lane
                                     // parities of a warp, the 64-byte skew keeps every half warp on 32 distinct banks
@@ -419,6 +428,62 @@ TMT_HD void x_inv2_unpack(const float (&s)[32], float2 (&v)[16]) {
 #pragma unroll
     for (int q = 0; q < 16; ++q) v[q] = make_float2(s[2 * q], s[2 * q + 1]);
 }
+
+// ---- pair mode: two 2048-point transforms in one 4096-wide pass ---------------------------------------------------------
+// z[2m + p] = frame_p[m] (p = 0, 1; m = 0..2047).  A decimation-in-time 4096-point transform of z that stops before its last
+// radix-2 butterfly IS the two 2048-point transforms of the even and the odd samples.  With n = 256*n1 + 16*n2 + n3 the parity
+// p is the lowest bit of n3, which no stage but C combines: stages A and B and both exchanges keep their layouts and only see
+// other twiddles -- m = 128*n1 + 8*n2 + n3' (n3 = 2*n3' + p), k = k1 + 16*k2 + 256*k3' (k3' = 0..7):
+//     stage A: DFT16 over n1, twiddle W2048^((8*n2 + n3')*k1) = (W4096^(t & ~1))^k1         (thread t = 16*n2 + n3)
+//     stage B: DFT16 over n2, twiddle W128^(n3'*k2)           = (W256^(n3 & ~1))^k2
+//     stage C: DFT8 over n3' = 2a + b1 for each p: the first radix-4 layer over a is the 4096 one (n3 = 4a + b, b = 2*b1 + p);
+//              the second layer shrinks to a radix-2 over b1 with twiddle W8^(b1*c): X_p[c + 4d'] = y[p][c] + (-1)^d' W8^c y[2+p][c]
+// After stage C register j = 8p + k3' of thread (k1, k2) holds bin k1 + 16*k2 + 256*k3' of frame p.
+template <int C>
+TMT_HD float2 w8() {                 // W8^C = e^{-2*pi*i*C/8}, C = 1, 3 (0 and 2 are handled without a multiply)
+    constexpr float kH = 0.70710678118654752440f;
+    static_assert(C == 1 || C == 3, "unsupported W8 power");
+    return (C == 1) ? make_float2(kH, -kH) : make_float2(-kH, -kH);
+}
+// forward, second layer of stage C: s (row order) holds y[b][c] (b = n3 & 3 just arrived, c = column group)
+TMT_HD void x_fwd2_finish_pair(const float (&s)[32], float2 (&v)[16]) {
+#pragma unroll
+    for (int p = 0; p < 2; ++p) {
+#define TMT_Y(b, c) make_float2(s[row_reg(b, c)], s[row_reg(b, c) + 1])
+        { const float2 lo = TMT_Y(p, 0), hi = TMT_Y(2 + p, 0); v[8 * p + 0] = cadd(lo, hi); v[8 * p + 4] = csub(lo, hi); }
+        { const float2 lo = TMT_Y(p, 1), t = cfma(lo, TMT_Y(2 + p, 1), w8<1>()); v[8 * p + 1] = t; v[8 * p + 5] = twice_minus(lo, t); }
+        { const float2 lo = TMT_Y(p, 2), hi = TMT_Y(2 + p, 2); v[8 * p + 2] = cadd_mi(lo, hi); v[8 * p + 6] = cadd_pi(lo, hi); }
+        { const float2 lo = TMT_Y(p, 3), t = cfma(lo, TMT_Y(2 + p, 3), w8<3>()); v[8 * p + 3] = t; v[8 * p + 7] = twice_minus(lo, t); }
+#undef TMT_Y
+    }
+}
+// inverse, first layer of stage C' (undoes x_fwd2_finish_pair): radix-2 over d' for each (c, p) with the real gains fused in,
+// inner twiddle conj(W8^(b1*c)), packed in row order with b = 2*b1 + p as the index that leaves
+TMT_HD void x_inv1_pack_pair(const float2 (&v)[16], float (&r)[32], const float* g = nullptr) {
+#pragma unroll
+    for (int p = 0; p < 2; ++p) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const float2 a = v[8 * p + c], b = v[8 * p + c + 4];
+            float2 y0, y1;
+            if (g) {
+                const float2 p2 = cscale(b, g[8 * p + c + 4]);
+                y0 = cfms(a, g[8 * p + c], p2);
+                y1 = cfmsn(a, g[8 * p + c], p2);
+            } else {
+                y0 = cadd(a, b);
+                y1 = csub(a, b);
+            }
+            if (c == 1) y1 = cmulc(y1, w8<1>());
+            if (c == 2) y1 = make_float2(-y1.y, y1.x);              // conj(-i) = +i
+            if (c == 3) y1 = cmulc(y1, w8<3>());
+            r[row_reg(p, c)] = y0.x; r[row_reg(p, c) + 1] = y0.y;
+            r[row_reg(2 + p, c)] = y1.x; r[row_reg(2 + p, c) + 1] = y1.y;
+        }
+    }
+}
+// bin of frame (j >> 3) held in register j of thread t after stage C in pair mode
+TMT_HD int bin_of_pair(int t, int j) { return c_k1(t) + 16 * c_k2(t) + 256 * (j & 7); }
 
 // The data movement of the round trips, for the CPU emulation (csrc/host_emul.cu): src/dst index a warp's 32 x 32 register image.
 // forward trip (st .32x32b, ld .16x256b): thread T register 16*I + 4*g + 2*h + e  <-  thread (16*I + 8*h + T/4) register 8*g + 2*(T%4) + e

@@ -18,12 +18,21 @@ extern "C" {
 // by their data movement (emul_trip_fwd / emul_trip_inv, verified on hardware by tools/mb_tmem_xpose.cu).
 // spec: if non-null, receives the spectrum in NATURAL bin order (before the gain); g_half: natural-order half-spectrum gain or
 // null (forward only).
-static void emul_frame(const float* z_in, const float* g_half, float* spec, float* z_out) {
-    auto tb = build_tw_bases();
+// pair: two 2048-point frames as the even / odd samples of z (fft4096.cuh, pair mode); spec then holds frame 0's 2048 bins
+// followed by frame 1's, g_half = two half spectra of 1025 gains (frame 0, frame 1)
+static void emul_frame(const float* z_in, const float* g_half, float* spec, float* z_out, bool pair = false) {
+    auto tb = build_tw_bases(pair);
     auto WA = [&](int t) { return TwBase{tb[4 * t], tb[4 * t + 1]}; };
     auto WB = [&](int t) { return TwBase{tb[4 * t + 2], tb[4 * t + 3]}; };
-    std::vector<float> gperm(4096, 1.0f);
-    if (g_half) permute_gain_row(g_half, gperm.data());
+    std::vector<float> gperm(4096, pair ? 1.0f / 2048.0f : 1.0f);
+    if (g_half && !pair) permute_gain_row(g_half, gperm.data(), false);
+    if (g_half && pair) {                         // registers 0-7 from the first frame's row, 8-15 from the second's
+        std::vector<float> g0(4096), g1(4096);
+        permute_gain_row(g_half, g0.data(), true);
+        permute_gain_row(g_half + 1025, g1.data(), true);
+        for (int t = 0; t < 256; ++t)
+            for (int j = 0; j < 16; ++j) gperm[t * 16 + j] = (j < 8 ? g0 : g1)[t * 16 + j];
+    }
     std::vector<float2> P(kE1Float2);
     std::vector<float> R(256 * 32), S(256 * 32);
     float2 v[16];
@@ -52,12 +61,19 @@ static void emul_frame(const float* z_in, const float* g_half, float* spec, floa
     for (int t = 0; t < 256; ++t) {                                   // second layer of C, gain, first layer of C'
         float s[32], r[32];
         for (int c = 0; c < 32; ++c) s[c] = S[t * 32 + c];
-        x_fwd2_finish(s, v);
+        if (pair) x_fwd2_finish_pair(s, v); else x_fwd2_finish(s, v);
         if (spec)
-            for (int j = 0; j < 16; ++j) { spec[2 * bin_of(t, j)] = v[j].x; spec[2 * bin_of(t, j) + 1] = v[j].y; }
+            for (int j = 0; j < 16; ++j) {
+                const int k = pair ? 2048 * (j >> 3) + bin_of_pair(t, j) : bin_of(t, j);
+                spec[2 * k] = v[j].x; spec[2 * k + 1] = v[j].y;
+            }
         if (!z_out) continue;
-        for (int j = 0; j < 16; ++j) { v[j].x *= gperm[t * 16 + j]; v[j].y *= gperm[t * 16 + j]; }
-        x_inv1_pack(v, r);
+        if (pair) {
+            x_inv1_pack_pair(v, r, gperm.data() + t * 16);
+        } else {
+            for (int j = 0; j < 16; ++j) { v[j].x *= gperm[t * 16 + j]; v[j].y *= gperm[t * 16 + j]; }
+            x_inv1_pack(v, r);
+        }
         for (int c = 0; c < 32; ++c) R[t * 32 + c] = r[c];
     }
     if (!z_out) return;
@@ -97,6 +113,18 @@ int tmt_emul_forward(const float* z_in, float* spec_out) {
 // half spectrum g[0..2048] (the 1/4096 is applied through the permuted gain row, as on the GPU).
 int tmt_emul_filter(const float* z_in, const float* g_half, float* z_out) {
     emul_frame(z_in, g_half, nullptr, z_out);
+    return 0;
+}
+
+// Pair mode: z_in = two 2048-point complex frames interleaved sample by sample (z[2m + p] = frame_p[m]); spec_out = frame 0's
+// 2048 bins followed by frame 1's
+int tmt_emul_forward_pair(const float* z_in, float* spec_out) {
+    emul_frame(z_in, nullptr, spec_out, nullptr, true);
+    return 0;
+}
+// g_half = [2][1025]: one natural-order half spectrum per frame of the pair (1/2048 applied through the permuted rows)
+int tmt_emul_filter_pair(const float* z_in, const float* g_half, float* z_out) {
+    emul_frame(z_in, g_half, nullptr, z_out, true);
     return 0;
 }
 
