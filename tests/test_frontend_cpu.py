@@ -143,17 +143,19 @@ def test_guard_and_error_exit_code_without_gpu(tmp_path, capsys):
 # ------------------------------------------------------------------ C ABI
 def test_library_exports_every_declared_symbol():
     from tomatis_audio_processor_b200 import _lib, build
-    if not os.path.exists(build.LIB_PATH):
-        build.build_library()
+    for n_fft, path in build.LIB_PATHS.items():            # one build per fused frame size (4096 / 2048, 2048 / 1024)
+        if not os.path.exists(path):
+            build.build_library(n_fft=n_fft)
     with open(os.path.join(ROOT, "include", "tomatis_b200.h")) as f:
         hdr = f.read()
     declared = set(re.findall(r"\b(tmt_[a-z0-9_]+)\s*\(", hdr))
     assert declared, "no prototypes found"
     assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
-    lib = ctypes.CDLL(build.LIB_PATH)
-    for name in declared:
-        getattr(lib, name)                     # AttributeError = missing export
-    assert _lib.load().tmt_version() >= 100
+    for n_fft, path in build.LIB_PATHS.items():
+        lib = ctypes.CDLL(path)
+        for name in declared:
+            getattr(lib, name)                 # AttributeError = missing export
+        assert _lib.load(n_fft).tmt_version() >= 100 and _lib.load(n_fft).n_fft == n_fft
 
 
 def test_no_cpu_fallback_without_cuda():

@@ -1,0 +1,120 @@
+"""`--n_fft 2048 --hop 1024` (the reference documentation's faster setting, docs/Tomatis技术说明.md:253-258) on the FUSED kernels:
+the second build of the library (csrc/libtomatis_b200_n2048.so, TMT_NFFT=2048), whose STFT kernel carries two consecutive
+2048-point frames through one 4096-wide pass ("pair mode", csrc/fft4096.cuh).  Everything is compared with the oracle run at the
+same sizes (which tests/test_oracle_vs_reference.py pins to the executed reference for non-default n_fft / hop): mean squares
+bit-exact, states / rows / chunk lengths / threshold search exact, PCM within 1e-5 of full scale."""
+import numpy as np
+import pytest
+
+from oracle import tomatis_oracle as orc
+from tomatis_audio_processor_b200 import build, synth
+from test_generic_sizes import _compare
+
+pytestmark = pytest.mark.gpu
+SZ = dict(n_fft=2048, hop=1024)
+
+
+def _q(x):
+    return synth.pcm16_to_float(synth.quantise_pcm16(x))
+
+
+def _engine():
+    from tomatis_audio_processor_b200 import engine
+    return engine
+
+
+def test_second_library_is_loaded_for_2048():
+    eng = _engine()
+    e = eng.get_engine(0, 2048, 1024)
+    assert e.n_fft == 2048 and e.hop == 1024 and e.lib.n_fft == 2048
+    assert eng.get_engine(0).lib.n_fft == 4096 and eng.get_engine(0) is not e
+    assert build.LIB_PATHS[2048].endswith("libtomatis_b200_n2048.so")
+
+
+@pytest.mark.parametrize("sr", [48000, 44100])
+def test_three_modes_match_oracle(sr):
+    eng = _engine()
+    xs = _q(synth.recipe_gated_pink(6.5, sr, 190, env_hz=1.3, hi_dbfs=-20.0))          # two limiter chunks at hop 1024 (flush after 240 000 samples)
+    for mode, kw in (("standard", dict(gate_ui=50, up_delay_ms=120.0, output_gain_db=-1.5)),
+                     ("xfade", dict(gate_ui=62, xfade_ms=150.0, up_delay_ms=60.0)), ("xfade", dict(gate_ui=55))):
+        r = eng.run(mode, [xs], sr, **SZ, **kw)[0]
+        _compare(mode, orc.run(mode, xs, sr, **SZ, **kw), orc.run(mode, xs, sr, fft_dtype="float64", **SZ, **kw), r)
+    for peak in (0.5, 0.08):                                                            # float32 and float64 pipelines
+        xa = _q(synth.recipe_swept_pink(5.0, sr, 191, period_s=0.8, peak=peak))
+        kw = dict(min_hold_ms=100.0, xfade_ms=200.0, **SZ)
+        r = eng.run("adaptive", [xa], sr, **kw)[0]
+        _compare("adaptive", orc.run("adaptive", xa, sr, **kw), orc.run("adaptive", xa, sr, fft_dtype="float64", **kw), r)
+
+
+def test_ragged_lengths_and_short_files():
+    """Every parity of frame count and unit length; files shorter than a frame, a hop, one sample; pad_end = 0."""
+    eng = _engine()
+    sr = 48000
+    rng = np.random.default_rng(5)
+    totals = [1, 700, 1024, 1500, 2047, 2048, 2049, 3072, 4096 + 17, 1024 * 9, 1024 * 10 + 1, 1024 * 40, 33333, 100001]
+    for k, total in enumerate(totals):
+        env = 10.0 ** (rng.uniform(-3.0, -0.6, size=(total // 700 + 1)).repeat(700)[:total, None])
+        x = _q((env * rng.standard_normal((total, 2))).astype(np.float32).clip(-1, 1))
+        mode = ("standard", "xfade", "adaptive")[k % 3]
+        if mode == "adaptive":
+            kw = dict(min_hold_ms=20.0, xfade_ms=60.0, **SZ)
+        else:
+            kw = dict(gate_ui=48.0 + k, up_delay_ms=float((0, 15, 40)[k % 3]), **SZ)
+            if mode == "xfade":
+                kw["xfade_ms"] = 45.0
+        r = eng.run(mode, [x], sr, **kw)[0]
+        o, o64 = orc.run(mode, x, sr, **kw), orc.run(mode, x, sr, fft_dtype="float64", **kw)
+        if mode == "adaptive" and len(o["states"]) == 0:
+            assert np.array_equal(r["out"], o["out"].astype(np.float32))
+            continue
+        _compare(mode, o, o64, r)
+
+
+def test_batch_of_uneven_tracks_with_forced_unit_lengths():
+    """One plan, several tracks, work units of 1, 2, 3, 7 and the default number of blocks: unit boundaries fall on both pass
+    parities, so the carry hand-over between the lanes of a pair, the half pass of warm-up and the odd last pass all run."""
+    eng = _engine()
+    sr = 48000
+    xs = [_q(synth.recipe_gated_pink(s, sr, 300 + i, env_hz=2.0, hi_dbfs=-19.0)) for i, s in enumerate((1.1, 2.37, 0.41, 5.3))]
+    kw = dict(gate_ui=50, up_delay_ms=50.0, **SZ)
+    want = [(orc.run("standard", x, sr, **kw), orc.run("standard", x, sr, fft_dtype="float64", **kw)) for x in xs]
+    outs = {}
+    for ub in (0, 1, 2, 3, 7):
+        rs = eng.run_streaming("standard", xs, sr, unit_blocks=ub, **kw)
+        for r, (o, o64) in zip(rs, want):
+            _compare("standard", o, o64, r)
+        outs[ub] = [r["out"] for r in rs]
+    for ub in (1, 2, 3, 7):                                        # the unit split changes nothing but the limiter's reduction order
+        for a, b in zip(outs[0], outs[ub]):
+            assert np.abs(a - b).max() <= 2e-7
+
+
+def test_five_minute_track_inside_a_batch_fused_limiter_at_scale():
+    """16 tracks x 5 min @ 44.1 kHz at 2048 / 1024: steady loop, dynamic queue and the fused per-chunk limiter at scale; track 3
+    against the oracle."""
+    import torch
+    eng = _engine()
+    sr, n = 44100, 16
+    xs = [synth.recipe_gated_pink(300.0, sr, 1000 + i, env_hz=0.2, hi_dbfs=-25.0) for i in range(n)]
+    kw = dict(gate_ui=50, **SZ)
+    xd = [torch.from_numpy(x).cuda() for x in xs]
+    rs = eng.run_streaming("standard", xd, sr, want_host=False, **kw)
+    r = dict(rs[3])
+    r["out"] = r["out"].cpu().numpy()
+    o, o64 = orc.run("standard", xs[3], sr, **kw), orc.run("standard", xs[3], sr, fft_dtype="float64", **kw)
+    _compare("standard", o, o64, r)
+    assert len(r["chunk_lengths"]) == len(o["chunk_lengths"]) >= 50
+
+
+def test_fused_2048_equals_the_general_size_path(monkeypatch):
+    """The fused pair-mode kernels and the plain general-size kernels (csrc/generic.cuh, TMT_FUSED_2048=0) on the same input."""
+    eng = _engine()
+    sr = 48000
+    x = _q(synth.recipe_gated_pink(3.0, sr, 77, env_hz=2.0, hi_dbfs=-21.0))
+    kw = dict(gate_ui=50, up_delay_ms=80.0, **SZ)
+    a = eng.run("standard", [x], sr, **kw)[0]
+    monkeypatch.setenv("TMT_FUSED_2048", "0")
+    b = eng.run("standard", [x], sr, **kw)[0]
+    assert np.array_equal(a["meansq"], b["meansq"]) and np.array_equal(a["states"], b["states"])
+    assert a["chunk_lengths"] == b["chunk_lengths"]
+    assert np.abs(a["out"].astype(np.float64) - b["out"]).max() <= 2e-6

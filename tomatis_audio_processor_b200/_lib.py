@@ -8,7 +8,7 @@ from __future__ import annotations
 import ctypes as C
 import os
 
-from .build import LIB_PATH
+from .build import LIB_PATH, LIB_PATHS
 
 OK = 0
 ERR_UNSUPPORTED = -3
@@ -98,19 +98,36 @@ SIGNATURES = {
     "tmt_requantise_scale": (C.c_int, [_P, C.c_int64, C.c_float, _P]),
 }
 
-_lib = None
+_libs = {}
+_last = None          # the library whose function was fetched last: its thread-local error text belongs to the failing call
 
 
 class TomatisError(RuntimeError):
     pass
 
 
-def load():
-    """Load the library (once).  Raises RuntimeError if it has not been built."""
-    global _lib
-    if _lib is not None:
-        return _lib
-    path = os.environ.get("TMT_LIB", LIB_PATH)            # dev: A/B a differently built library
+class _Lib:
+    """One loaded build of the library.  Attribute access hands out the ctypes function and remembers which build was used,
+    so that check() asks the right one for its error text (each .so has its own thread-local message buffer)."""
+
+    def __init__(self, cdll, n_fft):
+        object.__setattr__(self, "_cdll", cdll)
+        object.__setattr__(self, "n_fft", n_fft)
+
+    def __getattr__(self, name):
+        global _last
+        _last = self._cdll
+        return getattr(self._cdll, name)
+
+
+def load(n_fft: int = 4096):
+    """Load the library built for `n_fft` (once).  Raises RuntimeError if it has not been built."""
+    hit = _libs.get(n_fft)
+    if hit is not None:
+        return hit
+    if n_fft not in LIB_PATHS:
+        raise RuntimeError(f"no fused library for n_fft={n_fft} (built sizes: {sorted(LIB_PATHS)})")
+    path = os.environ.get("TMT_LIB", LIB_PATH) if n_fft == 4096 else os.environ.get("TMT_LIB_2048", LIB_PATHS[n_fft])   # dev: A/B builds
     if not os.path.exists(path):
         raise RuntimeError(
             f"CUDA library not built: {path} is missing. Run `python -c 'import __graft_entry__ as g; g.build()'` "
@@ -120,13 +137,13 @@ def load():
         fn = getattr(lib, name)       # AttributeError if the .so does not export a declared symbol
         fn.restype = res
         fn.argtypes = args
-    _lib = lib
-    return lib
+    _libs[n_fft] = _Lib(lib, n_fft)
+    return _libs[n_fft]
 
 
 def check(rc: int, what: str = ""):
     if rc != OK:
-        lib = load()
+        lib = _last if _last is not None else load()
         msg = lib.tmt_last_error().decode("utf-8", "replace")
         kind = lib.tmt_error_string(rc).decode()
         raise TomatisError(f"{what or 'libtomatis_b200'}: {kind} ({rc}): {msg}")

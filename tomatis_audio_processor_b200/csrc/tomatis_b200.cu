@@ -223,7 +223,7 @@ levels_kernel(const TrackDev* __restrict__ tracks, const float* __restrict__ in_
     const bool aligned = (((start - tr.in_origin) & 1LL) == 0) && ((reinterpret_cast<uintptr_t>(tr.in) & 15u) == 0);
     T tot[2];
 #pragma unroll
-    for (int ps = 0; ps < 2; ++ps) {
+    for (int ps = 0; ps < kHop / 1024; ++ps) {
         const long long base = start + (ps * 8 + leaf) * 128 + 2 * pr;
         float2 x0[16], x1[16];
         if (inside && aligned) {
@@ -281,7 +281,7 @@ levels_kernel(const TrackDev* __restrict__ tracks, const float* __restrict__ in_
         s = Arith<T>::add(s, __shfl_xor_sync(0xffffffffu, s, 16));           // 8 leaves = 1024 samples
         tot[ps] = s;
     }
-    if (lane == 0) hsum[tr.hs_base + q] = Arith<T>::add(tot[0], tot[1]);
+    if (lane == 0) hsum[tr.hs_base + q] = (kHop == 2048) ? Arith<T>::add(tot[0], tot[1]) : tot[0];
 }
 
 template <typename T>
@@ -350,7 +350,7 @@ levels_multi_kernel(const TrackDev* __restrict__ tracks, int n_tracks, const flo
     const int pr = lane & 3, leaf = lane >> 2;
     T tot[2];
 #pragma unroll
-    for (int ps = 0; ps < 2; ++ps) {
+    for (int ps = 0; ps < kHop / 1024; ++ps) {
         const long long base = start + (ps * 8 + leaf) * 128 + 2 * pr;
         T a0 = (T)0, a1 = (T)0;
         for (int i = 0; i < 16; ++i) {
@@ -369,7 +369,7 @@ levels_multi_kernel(const TrackDev* __restrict__ tracks, int n_tracks, const flo
         tot[ps] = s;
     }
     if (lane == 0) {
-        const T h = Arith<T>::add(tot[0], tot[1]);
+        const T h = (kHop == 2048) ? Arith<T>::add(tot[0], tot[1]) : tot[0];
         for (int k = 0; k < n_tracks; ++k) hsum[tracks[k].hs_base + q] = h;
     }
 }
@@ -1135,13 +1135,17 @@ struct StftParams {
 };
 
 // tensor-memory columns of a warp: synthesis window 16 | carry 16 | raw input halves 2 x 16 | stage-A twiddles 32 | E2 exchange 32
+constexpr int kPassHop = 2048;                       // sample-frames one pass of the kernel advances: one hop of 2048 or (pair mode) two of 1024
+constexpr int kSampStride = kPair ? 128 : 256;       // distance between a thread's consecutive samples of its frame
+// sample offset of thread t inside its frame (pair mode: lanes 2h and 2h + 1 hold sample h of the pass's first / second frame)
+__device__ __forceinline__ int samp_ofs(int t) { return kPair ? (t >> 1) : t; }
 constexpr int kTmemWarpCols = 128;
 constexpr int kTcSwin = 0, kTcCarry = 16, kTcHalf = 32, kTcTwA = 64, kTcXchg = 96;
 constexpr int kTmemCols = 256;                       // per CTA: 2 warps per lane quarter x 128 columns (2 CTAs = all 512)
 // shared memory: two E1 exchange buffers | analysis window, thread-private float4 quads [4][256] | tail (TMEM slot, reduction,
 // two mbarriers, queue)
 constexpr int kStftSmemE1 = 2 * kE1Float2 * (int)sizeof(float2);     // two frames in flight (frame pipeline of stft_kernel)
-constexpr int kStftSmemWin = kNfft * (int)sizeof(float);
+constexpr int kStftSmemWin = kPassLen * (int)sizeof(float);
 constexpr int kStftSmemWb = 0;
 constexpr int kStftSmem = kStftSmemE1 + kStftSmemWin + kStftSmemWb + 96;
 
@@ -1210,10 +1214,11 @@ struct Park {
         const int warp = __shfl_sync(0xffffffffu, t >> 5, 0);
         base = *slot + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((warp >> 2) * kTmemWarpCols);
         float4* awr = reinterpret_cast<float4*>(smem_win) + t;
+        const int so = samp_ofs(t);
 #pragma unroll
         for (int g = 0; g < 4; ++g)
-            awr[256 * g] = make_float4(__ldg(win + 256 * (4 * g) + t), __ldg(win + 256 * (4 * g + 1) + t), __ldg(win + 256 * (4 * g + 2) + t),
-                                       __ldg(win + 256 * (4 * g + 3) + t));
+            awr[256 * g] = make_float4(__ldg(win + kSampStride * (4 * g) + so), __ldg(win + kSampStride * (4 * g + 1) + so),
+                                       __ldg(win + kSampStride * (4 * g + 2) + so), __ldg(win + kSampStride * (4 * g + 3) + so));
         aw = awr;
         fill_tables(t, swin, tw_a, post_gain);
     }
@@ -1221,7 +1226,7 @@ struct Park {
     __device__ __forceinline__ void fill_tables(int t, const float* swin, const float2* tw_a, float post_gain) const {
         float r[16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) r[j] = __ldg(swin + 256 * j + t) * post_gain;   // output gain folded into the synthesis window
+        for (int j = 0; j < 16; ++j) r[j] = __ldg(swin + kSampStride * j + samp_ofs(t)) * post_gain;   // output gain folded into the synthesis window
         tmem_st16(base + kTcSwin, r);
         const float4* ta = reinterpret_cast<const float4*>(tw_a + 16 * t);
 #pragma unroll
@@ -1464,9 +1469,11 @@ __global__ void __launch_bounds__(kThreads, 2) stft_kernel(const StftParams prm)
         const TrackDev* trp = prm.tracks + un.track;
         const int n_frames = trp->n_frames;
         const long long upos = trp->first_start + (long long)(un.b0 - 1) * kHop;     // position of frame b0-1
-        const float2* in_u = trp->in + (upos - trp->in_origin);                     // sample 0 of frame b0-1 (uniform; the thread adds t)
+        const int so = samp_ofs(t);                                                 // this thread's sample offset inside a frame
+        const int tp = kPair ? (t & 1) : 0;                                         // pair mode: which frame of the pass this lane holds
+        const float2* in_u = trp->in + (upos - trp->in_origin);                     // sample 0 of frame b0-1 (uniform; the thread adds its offset)
         float2* out_u = trp->out + (upos - trp->out_origin);
-        const long long span = (long long)(un.b1 - un.b0 + 2) * kHop + kNfft;
+        const long long span = (long long)(un.b1 - un.b0 + 8) * kHop + 2 * kPassLen;
         const int in_lo = (int)max(-span, min(span, trp->in_lo - upos)), in_hi = (int)max(-span, min(span, trp->in_hi - upos));
         const int out_lo = (int)max(-span, min(span, trp->out_lo - upos)), out_hi = (int)max(-span, min(span, trp->out_hi - upos));
         const uint16_t* rows = prm.rows + trp->frame_base;
@@ -1478,34 +1485,50 @@ __global__ void __launch_bounds__(kThreads, 2) stft_kernel(const StftParams prm)
             park.store_carry(z);
         }
         float peak = 0.f;
-        const int last = un.b1 - un.b0;                    // frames of this unit: i = 0 .. last  (f = b0 - 1 + i)
+        // passes of this unit: i = 0 .. last.  4096 mode: pass i = frame f = b0 - 1 + i.  Pair mode: pass i = frames f = b0 - 1 + 2i
+        // (even lanes) and f + 1 (odd lanes); frames past the unit's last one (b1 - 1) are treated as absent.
+        const int last = kPair ? ((un.b1 - un.b0) >> 1) : (un.b1 - un.b0);
+        const int f_end = min(n_frames, un.b1);                                     // frames of this unit end here
+        auto frame_exists = [&](int f) { return (f >= 0) && (f < f_end); };
 
-        // raw half frame h of the unit = positions [h*hop, (h+1)*hop) relative to the unit, zero outside the file
-        auto load_half = [&](int h, float2 (&x)[8]) {
-            const int p0 = h * kHop;
-            const float2* src = in_u + p0 + t;
-            if (p0 >= in_lo && p0 + kHop <= in_hi) {
+        // 8 raw samples of the unit-relative hop block q (4096 mode: half frame q), zero outside the file or when `live` is false
+        auto load_blk = [&](int q, bool live, float2 (&x)[8]) {
+            const int p0 = q * kHop;
+            const float2* src = in_u + p0 + so;
+            if (live && p0 >= in_lo && p0 + kHop <= in_hi) {
 #pragma unroll
-                for (int j = 0; j < 8; ++j) x[j] = ld_stream(src + 256 * j);
+                for (int j = 0; j < 8; ++j) x[j] = ld_stream(src + kSampStride * j);
             } else {
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                    const int p = p0 + 256 * j + t;
-                    x[j] = (p >= in_lo && p < in_hi) ? __ldg(src + 256 * j) : make_float2(0.f, 0.f);
+                    const int p = p0 + kSampStride * j + so;
+                    x[j] = (live && p >= in_lo && p < in_hi) ? __ldg(src + kSampStride * j) : make_float2(0.f, 0.f);
                 }
             }
         };
-        {                                  // prologue: halves 0 and 1 of the unit -> staging slots 0 and 1
+        {                                  // prologue: the two staging slots of pass 0
             float2 x[8];
-            load_half(0, x);
-            park.stage_put(0, x);
-            load_half(1, x);
-            park.stage_put(1, x);
+            if (kPair) {                   // slot 0 = first half, slot 1 = second half of this lane's frame b0 - 1 + tp
+                const bool live = frame_exists(un.b0 - 1 + tp);
+                load_blk(tp, live, x);
+                park.stage_put(0, x);
+                load_blk(tp + 1, live, x);
+                park.stage_put(1, x);
+            } else {                       // halves 0 and 1 of the unit
+                load_blk(0, true, x);
+                park.stage_put(0, x);
+                load_blk(1, true, x);
+                park.stage_put(1, x);
+            }
         }
-        // gain-row index of the next frame, fetched one frame ahead (it heads a dependent chain: index -> row address -> gains)
+        // gain-row index of the next frame(s), fetched one pass ahead (it heads a dependent chain: index -> row address -> gains)
         auto row_of = [&](int f) { return (f >= 0 && f < n_frames) ? (int)__ldg(rows + f) : 0; };
         int row_next = row_of(un.b0 - 1);
-        auto have_frame = [&](int i) { const int f = un.b0 - 1 + i; return (f >= 0) && (f < n_frames); };
+        int row_next_b = kPair ? row_of(un.b0) : 0;
+        auto have_pass = [&](int i) {
+            const int f = un.b0 - 1 + (kPair ? 2 * i : i);
+            return kPair ? (frame_exists(f) || frame_exists(f + 1)) : ((f >= 0) && (f < n_frames));
+        };
 
         // Frame pipeline.  Per frame: R = window + stage A -> E1 buffer (A layout); Q = stages B, C, gain, C', B' on the same buffer
         // (B layout, in place); P = stage A' + overlap-add + output.  The loop runs Q(i), R(i+1), P(i) with frames i and i+1 in
@@ -1518,44 +1541,63 @@ __global__ void __launch_bounds__(kThreads, 2) stft_kernel(const StftParams prm)
             float2 v[16];
             float fa[16], fb[16];                   // forward stage-A twiddles
             park.sync_stores();
-            park.stage_get_windowed(par, v, fa, fb);                              // window + A
+            park.stage_get_windowed(kPair ? 0 : par, v, fa, fb);                  // window + A
             park.twiddle_a_fwd(v, fa, fb);
             st_e1a(v, t, bufP + par * kE1Float2);
             mbar_arrive(bar_y);
         };
-        if (have_frame(0)) stage_r(0);
+        if (have_pass(0)) stage_r(0);
 
-        // One frame of the pipeline.  STEADY = std::true_type for the interior iterations of a unit, where everything the general
-        // body has to ask is known: frames i and i+1 exist, half frames i+2 and i+3 lie inside the input window, the output block
-        // lies inside the output window and is no edge block.  The steady body has no branches besides the two hand-off waits.
-        // PAR = the frame's parity (which E1 buffer, which staging slot) when it is known at compile time -- the steady loop runs two
-        // frames per iteration -- or -1.
+        // One pass of the pipeline.  STEADY = std::true_type for the interior iterations of a unit, where everything the general
+        // body has to ask is known: passes i and i+1 exist (pair mode: all four frames), the input of passes i+1 and i+2 lies inside
+        // the input window, the output blocks lie inside the output window and are no edge blocks.  The steady body has no branches
+        // besides the two hand-off waits.  PAR = the pass's parity (which E1 buffer, which staging slot) when it is known at
+        // compile time -- the steady loop runs two passes per iteration -- or -1.
         auto frame_iter = [&](const int i, auto steady_tag, auto par_tag) {
             constexpr bool STEADY = decltype(steady_tag)::value;
             constexpr int PAR = decltype(par_tag)::value;
             const int par = PAR < 0 ? (i & 1) : PAR;
-            const int f = un.b0 - 1 + i;
-            const bool have = STEADY ? true : have_frame(i);
-            const int rel = i * kHop;                          // frame start relative to the unit
+            const int f = un.b0 - 1 + (kPair ? 2 * i : i);     // pair mode: the even lanes' frame, the odd lanes hold f + 1
+            const bool have = STEADY ? true : have_pass(i);
+            const int rel = i * kPassHop;                      // pass start relative to the unit
             float2* buf = bufP + par * kE1Float2;
-            // every input sample is read from global memory exactly once, ahead of its first use, and waits in tensor memory;
-            // the loads below belong to frame i+1 (its second half) and complete under this frame's butterflies
+            // every input sample is read from global memory ahead of its first use and waits in tensor memory (4096 mode: exactly
+            // once; pair mode: the middle hop block of a pass by both lanes of a pair, the second time from L2);
+            // the loads below belong to pass i+1 and complete under this pass's butterflies
             float2 pf[8];
             const bool do_pf = STEADY ? true : (i < last);
-            const int row = row_next;
+            const bool live_next = kPair ? frame_exists(f + 2 + tp) : true;      // pair mode, general body: this lane's frame of pass i+1
+            const int row = row_next, row_b = row_next_b;
             if (STEADY) {
-                row_next = (int)__ldg(rows + f + 1);
-                const float2* src = in_u + (i + 2) * kHop + t;
+                if (kPair) {
+                    row_next = (int)__ldg(rows + f + 2);
+                    row_next_b = (int)__ldg(rows + f + 3);
+                    const float2* src = in_u + (2 * i + 2 + tp) * kHop + so;      // first half of this lane's frame of pass i+1
 #pragma unroll
-                for (int j = 0; j < 8; ++j) pf[j] = ld_stream(src + 256 * j);
-                if (t < 32) {                                  // half i+3 -> L2: the first warp asks for all 128 lines of it
-                    const float2* q = in_u + (i + 3) * kHop + t * 16;
+                    for (int j = 0; j < 8; ++j) pf[j] = ld_stream(src + kSampStride * j);
+                    if (t < 32) {                              // the two new hop blocks of pass i+2 -> L2 (128 lines)
+                        const float2* q = in_u + (2 * i + 5) * kHop + t * 16;
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) prefetch_l2(q + 512 * j);
+                        for (int j = 0; j < 4; ++j) prefetch_l2(q + 512 * j);
+                    }
+                } else {
+                    row_next = (int)__ldg(rows + f + 1);
+                    const float2* src = in_u + (i + 2) * kHop + t;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) pf[j] = ld_stream(src + 256 * j);
+                    if (t < 32) {                              // half i+3 -> L2: the first warp asks for all 128 lines of it
+                        const float2* q = in_u + (i + 3) * kHop + t * 16;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) prefetch_l2(q + 512 * j);
+                    }
                 }
+            } else if (kPair) {
+                row_next = row_of(f + 2);
+                row_next_b = row_of(f + 3);
+                if (do_pf) load_blk(2 * i + 2 + tp, live_next, pf);
             } else {
                 row_next = row_of(f + 1);
-                if (do_pf) load_half(i + 2, pf);
+                if (do_pf) load_blk(i + 2, true, pf);
                 if (i + 1 < last && (t & 15) == 0) {           // half i+3 -> L2 (one 128-byte line per 16 lanes), so that next frame's loads are short
                     const int p0 = (i + 3) * kHop;
                     if (p0 >= in_lo && p0 + kHop <= in_hi) {
@@ -1564,6 +1606,16 @@ __global__ void __launch_bounds__(kThreads, 2) stft_kernel(const StftParams prm)
                     }
                 }
             }
+            // pair mode: the second half of this lane's frame of pass i+1, loaded into the registers the first half has just left
+            auto load_second = [&]() {
+                if (STEADY) {
+                    const float2* src = in_u + (2 * i + 3 + tp) * kHop + so;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) pf[j] = ld_stream(src + kSampStride * j);
+                } else {
+                    load_blk(2 * i + 3 + tp, live_next, pf);
+                }
+            };
             if (have) {                                                           // ---- Q(i)
                 float2 v[16];
                 mbar_wait(bar_y, py);
@@ -1574,19 +1626,23 @@ __global__ void __launch_bounds__(kThreads, 2) stft_kernel(const StftParams prm)
                 // E2: the 16 x 16 transposes between stages B and C run through tensor memory, one round trip on either side
                 // of C's first radix-4 layer (fft4096.cuh); no shared-memory traffic, no barrier
                 float r[32], q[32];
-                if (do_pf) park.stage_put(par, pf);            // slot of the half frame i no longer needs (its stage A is long done)
+                if (do_pf) park.stage_put(kPair ? 0 : par, pf);   // 4096 mode: slot of the half frame i no longer needs (its stage A is long done)
                 x_fwd1_pack(v, r);
+                if (kPair && do_pf) load_second();             // completes under the first round trip and C's first layer
                 park.trip_fwd(r);
                 // tilt gain x crossfade weight: one real row per frame, register order; issued before the second round trip
-                // (the few rows in use stay in L1; one trip earlier measured the same)
-                const float4* g4 = reinterpret_cast<const float4*>(prm.gperm + (size_t)row * kNfft + t * 16);
-                const float4 g0 = ld_table4(g4), g1 = ld_table4(g4 + 1), g2 = ld_table4(g4 + 2), g3 = ld_table4(g4 + 3);
+                // (the few rows in use stay in L1; one trip earlier measured the same).  Pair mode: registers 0-7 belong to the
+                // pass's first frame, 8-15 to its second, each with its own row.
+                const float4* g4 = reinterpret_cast<const float4*>(prm.gperm + (size_t)row * kPassLen + t * 16);
+                const float4* g4b = kPair ? reinterpret_cast<const float4*>(prm.gperm + (size_t)row_b * kPassLen + t * 16) : g4;
+                const float4 g0 = ld_table4(g4), g1 = ld_table4(g4 + 1), g2 = ld_table4(g4b + 2), g3 = ld_table4(g4b + 3);
                 x_layer_a<false>(r, q);                                           // C, first layer
+                if (kPair && do_pf) park.stage_put(1, pf);
                 park.trip_fwd(q);
-                x_fwd2_finish(q, v);                                              // C, second layer
+                if (kPair) x_fwd2_finish_pair(q, v); else x_fwd2_finish(q, v);    // C, second layer
                 {       // the gains are fused into the first butterflies of C' (8 packed instructions fewer per frame)
                     const float g[16] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w, g2.x, g2.y, g2.z, g2.w, g3.x, g3.y, g3.z, g3.w};
-                    x_inv1_pack(v, r, g);                                         // gain + C', first layer + inner twiddles
+                    if (kPair) x_inv1_pack_pair(v, r, g); else x_inv1_pack(v, r, g);   // gain + C', first layer + inner twiddles
                 }
                 park.trip_inv(r);
                 x_layer_c_inv(r, q);                                              // C', second layer
@@ -1601,8 +1657,11 @@ __global__ void __launch_bounds__(kThreads, 2) stft_kernel(const StftParams prm)
                 mbar_arrive(bar_x);
             }
             if (do_pf) {
-                if (!have) park.stage_put(par, pf);
-                if (STEADY || have_frame(i + 1)) stage_r(par ^ 1);               // ---- R(i+1)
+                if (!have) {
+                    park.stage_put(kPair ? 0 : par, pf);
+                    if (kPair) { load_second(); park.stage_put(1, pf); }
+                }
+                if (STEADY || have_pass(i + 1)) stage_r(par ^ 1);                // ---- R(i+1)
             }
             float2 v[16];                                                         // ---- P(i)
             float s[16];                                           // synthesis window x normalisation (x output gain)
@@ -1622,6 +1681,44 @@ __global__ void __launch_bounds__(kThreads, 2) stft_kernel(const StftParams prm)
             }
 
             // synthesis window, overlap-add with the carried half, interior normalisation (folded into swin)
+            if (kPair) {
+                // Block f = carried half (second half of frame f-1, held by the ODD lanes) + first half of frame f (even lanes);
+                // block f+1 = second half of frame f (even lanes) + first half of frame f+1 (odd lanes).  The lanes of a pair
+                // swap their raw first halves (the synthesis-window taps are the same for both): the odd lane then emits block f,
+                // the even lane block f+1, and the odd lane's second half is the next carry.
+                float2 b2[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    v[j].x = __shfl_xor_sync(0xffffffffu, v[j].x, 1);
+                    v[j].y = __shfl_xor_sync(0xffffffffu, v[j].y, 1);
+                    b2[j] = cscale(v[j + 8], s[j + 8]);
+                }
+                const int blk = f + 1 - tp;                                    // the block this lane emits
+                const int relb = rel + (1 - tp) * kHop;
+                const bool edge_blk = STEADY ? false : ((blk == 0 && edge_lo) || (blk == n_frames && edge_hi));
+                if (STEADY || (blk >= un.b0 && blk < un.b1 && !edge_blk)) {
+                    float2* dst = out_u + relb + so;
+                    if (STEADY || ((relb >= out_lo) && (relb + kHop <= out_hi))) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const float2 o = __ffma2_rn(v[j], make_float2(s[j], s[j]), tp ? c[j] : b2[j]);
+                            st_stream(dst + kSampStride * j, o);
+                            peak = fmaxf(peak, fmaxf(fabsf(o.x), fabsf(o.y)));
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const float2 o = __ffma2_rn(v[j], make_float2(s[j], s[j]), tp ? c[j] : b2[j]);
+                            const int p = relb + kSampStride * j + so;
+                            if (p >= out_lo && p < out_hi) {
+                                st_stream(dst + kSampStride * j, o);
+                                peak = fmaxf(peak, fmaxf(fabsf(o.x), fabsf(o.y)));
+                            }
+                        }
+                    }
+                }
+                park.store_carry(b2);
+            } else {
             const bool edge_blk = STEADY ? false : ((f == 0 && edge_lo) || (f == n_frames && edge_hi));   // single-frame blocks: edge_kernel
             if (STEADY || (f >= un.b0 && !edge_blk)) {       // emit output block f
                 float2* dst = out_u + rel + t;
@@ -1647,11 +1744,22 @@ __global__ void __launch_bounds__(kThreads, 2) stft_kernel(const StftParams prm)
 #pragma unroll
             for (int j = 0; j < 8; ++j) c[j] = cscale(v[j + 8], s[j + 8]);
             park.store_carry(c);
+            }
         };
         // steady interval [s_lo, s_hi) of this unit (all bounds are monotone in i; positions are relative to the unit)
-        int s_lo = max(1, 1 - un.b0 + (edge_lo ? 1 : 0)), s_hi = min(last - 1, n_frames - un.b0);
-        s_lo = max(s_lo, max(((in_lo + kHop - 1) >> 11) - 2, (out_lo + kHop - 1) >> 11));
-        s_hi = min(s_hi, min((in_hi >> 11) - 3, out_hi >> 11));
+        int s_lo, s_hi;
+        if (kPair) {
+            // passes i and i+1 hold existing frames of the unit (f + 3 < f_end), i >= 1 (block f is the unit's own and no edge block:
+            // f >= b0 >= 0, and f >= 1), the loads of pass i+1 ([2i+2, 2i+5) hop blocks) and the L2 prefetch of pass i+2 (up to
+            // 2i+7) inside the input window, the output blocks [2i, 2i+2) inside the output window
+            s_lo = max(1, max(((((in_lo + kHop - 1) >> 10) - 2) + 1) >> 1, (((out_lo + kHop - 1) >> 10) + 1) >> 1));
+            s_hi = min((f_end - un.b0 - 1) >> 1, min(((in_hi >> 10) - 5) >> 1, (out_hi >> 10) >> 1));
+            if (edge_lo && un.b0 == 0) s_lo = max(s_lo, 1);      // block 0 is pass 0's (never steady); block 1 = pass 1's f: no edge
+        } else {
+            s_lo = max(1, 1 - un.b0 + (edge_lo ? 1 : 0)), s_hi = min(last - 1, n_frames - un.b0);
+            s_lo = max(s_lo, max(((in_lo + kHop - 1) >> 11) - 2, (out_lo + kHop - 1) >> 11));
+            s_hi = min(s_hi, min((in_hi >> 11) - 3, out_hi >> 11));
+        }
         using Even = std::integral_constant<int, 0>;
         using Odd = std::integral_constant<int, 1>;
         using Any = std::integral_constant<int, -1>;
@@ -1696,9 +1804,10 @@ struct EdgeParams {
 };
 
 constexpr int kEdgeSmemBytes = kNfft * (int)sizeof(double2);
-constexpr int kEdgeKernelSmemBytes = kEdgeSmemBytes + (kNfft / 2) * (int)sizeof(double2);     // edge_kernel: + the twiddle table
+constexpr int kEdgeKernelSmemBytes = kEdgeSmemBytes + 2048 * (int)sizeof(double2);     // edge_kernel: + the twiddle table
 
-__device__ __forceinline__ int bitrev12(int x) { return (int)(__brev((unsigned)x) >> 20); }
+constexpr int kLog2N = kPair ? 11 : 12;
+__device__ __forceinline__ int bitrev12(int x) { return (int)(__brev((unsigned)x) >> (32 - kLog2N)); }   // bit reversal over log2(n_fft) bits
 
 // exp(-i*pi*k/2048), k < 2048: filled once per device by tw64_init_kernel with the very sincospi values the butterflies used to
 // compute on the fly (bit-identical results; the trigonometry was 3/4 of edge_kernel's 87 us)
@@ -1715,9 +1824,9 @@ __global__ void tw64_init_kernel() {
 // tw: the twiddle table, g_tw64 itself or a shared-memory copy of it (edge_kernel: a table read from global memory per
 // stage was a third of that latency-bound kernel)
 __device__ void fft4096_f64(double2* sm, int t, const double2* tw = g_tw64) {      // in: bit-reversed order, out: natural order, forward
-    for (int s = 1; s <= 12; ++s) {
+    for (int s = 1; s <= kLog2N; ++s) {          // the table holds exp(-2*pi*i*k/4096): stage s reads every (4096 >> s)-th entry
         const int half = 1 << (s - 1);
-        for (int b = t; b < 2048; b += 256) {
+        for (int b = t; b < kNfft / 2; b += 256) {
             const int pos = b & (half - 1);
             const int i = ((b >> (s - 1)) << s) + pos, j = i + half;
             const double2 w = tw[pos << (12 - s)];
@@ -1742,7 +1851,7 @@ __global__ void __launch_bounds__(256) edge_kernel(const EdgeParams prm) {
     const float sc = prm.in_scale ? prm.in_scale[ed.track] : 1.0f;
     const float osc = prm.out_scale ? prm.out_scale[ed.track] : 1.0f;
     double2* tw = sm + kNfft;                              // twiddles staged once per CTA (same values, same arithmetic)
-    for (int k = t; k < kNfft / 2; k += 256) tw[k] = g_tw64[k];
+    for (int k = t; k < 2048; k += 256) tw[k] = g_tw64[k];
     for (int n = t; n < kNfft; n += 256) {
         const long long p = pos0 + n;
         float2 x = (p >= tr.in_lo && p < tr.in_hi) ? tr.in[p - tr.in_origin] : make_float2(0.f, 0.f);
@@ -2608,10 +2717,10 @@ int tmt_engine_set_gain_rows(tmt_engine* e, const float* rows, int n_rows, int n
     if (!e || !rows || n_rows <= 0 || n_bins != kNfft / 2 + 1) return fail(TMT_ERR_INVALID, "gain rows must be [n_rows>0][%d]", kNfft / 2 + 1);
     if (n_rows > 65535) return fail(TMT_ERR_UNSUPPORTED, "at most 65535 gain rows");
     CUDA_TRY(cudaSetDevice(e->device));
-    std::vector<float> perm((size_t)n_rows * kNfft);
-    for (int r = 0; r < n_rows; ++r) permute_gain_row(rows + (size_t)r * n_bins, perm.data() + (size_t)r * kNfft);
-    if ((size_t)n_rows * kNfft > e->gperm.n) {
-        if (e->gperm.alloc((size_t)n_rows * kNfft) != cudaSuccess) return fail(TMT_ERR_NOMEM, "gain table allocation failed");
+    std::vector<float> perm((size_t)n_rows * kPassLen);
+    for (int r = 0; r < n_rows; ++r) permute_gain_row(rows + (size_t)r * n_bins, perm.data() + (size_t)r * kPassLen);
+    if ((size_t)n_rows * kPassLen > e->gperm.n) {
+        if (e->gperm.alloc((size_t)n_rows * kPassLen) != cudaSuccess) return fail(TMT_ERR_NOMEM, "gain table allocation failed");
     }
     CUDA_TRY(cudaMemcpy(e->gperm.p, perm.data(), sizeof(float) * perm.size(), cudaMemcpyHostToDevice));
     if ((size_t)n_rows * n_bins > e->gnat.n) {
@@ -2660,8 +2769,9 @@ int tmt_plan_create(tmt_engine* e, tmt_plan** out, int framing, int n_tracks, co
         // an SM that hosts an fp64 edge CTA (running beside the STFT kernel) has room for one STFT CTA only
         const long long slots = 2LL * e->n_sms - std::min<long long>(2LL * n_tracks, e->n_sms / 2);
         int one_wave = 0;
-        if (blocks > 0 && blocks <= 59LL * slots && (long long)lens.size() <= slots) {
-            for (int u = (int)std::max<long long>(1, (blocks + slots - 1) / slots); u <= 59 && !one_wave; ++u) {
+        constexpr int kBpp = 2048 / kHop;            // hop blocks per pass of the kernel: unit lengths scale with it
+        if (blocks > 0 && blocks <= 59LL * kBpp * slots && (long long)lens.size() <= slots) {
+            for (int u = (int)std::max<long long>(1, (blocks + slots - 1) / slots); u <= 59 * kBpp && !one_wave; ++u) {
                 long long n = 0;
                 for (int len : lens) n += (len + u - 1) / u;
                 if (n <= slots) one_wave = u;
@@ -2671,8 +2781,8 @@ int tmt_plan_create(tmt_engine* e, tmt_plan** out, int framing, int n_tracks, co
             unit_blocks = one_wave;
             jitter = false;
         } else {
-            unit_blocks = (int)std::lround(std::sqrt((double)blocks / (2.0 * e->n_sms)));
-            unit_blocks = std::max(8, std::min(59, unit_blocks));
+            unit_blocks = kBpp * (int)std::lround(std::sqrt((double)blocks / kBpp / (2.0 * e->n_sms)));
+            unit_blocks = std::max(8 * kBpp, std::min(59 * kBpp, unit_blocks));
         }
     }
     std::vector<UnitDev> units;

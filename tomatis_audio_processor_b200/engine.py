@@ -32,14 +32,14 @@ class Engine:
     """One per device: window, twiddles and the gain table (tmt_engine)."""
 
     def __init__(self, device: int = 0, n_fft: int = tb.N_FFT, hop: int = tb.HOP):
-        self.lib = L.load()
+        if not fused_size(n_fft, hop):
+            raise NotImplementedError(
+                f"the fused GPU path implements n_fft/hop = 4096/2048 (the reference defaults) and 2048/1024; got {n_fft}/{hop}")
+        self.lib = L.load(n_fft)                         # one build of the library per fused frame size
         torch = _torch()
         self.device = int(device)
         torch.cuda.set_device(self.device)
         torch.cuda.current_stream()                      # make sure the primary context exists
-        if n_fft != tb.N_FFT or hop != tb.HOP:
-            raise NotImplementedError(
-                f"GPU path implements n_fft={tb.N_FFT}, hop={tb.HOP} (the reference defaults); got {n_fft}/{hop}")
         h = C.c_void_p()
         L.check(self.lib.tmt_engine_create(C.byref(h), self.device, n_fft, hop), "tmt_engine_create")
         self.h = h
@@ -302,10 +302,21 @@ def whole_track_desc(x_dev, y_dev, total: Optional[int] = None) -> L.TrackDesc:
 _engines = {}
 
 
-def get_engine(device: int = 0) -> Engine:
-    if device not in _engines:
-        _engines[device] = Engine(device)
-    return _engines[device]
+def fused_size(n_fft, hop) -> bool:
+    """Frame sizes the fused kernels serve: the reference's defaults and its documented faster setting 2048 / 1024
+    (TMT_FUSED_2048=0 sends the latter to the general-size path, for comparisons)."""
+    import os
+    from .build import FUSED_SIZES
+    if FUSED_SIZES.get(n_fft) != hop:
+        return False
+    return n_fft == tb.N_FFT or os.environ.get("TMT_FUSED_2048", "1") != "0"
+
+
+def get_engine(device: int = 0, n_fft: int = tb.N_FFT, hop: int = tb.HOP) -> Engine:
+    key = device if n_fft == tb.N_FFT else (device, n_fft)
+    if key not in _engines:
+        _engines[key] = Engine(device, n_fft, hop)
+    return _engines[key]
 
 
 # ------------------------------------------------------------------------------------------------
@@ -393,8 +404,8 @@ def run_streaming(mode: str, xs: Sequence, sr: int, device: int = 0, want_host: 
     """standard / xfade on a batch of tracks.  Returns one dict per track: out (numpy [N,2] float32 if
     want_host else the device tensor), chunk_lengths, meansq, levels, states, rows, frame geometry."""
     torch = _torch()
-    eng = get_engine(device)
     n_fft, hop = params.get("n_fft", tb.N_FFT), params.get("hop", tb.HOP)
+    eng = get_engine(device, n_fft, hop) if fused_size(n_fft, hop) else get_engine(device)
     if n_fft != eng.n_fft or hop != eng.hop:
         from . import generic
         if generic.enabled():                                         # general-size path (csrc/generic.cuh)
@@ -471,10 +482,10 @@ def run_adaptive(xs: Sequence, sr: int, device: int = 0, want_host: bool = True,
     `_linked` = (interleaved device tensor, channels) is that function's hook: the tracks are the channel pairs of one file,
     so input peak, level and output peak are taken over all of them."""
     torch = _torch()
-    eng = get_engine(device)
+    eng = get_engine(device, n_fft, hop) if fused_size(n_fft, hop) else get_engine(device)
     if _linked is None and any(isinstance(x, np.ndarray) and x.ndim == 2 and x.shape[1] > 2 for x in xs):
-        if n_fft != eng.n_fft or hop != eng.hop:
-            raise NotImplementedError(f"files with more than two channels need n_fft={eng.n_fft}, hop={eng.hop}; got {n_fft}/{hop}")
+        if n_fft != tb.N_FFT or hop != tb.HOP:
+            raise NotImplementedError(f"files with more than two channels need n_fft={tb.N_FFT}, hop={tb.HOP}; got {n_fft}/{hop}")
         kw = dict(device=device, want_host=want_host, unit_blocks=unit_blocks, fc=fc, slope=slope, c1_low=c1_low, c1_high=c1_high,
                   c2_low=c2_low, c2_high=c2_high, target_c2=target_c2, hyst_db=hyst_db, min_hold_ms=min_hold_ms, xfade_ms=xfade_ms,
                   headroom_margin=headroom_margin, n_fft=n_fft, hop=hop)
