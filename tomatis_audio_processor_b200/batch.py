@@ -18,7 +18,7 @@ class DeviceBatch:
 
     def __init__(self, x, y, sr: int, mode: str = "standard", device: int = 0, unit_blocks: int = 0, **params):
         self.torch = _torch()
-        self.eng = get_engine(device)
+        self.eng = get_engine(device, params.get("n_fft", 4096), params.get("hop", 2048))      # a fused frame size (engine.fused_size)
         self.sp = streaming_params(mode, sr, **params)
         self.eng.set_gain_rows(self.sp.rows, key=self.sp.rows_key)
         self.x, self.y, self.sr = x, y, sr
@@ -71,7 +71,7 @@ class HostBatchPipeline:
         if in_format not in ("f32", "s16", "s24") or out_format not in ("f32", "s24"):
             raise ValueError("in_format: f32|s16|s24, out_format: f32|s24")
         self.in_format, self.out_format = in_format, out_format
-        self.eng = get_engine(device)
+        self.eng = get_engine(device, params.get("n_fft", 4096), params.get("hop", 2048))      # a fused frame size (engine.fused_size)
         self.sp = streaming_params(mode, sr, **params)
         self.eng.set_gain_rows(self.sp.rows, key=self.sp.rows_key)
         dev = f"cuda:{device}"

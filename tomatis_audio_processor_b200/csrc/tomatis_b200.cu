@@ -3430,7 +3430,7 @@ int tmt_plan_stft(tmt_plan* p, float post_gain, int skip_edges, void* stream) {
 }
 
 static bool stft_fused_limiter(const tmt_plan* p) {
-    bool fuse = p->total_blocks >= 48LL * p->e->n_sms;
+    bool fuse = p->total_blocks >= 48LL * (2048 / kHop) * p->e->n_sms;
     if (const char* fv = getenv("TMT_LIMITER_FUSED")) fuse = atoi(fv) != 0;        // dev switch: A/B of the two limiter placements
     return fuse;
 }
