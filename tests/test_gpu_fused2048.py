@@ -118,3 +118,49 @@ def test_fused_2048_equals_the_general_size_path(monkeypatch):
     assert np.array_equal(a["meansq"], b["meansq"]) and np.array_equal(a["states"], b["states"])
     assert a["chunk_lengths"] == b["chunk_lengths"]
     assert np.abs(a["out"].astype(np.float64) - b["out"]).max() <= 2e-6
+
+
+def test_adaptive_with_more_than_two_channels():
+    """Channel pairs as linked tracks of one plan (engine.run_adaptive_multichannel) at 2048 / 1024: shared level, gate, scale."""
+    eng = _engine()
+    sr = 48000
+    a = synth.recipe_swept_pink(3.0, sr, 401, period_s=0.7, peak=0.5)
+    b = synth.recipe_swept_pink(3.0, sr, 402, period_s=0.5, peak=0.3)
+    x = _q(np.concatenate([a, b[:, :1]], axis=1))                                       # 3 channels
+    kw = dict(min_hold_ms=80.0, xfade_ms=150.0, **SZ)
+    r = eng.run("adaptive", [x], sr, **kw)[0]
+    o, o64 = orc.run("adaptive", x, sr, **kw), orc.run("adaptive", x, sr, fft_dtype="float64", **kw)
+    assert r["out"].shape == x.shape
+    _compare("adaptive", o, o64, r)
+
+
+def test_static_eq_at_2048():
+    from oracle import layer2_oracle as l2
+    eng = _engine()
+    sr = 48000
+    x = _q(synth.recipe_gated_pink(1.7, sr, 71, env_hz=2.0, hi_dbfs=-14.0))
+    gain = l2.build_gain_per_bin(sr, 2048, np.array([20.0, 100.0, 500.0, 1000.0, 4000.0, 12000.0, 20000.0]),
+                                 np.array([6.0, 4.0, 0.0, -2.0, 3.0, 8.0, 10.0]))
+    for kw in (dict(), dict(pad=False, global_gain_db=-3.0, auto_gain_protect=False)):
+        r = eng.run_eq([x], sr, gain, **SZ, **kw)[0]
+        o, o64 = l2.apply_eq(x, sr, gain, **SZ, **kw), l2.apply_eq(x, sr, gain, fft_dtype="float64", **SZ, **kw)
+        assert r["out"].shape == o["out"].shape
+        d = np.abs(r["out"].astype(np.float64) - o["out"]).max(axis=1)
+        d64 = np.abs(r["out"].astype(np.float64) - o64["out"]).max(axis=1) / np.maximum(1.0, np.abs(o64["out"]).max(axis=1))
+        assert float(d[2048:-2048].max()) <= 1e-5 and float(d64.max()) <= 1e-5
+        assert abs(r["peak_seen"] - o64["peak_seen"]) <= 2e-5 * o64["peak_seen"]
+        assert (r["out_gp"] is None) == (o["out_gp"] is None)
+        if o["out_gp"] is not None:
+            assert np.array_equal(r["out_gp"], (l2.pcm24_roundtrip(r["out"]) * np.float32(r["scale"])).astype(np.float32))
+
+
+def test_channel_state_analyser_at_2048():
+    from oracle import analysis_oracle as ao
+    from test_channel_states import _check_result
+    eng = _engine()
+    sr = 44100
+    x = synth.recipe_swept_pink(4.0, sr, 31, period_s=0.9, peak=0.5)
+    x[:, 1] = np.roll(x[:, 1], 5000) * 0.6
+    x = _q(x)[:1024 * 150 + 333]
+    kw = dict(min_hold_ms=100.0, target_c2=0.4, **SZ)
+    _check_result(eng.run_channel_states([x], sr, **kw)[0], ao.analyze(x, sr, **kw))

@@ -1628,8 +1628,8 @@ __global__ void __launch_bounds__(kThreads, 2) stft_kernel(const StftParams prm)
                 float r[32], q[32];
                 if (do_pf) park.stage_put(kPair ? 0 : par, pf);   // 4096 mode: slot of the half frame i no longer needs (its stage A is long done)
                 x_fwd1_pack(v, r);
-                if (kPair && do_pf) load_second();             // completes under the first round trip and C's first layer
-                park.trip_fwd(r);
+                if (kPair && do_pf) load_second();             // completes under the first round trip and C's first layer (issued after
+                park.trip_fwd(r);                              // the trip or after the layer: same time, profiles/r02/fused2048_ab_load_position.txt)
                 // tilt gain x crossfade weight: one real row per frame, register order; issued before the second round trip
                 // (the few rows in use stay in L1; one trip earlier measured the same).  Pair mode: registers 0-7 belong to the
                 // pass's first frame, 8-15 to its second, each with its own row.

@@ -484,8 +484,8 @@ def run_adaptive(xs: Sequence, sr: int, device: int = 0, want_host: bool = True,
     torch = _torch()
     eng = get_engine(device, n_fft, hop) if fused_size(n_fft, hop) else get_engine(device)
     if _linked is None and any(isinstance(x, np.ndarray) and x.ndim == 2 and x.shape[1] > 2 for x in xs):
-        if n_fft != tb.N_FFT or hop != tb.HOP:
-            raise NotImplementedError(f"files with more than two channels need n_fft={tb.N_FFT}, hop={tb.HOP}; got {n_fft}/{hop}")
+        if not fused_size(n_fft, hop):
+            raise NotImplementedError(f"files with more than two channels need n_fft/hop = 4096/2048 or 2048/1024; got {n_fft}/{hop}")
         kw = dict(device=device, want_host=want_host, unit_blocks=unit_blocks, fc=fc, slope=slope, c1_low=c1_low, c1_high=c1_high,
                   c2_low=c2_low, c2_high=c2_high, target_c2=target_c2, hyst_db=hyst_db, min_hold_ms=min_hold_ms, xfade_ms=xfade_ms,
                   headroom_margin=headroom_margin, n_fft=n_fft, hop=hop)
@@ -656,9 +656,9 @@ def run_channel_states(xs: Sequence, sr: int, device: int = 0, target_c2=0.5, hy
     (src/analyze_stereo_state.py:79-128).  Device: both level passes and every gate simulation of the two searches, all
     tracks in lock step; host: percentiles and the search bookkeeping.  No audio is written (analysis-only plan)."""
     torch = _torch()
-    eng = get_engine(device)
-    if n_fft != eng.n_fft or hop != eng.hop:
-        raise NotImplementedError(f"GPU path implements n_fft={eng.n_fft}, hop={eng.hop}; got {n_fft}/{hop}")
+    if not fused_size(n_fft, hop):
+        raise NotImplementedError(f"GPU path implements n_fft/hop = 4096/2048 and 2048/1024 here; got {n_fft}/{hop}")
+    eng = get_engine(device, n_fft, hop)
     frame_ms = hop / sr * 1000                                        # :89-90
     hold = int(np.ceil(min_hold_ms / frame_ms))
     xd = _to_device(torch, xs, device)
@@ -856,9 +856,9 @@ def run_eq(xs: Sequence, sr: int, gain_bins: np.ndarray, device: int = 0, pad: b
     (n_frames+1)*hop, shifted by n_fft/2 when pad), peak_seen, scale and out_gp = the gain-protected second file
     (PCM_24 round trip of `out` times peak_target/peak) when the peak exceeds peak_target."""
     torch = _torch()
-    eng = get_engine(device)
-    if n_fft != eng.n_fft or hop != eng.hop:
-        raise NotImplementedError(f"GPU path implements n_fft={eng.n_fft}, hop={eng.hop}; got {n_fft}/{hop}")
+    if not fused_size(n_fft, hop):
+        raise NotImplementedError(f"GPU path implements n_fft/hop = 4096/2048 and 2048/1024 here; got {n_fft}/{hop}")
+    eng = get_engine(device, n_fft, hop)
     gain_bins = np.ascontiguousarray(gain_bins, dtype=np.float32).reshape(1, -1)
     eng.set_gain_rows(gain_bins, key=None)
     g_global = 10.0 ** (global_gain_db / 20.0)                      # db_to_lin, src/layer2_apply_eq.py:8-9,115
