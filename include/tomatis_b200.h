@@ -84,6 +84,10 @@ const char* tmt_error_string(int code);
 const char* tmt_last_error(void);
 
 /* ---- engine ------------------------------------------------------------------------------- */
+/* The library is built once per frame size the fused kernels serve (src/process_tomatis.py:174-175, `--n_fft/--hop`):
+ * libtomatis_b200.so = 4096 / 2048 (the reference's defaults), libtomatis_b200_n2048.so = 2048 / 1024 (the documented faster
+ * setting); both export exactly this header.  A build rejects every other (n_fft, hop) with TMT_ERR_UNSUPPORTED; other sizes
+ * go through the tmt_generic_* entry points. */
 int tmt_engine_create(tmt_engine** out, int device, int n_fft, int hop);
 int tmt_engine_destroy(tmt_engine* e);
 /* Analysis = synthesis window, `np.hanning(n_fft).astype(float32)` (src/process_tomatis.py:266).
