@@ -592,6 +592,31 @@ def longfile_measure(args, dist, rank, world, local, steps, want_cpu):
                "ms_per_step": float(ms[0]) / args.e2e_steps,
                "api": "sharded.StreamingShardSession.step with each rank's own range copied from / to pinned host float32 buffers",
                "host_peak_out": float(h_out.abs().max()) if n_own else 0.0}
+        if world == 1:
+            # one GPU: the streamed form of the same path -- time slabs on limiter-chunk boundaries through three device slots,
+            # copy-in / kernels / copy-out of consecutive slabs on three streams (streamed.HostFileStreamer), bounded device memory
+            from tomatis_audio_processor_b200.streamed import HostFileStreamer
+            whole = h_out.clone()
+            st = HostFileStreamer("standard", total, LF_SR, device=local, slab_seconds=args.lf_slab_seconds,
+                                  unit_blocks=args.unit_blocks, gate_ui=50)
+            st.process(h_in, h_out)
+            barrier()
+            a.record()
+            for _ in range(args.e2e_steps):
+                st.process(h_in, h_out)
+            b.record()
+            barrier()
+            ms_st = a.elapsed_time(b)
+            e2e = {"value": total / LF_SR * args.e2e_steps / (ms_st * 1e-3), "unit": UNIT,
+                   "h2d_bytes_per_step": int(sum(sh.in_hi - sh.in_lo for sh in st.shards) * 8), "d2h_bytes_per_step": int(total * 8),
+                   "steps": args.e2e_steps, "ms_per_step": ms_st / args.e2e_steps,
+                   "api": f"streamed.HostFileStreamer.process: pinned host float32 in / out, {len(st.slabs)} time slabs of "
+                          f"~{args.lf_slab_seconds:.0f} s through {len(st.slots)} device slots ({st.device_bytes() / 1e9:.2f} GB of HBM), "
+                          "H2D / kernels / D2H on 3 streams",
+                   "host_peak_out": float(h_out.abs().max()), "equals_whole_file_output": bool(torch.equal(whole, h_out)),
+                   "whole_file_in_hbm": {"ms_per_step": e2e["ms_per_step"], "value": e2e["value"], "api": e2e["api"]}}
+            st.close()
+            del whole
         del h_in, h_out
 
     peak_gbs, peak_src = measured_peak()
@@ -661,6 +686,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-longfile", dest="no_longfile", action="store_true", help="skip the long-file sub-record of the default line")
     ap.add_argument("--no-alt-size", dest="no_alt_size", action="store_true", help="skip the --n_fft 2048 --hop 1024 sub-record")
+    ap.add_argument("--lf-slab-seconds", dest="lf_slab_seconds", type=float, default=300.0,
+                    help="long file, one GPU, end to end: slab length of the streamed pipeline")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3                       # timing rule: at least 3 warm-up steps

@@ -305,7 +305,7 @@ class PeerExchange:
 class CudaShardBackend:
     """engine.Plan over one shard: input window + owned output buffer on this rank's GPU."""
 
-    def __init__(self, shard: Shard, window, device_index: int, gain_rows: np.ndarray, rows_key, unit_blocks: int = 0):
+    def __init__(self, shard: Shard, window, device_index: int, gain_rows: np.ndarray, rows_key, unit_blocks: int = 0, out=None):
         import torch
         from . import _lib as L
         from .engine import Plan, get_engine
@@ -313,7 +313,9 @@ class CudaShardBackend:
         self.eng = get_engine(device_index)
         self.eng.set_gain_rows(gain_rows, key=rows_key)
         self.window = window
-        self.out = torch.empty((shard.own_hi - shard.own_lo, 2), dtype=torch.float32, device=window.device)
+        # out: a caller-owned buffer for the shard's output (streamed.HostFileStreamer rotates a few device slots)
+        self.out = out if out is not None else torch.empty((shard.own_hi - shard.own_lo, 2), dtype=torch.float32, device=window.device)
+        assert self.out.shape[0] == shard.own_hi - shard.own_lo
         desc = L.TrackDesc(window.data_ptr(), self.out.data_ptr(), shard.total, shard.in_lo, shard.in_hi - shard.in_lo,
                            shard.own_lo, shard.own_hi - shard.own_lo, shard.block_lo, shard.block_hi)
         self.plan = Plan(self.eng, L.FRAMING_STREAMING if shard.framing == STREAMING else L.FRAMING_WHOLEFILE, [desc], unit_blocks)
