@@ -22,6 +22,25 @@ from .engine import _torch, streaming_params
 from .sharded import STREAMING, CudaShardBackend, plan_shards
 
 
+def plan_slabs(total: int, sr: int, slab_seconds: float = 300.0, n_fft: int = tb.N_FFT, hop: int = tb.HOP):
+    """Host-side geometry of the streamed pass: [(shard, hb_lo, hb_hi, f_hi)] in file order.  shard = the slab's block / sample
+    ranges (`sharded.plan_shards`, cut on limiter-chunk boundaries); [hb_lo, hb_hi) = the hop blocks the slab sums itself -- its
+    own and, when its right halo covers it, the one after them, which its last frame spans; f_hi = frames [0, f_hi) get their
+    mean square (and a valid gate state) when the slab runs: everything up to the slab's own last frame."""
+    n_frames = tb.streaming_frame_count(int(total), n_fft, hop)
+    n_chunks = max(1, len(tb.flush_chunk_blocks(n_frames, n_fft, hop)))
+    k = int(np.clip(round(total / max(1.0, slab_seconds * sr)), 1, n_chunks))
+    nb = n_frames + 1 if n_frames > 0 else 0
+    out = []
+    for s in plan_shards(int(total), k, STREAMING, n_fft, hop):
+        if s.own_hi <= s.own_lo:
+            continue
+        hb_lo = min(s.block_lo, nb)
+        hb_hi = min(s.block_hi + (1 if s.in_hi >= s.first_start + (s.block_hi + 1) * hop else 0), nb)
+        out.append((s, hb_lo, hb_hi, min(s.block_hi, n_frames)))
+    return out
+
+
 class HostFileStreamer:
     def __init__(self, mode: str, total: int, sr: int, device: int = 0, slab_seconds: float = 300.0, n_slots: int = 3,
                  unit_blocks: int = 0, **params):
@@ -31,10 +50,9 @@ class HostFileStreamer:
         self.total, self.sr = int(total), sr
         self.sp = streaming_params(mode, sr, **params)
         dev = torch.device(f"cuda:{device}")
-        n_frames = tb.streaming_frame_count(self.total, tb.N_FFT, tb.HOP)
-        n_chunks = max(1, len(tb.flush_chunk_blocks(n_frames, tb.N_FFT, tb.HOP)))
-        k = int(np.clip(round(self.total / max(1.0, slab_seconds * sr)), 1, n_chunks))
-        self.shards = [s for s in plan_shards(self.total, k, STREAMING) if s.own_hi > s.own_lo]
+        slabs = plan_slabs(self.total, sr, slab_seconds)
+        self.shards = [sl[0] for sl in slabs]
+        n_frames = self.shards[0].n_frames if self.shards else 0
         self.n_frames = n_frames
         max_in = max(s.in_hi - s.in_lo for s in self.shards)
         max_own = max(s.own_hi - s.own_lo for s in self.shards)
@@ -46,18 +64,13 @@ class HostFileStreamer:
         self.hsum = torch.zeros(n_frames + 2, dtype=torch.float32, device=dev)      # hop-block sums of the file, filled slab by slab
         self.s_in, self.s_c, self.s_out = (torch.cuda.Stream(device=dev) for _ in range(3))
         self.slabs = []
-        nb = n_frames + 1 if n_frames > 0 else 0
-        for i, s in enumerate(self.shards):
+        for i, (s, hb_lo, hb_hi, f_hi) in enumerate(slabs):
             sl = self.slots[i % n_slots]
             be = CudaShardBackend(s, sl["win"][:s.in_hi - s.in_lo], device, self.sp.rows, self.sp.rows_key, unit_blocks,
                                   out=sl["out"][:s.own_hi - s.own_lo])
             if be.plan.unfusable_chunks:
                 raise RuntimeError("slab cut through a limiter chunk")
-            # hop blocks this slab sums: its own and the one after them (inside its right halo) -- the last frame of the slab
-            # spans both; the sums of everything before come from the earlier slabs
-            hb_lo = min(s.block_lo, nb)
-            hb_hi = min(s.block_hi + (1 if s.in_hi >= s.first_start + (s.block_hi + 1) * tb.HOP else 0), nb)
-            be.plan.set_level_ranges(0, hb_lo, hb_hi, 0, min(s.block_hi, n_frames))
+            be.plan.set_level_ranges(0, hb_lo, hb_hi, 0, f_hi)
             self.slabs.append(dict(shard=s, be=be, slot=sl, hb=(hb_lo, hb_hi), thresholds=False))
         self.launches = 0
 
