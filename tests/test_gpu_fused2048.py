@@ -164,3 +164,28 @@ def test_channel_state_analyser_at_2048():
     x = _q(x)[:1024 * 150 + 333]
     kw = dict(min_hold_ms=100.0, target_c2=0.4, **SZ)
     _check_result(eng.run_channel_states([x], sr, **kw)[0], ao.analyze(x, sr, **kw))
+
+
+def test_batch_front_ends_at_2048():
+    """batch.DeviceBatch and batch.HostBatchPipeline with n_fft / hop keywords use the 2048 build; samples equal engine.run's."""
+    import torch
+    from tomatis_audio_processor_b200.batch import DeviceBatch, HostBatchPipeline
+    eng = _engine()
+    n, sr, T = 200000, 48000, 4
+    xs = np.stack([_q(synth.recipe_gated_pink(n / sr, sr, 60 + i, env_hz=1.1, hi_dbfs=-22.0))[:n] for i in range(T)])
+    want = [r["out"] for r in eng.run("standard", list(xs), sr, gate_ui=50, **SZ)]
+    h_in = torch.from_numpy(xs).pin_memory()
+    h_out = torch.empty_like(h_in).pin_memory()
+    p = HostBatchPipeline(n, sr, "standard", wave_tracks=2, gate_ui=50, **SZ)
+    assert p.eng.n_fft == 2048
+    p.process(h_in, h_out)
+    torch.cuda.synchronize()
+    p.close()
+    x = h_in.cuda()
+    y = torch.empty_like(x)
+    db = DeviceBatch(x, y, sr, "standard", gate_ui=50, **SZ)
+    db.step()
+    torch.cuda.synchronize()
+    db.close()
+    for i in range(T):
+        assert np.abs(h_out[i].numpy() - want[i]).max() <= 2e-7 and np.abs(y[i].cpu().numpy() - want[i]).max() <= 2e-7
