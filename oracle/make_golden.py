@@ -62,6 +62,22 @@ def cases():
     x = synth.recipe_swept_pink(2.0, 44100, 19, period_s=0.8, peak=0.4)
     c.append(("adaptive_44k1_tail", "adaptive", 44100, _q(x)[:2048 * 30 + 2047], dict(min_hold_ms=90.0, xfade_ms=150.0)))
     c.extend(multichannel_cases())
+    c.extend(small_frame_cases())
+    return c
+
+
+def small_frame_cases():
+    """--n_fft 2048 --hop 1024, the documentation's faster setting (docs/Tomatis技术说明.md:253-258), which the fused kernels serve
+    through the second build of the library: the reference itself at these sizes, all three modes."""
+    sz = dict(n_fft=2048, hop=1024)
+    c = []
+    # two limiter chunks at hop 1024 (first flush after 237 frames = 240 640 samples)
+    x = synth.recipe_gated_pink(5.4, 48000, 51, env_hz=1.2, hi_dbfs=-21.0)
+    c.append(("std_48k_n2048_two_chunks", "standard", 48000, _q(x), dict(gate_ui=50, up_delay_ms=120.0, **sz)))
+    x = synth.recipe_threshold_ramps(2.0, 44100, 52, t_on=-48.5, t_off=-51.5, period_s=0.8)
+    c.append(("xfade_44k1_n2048", "xfade", 44100, _q(x)[:44100 * 2 - 333], dict(gate_ui=50, xfade_ms=120.0, up_delay_ms=60.0, **sz)))
+    x = synth.recipe_swept_pink(2.0, 48000, 53, period_s=0.6, peak=0.5)
+    c.append(("adaptive_48k_n2048", "adaptive", 48000, _q(x), dict(min_hold_ms=100.0, xfade_ms=200.0, **sz)))
     return c
 
 
@@ -217,12 +233,13 @@ def main():
     if "--only-eq" in sys.argv:
         return make_eq()
     only_multi = "--only-multichannel" in sys.argv
-    if not only_multi:
+    only_small = "--only-small-frames" in sys.argv
+    if not only_multi and not only_small:
         make_chan()
         make_val()
         make_cal()
         make_eq()
-    for name, mode, sr, x, kw in (multichannel_cases() if only_multi else cases()):
+    for name, mode, sr, x, kw in (multichannel_cases() if only_multi else small_frame_cases() if only_small else cases()):
         r = rh.run_reference(mode, x, sr, **kw)
         q = synth.quantise_pcm16(x)
         assert np.array_equal(synth.pcm16_to_float(q), x)
