@@ -189,3 +189,25 @@ def test_batch_front_ends_at_2048():
     db.close()
     for i in range(T):
         assert np.abs(h_out[i].numpy() - want[i]).max() <= 2e-7 and np.abs(y[i].cpu().numpy() - want[i]).max() <= 2e-7
+
+
+def test_validators_at_2048():
+    """validate_layer1 / verify_tomatis_15db_v2 kernels (gate re-simulation, conditional spectrum, anchored variant) on a file
+    processed at 2048 / 1024, against the oracle restatement of the reference's functions at the same sizes."""
+    from oracle import validate_oracle as vo
+    from tomatis_audio_processor_b200 import validators as prod
+    eng = _engine()
+    sr = 48000
+    x = _q(synth.recipe_gated_pink(8.0, sr, 88, env_hz=0.6, hi_dbfs=-22.0))
+    y = eng.run("standard", [x], sr, gate_ui=50, up_delay_ms=100.0, **SZ)[0]["out"]
+    st_o, lv_o = vo.simulate_gate(x, sr, 2048, 1024, -40.0, 3.0, 100.0)
+    st, lv = prod.simulate_gate(x, sr, 2048, 1024, -40.0, 3.0, 100.0)
+    assert st == st_o and np.array_equal(np.array(lv), np.array(lv_o))
+    f, c1, c2, n1, n2 = prod.compute_conditional_spectrum(x, y, sr, st, 2048, 1024)
+    fo, o1, o2, m1, m2, _ = vo.compute_conditional_spectrum(x, y, sr, st_o, 2048, 1024)
+    assert (n1, n2) == (m1, m2) and n1 > 0 and n2 > 0 and np.array_equal(f, fo) and len(f) == 1025
+    assert max(float(np.abs(c1 - o1).max()), float(np.abs(c2 - o2).max())) < 2e-4
+    f, a1, a2, k1, k2 = prod.compute_conditional_spectrum_v2(x, y, sr, st, np.array(lv), 2048, 1024)
+    fo, b1, b2, j1, j2, _ = vo.compute_conditional_spectrum_v2(x, y, sr, st_o, np.array(lv_o), 2048, 1024)
+    assert (k1, k2) == (j1, j2)
+    assert max(float(np.abs(a1 - b1).max()), float(np.abs(a2 - b2).max())) < 2e-4

@@ -135,4 +135,4 @@ def test_validators_gpu_edge_cases():
     with pytest.raises(RuntimeError):
         engine.cond_spectrum_median(x, y, [len(x) // 2048])                              # frame past the end of the file
     with pytest.raises(NotImplementedError):
-        prod.simulate_gate(x, sr, 2048, 1024, -40.0, 3.0, 50.0)
+        prod.simulate_gate(x, sr, 1024, 512, -40.0, 3.0, 50.0)                           # neither 4096 / 2048 nor 2048 / 1024

@@ -28,9 +28,9 @@ TMT_HD float spec_mean_mag(const cplx64* Z, int k) {
     return (ml + mr) * 0.5f;
 }
 
-// bins of thread t: k = t + 256*i, i = 0..7, and bin 2048 for t == 0 (i == 8)
+// bins of thread t: k = t + 256*i, i < n_fft/512 (8 at 4096, 4 at 2048), and the Nyquist bin n_fft/2 for t == 0
 TMT_HD int spec_bin(int t, int i) { return t + 256 * i; }
-TMT_HD int spec_bins_of_thread(int t) { return t == 0 ? 9 : 8; }
+TMT_HD int spec_bins_of_thread(int t) { return kNfft / 512 + (t == 0 ? 1 : 0); }
 
 TMT_HD float spec_ratio(float ymag, float xmag) { return ymag / fmaxf(xmag, 1e-10f); }   // X = np.maximum(X, 1e-10); Y / X
 

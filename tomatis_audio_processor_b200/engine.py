@@ -714,12 +714,12 @@ def run_channel_states(xs: Sequence, sr: int, device: int = 0, target_c2=0.5, hy
 
 
 # ------------------------------------------------------------------------------------------- validators (N3)
-def frame_levels_wholefile(x, device: int = 0, mono: bool = False):
+def frame_levels_wholefile(x, device: int = 0, mono: bool = False, n_fft=tb.N_FFT, hop=tb.HOP):
     """float32 mean squares + levels of the frames [i*hop, i*hop + n_fft), i < len(x) // hop (zero padded past the end):
     the frames validate_layer1.simulate_gate keeps (src/validate_layer1.py:132-141).  Returns (meansq f32, levels f64,
     plan) -- the analysis-only plan stays open for gate runs; the caller closes it."""
     torch = _torch()
-    eng = get_engine(device)
+    eng = get_engine(device, n_fft, hop)
     xd = _to_device(torch, [x], device)[0]
     n = int(xd.shape[0])
     plan = Plan(eng, L.FRAMING_WHOLEFILE, [L.TrackDesc(xd.data_ptr(), None, n, 0, n, 0, 0, 0, -1)])
@@ -738,10 +738,10 @@ def to_device(arrays, device: int = 0):
     return _to_device(_torch(), arrays, device)
 
 
-def cond_spectrum_median(x, y, frames, anchor_bins=None, device: int = 0) -> np.ndarray:
+def cond_spectrum_median(x, y, frames, anchor_bins=None, device: int = 0, n_fft=tb.N_FFT, hop=tb.HOP) -> np.ndarray:
     """Per-bin median over `frames` of |Y| / |X| (tmt_cond_spectrum); x, y float32 [N, 2] (host or device)."""
     torch = _torch()
-    eng = get_engine(device)
+    eng = get_engine(device, n_fft, hop)
     xd, yd = _to_device(torch, [x, y], device)
     frames = np.ascontiguousarray(frames, dtype=np.int32)
     total = int(min(xd.shape[0], yd.shape[0]))

@@ -4,7 +4,7 @@ conditional spectrum, with the reference's function names, arguments and return 
 
 Frame levels, the gate automaton, the windowed FFTs of both files and the per-bin medians run in the CUDA library;
 frame selection (stable frames, level threshold / percentile) is host bookkeeping on the per-frame arrays.  There is no
-CPU path.  Supported: n_fft / hop = 4096 / 2048 (the reference defaults), one or two channels.
+CPU path.  Supported: n_fft / hop = 4096 / 2048 (the reference defaults) and 2048 / 1024, one or two channels.
 """
 from __future__ import annotations
 
@@ -30,8 +30,9 @@ def _stereo(a):
 
 
 def _check_fft(n_fft, hop):
-    if n_fft != tb.N_FFT or hop != tb.HOP:
-        raise NotImplementedError(f"GPU path implements n_fft={tb.N_FFT}, hop={tb.HOP}; got {n_fft}/{hop}")
+    from .engine import fused_size
+    if not fused_size(n_fft, hop):
+        raise NotImplementedError(f"GPU path implements n_fft/hop = 4096/2048 and 2048/1024 here; got {n_fft}/{hop}")
 
 
 def _names(states):
@@ -53,7 +54,7 @@ def simulate_gate(x, sr, n_fft, hop, threshold_dbfs, hyst_db, up_delay_ms):
     if mono:
         xs[:, 1] = 0.0                                  # single channel rides in the L lane (mono level formula)
     t_on, t_off = threshold_dbfs + hyst_db / 2, threshold_dbfs - hyst_db / 2
-    msq, levels, plan = engine.frame_levels_wholefile(xs, DEVICE, mono=mono)
+    msq, levels, plan = engine.frame_levels_wholefile(xs, DEVICE, mono=mono, n_fft=n_fft, hop=hop)
     try:
         plan.gate(L.GATE_UPDELAY, L.ARR_MEANSQ_F32, tb.meansq_threshold_on(t_on, np.float32),
                   tb.meansq_threshold_off(t_off, np.float32), tb.updelay_run_frames(sr, up_delay_ms, hop), 0)
@@ -81,7 +82,8 @@ def _median_db(x, y, frames, n_bins, anchor_bins=None):
     from . import engine
     if len(frames) == 0:
         return np.zeros(n_bins)                         # src/validate_layer1.py:380-381
-    med = engine.cond_spectrum_median(x, y, frames, anchor_bins, DEVICE)
+    n_fft = 2 * (n_bins - 1)                            # n_bins = len(rfftfreq(n_fft)); the fused sizes have hop = n_fft / 2
+    med = engine.cond_spectrum_median(x, y, frames, anchor_bins, DEVICE, n_fft=n_fft, hop=n_fft // 2)
     return 20 * np.log10(med + EPS)
 
 
@@ -102,7 +104,7 @@ def compute_conditional_spectrum(x, y, sr, states, n_fft, hop, level_threshold=-
     lx = xs.copy()
     if mono:
         lx[:, 1] = 0.0
-    _, levels, plan = engine.frame_levels_wholefile(lx, DEVICE, mono=mono)
+    _, levels, plan = engine.frame_levels_wholefile(lx, DEVICE, mono=mono, n_fft=n_fft, hop=hop)
     plan.close()
     freqs = np.fft.rfftfreq(n_fft, 1 / sr)
     xd, yd = engine.to_device([xs, ys], DEVICE)
