@@ -211,3 +211,56 @@ def test_validators_at_2048():
     fo, b1, b2, j1, j2, _ = vo.compute_conditional_spectrum_v2(x, y, sr, st_o, np.array(lv_o), 2048, 1024)
     assert (k1, k2) == (j1, j2)
     assert max(float(np.abs(a1 - b1).max()), float(np.abs(a2 - b2).max())) < 2e-4
+
+
+@pytest.mark.parametrize("mode,kw", [("standard", dict(gate_ui=50, up_delay_ms=80.0)), ("xfade", dict(gate_ui=60, xfade_ms=100.0)),
+                                     ("adaptive", dict(min_hold_ms=100.0, xfade_ms=200.0))])
+def test_time_sharded_equals_unsharded_at_2048(mode, kw):
+    """One file over three ranks (threads of this process on one GPU, tests/thread_comm.py) at 2048 / 1024: halos of one 1024-sample
+    hop, hop-sum exchange, redundant gate scan -- bit-identical to the whole-file call."""
+    import torch
+    from test_gpu_sharded import _run_threads
+    from tomatis_audio_processor_b200 import sharded
+    eng = _engine()
+    sr, world = 48000, 3
+    x = (synth.recipe_swept_pink(4.0, sr, 31, period_s=1.1, peak=0.5) if mode == "adaptive"
+         else synth.recipe_gated_pink(16.0, sr, 30, env_hz=0.9, hi_dbfs=-22.0))
+    total = len(x)
+    whole = eng.run(mode, [x], sr, **kw, **SZ)[0]
+    framing = sharded.WHOLEFILE if mode == "adaptive" else sharded.STREAMING
+    shards = sharded.plan_shards(total, world, framing, 2048, 1024)
+    assert all(s.hop == 1024 and s.n_fft == 2048 for s in shards)
+
+    def rank_fn(comm, r):
+        me = shards[r]
+        own = torch.from_numpy(x[me.own_lo:me.own_hi].copy()).cuda()
+        if mode == "adaptive":
+            out = sharded.run_adaptive_sharded(own, sr, total, comm, gather_to=0, **kw, **SZ)
+        else:
+            out = sharded.run_streaming_sharded(mode, own, sr, total, comm, gather_to=0, **kw, **SZ)
+        out["out"] = out["out"].cpu().numpy()
+        if out["full"] is not None:
+            out["full"] = out["full"].cpu().numpy()
+        return out
+    res = _run_threads(world, rank_fn)
+    for r, o in enumerate(res):
+        me = shards[r]
+        assert np.array_equal(o["meansq"], whole["meansq"]) and np.array_equal(o["states"], whole["states"])
+        assert np.array_equal(o["out"], whole["out"][me.own_lo:me.own_hi]), (mode, r)
+    assert np.array_equal(res[0]["full"], whole["out"])
+
+
+def test_streamed_file_at_2048():
+    import torch
+    from tomatis_audio_processor_b200.streamed import HostFileStreamer
+    eng = _engine()
+    sr = 48000
+    x = synth.recipe_gated_pink(31.0, sr, 501, env_hz=0.7, hi_dbfs=-21.0)
+    st = HostFileStreamer("standard", len(x), sr, slab_seconds=6.0, n_slots=2, gate_ui=50, **SZ)
+    assert len(st.slabs) >= 4
+    h_out = torch.empty((len(x), 2), dtype=torch.float32).pin_memory()
+    st.process(torch.from_numpy(x).pin_memory(), h_out)
+    torch.cuda.synchronize()
+    r = eng.run("standard", [x], sr, gate_ui=50, **SZ)[0]
+    assert np.array_equal(h_out.numpy(), r["out"]) and np.array_equal(st.states_rows()[0], r["states"])
+    st.close()

@@ -48,8 +48,9 @@ def process_sharded(mode: str, in_path: str, out_path: str, comm, device_index: 
     if total == 0:
         raise ValueError("empty input file")
     n_fft, hop = params.get("n_fft", tb.N_FFT), params.get("hop", tb.HOP)
-    if (n_fft, hop) != (tb.N_FFT, tb.HOP):                 # checked BEFORE any collective: every rank takes the same exit
-        raise NotImplementedError(f"the time-sharded path implements n_fft={tb.N_FFT}, hop={tb.HOP} (got {n_fft}/{hop}); "
+    from .engine import fused_size
+    if not fused_size(n_fft, hop):                         # checked BEFORE any collective: every rank takes the same exit
+        raise NotImplementedError(f"the time-sharded path implements n_fft/hop = 4096/2048 and 2048/1024 (got {n_fft}/{hop}); "
                                   f"other sizes run on one GPU (process_tomatis*.py)")
     framing = sharded.WHOLEFILE if mode == "adaptive" else sharded.STREAMING
     me = sharded.plan_shards(total, comm.world, framing, n_fft, hop)[comm.rank]

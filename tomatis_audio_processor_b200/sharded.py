@@ -49,6 +49,8 @@ class Shard:
     in_hi: int
     frame_lo: int         # frames whose level this rank is the owner of: [frame_lo, frame_hi)
     frame_hi: int
+    n_fft: int = tb.N_FFT # frame size of the plan (the fused kernels serve 4096 / 2048 and 2048 / 1024)
+    hop: int = tb.HOP
 
 
 def plan_shards(total: int, world: int, framing: int, n_fft=tb.N_FFT, hop=tb.HOP) -> List[Shard]:
@@ -79,7 +81,7 @@ def plan_shards(total: int, world: int, framing: int, n_fft=tb.N_FFT, hop=tb.HOP
             in_lo = in_hi = own_lo
         in_lo, in_hi = min(in_lo, own_lo), max(in_hi, own_hi)
         shards.append(Shard(r, world, total, framing, n_frames, first, blo, bhi, own_lo, own_hi, in_lo, in_hi,
-                            min(blo, n_frames), min(bhi, n_frames)))
+                            min(blo, n_frames), min(bhi, n_frames), n_fft, hop))
     return shards
 
 
@@ -148,7 +150,7 @@ class Comm:
         and last hop (32 KB per rank) instead of a group of point-to-point transfers -- the group's host-side launch cost
         (~0.25 ms) was a fifth of the 8-GPU step.  Anything else falls back to point-to-point."""
         torch, dist = self.torch, self.dist
-        hop = tb.HOP
+        hop = shard.hop
         if len(shards) == 1:
             return ("none", None, None)
         simple = all(s.own_hi - s.own_lo >= hop and s.own_lo - s.in_lo <= hop and s.in_hi - s.own_hi <= hop for s in shards)
@@ -184,7 +186,7 @@ class Comm:
             work.wait()
             left, right = shard.own_lo - shard.in_lo, shard.in_hi - shard.own_hi
             if left > 0:                                     # tail of the previous rank's last hop
-                window[:left] = data[shard.rank - 1, 1, tb.HOP - left:]
+                window[:left] = data[shard.rank - 1, 1, shard.hop - left:]
             if right > 0:                                    # head of the next rank's first hop
                 window[window.shape[0] - right:] = data[shard.rank + 1, 0, :right]
             return
@@ -228,7 +230,7 @@ class PeerExchange:
     def __init__(self, comm: "Comm", shard: Shard, device_index: int, timeout_s: float = 5.0):
         import ctypes as C
         from . import _lib as L
-        self.L, self.C, self.lib = L, C, L.load()
+        self.L, self.C, self.lib = L, C, L.load(shard.n_fft)
         self.comm, self.shard, self.device, self.timeout_s = comm, shard, device_index, timeout_s
         self.nb = shard.n_frames + 1 if shard.n_frames > 0 else 0
         self.own_ptr, self.peers, self.ok = None, {}, False
@@ -265,7 +267,7 @@ class PeerExchange:
         self.bases = (C.c_void_p * comm.world)(*[(self.own_ptr if r == comm.rank else self.peers[r]) for r in range(comm.world)])
 
     def publish(self, plan, own):
-        C, hop = self.C, tb.HOP
+        C, hop = self.C, self.shard.hop
         first = own.data_ptr() if self.shard.rank > 0 else None
         last = own[own.shape[0] - hop:].data_ptr() if self.shard.rank + 1 < self.shard.world else None
         from .engine import _stream_ptr
@@ -310,7 +312,7 @@ class CudaShardBackend:
         from . import _lib as L
         from .engine import Plan, get_engine
         self.L, self.shard = L, shard
-        self.eng = get_engine(device_index)
+        self.eng = get_engine(device_index, shard.n_fft, shard.hop)
         self.eng.set_gain_rows(gain_rows, key=rows_key)
         self.window = window
         # out: a caller-owned buffer for the shard's output (streamed.HostFileStreamer rotates a few device slots)
@@ -552,7 +554,7 @@ class StreamingShardSession:
         self.peer = None
         if use_peer is None:
             use_peer = os.environ.get("TMT_PEER_EXCHANGE", "1") != "0"
-        hop = tb.HOP
+        hop = self.me.hop
         simple = all(s.own_hi - s.own_lo >= hop and s.own_lo - s.in_lo <= hop and s.in_hi - s.own_hi <= hop for s in self.shards)
         if use_peer and comm.world > 1 and isinstance(comm, Comm) and comm.device.type == "cuda" and simple:
             px = PeerExchange(comm, self.me, device_index)

@@ -45,12 +45,14 @@ class HostFileStreamer:
     def __init__(self, mode: str, total: int, sr: int, device: int = 0, slab_seconds: float = 300.0, n_slots: int = 3,
                  unit_blocks: int = 0, **params):
         torch = self.torch = _torch()
-        if (params.get("n_fft", tb.N_FFT), params.get("hop", tb.HOP)) != (tb.N_FFT, tb.HOP):
-            raise NotImplementedError("HostFileStreamer implements n_fft=4096, hop=2048")
+        from .engine import fused_size
+        n_fft, hop = params.get("n_fft", tb.N_FFT), params.get("hop", tb.HOP)
+        if not fused_size(n_fft, hop):
+            raise NotImplementedError(f"HostFileStreamer implements n_fft/hop = 4096/2048 and 2048/1024; got {n_fft}/{hop}")
         self.total, self.sr = int(total), sr
         self.sp = streaming_params(mode, sr, **params)
         dev = torch.device(f"cuda:{device}")
-        slabs = plan_slabs(self.total, sr, slab_seconds)
+        slabs = plan_slabs(self.total, sr, slab_seconds, n_fft, hop)
         self.shards = [sl[0] for sl in slabs]
         n_frames = self.shards[0].n_frames if self.shards else 0
         self.n_frames = n_frames
