@@ -20,6 +20,8 @@ def main():
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
     comm = sharded.Comm(None, f"cuda:{local}")
+    n_fft = int(os.environ.get("TMT_TEST_NFFT", "4096"))       # 2048: the second build of the library (hop 1024)
+    sz = dict(n_fft=n_fft, hop=n_fft // 2) if n_fft != 4096 else {}
     cases = [("standard", 48000, synth.recipe_gated_pink(11.0, 48000, 30, env_hz=0.9, hi_dbfs=-22.0), dict(gate_ui=50)),
              ("xfade", 48000, synth.recipe_threshold_ramps(4.0, 48000, 3, t_on=-48.5, t_off=-51.5, period_s=1.3), dict(gate_ui=50, xfade_ms=300.0)),
              ("adaptive", 48000, synth.recipe_swept_pink(4.0, 48000, 4, period_s=1.1, peak=0.5), dict())]
@@ -30,7 +32,8 @@ def main():
         say(f"case {mode}")
         total = len(x)
         framing = sharded.WHOLEFILE if mode == "adaptive" else sharded.STREAMING
-        me = sharded.plan_shards(total, world, framing)[rank]
+        kw = dict(kw, **sz)
+        me = sharded.plan_shards(total, world, framing, n_fft, n_fft // 2)[rank]
         own = torch.from_numpy(x[me.own_lo:me.own_hi].copy()).cuda()
         if mode == "adaptive":
             r = sharded.run_adaptive_sharded(own, sr, total, comm, device_index=local, gather_to=0, **kw)
@@ -53,16 +56,16 @@ def main():
     x = cases[0][2]
     x2 = synth.recipe_gated_pink(11.0, 48000, 77, env_hz=1.3, hi_dbfs=-20.0)
     total = len(x)
-    me = sharded.plan_shards(total, world, sharded.STREAMING)[rank]
+    me = sharded.plan_shards(total, world, sharded.STREAMING, n_fft, n_fft // 2)[rank]
     outs = {}
     for flavour in ("peer", "collectives"):
         sess = sharded.StreamingShardSession("standard", torch.from_numpy(x[me.own_lo:me.own_hi].copy()).cuda(), 48000, total, comm,
-                                             device_index=local, gate_ui=50, use_peer=(flavour == "peer"))
+                                             device_index=local, gate_ui=50, use_peer=(flavour == "peer"), **sz)
         say(f"{flavour}: session created, unfusable chunks {sess.be.plan.unfusable_chunks}, graph {sess.use_graph}, "
             f"peer exchange {sess.peer is not None}")
         assert (sess.peer is not None) == (flavour == "peer"), "peer-memory exchange not available on this box"
         for src in (x, x2):
-            o = orc.run("standard", src, 48000, gate_ui=50)
+            o = orc.run("standard", src, 48000, gate_ui=50, **sz)
             sess.own.copy_(torch.from_numpy(src[me.own_lo:me.own_hi].copy()).cuda())
             for k in range(3 if src is x else 2):
                 sess.step()

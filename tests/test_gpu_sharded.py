@@ -110,13 +110,14 @@ def test_shard_session_repeated_steps(world):
         assert np.array_equal(yb, wb["out"][me.own_lo:me.own_hi]), r
 
 
-def test_nccl_two_gpus_torchrun():
+@pytest.mark.parametrize("n_fft", [4096, 2048])
+def test_nccl_two_gpus_torchrun(n_fft):
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
            "--master-port", "29517", os.path.join(HERE, "run_sharded_nccl.py")]
-    p = subprocess.run(cmd, capture_output=True, text=True, timeout=240)
+    p = subprocess.run(cmd, capture_output=True, text=True, timeout=240, env=dict(os.environ, TMT_TEST_NFFT=str(n_fft)))
     assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-3000:]
     assert "SHARDED-NCCL-OK" in p.stdout
 
