@@ -173,3 +173,22 @@ def test_product_never_imports_oracle():
         if fn.endswith(".py"):
             src = open(os.path.join(pkg, fn)).read()
             assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), fn
+
+
+def test_each_fused_frame_size_has_its_own_library_and_no_fallback(monkeypatch, tmp_path):
+    """engine.fused_size names the sizes the fused kernels serve; a missing build of the library is an error, not a fallback."""
+    from tomatis_audio_processor_b200 import _lib, build, engine
+    assert build.FUSED_SIZES == {4096: 2048, 2048: 1024} and set(build.LIB_PATHS) == set(build.FUSED_SIZES)
+    assert engine.fused_size(4096, 2048) and engine.fused_size(2048, 1024)
+    assert not engine.fused_size(2048, 512) and not engine.fused_size(1024, 512) and not engine.fused_size(4096, 1024)
+    monkeypatch.setenv("TMT_FUSED_2048", "0")                      # comparisons: send 2048 / 1024 to the general-size path
+    assert not engine.fused_size(2048, 1024) and engine.fused_size(4096, 2048)
+    monkeypatch.delenv("TMT_FUSED_2048")
+    with pytest.raises(NotImplementedError):
+        engine.Engine(0, 1024, 512)                                # checked before anything touches CUDA
+    monkeypatch.setattr(_lib, "_libs", {})
+    monkeypatch.setenv("TMT_LIB_2048", str(tmp_path / "missing.so"))
+    with pytest.raises(RuntimeError, match="not built"):
+        _lib.load(2048)
+    with pytest.raises(RuntimeError):
+        _lib.load(1024)
