@@ -42,3 +42,11 @@ def test_slab_chain_reproduces_the_whole_file_mean_squares(secs, slab, sr):
         f0 = max(0, s.block_lo - 1)
         assert np.allclose(msq[f0:f_hi], want[f0:f_hi], rtol=3e-6, atol=0)         # float32 summation order differs from the kernel's exact one
     assert have.all()
+
+
+def test_streamer_rejects_what_it_cannot_stream():
+    from tomatis_audio_processor_b200.streamed import HostFileStreamer
+    with pytest.raises(ValueError):
+        HostFileStreamer("standard", 0, 48000)
+    with pytest.raises(ValueError):
+        HostFileStreamer("adaptive", 48000, 48000)

@@ -10,7 +10,7 @@ the blocks it owns (plus the one block after them, which its right halo covers a
 device, and scans the gate over everything up to its own end -- a slab never needs anything from a LATER slab, so the pipeline
 never stalls.  Device memory: n_slots x (slab + two hops in, slab out), independent of the file length.
 
-The output is the bit-identical to the whole-file call (the same kernels on the same sample positions; the slabs are the shards of the
+The output is bit-identical to the whole-file call (the same kernels on the same sample positions; the slabs are the shards of the
 time-sharded path, whose output equals the unsharded one bit for bit, tests/test_gpu_sharded.py)."""
 from __future__ import annotations
 
@@ -44,6 +44,10 @@ def plan_slabs(total: int, sr: int, slab_seconds: float = 300.0, n_fft: int = tb
 class HostFileStreamer:
     def __init__(self, mode: str, total: int, sr: int, device: int = 0, slab_seconds: float = 300.0, n_slots: int = 3,
                  unit_blocks: int = 0, **params):
+        if int(total) <= 0:
+            raise ValueError("empty input file")
+        if mode not in ("standard", "xfade"):
+            raise ValueError("HostFileStreamer serves the streaming modes (standard, xfade); adaptive needs the whole file's peak first")
         torch = self.torch = _torch()
         from .engine import fused_size
         n_fft, hop = params.get("n_fft", tb.N_FFT), params.get("hop", tb.HOP)
