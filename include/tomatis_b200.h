@@ -244,6 +244,15 @@ int tmt_plan_stft_with_edges(tmt_plan* p, float post_gain, const float* in_scale
 int tmt_plan_run_streaming(tmt_plan* p, double m_on, double m_off, int run_frames, int xfade_frames,
                            float post_gain, float limit, void* stream);
 
+/* The same with integer PCM input: `pcm` holds the plan's tracks one after the other (track t at pcm + t * track_stride_bytes;
+ * int16 or packed 24-bit interleaved stereo, TMT_PCM_*), and ONE pass converts the samples into the plan's float input buffers
+ * (soundfile's read, src/process_tomatis.py:434) and sums the hop blocks for the levels (src/process_tomatis.py:370) -- no separate
+ * levels pass over the float samples.  tmt_plan_pcm_levels is that pass alone (= tmt_pcm_to_float + tmt_plan_levels with
+ * TMT_LEVELS_HOPSUM_ONLY, bit for bit).  Whole-track plans only. */
+int tmt_plan_pcm_levels(tmt_plan* p, const void* pcm, int64_t track_stride_bytes, int format, void* stream);
+int tmt_plan_run_streaming_pcm(tmt_plan* p, const void* pcm, int64_t track_stride_bytes, int format, double m_on, double m_off,
+                               int run_frames, int xfade_frames, float post_gain, float limit, void* stream);
+
 /* ---- PCM edge (device pointers) -------------------------------------------------------------- */
 #define TMT_PCM_S16 0 /* int16 little endian                  -> value / 32768    */
 #define TMT_PCM_S24 1 /* packed 3-byte little endian (PCM_24)  -> value / 8388608  */

@@ -372,3 +372,50 @@ def test_edges_beside_stft_and_fused_final_gate_equal_the_serial_launches(monkey
         assert np.array_equal(r["out"], r2["out"])
         assert np.array_equal(r["states"], r2["states"]) and np.array_equal(r["rows"], r2["rows"])
     assert a["optimal_T"] == a2["optimal_T"] and a["trace"] == a2["trace"]
+
+
+@pytest.mark.parametrize("fmt", ["s16", "s24"])
+@pytest.mark.parametrize("n", [300000, 123457])
+def test_pcm_conversion_fused_with_hop_sums_equals_the_two_passes(fmt, n, monkeypatch):
+    """tmt_plan_pcm_levels: integer PCM -> float input buffers + hop-block sums in one pass, against tmt_pcm_to_float followed by
+    the levels pass -- floats and sums bit for bit (odd lengths, tracks at odd byte offsets for the packed 24-bit case); and the
+    host-buffer pipeline with integer input gives the same bytes with the fused pass as with the separate ones."""
+    import torch
+    from tomatis_audio_processor_b200 import _lib as L, audio_io, synth
+    from tomatis_audio_processor_b200.batch import HostBatchPipeline
+    from tomatis_audio_processor_b200.engine import Plan, get_engine, pcm_to_float, whole_track_desc
+    eng = get_engine(0)
+    sr, T = 48000, 3
+    xs = np.stack([synth.recipe_gated_pink(n / sr + 0.01, sr, 80 + i, env_hz=1.3, hi_dbfs=-22.0)[:n] for i in range(T)])
+    if fmt == "s16":
+        raw = torch.from_numpy(np.stack([synth.quantise_pcm16(x) for x in xs])).cuda()                       # [T, n, 2] int16
+        code = L.PCM_S16
+    else:
+        raw = torch.from_numpy(np.stack([_pack24(audio_io.quantise_pcm24(x)).reshape(n, 6) for x in xs])).cuda()   # [T, n, 6] uint8
+        code = L.PCM_S24
+    x_a = torch.zeros((T, n, 2), dtype=torch.float32, device="cuda")
+    x_b = torch.zeros_like(x_a)
+    y = torch.empty_like(x_a)
+    pcm_to_float(raw, code, x_a)
+    pa = Plan(eng, L.FRAMING_STREAMING, [whole_track_desc(x_a[i], y[i]) for i in range(T)])
+    pa.levels(part="hopsums")
+    want = pa.read(L.ARR_HOPSUM_F32)
+    pa.close()
+    pb = Plan(eng, L.FRAMING_STREAMING, [whole_track_desc(x_b[i], y[i]) for i in range(T)])
+    pb.pcm_levels(raw, code)
+    got = pb.read(L.ARR_HOPSUM_F32)
+    pb.close()
+    assert torch.equal(x_a, x_b) and np.array_equal(got, want)
+    # the pipeline, fused pass against separate passes
+    outs = []
+    h_in = raw.cpu().pin_memory()
+    for fused in ("1", "0"):
+        monkeypatch.setenv("TMT_PCM_FUSED", fused)
+        p = HostBatchPipeline(n, sr, "standard", wave_tracks=1, in_format=fmt, out_format="s24", gate_ui=50)
+        assert p.fused_pcm == (fused == "1")
+        h_out = torch.empty((T, n, 6), dtype=torch.uint8).pin_memory()
+        p.process(h_in, h_out)
+        torch.cuda.synchronize()
+        outs.append((h_out.numpy().copy(), p.launches))
+        p.close()
+    assert np.array_equal(outs[0][0], outs[1][0]) and outs[0][1] == outs[1][1] - T          # one launch fewer per wave

@@ -85,6 +85,8 @@ SIGNATURES = {
     "tmt_calib_band_energies": (C.c_int, [_P, _P, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P]),
     "tmt_calib_gate_grid": (C.c_int, [_P, _P, _P, _P, C.c_int, _P, _P, _P, C.c_int, _P, _P, _P, _P]),
     "tmt_plan_run_streaming": (C.c_int, [_P, C.c_double, C.c_double, C.c_int, C.c_int, C.c_float, C.c_float, _P]),
+    "tmt_plan_pcm_levels": (C.c_int, [_P, _P, C.c_int64, C.c_int, _P]),
+    "tmt_plan_run_streaming_pcm": (C.c_int, [_P, _P, C.c_int64, C.c_int, C.c_double, C.c_double, C.c_int, C.c_int, C.c_float, C.c_float, _P]),
     "tmt_plan_launch_count": (C.c_int64, [_P]),
     "tmt_generic_meansq": (C.c_int, [_P, _P, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, _P, _P]),
     "tmt_generic_frames": (C.c_int, [_P, _P, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int, _P, _P, _P, C.c_float, C.c_int, _P, _P]),

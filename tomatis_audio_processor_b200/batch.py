@@ -71,6 +71,8 @@ class HostBatchPipeline:
         if in_format not in ("f32", "s16", "s24") or out_format not in ("f32", "s24"):
             raise ValueError("in_format: f32|s16|s24, out_format: f32|s24")
         self.in_format, self.out_format = in_format, out_format
+        import os
+        self.fused_pcm = os.environ.get("TMT_PCM_FUSED", "1") != "0"       # 0: separate conversion + levels pass (comparisons)
         self.eng = get_engine(device, params.get("n_fft", 4096), params.get("hop", 2048))      # a fused frame size (engine.fused_size)
         self.sp = streaming_params(mode, sr, **params)
         self.eng.set_gain_rows(self.sp.rows, key=self.sp.rows_key)
@@ -118,10 +120,15 @@ class HostBatchPipeline:
                 if sl["used"]:
                     self.s_c.wait_event(sl["ev_out"])         # previous copy-out of this slot has finished
                 before = sl["plan"].launch_count()
-                if sl["raw_in"] is not None:
-                    self._to_float(sl["raw_in"], L.PCM_S16 if self.in_format == "s16" else L.PCM_S24, sl["x"])
-                    self.launches += 1
-                sl["plan"].run_streaming(sp.m_on, sp.m_off, sp.run_frames, sp.xfade_frames, sp.post_gain)
+                if sl["raw_in"] is not None and self.fused_pcm:
+                    # integer input: conversion and hop-block sums in ONE pass over the samples, no levels pass over the floats
+                    sl["plan"].run_streaming_pcm(sl["raw_in"], L.PCM_S16 if self.in_format == "s16" else L.PCM_S24,
+                                                 sp.m_on, sp.m_off, sp.run_frames, sp.xfade_frames, sp.post_gain)
+                else:
+                    if sl["raw_in"] is not None:
+                        self._to_float(sl["raw_in"], L.PCM_S16 if self.in_format == "s16" else L.PCM_S24, sl["x"])
+                        self.launches += 1
+                    sl["plan"].run_streaming(sp.m_on, sp.m_off, sp.run_frames, sp.xfade_frames, sp.post_gain)
                 if sl["raw_out"] is not None:
                     self._to_pcm24(sl["y"], sl["raw_out"])
                     self.launches += 1

@@ -2007,6 +2007,88 @@ __global__ void __launch_bounds__(256) s24_to_float_kernel(const unsigned* __res
     }
 }
 
+// PCM edge fused with the levels pass (round 2): one warp per hop block converts the block's integer samples to float32 into the
+// plan's input buffer (soundfile's read: value / 2^(bits-1), exactly s16_to_float_kernel / s24_to_float_kernel) and, on the way,
+// sums the block in levels_kernel's lane layout and order -- the host-buffer pipeline with integer input then has no levels pass
+// over the float samples at all.  The hop blocks of a track tile [first_start, first_start + (n_frames + 1) * hop), which covers
+// the file, so every sample is converted exactly once.  FMT: 0 = int16, 1 = packed little-endian 24 bit.
+template <int FMT>
+__device__ __forceinline__ void pcm_pair(const unsigned char* __restrict__ src, long long p0, long long total, bool word_aligned,
+                                         float2& x0, float2& x1) {
+    x0 = x1 = make_float2(0.f, 0.f);
+    if (p0 + 1 < total && p0 >= 0 && word_aligned) {             // both sample-frames inside the file: 8 or 12 aligned bytes (p0 is even)
+        if (FMT == 0) {
+            const int2 w = *reinterpret_cast<const int2*>(src + 4 * p0);
+            x0 = make_float2((float)(short)(w.x & 0xffff) * (1.0f / 32768.0f), (float)(short)(w.x >> 16) * (1.0f / 32768.0f));
+            x1 = make_float2((float)(short)(w.y & 0xffff) * (1.0f / 32768.0f), (float)(short)(w.y >> 16) * (1.0f / 32768.0f));
+        } else {
+            const unsigned* q = reinterpret_cast<const unsigned*>(src + 6 * p0);
+            const unsigned a = q[0], b = q[1], c = q[2];
+            const float k = 1.0f / 8388608.0f;
+            x0 = make_float2((float)((int)(a << 8) >> 8) * k, (float)((int)(((a >> 24) | (b << 8)) << 8) >> 8) * k);
+            x1 = make_float2((float)((int)(((b >> 16) | (c << 16)) << 8) >> 8) * k, (float)((int)c >> 8) * k);
+        }
+        return;
+    }
+    auto one = [&](long long p) {
+        if (p < 0 || p >= total) return make_float2(0.f, 0.f);
+        if (FMT == 0) {
+            const short* q = reinterpret_cast<const short*>(src + 4 * p);
+            return make_float2((float)q[0] * (1.0f / 32768.0f), (float)q[1] * (1.0f / 32768.0f));
+        }
+        const unsigned char* q = src + 6 * p;
+        const int l = (int)((unsigned)q[0] | ((unsigned)q[1] << 8) | ((unsigned)q[2] << 16));
+        const int r = (int)((unsigned)q[3] | ((unsigned)q[4] << 8) | ((unsigned)q[5] << 16));
+        return make_float2((float)((l << 8) >> 8) * (1.0f / 8388608.0f), (float)((r << 8) >> 8) * (1.0f / 8388608.0f));
+    };
+    x0 = one(p0);
+    x1 = one(p0 + 1);
+}
+
+template <int FMT>
+__global__ void __launch_bounds__(kLevelWarps * 32)
+pcm_levels_kernel(const TrackDev* __restrict__ tracks, const unsigned char* __restrict__ pcm, long long track_stride, float* __restrict__ hsum) {
+    const TrackDev tr = tracks[blockIdx.y];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int q = blockIdx.x * kLevelWarps + warp;
+    if (tr.n_frames <= 0 || q > tr.n_frames) return;      // whole warp exits together
+    const unsigned char* src = pcm + (long long)blockIdx.y * track_stride;
+    const bool word_aligned = (reinterpret_cast<uintptr_t>(src) & (FMT == 0 ? 7u : 3u)) == 0;
+    float2* dst = const_cast<float2*>(tr.in);             // whole-track plans: in_origin = 0
+    const bool dst16 = (reinterpret_cast<uintptr_t>(dst) & 15u) == 0;
+    const long long start = tr.first_start + (long long)q * kHop;
+    const int pr = lane & 3, leaf = lane >> 2;
+    float tot[2];
+#pragma unroll
+    for (int ps = 0; ps < kHop / 1024; ++ps) {
+        const long long base = start + (ps * 8 + leaf) * 128 + 2 * pr;
+        float a0 = 0.f, a1 = 0.f;
+#pragma unroll 4
+        for (int i = 0; i < 16; ++i) {
+            const long long p0 = base + 8 * i;
+            float2 x0, x1;
+            pcm_pair<FMT>(src, p0, tr.total, word_aligned, x0, x1);
+            if (p0 >= 0 && p0 + 1 < tr.total && dst16) {
+                *reinterpret_cast<float4*>(dst + p0) = make_float4(x0.x, x0.y, x1.x, x1.y);
+            } else {
+                if (p0 >= 0 && p0 < tr.total) dst[p0] = x0;
+                if (p0 + 1 >= 0 && p0 + 1 < tr.total) dst[p0 + 1] = x1;
+            }
+            const float m0 = Arith<float>::msq(x0, 1.0f), m1 = Arith<float>::msq(x1, 1.0f);
+            a0 = i ? Arith<float>::add(a0, m0) : m0;
+            a1 = i ? Arith<float>::add(a1, m1) : m1;
+        }
+        float s = Arith<float>::add(a0, a1);
+        s = Arith<float>::add(s, __shfl_xor_sync(0xffffffffu, s, 1));
+        s = Arith<float>::add(s, __shfl_xor_sync(0xffffffffu, s, 2));
+        s = Arith<float>::add(s, __shfl_xor_sync(0xffffffffu, s, 4));
+        s = Arith<float>::add(s, __shfl_xor_sync(0xffffffffu, s, 8));
+        s = Arith<float>::add(s, __shfl_xor_sync(0xffffffffu, s, 16));
+        tot[ps] = s;
+    }
+    if (lane == 0 && q >= tr.hb_lo && q < tr.hb_hi) hsum[tr.hs_base + q] = (kHop == 2048) ? Arith<float>::add(tot[0], tot[1]) : tot[0];
+}
+
 // float -> PCM_24 as libsndfile writes it into a FLAC with clipping switched on (what python-soundfile does; restated in
 // audio_io.quantise_pcm24 from src/flac.c f2flac24_clip_array): lrintf(x * 2^23), pinned to [-2^23, 2^23 - 1].  The scale is a
 // power of two, so the product is exact and the only rounding is the round-half-even conversion (which saturates).
@@ -3550,11 +3632,50 @@ int tmt_plan_limiter(tmt_plan* p, float limit, void* stream) {
     return TMT_OK;
 }
 
+static int run_streaming_tail(tmt_plan* p, double m_on, double m_off, int run_frames, int xfade_frames, float post_gain, float limit,
+                              void* stream);
+
 int tmt_plan_run_streaming(tmt_plan* p, double m_on, double m_off, int run_frames, int xfade_frames, float post_gain,
                            float limit, void* stream) {
     if (!p) return fail(TMT_ERR_INVALID, "plan is NULL");
     int rc = tmt_plan_levels(p, 0, nullptr, stream);
     if (rc) return rc;
+    return run_streaming_tail(p, m_on, m_off, run_frames, xfade_frames, post_gain, limit, stream);
+}
+
+int tmt_plan_pcm_levels(tmt_plan* p, const void* pcm, int64_t track_stride_bytes, int format, void* stream) {
+    if (!p || !pcm) return fail(TMT_ERR_INVALID, "bad arguments");
+    if (format != TMT_PCM_S16 && format != TMT_PCM_S24) return fail(TMT_ERR_INVALID, "unknown PCM format %d", format);
+    if (p->n_tracks == 0) return TMT_OK;
+    for (const HostTrack& h : p->ht)
+        if (h.d.in_origin != 0 || h.d.in_len != h.d.total || h.hb_lo != 0 || (h.n_frames > 0 && h.hb_hi != h.n_frames + 1))
+            return fail(TMT_ERR_UNSUPPORTED, "tmt_plan_pcm_levels needs whole-track plans (input window = the file, all hop blocks)");
+    CUDA_TRY(cudaSetDevice(p->e->device));
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const dim3 grid(ceil_div(p->max_frames + 1, kLevelWarps), p->n_tracks);
+    if (format == TMT_PCM_S16)
+        pcm_levels_kernel<0><<<grid, kLevelWarps * 32, 0, st>>>(p->tracks.p, reinterpret_cast<const unsigned char*>(pcm), track_stride_bytes,
+                                                              reinterpret_cast<float*>(p->hsum.p));
+    else
+        pcm_levels_kernel<1><<<grid, kLevelWarps * 32, 0, st>>>(p->tracks.p, reinterpret_cast<const unsigned char*>(pcm), track_stride_bytes,
+                                                              reinterpret_cast<float*>(p->hsum.p));
+    p->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return TMT_OK;
+}
+
+int tmt_plan_run_streaming_pcm(tmt_plan* p, const void* pcm, int64_t track_stride_bytes, int format, double m_on, double m_off,
+                               int run_frames, int xfade_frames, float post_gain, float limit, void* stream) {
+    int rc = tmt_plan_pcm_levels(p, pcm, track_stride_bytes, format, stream);      // conversion + hop-block sums in one pass
+    if (rc) return rc;
+    rc = tmt_plan_levels(p, TMT_LEVELS_MEANSQ_ONLY, nullptr, stream);
+    if (rc) return rc;
+    return run_streaming_tail(p, m_on, m_off, run_frames, xfade_frames, post_gain, limit, stream);
+}
+
+static int run_streaming_tail(tmt_plan* p, double m_on, double m_off, int run_frames, int xfade_frames, float post_gain, float limit,
+                              void* stream) {
+    int rc;
     std::vector<double> on((size_t)std::max(p->n_tracks, 1), m_on), off((size_t)std::max(p->n_tracks, 1), m_off);
     rc = tmt_plan_gate(p, TMT_GATE_UPDELAY, TMT_ARR_MEANSQ_F32, on.data(), off.data(), run_frames, xfade_frames, 0, 0, stream);
     if (rc) return rc;

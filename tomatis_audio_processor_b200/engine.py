@@ -261,6 +261,20 @@ class Plan:
                                                 float(post_gain), float(np.float32(limit)), _stream_ptr(_torch())),
                 "tmt_plan_run_streaming")
 
+    def pcm_levels(self, pcm_dev, fmt: int):
+        """Integer PCM of all tracks (device tensor [T, N, 2] int16 or [T, N, 6] uint8) -> the plan's float input buffers and
+        the hop-block sums, one pass (tmt_plan_pcm_levels)."""
+        stride = pcm_dev.stride(0) * pcm_dev.element_size() if pcm_dev.dim() == 3 else pcm_dev.numel() * pcm_dev.element_size()
+        L.check(self.lib.tmt_plan_pcm_levels(self.h, C.c_void_p(pcm_dev.data_ptr()), int(stride), int(fmt), _stream_ptr(_torch())),
+                "tmt_plan_pcm_levels")
+
+    def run_streaming_pcm(self, pcm_dev, fmt: int, m_on, m_off, run_frames, xfade_frames, post_gain=1.0, limit=tb.PEAK_LIMIT):
+        """run_streaming with integer PCM input: conversion and hop-block sums in one pass (tmt_plan_run_streaming_pcm)."""
+        stride = pcm_dev.stride(0) * pcm_dev.element_size() if pcm_dev.dim() == 3 else pcm_dev.numel() * pcm_dev.element_size()
+        L.check(self.lib.tmt_plan_run_streaming_pcm(self.h, C.c_void_p(pcm_dev.data_ptr()), int(stride), int(fmt), float(m_on), float(m_off),
+                                                    int(run_frames), int(xfade_frames), float(post_gain), float(np.float32(limit)),
+                                                    _stream_ptr(_torch())), "tmt_plan_run_streaming_pcm")
+
     def launch_count(self) -> int:
         return int(self.lib.tmt_plan_launch_count(self.h))
 
