@@ -3,6 +3,8 @@ the second build of the library (csrc/libtomatis_b200_n2048.so, TMT_NFFT=2048), 
 2048-point frames through one 4096-wide pass ("pair mode", csrc/fft4096.cuh).  Everything is compared with the oracle run at the
 same sizes (which tests/test_oracle_vs_reference.py pins to the executed reference for non-default n_fft / hop): mean squares
 bit-exact, states / rows / chunk lengths / threshold search exact, PCM within 1e-5 of full scale."""
+import os
+
 import numpy as np
 import pytest
 
@@ -264,3 +266,34 @@ def test_streamed_file_at_2048():
     r = eng.run("standard", [x], sr, gate_ui=50, **SZ)[0]
     assert np.array_equal(h_out.numpy(), r["out"]) and np.array_equal(st.states_rows()[0], r["states"])
     st.close()
+
+
+def test_integer_pcm_pipeline_at_2048():
+    """HostBatchPipeline with int16 in / PCM_24 out at 2048 / 1024: the fused conversion + hop-sum pass of the second build against
+    the separate passes, byte for byte, and against the float pipeline quantised on the host."""
+    import torch
+    from tomatis_audio_processor_b200 import audio_io
+    from tomatis_audio_processor_b200.batch import HostBatchPipeline
+    n, sr, T = 150001, 48000, 2
+    xs = np.stack([_q(synth.recipe_gated_pink(n / sr + 0.01, sr, 90 + i, env_hz=1.1, hi_dbfs=-22.0))[:n] for i in range(T)])
+    s_in = torch.from_numpy(np.stack([synth.quantise_pcm16(x) for x in xs])).pin_memory()
+    outs = []
+    for fused in ("1", "0"):
+        os.environ["TMT_PCM_FUSED"] = fused
+        try:
+            p = HostBatchPipeline(n, sr, "standard", wave_tracks=1, in_format="s16", out_format="s24", gate_ui=50, **SZ)
+        finally:
+            os.environ.pop("TMT_PCM_FUSED")
+        s_out = torch.empty((T, n, 6), dtype=torch.uint8).pin_memory()
+        p.process(s_in, s_out)
+        torch.cuda.synchronize()
+        p.close()
+        outs.append(s_out.numpy().copy())
+    assert np.array_equal(outs[0], outs[1])
+    want = _engine().run("standard", list(xs), sr, gate_ui=50, **SZ)
+    for i in range(T):
+        q = audio_io.quantise_pcm24(want[i]["out"]).reshape(-1)
+        got = outs[0][i].reshape(-1, 3).astype(np.int32)
+        got = got[:, 0] | (got[:, 1] << 8) | (got[:, 2] << 16)
+        got = np.where(got & 0x800000, got - 0x1000000, got)
+        assert np.abs(got - q).max() <= 2                          # the batch plan's unit split can move a limited chunk by an LSB or two
