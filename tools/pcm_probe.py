@@ -47,3 +47,7 @@ sf = T * n
 print(f"{T} tracks x 300 s, int16 in: separate conversion + levels + rest {t_sep:.3f} ms | fused {t_fus:.3f} ms ({100 * (1 - t_fus / t_sep):.1f} % less)")
 print(f"  conversion alone {t_conv:.3f} ms ({12.0 * sf / t_conv / 1e6:.0f} GB/s), hop sums alone {t_lev:.3f} ms ({8.0 * sf / t_lev / 1e6:.0f} GB/s), "
       f"fused pass {t_pl:.3f} ms ({12.0 * sf / t_pl / 1e6:.0f} GB/s of 4 B read + 8 B written per sample-frame)")
+from tomatis_audio_processor_b200.engine import float_to_pcm24          # noqa: E402
+out24 = torch.empty((T, n, 6), dtype=torch.uint8, device="cuda")
+t_o = timed(lambda: float_to_pcm24(y, out24))
+print(f"  float -> PCM_24 of the output: {t_o:.3f} ms ({14.0 * sf / t_o / 1e6:.0f} GB/s of 8 B read + 6 B written per sample-frame)")
